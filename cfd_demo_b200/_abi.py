@@ -1,0 +1,65 @@
+"""ctypes mirror of include/cfd_b200.h (PODs and constants only; no library is loaded here)."""
+import ctypes as C
+
+CFD_ABI_VERSION = 1
+
+CFD_OK = 0
+CFD_ERR_INVALID_ARGUMENT = 1
+CFD_ERR_CUDA = 2
+CFD_ERR_UNSUPPORTED = 3
+CFD_ERR_NCCL = 4
+
+SCHEME_FIRST_ORDER, SCHEME_SECOND_ORDER = 0, 1
+INLET_UNIFORM, INLET_PARABOLIC = 0, 1
+SOLVER_JACOBI, SOLVER_CG = 0, 1
+SCENARIO_CHANNEL, SCENARIO_CAVITY = 0, 1
+
+FIELD_P, FIELD_U, FIELD_V, FIELD_U_STAR, FIELD_V_STAR, FIELD_RHS, FIELD_P_PRIME = range(7)
+FIELD_U_OLD, FIELD_V_OLD, FIELD_MASK_U, FIELD_MASK_V = 7, 8, 9, 10
+FIELD_NAMES = {
+    FIELD_P: "p", FIELD_U: "u", FIELD_V: "v", FIELD_U_STAR: "u_star", FIELD_V_STAR: "v_star",
+    FIELD_RHS: "rhs", FIELD_P_PRIME: "p_prime", FIELD_U_OLD: "u_old", FIELD_V_OLD: "v_old",
+    FIELD_MASK_U: "mask_u", FIELD_MASK_V: "mask_v",
+}
+
+FLAG_NO_GRAPH = 1
+FLAG_BASELINE_SWEEP = 2
+
+
+class CfdGrid(C.Structure):
+    _fields_ = [("nx", C.c_uint64), ("ny", C.c_uint64),
+                ("lx", C.c_float), ("ly", C.c_float), ("dx", C.c_float), ("dy", C.c_float),
+                ("has_obstacle", C.c_int32),
+                ("center_x", C.c_float), ("center_y", C.c_float), ("radius", C.c_float)]
+
+
+class CfdParams(C.Structure):
+    _fields_ = [("dt", C.c_float), ("viscosity", C.c_float), ("target_inlet_velocity", C.c_float),
+                ("velocity_scheme", C.c_int32), ("inlet_profile", C.c_int32),
+                ("pressure_solver", C.c_int32), ("scenario", C.c_int32)]
+
+
+class CfdSolverConsts(C.Structure):
+    _fields_ = [("ramp_up_steps", C.c_int32), ("jacobi_iterations", C.c_int32),
+                ("outer_rounds", C.c_int32), ("cg_max_iterations", C.c_int32),
+                ("jacobi_omega", C.c_double), ("pressure_tolerance", C.c_double),
+                ("outer_tolerance", C.c_double), ("cfl", C.c_double), ("cg_tolerance", C.c_double)]
+
+
+class CfdOptions(C.Structure):
+    _fields_ = [("precision", C.c_int32), ("device", C.c_int32), ("rank", C.c_int32),
+                ("world_size", C.c_int32), ("nccl_unique_id", C.c_void_p), ("flags", C.c_uint32),
+                ("consts", CfdSolverConsts)]
+
+
+class CfdResiduals(C.Structure):
+    _fields_ = [("simulation_step", C.c_uint64),
+                ("simulation_time", C.c_float), ("dt", C.c_float), ("p", C.c_float),
+                ("u", C.c_float), ("v", C.c_float),
+                ("step_seconds", C.c_double), ("piso_substeps", C.c_uint64),
+                ("jacobi_calls", C.c_uint64), ("sweeps", C.c_uint64),
+                ("simulation_time_f64", C.c_double), ("dt_f64", C.c_double), ("p_f64", C.c_double),
+                ("u_f64", C.c_double), ("v_f64", C.c_double)]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}

@@ -1,0 +1,628 @@
+// cfd_model.cu — host orchestration of one timestep + the C ABI of include/cfd_b200.h.
+//
+// Replaces the inside of the reference's `Model` (src/model.rs:166-379, 529-730, 1250-1280): the fields
+// live in HBM as structure-of-arrays, every stage is a kernel from cfd_kernels.cuh, the full-field copies
+// of the reference (u_old <- u :307-308, u_star <- u :698-699) are buffer rotations, and the only
+// device->host traffic per step is a handful of scalars (sweep counts, max-reductions).
+// There is no CPU fallback: every entry point fails with CFD_ERR_CUDA if the device is unusable.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/cfd_b200.h"
+#include "cfd_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define CFD_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return fail(CFD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                                    ":" + std::to_string(__LINE__) + ")");                          \
+  } while (0)
+
+void consts_default(cfd_solver_consts* c) {
+  c->ramp_up_steps = 100;        // src/model.rs:269
+  c->jacobi_iterations = 50;     // :737
+  c->outer_rounds = 20;          // :696
+  c->cg_max_iterations = 20000;  // extension
+  c->jacobi_omega = 0.75;        // :735
+  c->pressure_tolerance = 1e-4;  // :736
+  c->outer_tolerance = 1e-4;     // :721
+  c->cfl = 0.2;                  // :885
+  c->cg_tolerance = 1e-8;        // extension
+}
+
+constexpr int kMaxSweepSlots = 256;
+constexpr int kJacobiRows = 32;
+
+struct ModelBase {
+  virtual ~ModelBase() {}
+  virtual int init() = 0;
+  virtual int update() = 0;
+  virtual int set_params(const cfd_params& p) = 0;
+  virtual int get_snapshot(float* p, float* u, float* v, float* dt) = 0;
+  virtual int get_residuals(cfd_residuals* out) = 0;
+  virtual int field_len(int field, uint64_t* len) = 0;
+  virtual int get_field_f64(int field, double* out, uint64_t len) = 0;
+  virtual int set_field_f64(int field, const double* in, uint64_t len) = 0;
+  virtual int rows(uint64_t* j0, uint64_t* j1) = 0;
+  virtual int last_timing(double* step_ms, double* sweep_ms, uint64_t* launches) = 0;
+};
+
+template <class R>
+struct ModelImpl final : ModelBase {
+  // ---- problem definition ----
+  cfd_grid grid;
+  cfd_options opt;
+  int nx, ny;
+  size_t n_p, n_u, n_v;
+  // ---- scalars kept on the host in R precision, same arithmetic as the reference (update(), :304-379) ----
+  R dx, dy, lx, ly, dt, nu;
+  R current_inlet_velocity = 0, target_inlet_velocity = 0;
+  R last_pressure_residual = 0, last_u_residual = 0, last_v_residual = 0, simulation_time = 0;
+  uint64_t simulation_step = 0, substep_count = 1, last_piso_substeps = 0;
+  int velocity_scheme = 0, pressure_solver = 0, inlet_profile = 0, scenario = 0;
+  uint64_t last_K = 0, last_S = 0;
+  double last_step_seconds = 0, last_step_ms = 0, last_sweep_ms = 0;
+  uint64_t last_launches = 0, launches = 0;
+  // ---- device state ----
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  R* ubuf[3] = {nullptr, nullptr, nullptr};
+  R* vbuf[3] = {nullptr, nullptr, nullptr};
+  int iu = 0, ius = 1, ifree = 2;  // roles of the three u (and v) buffers: current, star, free
+  R* p = nullptr;
+  R* rhs = nullptr;
+  R* pp[2] = {nullptr, nullptr};
+  int ipp = 0;  // pp[ipp] is p_prime, the other one p_prime_new
+  uint8_t *mask_u = nullptr, *mask_v = nullptr, *solid = nullptr;
+  unsigned long long* err_slots = nullptr;   // kMaxSweepSlots
+  unsigned long long* step_slots = nullptr;  // 4
+  cfdk::JacobiResult* h_jres = nullptr;      // pinned, device-visible
+  unsigned long long* h_step = nullptr;      // pinned, 4
+  void* staging = nullptr;                   // device scratch for read-back conversions
+  size_t staging_bytes = 0;
+  void* h_staging = nullptr;                 // pinned host scratch
+  size_t h_staging_bytes = 0;
+  cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
+  std::vector<cudaEvent_t> ev_sweep;  // pairs
+  bool ready = false;
+
+  ModelImpl(const cfd_grid& g, const cfd_params& prm, const cfd_options& o) : grid(g), opt(o) {
+    nx = (int)g.nx;
+    ny = (int)g.ny;
+    n_p = (size_t)nx * ny;
+    n_u = (size_t)(nx + 1) * ny;
+    n_v = (size_t)nx * (ny + 1);
+    dx = R(g.dx); dy = R(g.dy); lx = R(g.lx); ly = R(g.ly);
+    dt = R(prm.dt);          // src/model.rs:265
+    nu = R(prm.viscosity);   // :266
+    target_inlet_velocity = R(prm.target_inlet_velocity);
+    velocity_scheme = prm.velocity_scheme;
+    pressure_solver = prm.pressure_solver;
+    inlet_profile = prm.inlet_profile;
+    scenario = prm.scenario;
+  }
+
+  ~ModelImpl() override {
+    if (device >= 0) cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    for (auto& b : ubuf) cudaFree(b);
+    for (auto& b : vbuf) cudaFree(b);
+    cudaFree(p); cudaFree(rhs); cudaFree(pp[0]); cudaFree(pp[1]);
+    cudaFree(mask_u); cudaFree(mask_v); cudaFree(solid);
+    cudaFree(err_slots); cudaFree(step_slots); cudaFree(staging);
+    if (h_jres) cudaFreeHost(h_jres);
+    if (h_step) cudaFreeHost(h_step);
+    if (h_staging) cudaFreeHost(h_staging);
+    if (ev_step0) cudaEventDestroy(ev_step0);
+    if (ev_step1) cudaEventDestroy(ev_step1);
+    for (auto e : ev_sweep) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  template <class T>
+  int dalloc(T** ptr, size_t count) {
+    CFD_CUDA(cudaMalloc((void**)ptr, count * sizeof(T)));
+    CFD_CUDA(cudaMemsetAsync(*ptr, 0, count * sizeof(T), stream));
+    return CFD_OK;
+  }
+
+  // Model::new, src/model.rs:219-299: zero fields, masks from the cylinder
+  int init() override {
+    int ndev = 0;
+    CFD_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) return fail(CFD_ERR_CUDA, "no CUDA device: cfd_b200 has no CPU fallback");
+    if (opt.device >= 0) {
+      CFD_CUDA(cudaSetDevice(opt.device));
+      device = opt.device;
+    } else {
+      CFD_CUDA(cudaGetDevice(&device));
+    }
+    CFD_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    int rc;
+    for (int k = 0; k < 3; ++k) {
+      if ((rc = dalloc(&ubuf[k], n_u))) return rc;
+      if ((rc = dalloc(&vbuf[k], n_v))) return rc;
+    }
+    if ((rc = dalloc(&p, n_p))) return rc;
+    if ((rc = dalloc(&rhs, n_p))) return rc;
+    if ((rc = dalloc(&pp[0], n_p))) return rc;
+    if ((rc = dalloc(&pp[1], n_p))) return rc;
+    if ((rc = dalloc(&mask_u, n_u))) return rc;
+    if ((rc = dalloc(&mask_v, n_v))) return rc;
+    if ((rc = dalloc(&solid, n_p))) return rc;
+    if ((rc = dalloc(&err_slots, (size_t)kMaxSweepSlots))) return rc;
+    if ((rc = dalloc(&step_slots, (size_t)4))) return rc;
+    CFD_CUDA(cudaHostAlloc((void**)&h_jres, sizeof(cfdk::JacobiResult), cudaHostAllocMapped));
+    CFD_CUDA(cudaHostAlloc((void**)&h_step, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    CFD_CUDA(cudaEventCreate(&ev_step0));
+    CFD_CUDA(cudaEventCreate(&ev_step1));
+    const int n_pairs = 2 * (opt.consts.outer_rounds + 1);
+    ev_sweep.resize(n_pairs);
+    for (auto& e : ev_sweep) CFD_CUDA(cudaEventCreate(&e));
+
+    cfdk::MaskGeom g;
+    g.nx = nx; g.ny = ny;
+    g.has_obstacle = grid.has_obstacle != 0;
+    g.cavity = scenario == CFD_SCENARIO_CAVITY;
+    g.dx = grid.dx; g.dy = grid.dy; g.cx = grid.center_x; g.cy = grid.center_y; g.radius = grid.radius;
+    dim3 blk(256), grd((nx + 1 + 255) / 256, ny + 1);
+    cfdk::k_build_masks<<<grd, blk, 0, stream>>>(g, solid, mask_u, mask_v);
+    CFD_CUDA(cudaGetLastError());
+    CFD_CUDA(cudaStreamSynchronize(stream));
+    ready = true;
+    return CFD_OK;
+  }
+
+  cfdk::StepScalars<R> scalars(R dt_sub) const {
+    cfdk::StepScalars<R> s;
+    s.dx = dx; s.dy = dy; s.dt = dt_sub; s.nu = nu; s.nx = nx; s.ny = ny;
+    return s;
+  }
+
+  // ---- one pressure solve: recompute_divergence (:1406-1440) + jacobi_pressure (:734-824) ----
+  int pressure_solve(R dt_sub, const R* us, const R* vs, int call_index, R* residual_out) {
+    const int iters = opt.consts.jacobi_iterations;
+    {
+      dim3 blk(256), grd((nx + 255) / 256, ny);
+      cfdk::k_divergence<R><<<grd, blk, 0, stream>>>(scalars(dt_sub), us, vs, rhs, 0, ny, err_slots, iters);
+      ++launches;
+    }
+    if (pressure_solver != CFD_SOLVER_JACOBI)
+      return fail(CFD_ERR_UNSUPPORTED, "pressure_solver: only Jacobi is implemented in this build");
+    cfdk::JacobiConsts<R> c;
+    c.dx_sq = dx * dx;                                   // :740
+    c.dy_sq = dy * dy;                                   // :742
+    c.denom = R(2.0) / (dx * dx) + R(2.0) / (dy * dy);   // :746
+    c.omega = R(opt.consts.jacobi_omega);
+    c.one_minus_omega = R(1.0) - c.omega;                // :745
+    c.tol = R(opt.consts.pressure_tolerance);
+    c.nx = nx; c.ny = ny; c.cavity = scenario == CFD_SCENARIO_CAVITY;
+    CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index], stream));
+    dim3 blk(256), grd((nx - 2 + 255) / 256, (ny - 2 + kJacobiRows - 1) / kJacobiRows);
+    for (int s = 0; s < iters; ++s) {
+      cfdk::k_jacobi_sweep<R, kJacobiRows><<<grd, blk, 0, stream>>>(c, pp[(ipp + s) & 1], rhs, pp[(ipp + s + 1) & 1],
+                                                                    err_slots, s);
+      ++launches;
+    }
+    cfdk::k_jacobi_finalize<R><<<1, 32, 0, stream>>>(err_slots, iters, c.tol, h_jres);
+    ++launches;
+    CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index + 1], stream));
+    CFD_CUDA(cudaGetLastError());
+    CFD_CUDA(cudaStreamSynchronize(stream));
+    const int ran = h_jres->sweeps;
+    ipp = (ipp + ran) & 1;
+    last_S += (uint64_t)ran;
+    last_K += 1;
+    *residual_out = (R)h_jres->last_error;
+    return CFD_OK;
+  }
+
+  int corrector(R dt_sub, const R* us, const R* vs, const R* uk, const R* vk, R* uo, R* vo) {
+    dim3 blk(256), grd((nx + 1 + 255) / 256, ny + 1);
+    cfdk::k_corrector<R><<<grd, blk, 0, stream>>>(scalars(dt_sub), us, vs, uk, vk, pp[ipp], uo, vo, p, 0, ny, ny + 1);
+    ++launches;
+    CFD_CUDA(cudaGetLastError());
+    return CFD_OK;
+  }
+
+  // Model::update, src/model.rs:304-379 (with piso_step :529-730 inlined)
+  int update() override {
+    if (!ready) return fail(CFD_ERR_INVALID_ARGUMENT, "model not initialised");
+    CFD_CUDA(cudaSetDevice(device));
+    const auto t0 = std::chrono::steady_clock::now();
+    launches = 0;
+    CFD_CUDA(cudaEventRecord(ev_step0, stream));
+    // u_old <- u, v_old <- v (:307-308): the current buffers simply stay untouched until the step ends
+    const int X = iu, Y = ius, Z = ifree;
+    if (simulation_step < (uint64_t)opt.consts.ramp_up_steps) {  // :311-316
+      current_inlet_velocity = (R(simulation_step) / R(opt.consts.ramp_up_steps)) * target_inlet_velocity;
+    } else {
+      current_inlet_velocity = target_inlet_velocity;
+    }
+    const R dt_sub = dt / R(substep_count);  // :317
+    last_piso_substeps = substep_count;
+    last_K = 0;
+    last_S = 0;
+    int rc;
+    // ---- predictor (:538-670): reads u, v; writes the interior of u_star, v_star (the rest is carried state)
+    {
+      const auto s = scalars(dt_sub);
+      dim3 blk(256);
+      dim3 gu((nx + 255) / 256, ny - 2), gv((nx - 1 + 255) / 256, ny - 1);
+      if (velocity_scheme == CFD_SCHEME_SECOND_ORDER) {
+        cfdk::k_predict_u<R, true><<<gu, blk, 0, stream>>>(s, ubuf[X], vbuf[X], mask_u, ubuf[Y], 1, ny - 1);
+        cfdk::k_predict_v<R, true><<<gv, blk, 0, stream>>>(s, ubuf[X], vbuf[X], mask_v, vbuf[Y], 1, ny);
+      } else {
+        cfdk::k_predict_u<R, false><<<gu, blk, 0, stream>>>(s, ubuf[X], vbuf[X], mask_u, ubuf[Y], 1, ny - 1);
+        cfdk::k_predict_v<R, false><<<gv, blk, 0, stream>>>(s, ubuf[X], vbuf[X], mask_v, vbuf[Y], 1, ny);
+      }
+      launches += 2;
+      CFD_CUDA(cudaGetLastError());
+    }
+    // ---- first pressure solve + corrector (:676-693): new u, v go to the free buffer, keeping X as u_old
+    R residual = 0;
+    if ((rc = pressure_solve(dt_sub, ubuf[Y], vbuf[Y], 0, &residual))) return rc;
+    last_pressure_residual = residual;
+    if ((rc = corrector(dt_sub, ubuf[Y], vbuf[Y], ubuf[X], vbuf[X], ubuf[Z], vbuf[Z]))) return rc;
+    int cur = Z, star = Y;
+    // ---- outer re-correction loop (:696-724): `star <- current` is a role swap
+    for (int it = 0; it < opt.consts.outer_rounds; ++it) {
+      const int t = star; star = cur; cur = t;  // star now aliases the latest u, v; `cur` is overwritten in full
+      if ((rc = pressure_solve(dt_sub, ubuf[star], vbuf[star], it + 1, &residual))) return rc;
+      last_pressure_residual = residual;
+      if ((rc = corrector(dt_sub, ubuf[star], vbuf[star], ubuf[star], vbuf[star], ubuf[cur], vbuf[cur]))) return rc;
+      if (last_pressure_residual < R(opt.consts.outer_tolerance)) break;  // :721
+    }
+    // ---- boundary conditions (:728 -> :827-875)
+    {
+      cfdk::BcScalars<R> b;
+      b.dy = dy; b.ly = ly; b.inlet = current_inlet_velocity; b.nx = nx; b.ny = ny;
+      b.parabolic = inlet_profile == CFD_INLET_PARABOLIC;
+      b.cavity = scenario == CFD_SCENARIO_CAVITY;
+      const int n = (nx > ny ? nx : ny) + 1;
+      cfdk::k_bc_edges<R><<<(n + 255) / 256, 256, 0, stream>>>(b, ubuf[cur], vbuf[cur], 0, ny, 1, 1);
+      dim3 blk(256), grd((nx + 255) / 256, ny);
+      cfdk::k_bc_solids<R><<<grd, blk, 0, stream>>>(nx, solid, ubuf[cur], vbuf[cur], 0, ny);
+      launches += 2;
+    }
+    // ---- residuals and CFL maxima (:333-348, :878-881)
+    CFD_CUDA(cudaMemsetAsync(step_slots, 0, 4 * sizeof(unsigned long long), stream));
+    cfdk::k_step_maxima<R><<<148 * 8, 256, 0, stream>>>(ubuf[cur], ubuf[X], n_u, vbuf[cur], vbuf[X], n_v, step_slots);
+    ++launches;
+    CFD_CUDA(cudaMemcpyAsync(h_step, step_slots, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    CFD_CUDA(cudaEventRecord(ev_step1, stream));
+    CFD_CUDA(cudaGetLastError());
+    CFD_CUDA(cudaStreamSynchronize(stream));
+    iu = cur; ius = star; ifree = X;
+    last_u_residual = (R)cfdk::bits_nonneg(h_step[0]);
+    last_v_residual = (R)cfdk::bits_nonneg(h_step[1]);
+    simulation_step += 1;    // :350
+    simulation_time += dt;   // :365
+    // compute_automatic_time_step (:878-889) + the (dead) growth limiter (:368-377)
+    {
+      const R max_u = (R)cfdk::bits_nonneg(h_step[2]), max_v = (R)cfdk::bits_nonneg(h_step[3]);
+      const R max_vel = max_u > max_v ? max_u : max_v;
+      R new_dt;
+      if (max_vel == R(0)) {
+        new_dt = dt;
+      } else {
+        const R cfl = R(opt.consts.cfl);
+        const R dt_cfl = cfl * (dx < dy ? dx : dy) / max_vel;
+        new_dt = dt_cfl < dt ? dt_cfl : dt;
+      }
+      const R previous_dt = dt;
+      const R max_increase_factor = R(1.1);
+      if (new_dt > previous_dt) {
+        const R lim = previous_dt * max_increase_factor;
+        dt = new_dt < lim ? new_dt : lim;
+      } else {
+        dt = new_dt;
+      }
+    }
+    float ms = 0;
+    CFD_CUDA(cudaEventElapsedTime(&ms, ev_step0, ev_step1));
+    last_step_ms = ms;
+    last_sweep_ms = 0;
+    for (uint64_t k = 0; k < last_K; ++k) {
+      CFD_CUDA(cudaEventElapsedTime(&ms, ev_sweep[2 * k], ev_sweep[2 * k + 1]));
+      last_sweep_ms += ms;
+    }
+    last_launches = launches;
+    last_step_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();  // :378
+    return CFD_OK;
+  }
+
+  // Model::set_parameters, src/model.rs:1250-1257
+  int set_params(const cfd_params& prm) override {
+    if (prm.pressure_solver != CFD_SOLVER_JACOBI && prm.pressure_solver != CFD_SOLVER_CG)
+      return fail(CFD_ERR_INVALID_ARGUMENT, "pressure_solver out of range");
+    nu = R(prm.viscosity);
+    dt = R(prm.dt);
+    target_inlet_velocity = R(prm.target_inlet_velocity);
+    velocity_scheme = prm.velocity_scheme;
+    pressure_solver = prm.pressure_solver;
+    inlet_profile = prm.inlet_profile;
+    return CFD_OK;
+  }
+
+  int ensure_staging(size_t bytes) {
+    if (bytes > staging_bytes) {
+      cudaFree(staging);
+      staging = nullptr; staging_bytes = 0;
+      CFD_CUDA(cudaMalloc(&staging, bytes));
+      staging_bytes = bytes;
+    }
+    if (bytes > h_staging_bytes) {
+      if (h_staging) cudaFreeHost(h_staging);
+      h_staging = nullptr; h_staging_bytes = 0;
+      CFD_CUDA(cudaHostAlloc(&h_staging, bytes, cudaHostAllocDefault));
+      h_staging_bytes = bytes;
+    }
+    return CFD_OK;
+  }
+
+  // Model::get_snapshot, src/model.rs:1259-1267: p, u, v narrowed to f32 on the device, then D2H
+  int get_snapshot(float* hp, float* hu, float* hv, float* hdt) override {
+    CFD_CUDA(cudaSetDevice(device));
+    const size_t total = n_p + n_u + n_v;
+    int rc;
+    if ((rc = ensure_staging(total * sizeof(float)))) return rc;
+    float* d = (float*)staging;
+    float* h = (float*)h_staging;
+    const int grid_sz = 148 * 8;
+    if (hp) cfdk::k_to_f32<R><<<grid_sz, 256, 0, stream>>>(p, d, n_p);
+    if (hu) cfdk::k_to_f32<R><<<grid_sz, 256, 0, stream>>>(ubuf[iu], d + n_p, n_u);
+    if (hv) cfdk::k_to_f32<R><<<grid_sz, 256, 0, stream>>>(vbuf[iu], d + n_p + n_u, n_v);
+    CFD_CUDA(cudaGetLastError());
+    CFD_CUDA(cudaMemcpyAsync(h, d, total * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CFD_CUDA(cudaStreamSynchronize(stream));
+    if (hp) memcpy(hp, h, n_p * sizeof(float));
+    if (hu) memcpy(hu, h + n_p, n_u * sizeof(float));
+    if (hv) memcpy(hv, h + n_p + n_u, n_v * sizeof(float));
+    if (hdt) *hdt = (float)dt;
+    return CFD_OK;
+  }
+
+  // Model::get_residuals, src/model.rs:1269-1280
+  int get_residuals(cfd_residuals* out) override {
+    out->simulation_step = simulation_step;
+    out->simulation_time = (float)simulation_time;
+    out->dt = (float)dt;
+    out->p = (float)last_pressure_residual;
+    out->u = (float)last_u_residual;
+    out->v = (float)last_v_residual;
+    out->step_seconds = last_step_seconds;
+    out->piso_substeps = last_piso_substeps;
+    out->jacobi_calls = last_K;
+    out->sweeps = last_S;
+    out->simulation_time_f64 = (double)simulation_time;
+    out->dt_f64 = (double)dt;
+    out->p_f64 = (double)last_pressure_residual;
+    out->u_f64 = (double)last_u_residual;
+    out->v_f64 = (double)last_v_residual;
+    return CFD_OK;
+  }
+
+  R* real_field(int field, size_t* n) {
+    switch (field) {
+      case CFD_FIELD_P: *n = n_p; return p;
+      case CFD_FIELD_U: *n = n_u; return ubuf[iu];
+      case CFD_FIELD_V: *n = n_v; return vbuf[iu];
+      case CFD_FIELD_U_STAR: *n = n_u; return ubuf[ius];
+      case CFD_FIELD_V_STAR: *n = n_v; return vbuf[ius];
+      case CFD_FIELD_RHS: *n = n_p; return rhs;
+      case CFD_FIELD_P_PRIME: *n = n_p; return pp[ipp];
+      // after a step the free buffer still holds the fields the step started from (u_old, v_old)
+      case CFD_FIELD_U_OLD: *n = n_u; return ubuf[ifree];
+      case CFD_FIELD_V_OLD: *n = n_v; return vbuf[ifree];
+      default: *n = 0; return nullptr;
+    }
+  }
+
+  int field_len(int field, uint64_t* len) override {
+    if (field == CFD_FIELD_MASK_U) { *len = n_u; return CFD_OK; }
+    if (field == CFD_FIELD_MASK_V) { *len = n_v; return CFD_OK; }
+    size_t n;
+    if (!real_field(field, &n)) return fail(CFD_ERR_INVALID_ARGUMENT, "unknown field id");
+    *len = n;
+    return CFD_OK;
+  }
+
+  int get_field_f64(int field, double* out, uint64_t len) override {
+    CFD_CUDA(cudaSetDevice(device));
+    uint64_t n64;
+    int rc;
+    if ((rc = field_len(field, &n64))) return rc;
+    if (len != n64) return fail(CFD_ERR_INVALID_ARGUMENT, "get_field_f64: wrong length");
+    if ((rc = ensure_staging(n64 * sizeof(double)))) return rc;
+    double* d = (double*)staging;
+    if (field == CFD_FIELD_MASK_U || field == CFD_FIELD_MASK_V) {
+      cfdk::k_u8_to_f64<<<148 * 8, 256, 0, stream>>>(field == CFD_FIELD_MASK_U ? mask_u : mask_v, d, (size_t)n64);
+    } else {
+      size_t n;
+      R* src = real_field(field, &n);
+      cfdk::k_to_f64<R><<<148 * 8, 256, 0, stream>>>(src, d, n);
+    }
+    CFD_CUDA(cudaGetLastError());
+    CFD_CUDA(cudaMemcpyAsync(h_staging, d, n64 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CFD_CUDA(cudaStreamSynchronize(stream));
+    memcpy(out, h_staging, n64 * sizeof(double));
+    return CFD_OK;
+  }
+
+  int set_field_f64(int field, const double* in, uint64_t len) override {
+    CFD_CUDA(cudaSetDevice(device));
+    size_t n;
+    R* dst = real_field(field, &n);
+    if (!dst) return fail(CFD_ERR_INVALID_ARGUMENT, "set_field_f64: field is not writable");
+    if (len != n) return fail(CFD_ERR_INVALID_ARGUMENT, "set_field_f64: wrong length");
+    int rc;
+    if ((rc = ensure_staging(n * sizeof(double)))) return rc;
+    memcpy(h_staging, in, n * sizeof(double));
+    CFD_CUDA(cudaMemcpyAsync(staging, h_staging, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+    cfdk::k_from_f64<R><<<148 * 8, 256, 0, stream>>>((const double*)staging, dst, n);
+    CFD_CUDA(cudaGetLastError());
+    CFD_CUDA(cudaStreamSynchronize(stream));
+    return CFD_OK;
+  }
+
+  int rows(uint64_t* j0, uint64_t* j1) override {
+    *j0 = 0;
+    *j1 = (uint64_t)ny;
+    return CFD_OK;
+  }
+
+  int last_timing(double* step_ms, double* sweep_ms, uint64_t* n_launches) override {
+    if (step_ms) *step_ms = last_step_ms;
+    if (sweep_ms) *sweep_ms = last_sweep_ms;
+    if (n_launches) *n_launches = last_launches;
+    return CFD_OK;
+  }
+};
+
+}  // namespace
+
+struct cfd_model {
+  std::unique_ptr<ModelBase> impl;
+};
+
+extern "C" {
+
+void cfd_solver_consts_default(cfd_solver_consts* out) {
+  if (out) consts_default(out);
+}
+
+void cfd_options_default(cfd_options* out) {
+  if (!out) return;
+  memset(out, 0, sizeof *out);
+  out->precision = 64;
+  out->device = -1;
+  out->rank = 0;
+  out->world_size = 1;
+  out->nccl_unique_id = nullptr;
+  out->flags = 0;
+  consts_default(&out->consts);
+}
+
+int cfd_model_create_ex(const cfd_grid* grid, const cfd_params* params, const cfd_options* opts, cfd_model** out) {
+  if (!grid || !params || !out) return fail(CFD_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  cfd_options o;
+  if (opts) o = *opts; else cfd_options_default(&o);
+  // the reference's 8-lane chunking panics unless nx % 8 is 0 (or 1); this build takes 0 only.
+  if (grid->nx % 8 != 0 || grid->nx < 16 || grid->ny < 4)
+    return fail(CFD_ERR_INVALID_ARGUMENT, "grid: need nx % 8 == 0, nx >= 16, ny >= 4 (the reference panics otherwise)");
+  if (grid->nx > (1u << 30) || grid->ny > (1u << 30)) return fail(CFD_ERR_INVALID_ARGUMENT, "grid too large");
+  if (!(grid->dx > 0.0f) || !(grid->dy > 0.0f)) return fail(CFD_ERR_INVALID_ARGUMENT, "grid: dx, dy must be positive");
+  if (o.precision != 64 && o.precision != 32) return fail(CFD_ERR_INVALID_ARGUMENT, "precision must be 64 or 32");
+  if (o.world_size != 1) return fail(CFD_ERR_UNSUPPORTED, "world_size > 1 is not available in this build");
+  if (o.consts.jacobi_iterations < 1 || o.consts.jacobi_iterations > kMaxSweepSlots)
+    return fail(CFD_ERR_INVALID_ARGUMENT, "jacobi_iterations must be in 1..256");
+  if (o.consts.outer_rounds < 0 || o.consts.outer_rounds > 1000) return fail(CFD_ERR_INVALID_ARGUMENT, "outer_rounds out of range");
+  if (params->velocity_scheme < 0 || params->velocity_scheme > 1 || params->inlet_profile < 0 ||
+      params->inlet_profile > 1 || params->scenario < 0 || params->scenario > 1 || params->pressure_solver < 0 ||
+      params->pressure_solver > 1)
+    return fail(CFD_ERR_INVALID_ARGUMENT, "params: enum value out of range");
+  std::unique_ptr<cfd_model> m(new cfd_model());
+  if (o.precision == 32) m->impl.reset(new ModelImpl<float>(*grid, *params, o));
+  else m->impl.reset(new ModelImpl<double>(*grid, *params, o));
+  const int rc = m->impl->init();
+  if (rc) return rc;
+  *out = m.release();
+  return CFD_OK;
+}
+
+int cfd_model_create(const cfd_grid* grid, const cfd_params* params, cfd_model** out) {
+  return cfd_model_create_ex(grid, params, nullptr, out);
+}
+
+void cfd_model_destroy(cfd_model* m) { delete m; }
+
+#define CFD_CHECK_MODEL(m) \
+  if (!(m) || !(m)->impl) return fail(CFD_ERR_INVALID_ARGUMENT, "null model")
+
+int cfd_model_update(cfd_model* m) {
+  CFD_CHECK_MODEL(m);
+  return m->impl->update();
+}
+
+int cfd_model_update_n(cfd_model* m, uint64_t n) {
+  CFD_CHECK_MODEL(m);
+  for (uint64_t k = 0; k < n; ++k) {
+    const int rc = m->impl->update();
+    if (rc) return rc;
+  }
+  return CFD_OK;
+}
+
+int cfd_model_set_params(cfd_model* m, const cfd_params* params) {
+  CFD_CHECK_MODEL(m);
+  if (!params) return fail(CFD_ERR_INVALID_ARGUMENT, "null params");
+  return m->impl->set_params(*params);
+}
+
+int cfd_model_get_snapshot(cfd_model* m, float* p, float* u, float* v, float* dt) {
+  CFD_CHECK_MODEL(m);
+  return m->impl->get_snapshot(p, u, v, dt);
+}
+
+int cfd_model_get_residuals(cfd_model* m, cfd_residuals* out) {
+  CFD_CHECK_MODEL(m);
+  if (!out) return fail(CFD_ERR_INVALID_ARGUMENT, "null out");
+  return m->impl->get_residuals(out);
+}
+
+int cfd_model_field_len(cfd_model* m, int32_t field, uint64_t* len) {
+  CFD_CHECK_MODEL(m);
+  if (!len) return fail(CFD_ERR_INVALID_ARGUMENT, "null len");
+  return m->impl->field_len(field, len);
+}
+
+int cfd_model_get_field_f64(cfd_model* m, int32_t field, double* out, uint64_t len) {
+  CFD_CHECK_MODEL(m);
+  if (!out) return fail(CFD_ERR_INVALID_ARGUMENT, "null out");
+  return m->impl->get_field_f64(field, out, len);
+}
+
+int cfd_model_set_field_f64(cfd_model* m, int32_t field, const double* in, uint64_t len) {
+  CFD_CHECK_MODEL(m);
+  if (!in) return fail(CFD_ERR_INVALID_ARGUMENT, "null in");
+  return m->impl->set_field_f64(field, in, len);
+}
+
+int cfd_model_rows(cfd_model* m, uint64_t* j0, uint64_t* j1) {
+  CFD_CHECK_MODEL(m);
+  if (!j0 || !j1) return fail(CFD_ERR_INVALID_ARGUMENT, "null out");
+  return m->impl->rows(j0, j1);
+}
+
+int cfd_model_last_timing(cfd_model* m, double* step_ms, double* sweep_ms, uint64_t* kernel_launches) {
+  CFD_CHECK_MODEL(m);
+  return m->impl->last_timing(step_ms, sweep_ms, kernel_launches);
+}
+
+int cfd_nccl_unique_id(void* out128) {
+  (void)out128;
+  return fail(CFD_ERR_UNSUPPORTED, "multi-GPU strips are not available in this build");
+}
+
+const char* cfd_last_error(void) { return g_last_error.c_str(); }
+
+int cfd_abi_version(void) { return CFD_ABI_VERSION; }
+
+}  // extern "C"

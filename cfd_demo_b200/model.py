@@ -1,0 +1,272 @@
+"""Host-side mirror of the reference `Model` / `SimulationControlHandle` (reference: src/model.rs) over the
+C ABI of include/cfd_b200.h (libcfd_b200.so, hand-written sm_100a kernels).
+
+Same names, argument meaning and error behaviour as the reference: `Model.new(grid, params)` (:219),
+`update()` (:304), `set_parameters()` (:1250), `get_snapshot()` (:1259), `get_residuals()` (:1269),
+`run()` -> `SimulationControlHandle` (:1282) with `stop / pause / resume / set_params /
+request_snapshot / get_last_available_snapshot / get_new_log_messages` (:71-117).  Where the reference
+panics (invalid grid, a call on a dropped model) this raises `CfdError`.
+
+There is NO CPU fallback: if libcfd_b200.so is missing or no CUDA device is usable, construction fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import queue
+import threading
+import time
+from typing import List, Optional
+
+import numpy as np
+
+from . import _abi
+from .types import Grid, Residuals, SimSnapshot, SimulationParams
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcfd_b200.so")
+_lib = None
+
+
+class CfdError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"cfd_b200 error {code}: {message}")
+        self.code = code
+
+
+def load_library():
+    """Load libcfd_b200.so (built in-tree by `__graft_entry__.build()` / csrc/Makefile). Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CfdError(_abi.CFD_ERR_CUDA,
+                       f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    lib.cfd_abi_version.restype = C.c_int
+    lib.cfd_last_error.restype = C.c_char_p
+    lib.cfd_solver_consts_default.argtypes = [P(_abi.CfdSolverConsts)]
+    lib.cfd_options_default.argtypes = [P(_abi.CfdOptions)]
+    lib.cfd_model_create.argtypes = [P(_abi.CfdGrid), P(_abi.CfdParams), P(C.c_void_p)]
+    lib.cfd_model_create_ex.argtypes = [P(_abi.CfdGrid), P(_abi.CfdParams), P(_abi.CfdOptions), P(C.c_void_p)]
+    lib.cfd_model_destroy.argtypes = [C.c_void_p]
+    lib.cfd_model_destroy.restype = None
+    lib.cfd_model_update.argtypes = [C.c_void_p]
+    lib.cfd_model_update_n.argtypes = [C.c_void_p, C.c_uint64]
+    lib.cfd_model_set_params.argtypes = [C.c_void_p, P(_abi.CfdParams)]
+    lib.cfd_model_get_snapshot.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, P(C.c_float)]
+    lib.cfd_model_get_residuals.argtypes = [C.c_void_p, P(_abi.CfdResiduals)]
+    lib.cfd_model_field_len.argtypes = [C.c_void_p, C.c_int32, P(C.c_uint64)]
+    lib.cfd_model_get_field_f64.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64]
+    lib.cfd_model_set_field_f64.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64]
+    lib.cfd_model_rows.argtypes = [C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
+    lib.cfd_model_last_timing.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double), P(C.c_uint64)]
+    lib.cfd_nccl_unique_id.argtypes = [C.c_void_p]
+    if lib.cfd_abi_version() != _abi.CFD_ABI_VERSION:
+        raise CfdError(_abi.CFD_ERR_UNSUPPORTED, "libcfd_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def _check(lib, rc: int):
+    if rc != 0:
+        raise CfdError(rc, (lib.cfd_last_error() or b"").decode())
+
+
+def default_options() -> _abi.CfdOptions:
+    o = _abi.CfdOptions()
+    load_library().cfd_options_default(C.byref(o))
+    return o
+
+
+def nccl_unique_id() -> bytes:
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    _check(lib, lib.cfd_nccl_unique_id(buf))
+    return buf.raw
+
+
+class Model:
+    """The simulation model (reference: `pub struct Model`, src/model.rs:166-214), state resident in HBM."""
+
+    def __init__(self, grid: Grid, params: SimulationParams, precision: int = 64,
+                 options: Optional[_abi.CfdOptions] = None):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.grid = grid
+        g, p = grid.to_c(), params.to_c()
+        opts = options if options is not None else default_options()
+        if options is None:
+            opts.precision = precision
+        self.precision = int(opts.precision)
+        self._keepalive = opts
+        _check(self._lib, self._lib.cfd_model_create_ex(C.byref(g), C.byref(p), C.byref(opts), C.byref(self._h)))
+        self.nx, self.ny = int(grid.nx), int(grid.ny)
+
+    @classmethod
+    def new(cls, grid: Grid, params: SimulationParams, **kw) -> "Model":
+        """`Model::new(grid, &params)` (src/model.rs:219)."""
+        return cls(grid, params, **kw)
+
+    # -- lifecycle ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.cfd_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _handle(self):
+        if not self._h:
+            raise CfdError(_abi.CFD_ERR_INVALID_ARGUMENT, "model was dropped")
+        return self._h
+
+    # -- the reference API ---------------------------------------------------------------------------
+    def update(self):
+        """`Model::update(&mut self)` (src/model.rs:304-379): one timestep."""
+        _check(self._lib, self._lib.cfd_model_update(self._handle()))
+
+    def update_n(self, n: int):
+        _check(self._lib, self._lib.cfd_model_update_n(self._handle(), int(n)))
+
+    def set_parameters(self, params: SimulationParams):
+        """`Model::set_parameters` (src/model.rs:1250-1257)."""
+        p = params.to_c()
+        _check(self._lib, self._lib.cfd_model_set_params(self._handle(), C.byref(p)))
+
+    def get_snapshot(self) -> SimSnapshot:
+        """`Model::get_snapshot` (src/model.rs:1259-1267): owned f32 copies of p, u, v in reference layout."""
+        nx, ny = self.nx, self.ny
+        p = np.empty(nx * ny, dtype=np.float32)
+        u = np.empty((nx + 1) * ny, dtype=np.float32)
+        v = np.empty(nx * (ny + 1), dtype=np.float32)
+        dt = C.c_float()
+        _check(self._lib, self._lib.cfd_model_get_snapshot(self._handle(), p.ctypes.data, u.ctypes.data,
+                                                           v.ctypes.data, C.byref(dt)))
+        return SimSnapshot(p=p, u=u, v=v, dt=float(dt.value), paused=False)
+
+    def get_residuals(self) -> Residuals:
+        """`Model::get_residuals` (src/model.rs:1269-1280)."""
+        r = _abi.CfdResiduals()
+        _check(self._lib, self._lib.cfd_model_get_residuals(self._handle(), C.byref(r)))
+        return Residuals.from_c(r)
+
+    def run(self) -> "SimulationControlHandle":
+        """`Model::run(self)` (src/model.rs:1282-1332): moves the model into one solver thread."""
+        return SimulationControlHandle(self)
+
+    # -- parity / measurement hooks --------------------------------------------------------------------
+    def field(self, fid: int) -> np.ndarray:
+        n = C.c_uint64()
+        _check(self._lib, self._lib.cfd_model_field_len(self._handle(), fid, C.byref(n)))
+        out = np.empty(n.value, dtype=np.float64)
+        _check(self._lib, self._lib.cfd_model_get_field_f64(self._handle(), fid, out.ctypes.data, n.value))
+        return out
+
+    def set_field(self, fid: int, values: np.ndarray):
+        a = np.ascontiguousarray(values, dtype=np.float64)
+        _check(self._lib, self._lib.cfd_model_set_field_f64(self._handle(), fid, a.ctypes.data, a.size))
+
+    def rows(self):
+        j0, j1 = C.c_uint64(), C.c_uint64()
+        _check(self._lib, self._lib.cfd_model_rows(self._handle(), C.byref(j0), C.byref(j1)))
+        return int(j0.value), int(j1.value)
+
+    def last_timing(self):
+        step_ms, sweep_ms, launches = C.c_double(), C.c_double(), C.c_uint64()
+        _check(self._lib, self._lib.cfd_model_last_timing(self._handle(), C.byref(step_ms), C.byref(sweep_ms),
+                                                          C.byref(launches)))
+        return float(step_ms.value), float(sweep_ms.value), int(launches.value)
+
+
+class _Command:
+    STOP, GET_SNAPSHOT, SET_PARAMS, PAUSE, RESUME = range(5)
+
+
+class SimulationControlHandle:
+    """`SimulationControlHandle` (src/model.rs:65-117) + the solver thread of `Model::run` (:1287-1325).
+
+    Three queues stand in for the three mpsc channels.  Unlike the reference — whose `Command::Stop` only
+    leaves the inner `for` and whose thread dies by panicking on a closed channel (:1296, :1319) — `stop()`
+    ends the thread and releases the device memory.
+    """
+
+    def __init__(self, model: Model):
+        self._commands: "queue.Queue" = queue.Queue()
+        self._snapshots: "queue.Queue" = queue.Queue()
+        self._residuals: "queue.Queue" = queue.Queue()
+        self._model = model
+        self._thread = threading.Thread(target=self._loop, name="cfd-solver", daemon=True)
+        self._thread.start()
+
+    def _loop(self):
+        model, paused = self._model, False
+        while True:
+            snapshot_sent = False
+            stop = False
+            while True:  # command_receiver.try_iter()
+                try:
+                    cmd, arg = self._commands.get_nowait()
+                except queue.Empty:
+                    break
+                if cmd == _Command.STOP:
+                    stop = True
+                    break
+                if cmd == _Command.SET_PARAMS:
+                    model.set_parameters(arg)
+                elif cmd == _Command.GET_SNAPSHOT:
+                    if not snapshot_sent:
+                        snap = model.get_snapshot()
+                        snap.paused = paused
+                        self._snapshots.put(snap)
+                        snapshot_sent = True
+                elif cmd == _Command.PAUSE:
+                    paused = True
+                elif cmd == _Command.RESUME:
+                    paused = False
+            if stop:
+                break
+            if not paused:
+                model.update()
+                self._residuals.put(model.get_residuals())
+            else:
+                time.sleep(0.016)
+        model.close()
+
+    def stop(self):
+        self._commands.put((_Command.STOP, None))
+        self._thread.join()
+
+    def get_last_available_snapshot(self) -> Optional[SimSnapshot]:
+        last = None
+        while True:
+            try:
+                last = self._snapshots.get_nowait()
+            except queue.Empty:
+                return last
+
+    def get_new_log_messages(self) -> List[Residuals]:
+        out = []
+        while True:
+            try:
+                out.append(self._residuals.get_nowait())
+            except queue.Empty:
+                return out
+
+    def request_snapshot(self):
+        self._commands.put((_Command.GET_SNAPSHOT, None))
+
+    def set_params(self, params: SimulationParams):
+        self._commands.put((_Command.SET_PARAMS, params))
+
+    def pause(self):
+        self._commands.put((_Command.PAUSE, None))
+
+    def resume(self):
+        self._commands.put((_Command.RESUME, None))

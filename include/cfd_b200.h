@@ -1,0 +1,169 @@
+/*
+ * cfd_b200.h — C ABI of the B200-native replacement for cfd-demo's solver hot path.
+ *
+ * The reference has no FFI today; its boundary is the Rust pub API of `src/model.rs` as consumed by
+ * `src/app.rs`.  Every entry point below names the reference item it replaces (paths relative to the
+ * reference repo).  The Rust shim in `cfd_demo_b200/rust/` and the C++ mirror in `cfd_demo_b200/host/`
+ * bind exactly these symbols; see INTEGRATION.md.
+ *
+ * Conventions: all pointers are HOST memory; return 0 (CFD_OK) on success, non-zero on error with a
+ * thread-local message from cfd_last_error(); a model is owned by one thread at a time (the reference
+ * moves `Model` into one solver thread, src/model.rs:1282-1287); distinct models are independent.
+ * API scalars stay f32 where the reference's are f32 (Grid / SimulationParams / Residuals / SimSnapshot);
+ * the shipped arithmetic is fp64 (precision 64) and promotes them on entry.
+ */
+#ifndef CFD_B200_H
+#define CFD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFD_ABI_VERSION 1
+
+/* ---- status codes ---------------------------------------------------------------------------- */
+#define CFD_OK 0
+#define CFD_ERR_INVALID_ARGUMENT 1 /* reference behaviour: panic (slice index / unwrap)            */
+#define CFD_ERR_CUDA 2
+#define CFD_ERR_UNSUPPORTED 3
+#define CFD_ERR_NCCL 4
+
+/* ---- enums (values are ABI) -------------------------------------------------------------------- */
+/* VelocityScheme, src/model.rs:142-146 */
+#define CFD_SCHEME_FIRST_ORDER 0
+#define CFD_SCHEME_SECOND_ORDER 1
+/* InletProfile, src/model.rs:155-159 */
+#define CFD_INLET_UNIFORM 0
+#define CFD_INLET_PARABOLIC 1
+/* PressureSolver, src/model.rs:149-152 (Jacobi is the reference's only variant; CG is an extension) */
+#define CFD_SOLVER_JACOBI 0
+#define CFD_SOLVER_CG 1
+/* Scenario: the reference hard-codes the channel (src/model.rs:807-815,827-875); cavity is an extension */
+#define CFD_SCENARIO_CHANNEL 0
+#define CFD_SCENARIO_CAVITY 1
+
+/* field ids for cfd_model_get_field_f64 / cfd_model_field_len (Model fields, src/model.rs:181-205) */
+#define CFD_FIELD_P 0
+#define CFD_FIELD_U 1
+#define CFD_FIELD_V 2
+#define CFD_FIELD_U_STAR 3
+#define CFD_FIELD_V_STAR 4
+#define CFD_FIELD_RHS 5
+#define CFD_FIELD_P_PRIME 6
+#define CFD_FIELD_U_OLD 7
+#define CFD_FIELD_V_OLD 8
+#define CFD_FIELD_MASK_U 9  /* 0/1 as double */
+#define CFD_FIELD_MASK_V 10 /* 0/1 as double */
+#define CFD_FIELD_COUNT 11
+
+/* ---- PODs ---------------------------------------------------------------------------------------- */
+/* Grid + Option<Cylinder>, src/model.rs:121-139 */
+typedef struct cfd_grid {
+  uint64_t nx, ny;     /* pressure cells */
+  float lx, ly, dx, dy;
+  int32_t has_obstacle; /* Option<Cylinder>: 0 = None */
+  float center_x, center_y, radius;
+} cfd_grid;
+
+/* SimulationParams, src/model.rs:13-21 (defaults :44-55) + the `scenario` extension (0 = reference) */
+typedef struct cfd_params {
+  float dt, viscosity, target_inlet_velocity;
+  int32_t velocity_scheme, inlet_profile, pressure_solver, scenario;
+} cfd_params;
+
+/* Solver literals of the reference, made data so that the extensions are additive.
+ * Defaults (cfd_solver_consts_default) are the reference's: src/model.rs:269 (ramp 100),
+ * :735-737 (omega .75, tol 1e-4, 50 sweeps), :696,:721 (20 outer rounds, 1e-4), :885 (CFL .2). */
+typedef struct cfd_solver_consts {
+  int32_t ramp_up_steps;
+  int32_t jacobi_iterations;
+  int32_t outer_rounds;
+  int32_t cg_max_iterations; /* extension (CFD_SOLVER_CG) */
+  double jacobi_omega;
+  double pressure_tolerance;
+  double outer_tolerance;
+  double cfl;
+  double cg_tolerance;       /* extension: relative L2 of the Poisson residual */
+} cfd_solver_consts;
+
+typedef struct cfd_options {
+  int32_t precision;   /* 64 (shipped path) or 32 (the reference's own f32 arithmetic) */
+  int32_t device;      /* CUDA ordinal; -1 = current device */
+  int32_t rank;        /* strip decomposition over rows; world_size 1 = whole grid on one GPU */
+  int32_t world_size;
+  const void* nccl_unique_id; /* 128-byte ncclUniqueId, same on every rank, when world_size > 1 */
+  uint32_t flags;      /* CFD_FLAG_* */
+  cfd_solver_consts consts;
+} cfd_options;
+
+#define CFD_FLAG_NO_GRAPH 1u      /* launch kernels directly instead of replaying the captured step graph */
+#define CFD_FLAG_BASELINE_SWEEP 2u /* one-sweep-per-launch Jacobi kernel (the simple path kept as a cross-check) */
+
+/* Residuals, src/model.rs:23-32.  f32 members mirror the reference; the trailing members are
+ * additions (solver counters for the roofline accounting, full-precision copies for parity tests). */
+typedef struct cfd_residuals {
+  uint64_t simulation_step;
+  float simulation_time, dt, p, u, v;
+  double step_seconds;        /* Residuals::step_time */
+  uint64_t piso_substeps;
+  uint64_t jacobi_calls;      /* K: pressure solves in the last step (2..21) */
+  uint64_t sweeps;            /* S: Jacobi sweeps (or CG iterations) in the last step */
+  double simulation_time_f64, dt_f64, p_f64, u_f64, v_f64;
+} cfd_residuals;
+
+typedef struct cfd_model cfd_model; /* opaque: owns device buffers, streams, graphs, (optional) NCCL comm */
+
+/* ---- lifecycle ------------------------------------------------------------------------------------ */
+void cfd_solver_consts_default(cfd_solver_consts* out);
+void cfd_options_default(cfd_options* out);
+
+/* Model::new(grid, &params), src/model.rs:219-299.  fp64, current device, reference constants.
+ * Requires nx % 8 == 0, nx >= 16, ny >= 4 (the reference panics for nx % 8 not in {0,1}: SURVEY N1). */
+int cfd_model_create(const cfd_grid* grid, const cfd_params* params, cfd_model** out);
+int cfd_model_create_ex(const cfd_grid* grid, const cfd_params* params, const cfd_options* opts,
+                        cfd_model** out);
+/* Drop for Model (the reference's solver thread ends by panic, src/model.rs:1319; the shim frees here). */
+void cfd_model_destroy(cfd_model* m);
+
+/* ---- stepping -------------------------------------------------------------------------------------- */
+/* Model::update(&mut self), src/model.rs:304-379: exactly one timestep, synchronous. */
+int cfd_model_update(cfd_model* m);
+/* Extension: n timesteps with no host round trip between them (dt control stays on the device).
+ * Equivalent to n calls of cfd_model_update. */
+int cfd_model_update_n(cfd_model* m, uint64_t n);
+/* Model::set_parameters(&mut self, &params), src/model.rs:1250-1257 (`scenario` is ignored here, as
+ * the reference has no such parameter to change). */
+int cfd_model_set_params(cfd_model* m, const cfd_params* params);
+
+/* ---- state read-back -------------------------------------------------------------------------------- */
+/* Model::get_snapshot(&self) -> SimSnapshot{p,u,v: Vec<f32>, dt}, src/model.rs:1259-1267.
+ * Caller-allocated, reference layout: p nx*ny, u (nx+1)*ny, v nx*(ny+1); any pointer may be NULL.
+ * With world_size > 1 each rank receives its own rows only (see cfd_model_rows). */
+int cfd_model_get_snapshot(cfd_model* m, float* p, float* u, float* v, float* dt);
+/* Model::get_residuals(&self), src/model.rs:1269-1280. */
+int cfd_model_get_residuals(cfd_model* m, cfd_residuals* out);
+/* Parity harness: any field (CFD_FIELD_*) widened to double, reference layout. */
+int cfd_model_field_len(cfd_model* m, int32_t field, uint64_t* len);
+int cfd_model_get_field_f64(cfd_model* m, int32_t field, double* out, uint64_t len);
+/* Parity harness / restart: overwrite a field from host doubles (reference layout). */
+int cfd_model_set_field_f64(cfd_model* m, int32_t field, const double* in, uint64_t len);
+/* Rows [j0, j1) of pressure cells owned by this rank (whole grid when world_size == 1). */
+int cfd_model_rows(cfd_model* m, uint64_t* j0, uint64_t* j1);
+
+/* ---- measurement hooks (bench.py / profiles; no reference counterpart) ------------------------------- */
+/* Device time in ms of the last cfd_model_update / update_n, and of the Jacobi sweeps inside it,
+ * both from CUDA events on the model's own stream. */
+int cfd_model_last_timing(cfd_model* m, double* step_ms, double* sweep_ms, uint64_t* kernel_launches);
+
+/* ---- misc ------------------------------------------------------------------------------------------- */
+/* Fills 128 bytes with a fresh ncclUniqueId (call on rank 0, broadcast to the others). */
+int cfd_nccl_unique_id(void* out128);
+const char* cfd_last_error(void);
+int cfd_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFD_B200_H */

@@ -1,0 +1,80 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/cfd_b200.h declares.
+No compute call is made here (there is no GPU); the product has no CPU fallback, which is also checked."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import __graft_entry__ as entry
+from cfd_demo_b200 import _abi, model
+from cfd_demo_b200.types import SimulationParams, default_grid
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(model.LIB_PATH):
+        entry.build()
+    return model.load_library()
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "cfd_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cfd_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_reference_api():
+    names = declared_functions()
+    for must in ["cfd_model_create", "cfd_model_update", "cfd_model_set_params", "cfd_model_get_snapshot",
+                 "cfd_model_get_residuals", "cfd_model_destroy", "cfd_last_error"]:
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(lib):
+    missing = [n for n in declared_functions() if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.cfd_abi_version() == _abi.CFD_ABI_VERSION
+
+
+def test_struct_layouts_match_the_header(lib):
+    # sizes follow from the header's member lists (natural alignment)
+    assert C.sizeof(_abi.CfdGrid) == 48
+    assert C.sizeof(_abi.CfdParams) == 28
+    assert C.sizeof(_abi.CfdSolverConsts) == 56
+    assert C.sizeof(_abi.CfdOptions) == 32 + 56
+    assert C.sizeof(_abi.CfdResiduals) == 8 + 5 * 4 + 4 + 8 + 3 * 8 + 5 * 8
+    o = model.default_options()
+    assert (o.precision, o.device, o.rank, o.world_size) == (64, -1, 0, 1)
+    c = o.consts
+    assert (c.ramp_up_steps, c.jacobi_iterations, c.outer_rounds) == (100, 50, 20)
+    assert (c.jacobi_omega, c.pressure_tolerance, c.outer_tolerance, c.cfl) == (0.75, 1e-4, 1e-4, 0.2)
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    from cfd_demo_b200.types import Grid
+    with pytest.raises(model.CfdError) as e:
+        model.Model(Grid.uniform(20, 8, 1.0, 1.0), SimulationParams())  # nx % 8 != 0: the reference panics
+    assert e.value.code == _abi.CFD_ERR_INVALID_ARGUMENT
+    with pytest.raises(model.CfdError):
+        model.Model(Grid.uniform(16, 2, 1.0, 1.0), SimulationParams())
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(model.CfdError) as e:
+        model.Model(default_grid(), SimulationParams())
+    assert e.value.code == _abi.CFD_ERR_CUDA
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "cfd_demo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".rs")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "cfd_oracle" not in text and "cpu_oracle" not in text and "import oracle" not in text, f
