@@ -24,6 +24,7 @@ FIELD_NAMES = {
 
 FLAG_NO_GRAPH = 1
 FLAG_BASELINE_SWEEP = 2
+FLAG_REGISTER_SWEEP = 4
 
 
 class CfdGrid(C.Structure):

@@ -85,8 +85,11 @@ struct ModelImpl final : ModelBase {
   R* vbuf[3] = {nullptr, nullptr, nullptr};
   int iu = 0, ius = 1, ifree = 2;  // roles of the three u (and v) buffers: current, star, free
   R* p = nullptr;
+  static constexpr size_t kFront = 256 / sizeof(R);
   R* rhs = nullptr;
+  R* rhs_base = nullptr;
   R* pp[2] = {nullptr, nullptr};
+  R* pp_base[2] = {nullptr, nullptr};
   int ipp = 0;  // pp[ipp] is p_prime, the other one p_prime_new
   uint8_t *mask_u = nullptr, *mask_v = nullptr, *solid = nullptr;
   unsigned long long* err_slots = nullptr;   // kMaxSweepSlots
@@ -97,6 +100,8 @@ struct ModelImpl final : ModelBase {
   size_t staging_bytes = 0;
   void* h_staging = nullptr;                 // pinned host scratch
   size_t h_staging_bytes = 0;
+  cfdk::DivG<R> div_dx_sq, div_dy_sq, div_denom;  // divisors of the Jacobi update with hoisted reciprocals
+  int sweep_rows_per_block = 32;
   cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
   std::vector<cudaEvent_t> ev_sweep;  // pairs
   bool ready = false;
@@ -122,7 +127,7 @@ struct ModelImpl final : ModelBase {
     if (stream) cudaStreamSynchronize(stream);
     for (auto& b : ubuf) cudaFree(b);
     for (auto& b : vbuf) cudaFree(b);
-    cudaFree(p); cudaFree(rhs); cudaFree(pp[0]); cudaFree(pp[1]);
+    cudaFree(p); cudaFree(rhs_base); cudaFree(pp_base[0]); cudaFree(pp_base[1]);
     cudaFree(mask_u); cudaFree(mask_v); cudaFree(solid);
     cudaFree(err_slots); cudaFree(step_slots); cudaFree(staging);
     if (h_jres) cudaFreeHost(h_jres);
@@ -159,9 +164,13 @@ struct ModelImpl final : ModelBase {
       if ((rc = dalloc(&vbuf[k], n_v))) return rc;
     }
     if ((rc = dalloc(&p, n_p))) return rc;
-    if ((rc = dalloc(&rhs, n_p))) return rc;
-    if ((rc = dalloc(&pp[0], n_p))) return rc;
-    if ((rc = dalloc(&pp[1], n_p))) return rc;
+    // slack around the p'-like buffers: the tuned sweeps stage rows with a 16-byte halo and prefetch up to
+    // 3 rows past row ny-1 without clamping; kFront elements (256 B) in front keep row 0 256-byte aligned
+    const size_t slack = 4 * (size_t)nx;
+    if ((rc = dalloc(&rhs_base, kFront + n_p + slack))) return rc;
+    if ((rc = dalloc(&pp_base[0], kFront + n_p + slack))) return rc;
+    if ((rc = dalloc(&pp_base[1], kFront + n_p + slack))) return rc;
+    rhs = rhs_base + kFront; pp[0] = pp_base[0] + kFront; pp[1] = pp_base[1] + kFront;
     if ((rc = dalloc(&mask_u, n_u))) return rc;
     if ((rc = dalloc(&mask_v, n_v))) return rc;
     if ((rc = dalloc(&solid, n_p))) return rc;
@@ -184,7 +193,66 @@ struct ModelImpl final : ModelBase {
     cfdk::k_build_masks<<<grd, blk, 0, stream>>>(g, solid, mask_u, mask_v);
     CFD_CUDA(cudaGetLastError());
     CFD_CUDA(cudaStreamSynchronize(stream));
+    if ((rc = init_sweep_constants())) return rc;
     ready = true;
+    return CFD_OK;
+  }
+
+  // divisors of the Jacobi update (src/model.rs:740-746) and, for fp64, their reciprocals refined by the
+  // same instruction sequence the compiler's division uses (cfdk::div_c); launch geometry of the sweep
+  int init_sweep_constants() {
+    div_dx_sq.y = dx * dx;                                      // :740
+    div_dy_sq.y = dy * dy;                                      // :742
+    div_denom.y = R(2.0) / (dx * dx) + R(2.0) / (dy * dy);      // :746
+    div_dx_sq.r = div_dy_sq.r = div_denom.r = R(0);
+    div_dx_sq.lo = div_dy_sq.lo = div_denom.lo = 0u;
+    div_dx_sq.span = div_dy_sq.span = div_denom.span = 0u;
+    if (sizeof(R) == 8) {
+      double hy[3] = {(double)div_dx_sq.y, (double)div_dy_sq.y, (double)div_denom.y}, hr[3];
+      double* d = nullptr;
+      CFD_CUDA(cudaMalloc((void**)&d, 6 * sizeof(double)));
+      CFD_CUDA(cudaMemcpyAsync(d, hy, sizeof hy, cudaMemcpyHostToDevice, stream));
+      cfdk::k_init_divc<<<1, 32, 0, stream>>>(d, d + 3, 3);
+      CFD_CUDA(cudaMemcpyAsync(hr, d + 3, sizeof hr, cudaMemcpyDeviceToHost, stream));
+      CFD_CUDA(cudaStreamSynchronize(stream));
+      CFD_CUDA(cudaFree(d));
+      div_dx_sq.r = (R)hr[0]; div_dy_sq.r = (R)hr[1]; div_denom.r = (R)hr[2];
+      // dividend exponent window in which x / y is normal and finite for any significands, and
+      // x >= 2^-969 (the lower bound of the compiler's own fast path)
+      auto window = [](double y, unsigned* lo, unsigned* span) {
+        uint64_t bits;
+        memcpy(&bits, &y, sizeof bits);
+        const int ey = (int)((bits >> 52) & 0x7ff);
+        int lo_e = ey - 1018, hi_e = ey + 1020;
+        if (lo_e < 0x036) lo_e = 0x036;
+        if (hi_e > 0x7f8) hi_e = 0x7f8;
+        if (ey < 1 || ey > 0x7fd || hi_e <= lo_e) { *lo = 0u; *span = 0u; return; }
+        *lo = (unsigned)lo_e << 20;
+        *span = (unsigned)(hi_e - lo_e) << 20;
+      };
+      window(hy[0], &div_dx_sq.lo, &div_dx_sq.span);
+      window(hy[1], &div_dy_sq.lo, &div_dy_sq.span);
+      window(hy[2], &div_denom.lo, &div_denom.span);
+    }
+    // one thread per column pair, 128 threads per block; pick the rows per block so that the grid is a
+    // whole number of waves of (SM count x resident blocks per SM)
+    cudaDeviceProp prop;
+    CFD_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int sms = prop.multiProcessorCount;
+    const int bx = (nx / 2 + 127) / 128;
+    int per_sm = 4;
+    if (opt.flags & CFD_FLAG_REGISTER_SWEEP)
+      CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep2<R>, 128, 0));
+    else
+      CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep3<R>, 128, 0));
+    if (per_sm < 1) per_sm = 1;
+    const int resident = sms * per_sm;
+    int gy = (resident + bx - 1) / bx;            // one wave
+    const int rows = ny - 2;
+    if (gy > rows) gy = rows;
+    int rpb = (rows + gy - 1) / gy;
+    if (rpb < 8 && rows >= 8) rpb = 8;            // keep the halo re-read (2 rows per block) below 25 %
+    sweep_rows_per_block = rpb;
     return CFD_OK;
   }
 
@@ -213,11 +281,28 @@ struct ModelImpl final : ModelBase {
     c.tol = R(opt.consts.pressure_tolerance);
     c.nx = nx; c.ny = ny; c.cavity = scenario == CFD_SCENARIO_CAVITY;
     CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index], stream));
-    dim3 blk(256), grd((nx - 2 + 255) / 256, (ny - 2 + kJacobiRows - 1) / kJacobiRows);
-    for (int s = 0; s < iters; ++s) {
-      cfdk::k_jacobi_sweep<R, kJacobiRows><<<grd, blk, 0, stream>>>(c, pp[(ipp + s) & 1], rhs, pp[(ipp + s + 1) & 1],
-                                                                    err_slots, s);
-      ++launches;
+    if (opt.flags & CFD_FLAG_BASELINE_SWEEP) {
+      dim3 blk(256), grd((nx - 2 + 255) / 256, (ny - 2 + kJacobiRows - 1) / kJacobiRows);
+      for (int s = 0; s < iters; ++s) {
+        cfdk::k_jacobi_sweep<R, kJacobiRows><<<grd, blk, 0, stream>>>(c, pp[(ipp + s) & 1], rhs,
+                                                                      pp[(ipp + s + 1) & 1], err_slots, s);
+        ++launches;
+      }
+    } else {
+      cfdk::JacobiConsts2<R> c2;
+      c2.dx_sq = div_dx_sq; c2.dy_sq = div_dy_sq; c2.denom = div_denom;
+      c2.omega = c.omega; c2.one_minus_omega = c.one_minus_omega; c2.tol = c.tol;
+      c2.nx = nx; c2.ny = ny; c2.cavity = c.cavity; c2.rows_per_block = sweep_rows_per_block;
+      dim3 blk(128), grd((nx / 2 + 127) / 128, (ny - 2 + sweep_rows_per_block - 1) / sweep_rows_per_block);
+      for (int s = 0; s < iters; ++s) {
+        if (opt.flags & CFD_FLAG_REGISTER_SWEEP)
+          cfdk::k_jacobi_sweep2<R><<<grd, blk, 0, stream>>>(c2, pp[(ipp + s) & 1], rhs, pp[(ipp + s + 1) & 1],
+                                                            err_slots, s);
+        else
+          cfdk::k_jacobi_sweep3<R><<<grd, blk, 0, stream>>>(c2, pp[(ipp + s) & 1], rhs, pp[(ipp + s + 1) & 1],
+                                                            err_slots, s);
+        ++launches;
+      }
     }
     cfdk::k_jacobi_finalize<R><<<1, 32, 0, stream>>>(err_slots, iters, c.tol, h_jres);
     ++launches;
@@ -619,6 +704,24 @@ int cfd_model_last_timing(cfd_model* m, double* step_ms, double* sweep_ms, uint6
 int cfd_nccl_unique_id(void* out128) {
   (void)out128;
   return fail(CFD_ERR_UNSUPPORTED, "multi-GPU strips are not available in this build");
+}
+
+int cfd_selftest_division(double divisor, uint64_t samples, uint64_t seed, int32_t mode, uint64_t* mismatches,
+                           uint64_t* fast_path_taken) {
+  if (!mismatches || !(divisor > 0.0) || mode < 0 || mode > 3) return fail(CFD_ERR_INVALID_ARGUMENT, "selftest_division: bad argument");
+  unsigned long long* d = nullptr;
+  CFD_CUDA(cudaMalloc((void**)&d, 2 * sizeof(unsigned long long)));
+  CFD_CUDA(cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
+  const int blocks = 148 * 4, threads = 256;
+  const unsigned long long per_thread = (samples + (uint64_t)blocks * threads - 1) / ((uint64_t)blocks * threads);
+  cfdk::k_selftest_division<<<blocks, threads>>>(divisor, per_thread, seed, mode, d, d + 1);
+  CFD_CUDA(cudaGetLastError());
+  unsigned long long h[2];
+  CFD_CUDA(cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost));
+  CFD_CUDA(cudaFree(d));
+  *mismatches = h[0];
+  if (fast_path_taken) *fast_path_taken = h[1];
+  return CFD_OK;
 }
 
 const char* cfd_last_error(void) { return g_last_error.c_str(); }

@@ -64,6 +64,8 @@ def load_library():
     lib.cfd_model_rows.argtypes = [C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
     lib.cfd_model_last_timing.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double), P(C.c_uint64)]
     lib.cfd_nccl_unique_id.argtypes = [C.c_void_p]
+    lib.cfd_selftest_division.argtypes = [C.c_double, C.c_uint64, C.c_uint64, C.c_int32, P(C.c_uint64),
+                                          P(C.c_uint64)]
     if lib.cfd_abi_version() != _abi.CFD_ABI_VERSION:
         raise CfdError(_abi.CFD_ERR_UNSUPPORTED, "libcfd_b200.so ABI version mismatch; rebuild")
     _lib = lib
@@ -86,6 +88,15 @@ def nccl_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     _check(lib, lib.cfd_nccl_unique_id(buf))
     return buf.raw
+
+
+def selftest_division(divisor: float, samples: int, seed: int = 1, mode: int = 0):
+    """Counts dividends for which the kernels' hoisted-reciprocal division differs from `x / divisor`."""
+    lib = load_library()
+    bad, fast = C.c_uint64(), C.c_uint64()
+    _check(lib, lib.cfd_selftest_division(float(divisor), int(samples), int(seed), int(mode), C.byref(bad),
+                                          C.byref(fast)))
+    return int(bad.value), int(fast.value)
 
 
 class Model:

@@ -99,7 +99,8 @@ typedef struct cfd_options {
 } cfd_options;
 
 #define CFD_FLAG_NO_GRAPH 1u      /* launch kernels directly instead of replaying the captured step graph */
-#define CFD_FLAG_BASELINE_SWEEP 2u /* one-sweep-per-launch Jacobi kernel (the simple path kept as a cross-check) */
+#define CFD_FLAG_BASELINE_SWEEP 2u /* simple one-column-per-thread Jacobi kernel, compiler divisions (cross-check) */
+#define CFD_FLAG_REGISTER_SWEEP 4u /* register-prefetch Jacobi kernel instead of the TMA-staged one (A/B) */
 
 /* Residuals, src/model.rs:23-32.  f32 members mirror the reference; the trailing members are
  * additions (solver counters for the roofline accounting, full-precision copies for parity tests). */
@@ -156,6 +157,12 @@ int cfd_model_rows(cfd_model* m, uint64_t* j0, uint64_t* j1);
 /* Device time in ms of the last cfd_model_update / update_n, and of the Jacobi sweeps inside it,
  * both from CUDA events on the model's own stream. */
 int cfd_model_last_timing(cfd_model* m, double* step_ms, double* sweep_ms, uint64_t* kernel_launches);
+
+/* Self-test of the hot kernels' exact division by a loop-invariant divisor (cfdk::div_c): draws `samples`
+ * dividends (mode 0 random bit patterns, 1 moderate magnitudes, 2 near representable quotients, 3 near
+ * rounding midpoints) and counts those whose result differs bitwise from the compiler's `x / divisor`. */
+int cfd_selftest_division(double divisor, uint64_t samples, uint64_t seed, int32_t mode, uint64_t* mismatches,
+                          uint64_t* fast_path_taken);
 
 /* ---- misc ------------------------------------------------------------------------------------------- */
 /* Fills 128 bytes with a fresh ncclUniqueId (call on rank 0, broadcast to the others). */

@@ -161,3 +161,47 @@ def test_errors():
     m.close()
     with pytest.raises(CfdError):
         m.update()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_division_by_constant_is_exact(mode):
+    """cfdk::div_c / div_fast (hoisted reciprocal, the compiler's own fast-path sequence) must return bit for
+    bit what `x / y` returns: random bit patterns, the solver's working range, dividends next to exactly
+    representable quotients and next to rounding midpoints; divisors = the actual Jacobi divisors of the
+    BASELINE grids plus awkward significands."""
+    from cfd_demo_b200.model import selftest_division
+    f = np.float32
+    divisors = []
+    for nx, lx in ((800, 30.0), (1024, 1.0), (4096, 1.0), (8192, 40.0), (16384, 1.0)):
+        dx = float(f(lx) / f(nx))
+        divisors += [dx * dx, 2.0 / (dx * dx) + 2.0 / (dx * dx)]
+    dy = float(f(10.0) / f(264))
+    divisors += [dy * dy, 2.0 / (0.0375 * 0.0375) + 2.0 / (dy * dy), 3.0, 1.0 / 3.0, 1.9999999999999998, 1.0000000000000002,
+                 7.0e-300, 3.0e300]
+    for y in divisors:
+        bad, fast = selftest_division(y, 20_000_000, seed=42 + mode, mode=mode)
+        assert bad == 0, (y, mode, bad)
+        if mode in (1, 2, 3) and 1e-200 < y < 1e200:
+            assert fast > 0
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+@pytest.mark.parametrize("other", [_abi.FLAG_BASELINE_SWEEP, _abi.FLAG_REGISTER_SWEEP])
+def test_tuned_sweep_equals_baseline_sweep(precision, other):
+    """The default sweep (TMA-staged rows, hoisted reciprocals) against the simple one-column kernel
+    (CFD_FLAG_BASELINE_SWEEP) and the register-prefetch variant, on a grid wide enough to use several
+    blocks per row and whose last 64-column strip is partial."""
+    from cfd_demo_b200.model import default_options
+    g = channel_grid(1040, 61)
+    a = Model(g, SimulationParams(), precision=precision)
+    o = default_options()
+    o.precision = precision
+    o.flags = other
+    b = Model(g, SimulationParams(), options=o)
+    for s in range(14):
+        a.update()
+        b.update()
+    for fid in STATE_FIELDS:
+        assert np.array_equal(a.field(fid), b.field(fid)), _abi.FIELD_NAMES[fid]
+    ra, rb = a.get_residuals(), b.get_residuals()
+    assert (ra.jacobi_calls, ra.sweeps, ra.f64["p"]) == (rb.jacobi_calls, rb.sweeps, rb.f64["p"])
