@@ -25,6 +25,7 @@ FIELD_NAMES = {
 FLAG_NO_GRAPH = 1
 FLAG_BASELINE_SWEEP = 2
 FLAG_REGISTER_SWEEP = 4
+FLAG_BULK_SWEEP = 8
 
 
 class CfdGrid(C.Structure):

@@ -100,6 +100,7 @@ struct ModelImpl final : ModelBase {
   size_t staging_bytes = 0;
   void* h_staging = nullptr;                 // pinned host scratch
   size_t h_staging_bytes = 0;
+  CUtensorMap tmap_pp[2], tmap_rhs;  // 2-D tiled views of p' (ping, pong) and rhs for the tensor-TMA sweep
   cfdk::DivG<R> div_dx_sq, div_dy_sq, div_denom;  // divisors of the Jacobi update with hoisted reciprocals
   int sweep_rows_per_block = 32;
   cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
@@ -198,6 +199,31 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
 
+  // 2-D tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point; libcuda is not linked)
+  int make_tensor_map(CUtensorMap* map, R* base, int box_cols) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      CFD_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+      if (!fn || q != cudaDriverEntryPointSuccess) return fail(CFD_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+      encode = (EncodeFn)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)nx, (cuuint64_t)ny};
+    const cuuint64_t strides[1] = {(cuuint64_t)nx * sizeof(R)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)cfdk::kChunkRows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(map, sizeof(R) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                              (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(CFD_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return CFD_OK;
+  }
+
   // divisors of the Jacobi update (src/model.rs:740-746) and, for fp64, their reciprocals refined by the
   // same instruction sequence the compiler's division uses (cfdk::div_c); launch geometry of the sweep
   int init_sweep_constants() {
@@ -234,6 +260,15 @@ struct ModelImpl final : ModelBase {
       window(hy[1], &div_dy_sq.lo, &div_dy_sq.span);
       window(hy[2], &div_denom.lo, &div_denom.span);
     }
+    {
+      using Ring = cfdk::SweepChunkRing<R>;
+      int rc2;
+      if ((rc2 = make_tensor_map(&tmap_pp[0], pp[0], Ring::kPCols))) return rc2;
+      if ((rc2 = make_tensor_map(&tmap_pp[1], pp[1], Ring::kPCols))) return rc2;
+      if ((rc2 = make_tensor_map(&tmap_rhs, rhs, cfdk::kStripCols))) return rc2;
+      CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep4<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(Ring)));
+    }
     // one thread per column pair, 128 threads per block; pick the rows per block so that the grid is a
     // whole number of waves of (SM count x resident blocks per SM)
     cudaDeviceProp prop;
@@ -243,8 +278,11 @@ struct ModelImpl final : ModelBase {
     int per_sm = 4;
     if (opt.flags & CFD_FLAG_REGISTER_SWEEP)
       CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep2<R>, 128, 0));
-    else
+    else if (opt.flags & CFD_FLAG_BULK_SWEEP)
       CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep3<R>, 128, 0));
+    else
+      CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep4<R>, 128,
+                                                             sizeof(cfdk::SweepChunkRing<R>)));
     if (per_sm < 1) per_sm = 1;
     const int resident = sms * per_sm;
     int gy = (resident + bx - 1) / bx;            // one wave
@@ -298,9 +336,12 @@ struct ModelImpl final : ModelBase {
         if (opt.flags & CFD_FLAG_REGISTER_SWEEP)
           cfdk::k_jacobi_sweep2<R><<<grd, blk, 0, stream>>>(c2, pp[(ipp + s) & 1], rhs, pp[(ipp + s + 1) & 1],
                                                             err_slots, s);
-        else
+        else if (opt.flags & CFD_FLAG_BULK_SWEEP)
           cfdk::k_jacobi_sweep3<R><<<grd, blk, 0, stream>>>(c2, pp[(ipp + s) & 1], rhs, pp[(ipp + s + 1) & 1],
                                                             err_slots, s);
+        else
+          cfdk::k_jacobi_sweep4<R><<<grd, blk, sizeof(cfdk::SweepChunkRing<R>), stream>>>(
+              c2, tmap_pp[(ipp + s) & 1], tmap_rhs, pp[(ipp + s + 1) & 1], err_slots, s);
         ++launches;
       }
     }
