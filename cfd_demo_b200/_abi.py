@@ -26,6 +26,7 @@ FLAG_NO_GRAPH = 1
 FLAG_BASELINE_SWEEP = 2
 FLAG_REGISTER_SWEEP = 4
 FLAG_BULK_SWEEP = 8
+FLAG_SWEEP4 = 16
 
 
 class CfdGrid(C.Structure):

@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -268,6 +269,8 @@ struct ModelImpl final : ModelBase {
       if ((rc2 = make_tensor_map(&tmap_rhs, rhs, cfdk::kStripCols))) return rc2;
       CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep4<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(Ring)));
+      CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep5<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(Ring)));
     }
     // one thread per column pair, 128 threads per block; pick the rows per block so that the grid is a
     // whole number of waves of (SM count x resident blocks per SM)
@@ -280,16 +283,37 @@ struct ModelImpl final : ModelBase {
       CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep2<R>, 128, 0));
     else if (opt.flags & CFD_FLAG_BULK_SWEEP)
       CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep3<R>, 128, 0));
-    else
+    else if (opt.flags & CFD_FLAG_SWEEP4)
       CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep4<R>, 128,
+                                                             sizeof(cfdk::SweepChunkRing<R>)));
+    else
+      CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep5<R>, 128,
                                                              sizeof(cfdk::SweepChunkRing<R>)));
     if (per_sm < 1) per_sm = 1;
     const int resident = sms * per_sm;
-    int gy = (resident + bx - 1) / bx;            // one wave
     const int rows = ny - 2;
-    if (gy > rows) gy = rows;
-    int rpb = (rows + gy - 1) / gy;
-    if (rpb < 8 && rows >= 8) rpb = 8;            // keep the halo re-read (2 rows per block) below 25 %
+    int rpb;
+    if (opt.flags & (CFD_FLAG_REGISTER_SWEEP | CFD_FLAG_BULK_SWEEP)) {
+      int gy = (resident + bx - 1) / bx;  // one wave
+      if (gy > rows) gy = rows;
+      rpb = (rows + gy - 1) / gy;
+      if (rpb < 8 && rows >= 8) rpb = 8;
+    } else {
+      // Tile height of the tensor-TMA sweeps.  SMs progress at visibly different rates (profiles/
+      // r1_sweep4.md: sm__cycles_active min 95k / max 194k at equal work), so the grid is cut into several
+      // waves of short tiles that the block scheduler hands out dynamically; 22 rows (+2 halo rows = six
+      // 4-row TMA boxes exactly) measured best at 4096^2 (tools/tune_sweep.py).  Small grids get shorter
+      // tiles so that every SM still has work.
+      const long target_blocks = 4L * resident;
+      long want = ((long)rows * bx) / target_blocks;
+      if (want > 22) want = 22;
+      if (want < 6) want = 6;
+      rpb = (int)(((want - 2) / 4) * 4 + 2);  // rows + 2 halo rows = whole number of 4-row boxes
+    }
+    if (const char* e = getenv("CFD_SWEEP_ROWS")) {  // tuning hook (tools/tune_sweep.py)
+      const int v = atoi(e);
+      if (v >= 2) rpb = v;
+    }
     sweep_rows_per_block = rpb;
     return CFD_OK;
   }
@@ -339,8 +363,11 @@ struct ModelImpl final : ModelBase {
         else if (opt.flags & CFD_FLAG_BULK_SWEEP)
           cfdk::k_jacobi_sweep3<R><<<grd, blk, 0, stream>>>(c2, pp[(ipp + s) & 1], rhs, pp[(ipp + s + 1) & 1],
                                                             err_slots, s);
-        else
+        else if (opt.flags & CFD_FLAG_SWEEP4)
           cfdk::k_jacobi_sweep4<R><<<grd, blk, sizeof(cfdk::SweepChunkRing<R>), stream>>>(
+              c2, tmap_pp[(ipp + s) & 1], tmap_rhs, pp[(ipp + s + 1) & 1], err_slots, s);
+        else
+          cfdk::k_jacobi_sweep5<R><<<grd, blk, sizeof(cfdk::SweepChunkRing<R>), stream>>>(
               c2, tmap_pp[(ipp + s) & 1], tmap_rhs, pp[(ipp + s + 1) & 1], err_slots, s);
         ++launches;
       }
