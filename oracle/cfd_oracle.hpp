@@ -509,27 +509,39 @@ class Model {
     const R denom = R(2.0) / (dx * dx) + R(2.0) / (dy * dy);  // :746
     R max_error = 0;
     const size_t j_lo = std::max<size_t>(1, ja), j_hi = std::min(ny - 1, jb);
+    const R* __restrict pp = p_prime.data();
+    const R* __restrict rh = rhs.data();
+    R* __restrict pn = p_prime_new.data();
     for (size_t j = j_lo; j < j_hi; ++j) {
-      for (size_t i = 1; i < nx - 1; i += LANES) {
+      size_t i = 1;
+      // 8-lane chunks (:774-801); written so that the compiler vectorises the lanes like std::simd does
+      for (; i + LANES <= nx - 1; i += LANES) {
         const size_t stride = j * nx + i;
-        const bool tail = i + LANES > nx - 1;
-        const size_t lanes = tail ? (nx - i) : LANES;
-        for (size_t k = 0; k < lanes; ++k) {
+        R err[LANES];
+#pragma omp simd
+        for (size_t k = 0; k < LANES; ++k) {
           const size_t idx = stride + k;
-          const R right = CFDO_AT(p_prime, idx + 1), left = CFDO_AT(p_prime, idx - 1);
-          const R top = CFDO_AT(p_prime, idx + nx), bot = CFDO_AT(p_prime, idx - nx);
-          const R center = CFDO_AT(p_prime, idx);
-          const R r = CFDO_AT(rhs, idx);
-          const R horizontal = (right + left) / dx_sq;
-          const R vertical = (top + bot) / dy_sq;
-          const R p_update = (horizontal + vertical - r) / denom;
+          const R center = pp[idx];
+          const R horizontal = (pp[idx + 1] + pp[idx - 1]) / dx_sq;
+          const R vertical = (pp[idx + nx] + pp[idx - nx]) / dy_sq;
+          const R p_update = (horizontal + vertical - rh[idx]) / denom;
           const R new_val = omega * p_update + one_minus * center;
-          if (!tail) {
-            const R error = std::fabs(new_val - center);
-            if (error > max_error) max_error = error;
-          }
-          CFDO_AT(p_prime_new, idx) = new_val;
+          err[k] = std::fabs(new_val - center);
+          pn[idx] = new_val;
         }
+        for (size_t k = 0; k < LANES; ++k)  // reduce_max + `if error > max_error` (:795-798); NaN never wins
+          if (err[k] > max_error) max_error = err[k];
+      }
+      // scalar tail (:755-771): the remaining nx - i columns, no contribution to max_error
+      for (size_t k = 0; k < nx - i; ++k) {
+        const size_t idx = j * nx + i + k;
+        const R right = CFDO_AT(p_prime, idx + 1), left = CFDO_AT(p_prime, idx - 1);
+        const R top = CFDO_AT(p_prime, idx + nx), bot = CFDO_AT(p_prime, idx - nx);
+        const R center = CFDO_AT(p_prime, idx);
+        const R horizontal = (right + left) / dx_sq;
+        const R vertical = (top + bot) / dy_sq;
+        const R p_update = (horizontal + vertical - CFDO_AT(rhs, idx)) / denom;
+        CFDO_AT(p_prime_new, idx) = omega * p_update + one_minus * center;
       }
     }
     return max_error;

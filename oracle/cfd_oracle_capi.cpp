@@ -145,6 +145,16 @@ double cfdo_stage(void* hv, int stage) {
   return h->f ? stage_t(*h->f, stage) : stage_t(*h->d, stage);
 }
 
+// restart support for the tests / bench: scalars that are not fields (simulation_step, time, dt)
+void cfdo_set_scalars(void* hv, uint64_t simulation_step, double simulation_time, double dt) {
+  auto* h = static_cast<Handle*>(hv);
+  if (h->f) {
+    h->f->simulation_step = simulation_step; h->f->simulation_time = float(simulation_time); h->f->dt = float(dt);
+  } else {
+    h->d->simulation_step = simulation_step; h->d->simulation_time = simulation_time; h->d->dt = dt;
+  }
+}
+
 uint64_t cfdo_total_sweeps(void* hv) {
   auto* h = static_cast<Handle*>(hv);
   return h->f ? h->f->total_sweeps : h->d->total_sweeps;

@@ -51,6 +51,7 @@ def _load(checked: bool = False):
     lib.cfdo_current_inlet_velocity.argtypes = [C.c_void_p]
     lib.cfdo_stage.restype = C.c_double
     lib.cfdo_stage.argtypes = [C.c_void_p, C.c_int]
+    lib.cfdo_set_scalars.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_double]
     lib.cfdo_total_sweeps.restype = C.c_uint64
     lib.cfdo_total_sweeps.argtypes = [C.c_void_p]
     lib.cfd_solver_consts_default.argtypes = [C.POINTER(_abi.CfdSolverConsts)]
@@ -119,6 +120,9 @@ class OracleModel:
 
     def stage(self, stage: int) -> float:
         return float(self._lib.cfdo_stage(self._h, stage))
+
+    def set_scalars(self, simulation_step: int, simulation_time: float, dt: float):
+        self._lib.cfdo_set_scalars(self._h, int(simulation_step), float(simulation_time), float(dt))
 
     def total_sweeps(self) -> int:
         return int(self._lib.cfdo_total_sweeps(self._h))
