@@ -1,0 +1,192 @@
+//! Drop-in replacement for the reference's `src/model.rs`: the same pub types and `Model` API, with the fields
+//! resident on a B200 behind the C ABI of `include/cfd_b200.h`.  `app.rs` compiles against it unchanged
+//! (it only uses `Grid`, `Cylinder`, `SimulationParams`, the three enums, `Model::{new, run}`,
+//! `SimulationControlHandle::*`, `SimSnapshot`, `Residuals`).
+//!
+//! SOURCE ONLY — never compiled: there is no Rust toolchain in this repository's build environment
+//!.  The tested boundary is the C ABI these `extern "C"` items bind.
+use std::{
+    os::raw::{c_char, c_int},
+    sync::mpsc::{self, TryRecvError},
+    thread,
+    time::{Duration, Instant},
+};
+
+// ---- the C ABI (include/cfd_b200.h) -------------------------------------------------------------------
+#[repr(C)]
+struct CfdGrid { nx: u64, ny: u64, lx: f32, ly: f32, dx: f32, dy: f32, has_obstacle: i32, center_x: f32, center_y: f32, radius: f32 }
+#[repr(C)]
+struct CfdParams { dt: f32, viscosity: f32, target_inlet_velocity: f32, velocity_scheme: i32, inlet_profile: i32, pressure_solver: i32, scenario: i32 }
+#[repr(C)]
+#[derive(Default)]
+struct CfdResiduals {
+    simulation_step: u64, simulation_time: f32, dt: f32, p: f32, u: f32, v: f32, step_seconds: f64,
+    piso_substeps: u64, jacobi_calls: u64, sweeps: u64,
+    simulation_time_f64: f64, dt_f64: f64, p_f64: f64, u_f64: f64, v_f64: f64,
+}
+#[repr(C)]
+struct CfdModel { _private: [u8; 0] }
+
+extern "C" {
+    fn cfd_model_create(grid: *const CfdGrid, params: *const CfdParams, out: *mut *mut CfdModel) -> c_int;
+    fn cfd_model_destroy(m: *mut CfdModel);
+    fn cfd_model_update(m: *mut CfdModel) -> c_int;
+    fn cfd_model_set_params(m: *mut CfdModel, params: *const CfdParams) -> c_int;
+    fn cfd_model_get_snapshot(m: *mut CfdModel, p: *mut f32, u: *mut f32, v: *mut f32, dt: *mut f32) -> c_int;
+    fn cfd_model_get_residuals(m: *mut CfdModel, out: *mut CfdResiduals) -> c_int;
+    fn cfd_last_error() -> *const c_char;
+}
+
+fn check(rc: c_int) {
+    if rc != 0 {
+        let msg = unsafe { std::ffi::CStr::from_ptr(cfd_last_error()) }.to_string_lossy().into_owned();
+        panic!("cfd_b200: {msg}"); // the reference panics on every error path too (unwrap / slice index)
+    }
+}
+
+// ---- the reference's pub types, unchanged (src/model.rs:13-63, 121-159) --------------------------------
+#[derive(Clone)]
+pub struct SimulationParams {
+    pub dt: f32,
+    pub viscosity: f32,
+    pub target_inlet_velocity: f32,
+    pub velocity_scheme: VelocityScheme,
+    pub inlet_profile: InletProfile,
+    pub pressure_solver: PressureSolver,
+}
+pub struct Residuals {
+    pub simulation_step: usize, pub simulation_time: f32, pub dt: f32, pub p: f32, pub u: f32, pub v: f32,
+    pub step_time: Duration, pub piso_substeps: usize,
+}
+#[derive(Clone)]
+pub struct SimSnapshot { pub p: Vec<f32>, pub u: Vec<f32>, pub v: Vec<f32>, pub dt: f32, pub paused: bool }
+impl Default for SimulationParams {
+    fn default() -> Self {
+        Self { dt: 0.005, viscosity: 0.000001, target_inlet_velocity: 1.0, velocity_scheme: VelocityScheme::FirstOrder,
+               inlet_profile: InletProfile::Uniform, pressure_solver: PressureSolver::Jacobi }
+    }
+}
+pub enum Command { Stop, GetSnapshot, SetParams(SimulationParams), Pause, Resume }
+#[derive(Clone)]
+pub struct Grid { pub nx: usize, pub ny: usize, pub lx: f32, pub ly: f32, pub dx: f32, pub dy: f32, pub obstacle: Option<Cylinder> }
+#[derive(Clone)]
+pub struct Cylinder { pub center_x: f32, pub center_y: f32, pub radius: f32 }
+#[derive(Debug, Clone, Copy, PartialEq, Eq)]
+pub enum VelocityScheme { FirstOrder, SecondOrder }
+#[derive(Debug, Clone, Copy, PartialEq, Eq)]
+pub enum PressureSolver { Jacobi }
+#[derive(Debug, Clone, Copy, PartialEq, Eq)]
+pub enum InletProfile { Uniform, Parabolic }
+
+fn params_to_c(p: &SimulationParams) -> CfdParams {
+    CfdParams {
+        dt: p.dt, viscosity: p.viscosity, target_inlet_velocity: p.target_inlet_velocity,
+        velocity_scheme: match p.velocity_scheme { VelocityScheme::FirstOrder => 0, VelocityScheme::SecondOrder => 1 },
+        inlet_profile: match p.inlet_profile { InletProfile::Uniform => 0, InletProfile::Parabolic => 1 },
+        pressure_solver: 0, scenario: 0,
+    }
+}
+
+// ---- Model: an owning handle; all fields live in HBM ----------------------------------------------------
+pub struct Model { pub grid: Grid, handle: *mut CfdModel }
+unsafe impl Send for Model {} // moved into exactly one solver thread, like the reference (src/model.rs:1287)
+
+impl Model {
+    pub fn new(grid: Grid, params: &SimulationParams) -> Self {
+        let g = CfdGrid {
+            nx: grid.nx as u64, ny: grid.ny as u64, lx: grid.lx, ly: grid.ly, dx: grid.dx, dy: grid.dy,
+            has_obstacle: grid.obstacle.is_some() as i32,
+            center_x: grid.obstacle.as_ref().map_or(0.0, |c| c.center_x),
+            center_y: grid.obstacle.as_ref().map_or(0.0, |c| c.center_y),
+            radius: grid.obstacle.as_ref().map_or(0.0, |c| c.radius),
+        };
+        let mut handle = std::ptr::null_mut();
+        check(unsafe { cfd_model_create(&g, &params_to_c(params), &mut handle) });
+        Self { grid, handle }
+    }
+    pub fn update(&mut self) { check(unsafe { cfd_model_update(self.handle) }) }
+    pub fn set_parameters(&mut self, params: &SimulationParams) {
+        check(unsafe { cfd_model_set_params(self.handle, &params_to_c(params)) })
+    }
+    pub fn get_snapshot(&self) -> SimSnapshot {
+        let (nx, ny) = (self.grid.nx, self.grid.ny);
+        let (mut p, mut u, mut v) = (vec![0.0f32; nx * ny], vec![0.0f32; (nx + 1) * ny], vec![0.0f32; nx * (ny + 1)]);
+        let mut dt = 0.0f32;
+        check(unsafe { cfd_model_get_snapshot(self.handle, p.as_mut_ptr(), u.as_mut_ptr(), v.as_mut_ptr(), &mut dt) });
+        SimSnapshot { p, u, v, dt, paused: false }
+    }
+    pub fn get_residuals(&self) -> Residuals {
+        let mut r = CfdResiduals::default();
+        check(unsafe { cfd_model_get_residuals(self.handle, &mut r) });
+        Residuals { simulation_step: r.simulation_step as usize, simulation_time: r.simulation_time, dt: r.dt, p: r.p,
+                    u: r.u, v: r.v, step_time: Duration::from_secs_f64(r.step_seconds), piso_substeps: r.piso_substeps as usize }
+    }
+    /// Same thread/channel protocol as the reference (src/model.rs:1282-1332).
+    pub fn run(mut self) -> SimulationControlHandle {
+        let (command_sender, command_receiver) = mpsc::channel();
+        let (snapshot_sender, snapshot_receiver) = mpsc::channel();
+        let (residuals_sender, residuals_receiver) = mpsc::channel();
+        thread::spawn(move || {
+            let mut paused = false;
+            loop {
+                let _start = Instant::now();
+                let mut snapshot_sent = false;
+                for command in command_receiver.try_iter() {
+                    match command {
+                        Command::Stop => break,
+                        Command::SetParams(params) => self.set_parameters(&params),
+                        Command::GetSnapshot => {
+                            if !snapshot_sent {
+                                let mut snapshot = self.get_snapshot();
+                                snapshot.paused = paused;
+                                snapshot_sender.send(snapshot).unwrap();
+                                snapshot_sent = true;
+                            }
+                        }
+                        Command::Pause => paused = true,
+                        Command::Resume => paused = false,
+                    }
+                }
+                if !paused {
+                    self.update();
+                    residuals_sender.send(self.get_residuals()).unwrap(); // panics when the UI drops the handle;
+                } else {                                                   // unwinding runs Drop below
+                    thread::sleep(Duration::from_millis(16));
+                }
+            }
+        });
+        SimulationControlHandle { command_sender, snapshot_receiver, residuals_receiver }
+    }
+}
+impl Drop for Model {
+    fn drop(&mut self) { unsafe { cfd_model_destroy(self.handle) } }
+}
+
+// ---- SimulationControlHandle: verbatim protocol of the reference (src/model.rs:65-117) -----------------
+pub struct SimulationControlHandle {
+    command_sender: mpsc::Sender<Command>,
+    snapshot_receiver: mpsc::Receiver<SimSnapshot>,
+    residuals_receiver: mpsc::Receiver<Residuals>,
+}
+impl SimulationControlHandle {
+    pub fn stop(&self) { self.command_sender.send(Command::Stop).unwrap(); }
+    pub fn get_last_available_snapshot(&self) -> Option<SimSnapshot> {
+        let mut last = None;
+        loop {
+            match self.snapshot_receiver.try_recv() {
+                Ok(s) => last = Some(s),
+                Err(TryRecvError::Empty) | Err(TryRecvError::Disconnected) => break,
+            }
+        }
+        last
+    }
+    pub fn get_new_log_messages(&self) -> Vec<Residuals> {
+        let mut out = vec![];
+        while let Ok(r) = self.residuals_receiver.try_recv() { out.push(r); }
+        out
+    }
+    pub fn request_snapshot(&self) { self.command_sender.send(Command::GetSnapshot).unwrap(); }
+    pub fn set_params(&self, params: SimulationParams) { self.command_sender.send(Command::SetParams(params)).unwrap(); }
+    pub fn pause(&self) { self.command_sender.send(Command::Pause).unwrap(); }
+    pub fn resume(&self) { self.command_sender.send(Command::Resume).unwrap(); }
+}

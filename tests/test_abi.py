@@ -78,3 +78,17 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".rs")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "cfd_oracle" not in text and "cpu_oracle" not in text and "import oracle" not in text, f
+
+
+def test_cpp_host_mirror_builds_and_fails_loudly_without_gpu(lib):
+    """host/cfd_model.hpp (C++ mirror of the reference API) links against the C ABI; without a GPU the headless
+    driver must exit non-zero with the library's error (no CPU fallback)."""
+    import subprocess
+    import torch
+    exe = os.path.join(ROOT, "cfd_demo_b200", "host", "cfd_headless")
+    assert os.path.exists(exe)
+    r = subprocess.run([exe, "2"], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "step 2" in r.stdout
+    else:
+        assert r.returncode != 0 and "cfd_b200" in r.stderr

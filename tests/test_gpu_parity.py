@@ -205,3 +205,17 @@ def test_tuned_sweep_equals_baseline_sweep(precision, other):
         assert np.array_equal(a.field(fid), b.field(fid)), _abi.FIELD_NAMES[fid]
     ra, rb = a.get_residuals(), b.get_residuals()
     assert (ra.jacobi_calls, ra.sweeps, ra.f64["p"]) == (rb.jacobi_calls, rb.sweeps, rb.f64["p"])
+
+
+def test_cpp_headless_driver_matches_python_mirror():
+    """The C++ mirror (host/cfd_model.hpp) drives the same C ABI: its residual log equals the Python mirror's."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cfd_demo_b200", "host", "cfd_headless")
+    r = subprocess.run([exe, "5"], capture_output=True, text=True, check=True)
+    m = Model(default_grid(), SimulationParams())
+    for _ in range(5):
+        m.update()
+    res = m.get_residuals()
+    line = [l for l in r.stdout.splitlines() if l.startswith("step 5 ")][0]
+    assert f"K={res.jacobi_calls} S={res.sweeps}" in line and f"u={res.u:.3e}" in line
