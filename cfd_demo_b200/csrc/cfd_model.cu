@@ -101,6 +101,12 @@ struct ModelImpl final : ModelBase {
   size_t staging_bytes = 0;
   void* h_staging = nullptr;                 // pinned host scratch
   size_t h_staging_bytes = 0;
+  // Mode C (CG) work space, allocated on first use
+  R* cg_r = nullptr;
+  R* cg_d = nullptr;
+  double* cg_partials = nullptr;
+  cfdk::CgScalars* cg_scalars = nullptr;   // device
+  cfdk::CgScalars* h_cg = nullptr;         // pinned host copy
   CUtensorMap tmap_pp[2], tmap_rhs;  // 2-D tiled views of p' (ping, pong) and rhs for the tensor-TMA sweep
   cfdk::DivG<R> div_dx_sq, div_dy_sq, div_denom;  // divisors of the Jacobi update with hoisted reciprocals
   int sweep_rows_per_block = 32;
@@ -132,6 +138,8 @@ struct ModelImpl final : ModelBase {
     cudaFree(p); cudaFree(rhs_base); cudaFree(pp_base[0]); cudaFree(pp_base[1]);
     cudaFree(mask_u); cudaFree(mask_v); cudaFree(solid);
     cudaFree(err_slots); cudaFree(step_slots); cudaFree(staging);
+    cudaFree(cg_r); cudaFree(cg_d); cudaFree(cg_partials); cudaFree(cg_scalars);
+    if (h_cg) cudaFreeHost(h_cg);
     if (h_jres) cudaFreeHost(h_jres);
     if (h_step) cudaFreeHost(h_step);
     if (h_staging) cudaFreeHost(h_staging);
@@ -332,8 +340,7 @@ struct ModelImpl final : ModelBase {
       cfdk::k_divergence<R><<<grd, blk, 0, stream>>>(scalars(dt_sub), us, vs, rhs, 0, ny, err_slots, iters);
       ++launches;
     }
-    if (pressure_solver != CFD_SOLVER_JACOBI)
-      return fail(CFD_ERR_UNSUPPORTED, "pressure_solver: only Jacobi is implemented in this build");
+    if (pressure_solver == CFD_SOLVER_CG) return cg_solve(dt_sub, call_index, residual_out);
     cfdk::JacobiConsts<R> c;
     c.dx_sq = dx * dx;                                   // :740
     c.dy_sq = dy * dy;                                   // :742
@@ -382,6 +389,61 @@ struct ModelImpl final : ModelBase {
     last_S += (uint64_t)ran;
     last_K += 1;
     *residual_out = (R)h_jres->last_error;
+    return CFD_OK;
+  }
+
+  // EXTENSION, Mode C: conjugate gradients on the Jacobi iteration's own discrete problem (cfd_kernels.cuh)
+  int cg_solve(R dt_sub, int call_index, R* residual_out) {
+    int rc;
+    const dim3 blk(cfdk::kCgThreads);
+    const dim3 g_all((nx + cfdk::kCgThreads - 1) / cfdk::kCgThreads, ny);
+    const dim3 g_int((nx - 2 + cfdk::kCgThreads - 1) / cfdk::kCgThreads, ny - 2);
+    const int n_all = (int)(g_all.x * g_all.y), n_int = (int)(g_int.x * g_int.y);
+    if (!cg_r) {
+      if ((rc = dalloc(&cg_r, n_p))) return rc;
+      if ((rc = dalloc(&cg_d, n_p))) return rc;
+      if ((rc = dalloc(&cg_partials, (size_t)n_all))) return rc;
+      if ((rc = dalloc(&cg_scalars, (size_t)1))) return rc;
+      CFD_CUDA(cudaHostAlloc((void**)&h_cg, sizeof(cfdk::CgScalars), cudaHostAllocDefault));
+    }
+    cfdk::CgConsts<R> c;
+    c.dx_sq = dx * dx; c.dy_sq = dy * dy; c.dt = dt_sub; c.tol = R(opt.consts.cg_tolerance);
+    c.n_unknowns = R((size_t)(nx - 2) * (size_t)(ny - 2));
+    c.nx = nx; c.ny = ny; c.cavity = scenario == CFD_SCENARIO_CAVITY;
+    R* x = pp[ipp];
+    R* q = pp[ipp ^ 1];
+    cfdk::CgScalars init;
+    memset(&init, 0, sizeof init);
+    init.max_iterations = opt.consts.cg_max_iterations;
+    *h_cg = init;
+    CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index], stream));
+    CFD_CUDA(cudaMemcpyAsync(cg_scalars, h_cg, sizeof init, cudaMemcpyHostToDevice, stream));
+    cfdk::k_cg_init<R><<<g_all, blk, 0, stream>>>(c, rhs, x, cg_r, cg_d, cg_partials);
+    cfdk::k_cg_reduce<R><<<1, 1024, 0, stream>>>(c, cg_scalars, cg_partials, n_all, 0);
+    launches += 2;
+    const int batch = 32;
+    for (;;) {
+      CFD_CUDA(cudaMemcpyAsync(h_cg, cg_scalars, sizeof init, cudaMemcpyDeviceToHost, stream));
+      CFD_CUDA(cudaStreamSynchronize(stream));
+      if (h_cg->done) break;
+      for (int it = 0; it < batch; ++it) {
+        cfdk::k_cg_apply<R><<<g_int, blk, 0, stream>>>(c, cg_scalars, cg_d, q, cg_partials);
+        cfdk::k_cg_reduce<R><<<1, 1024, 0, stream>>>(c, cg_scalars, cg_partials, n_int, 1);
+        cfdk::k_cg_update<R><<<g_int, blk, 0, stream>>>(c, cg_scalars, cg_d, q, x, cg_r, cg_partials);
+        cfdk::k_cg_reduce<R><<<1, 1024, 0, stream>>>(c, cg_scalars, cg_partials, n_int, 2);
+        cfdk::k_cg_direction<R><<<g_int, blk, 0, stream>>>(c, cg_scalars, cg_r, cg_d);
+        launches += 5;
+      }
+      CFD_CUDA(cudaGetLastError());
+    }
+    const int n_edge = (nx > ny ? nx : ny);
+    cfdk::k_cg_fill_boundary<R><<<(n_edge + 255) / 256, 256, 0, stream>>>(nx, ny, c.cavity, x);
+    ++launches;
+    CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index + 1], stream));
+    CFD_CUDA(cudaGetLastError());
+    last_S += (uint64_t)h_cg->iterations;
+    last_K += 1;
+    *residual_out = (R)h_cg->measure;
     return CFD_OK;
   }
 

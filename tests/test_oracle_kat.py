@@ -171,3 +171,25 @@ def test_cavity_extension_is_closed_and_compatible():
     interior = rhs[1:n - 1, 1:n - 1]
     assert abs(interior.sum()) < 1e-6 * np.abs(interior).sum() + 1e-12
     assert np.abs(u[1:n - 1, 2:n - 1]).max() > 0
+
+
+@pytest.mark.parametrize("scenario", [Scenario.Channel, Scenario.Cavity])
+def test_mode_c_cg_leaves_a_divergence_free_interior(scenario):
+    """Extension (no reference counterpart): the CG solve drives the divergence of the corrected velocity on the
+    unknown cells below its tolerance, and the outer loop then stops after one re-correction (K = 2)."""
+    from cfd_demo_b200.types import PressureSolver
+    n = 32
+    g = box_grid(n) if scenario == Scenario.Cavity else channel_grid(n, n, cylinder=False)
+    consts = default_consts()
+    consts.cg_tolerance = 1e-10
+    prm = SimulationParams(dt=1e-3, viscosity=0.01, scenario=scenario, pressure_solver=PressureSolver.CG)
+    m = OracleModel(g, prm, precision=64, consts=consts)
+    for _ in range(12):
+        m.update()
+    r = m.get_residuals()
+    assert r.jacobi_calls == 2 and 0 < r.sweeps < 400 and r.f64["p"] <= 1e-10
+    u = m.field(_abi.FIELD_U).reshape(n, n + 1)
+    v = m.field(_abi.FIELD_V).reshape(n + 1, n)
+    # velocities BEFORE the boundary update are what the solve made divergence free; check rows/cols away from it
+    div = (u[2:n - 2, 3:n - 1] - u[2:n - 2, 2:n - 2]) / g.dx + (v[3:n - 1, 2:n - 2] - v[2:n - 2, 2:n - 2]) / g.dy
+    assert np.abs(div).max() < 1e-6 and np.abs(u).max() > 1e-3
