@@ -14,6 +14,9 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include "../../include/cfd_b200.h"
 #include "cfd_kernels.cuh"
 
@@ -31,6 +34,60 @@ int fail(int code, const std::string& msg) {
     cudaError_t _e = (expr);                                                                        \
     if (_e != cudaSuccess)                                                                          \
       return fail(CFD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                                    ":" + std::to_string(__LINE__) + ")");                          \
+  } while (0)
+
+// NCCL is resolved at run time (dlopen by SONAME) instead of being a link-time dependency: a process that
+// also hosts PyTorch must end up with ONE libnccl.so.2 — whichever is loaded first is shared — and a process that
+// never goes multi-GPU (the reference UI, the single-GPU tests) never loads NCCL at all.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (h) {
+#define CFD_SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, name))
+      CFD_SYM(GetUniqueId, "ncclGetUniqueId");
+      CFD_SYM(CommInitRank, "ncclCommInitRank");
+      CFD_SYM(CommDestroy, "ncclCommDestroy");
+      CFD_SYM(Send, "ncclSend");
+      CFD_SYM(Recv, "ncclRecv");
+      CFD_SYM(AllReduce, "ncclAllReduce");
+      CFD_SYM(GroupStart, "ncclGroupStart");
+      CFD_SYM(GroupEnd, "ncclGroupEnd");
+      CFD_SYM(GetErrorString, "ncclGetErrorString");
+#undef CFD_SYM
+      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.AllReduce &&
+               api.GroupStart && api.GroupEnd && api.GetErrorString;
+    }
+  }
+  return api;
+}
+
+#define CFD_NCCL_READY()                                                                            \
+  do {                                                                                              \
+    if (!nccl_api().ok) return fail(CFD_ERR_NCCL, "libnccl.so.2 could not be loaded (needed for world_size > 1)"); \
+  } while (0)
+
+#define CFD_NCCL(expr)                                                                              \
+  do {                                                                                              \
+    ncclResult_t _r = (expr);                                                                       \
+    if (_r != ncclSuccess)                                                                          \
+      return fail(CFD_ERR_NCCL, std::string(#expr) + ": " + nccl_api().GetErrorString(_r) + " (" + __FILE__ + \
                                     ":" + std::to_string(__LINE__) + ")");                          \
   } while (0)
 
@@ -63,6 +120,20 @@ struct ModelBase {
   virtual int last_timing(double* step_ms, double* sweep_ms, uint64_t* launches) = 0;
 };
 
+// One rotating / plain field: `base` is the allocation, `v` the VIRTUAL ORIGIN such that v[j * rowlen + i] is
+// entry (i, j) in GLOBAL row numbering.  A rank of a strip decomposition allocates only its own rows plus kHalo
+// rows on each side, and every kernel keeps the reference's global flat indexing (so the "next row" wrap-around
+// reads, SURVEY N2, still fall out of the index arithmetic).
+template <class T>
+struct Field {
+  T* base = nullptr;
+  T* v = nullptr;
+  size_t rowlen = 0;
+  T* row(long j) const { return v + j * (long)rowlen; }
+};
+
+constexpr int kHalo = 2;  // rows: the second-order predictor reaches j +- 2 (src/model.rs:999, 1044, 1195, 1239)
+
 template <class R>
 struct ModelImpl final : ModelBase {
   // ---- problem definition ----
@@ -70,6 +141,11 @@ struct ModelImpl final : ModelBase {
   cfd_options opt;
   int nx, ny;
   size_t n_p, n_u, n_v;
+  // ---- strip owned by this rank: pressure / u rows [ja, jb); v rows [ja, jb) (+ row ny on the last rank) ----
+  int rank = 0, world = 1, ja = 0, jb = 0;
+  bool owns_bottom = true, owns_top = true;
+  int rows_alloc = 0;  // jb - ja + 2*kHalo + 1
+  ncclComm_t comm = nullptr;
   // ---- scalars kept on the host in R precision, same arithmetic as the reference (update(), :304-379) ----
   R dx, dy, lx, ly, dt, nu;
   R current_inlet_velocity = 0, target_inlet_velocity = 0;
@@ -82,17 +158,12 @@ struct ModelImpl final : ModelBase {
   // ---- device state ----
   int device = 0;
   cudaStream_t stream = nullptr;
-  R* ubuf[3] = {nullptr, nullptr, nullptr};
-  R* vbuf[3] = {nullptr, nullptr, nullptr};
-  int iu = 0, ius = 1, ifree = 2;  // roles of the three u (and v) buffers: current, star, free
-  R* p = nullptr;
   static constexpr size_t kFront = 256 / sizeof(R);
-  R* rhs = nullptr;
-  R* rhs_base = nullptr;
-  R* pp[2] = {nullptr, nullptr};
-  R* pp_base[2] = {nullptr, nullptr};
+  Field<R> ubuf[3], vbuf[3];
+  int iu = 0, ius = 1, ifree = 2;  // roles of the three u (and v) buffers: current, star, free
+  Field<R> p, rhs, pp[2];
   int ipp = 0;  // pp[ipp] is p_prime, the other one p_prime_new
-  uint8_t *mask_u = nullptr, *mask_v = nullptr, *solid = nullptr;
+  Field<uint8_t> mask_u, mask_v, solid;
   unsigned long long* err_slots = nullptr;   // kMaxSweepSlots
   unsigned long long* step_slots = nullptr;  // 4
   cfdk::JacobiResult* h_jres = nullptr;      // pinned, device-visible
@@ -102,8 +173,7 @@ struct ModelImpl final : ModelBase {
   void* h_staging = nullptr;                 // pinned host scratch
   size_t h_staging_bytes = 0;
   // Mode C (CG) work space, allocated on first use
-  R* cg_r = nullptr;
-  R* cg_d = nullptr;
+  Field<R> cg_r, cg_d;
   double* cg_partials = nullptr;
   cfdk::CgScalars* cg_scalars = nullptr;   // device
   cfdk::CgScalars* h_cg = nullptr;         // pinned host copy
@@ -128,17 +198,26 @@ struct ModelImpl final : ModelBase {
     pressure_solver = prm.pressure_solver;
     inlet_profile = prm.inlet_profile;
     scenario = prm.scenario;
+    rank = o.rank;
+    world = o.world_size;
+    const int base = ny / world, rem = ny % world;
+    ja = rank * base + (rank < rem ? rank : rem);
+    jb = ja + base + (rank < rem ? 1 : 0);
+    owns_bottom = rank == 0;
+    owns_top = rank == world - 1;
+    rows_alloc = (jb - ja) + 2 * kHalo + 1;
   }
 
   ~ModelImpl() override {
     if (device >= 0) cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
-    for (auto& b : ubuf) cudaFree(b);
-    for (auto& b : vbuf) cudaFree(b);
-    cudaFree(p); cudaFree(rhs_base); cudaFree(pp_base[0]); cudaFree(pp_base[1]);
-    cudaFree(mask_u); cudaFree(mask_v); cudaFree(solid);
+    if (comm) nccl_api().CommDestroy(comm);
+    for (auto& f : ubuf) cudaFree(f.base);
+    for (auto& f : vbuf) cudaFree(f.base);
+    cudaFree(p.base); cudaFree(rhs.base); cudaFree(pp[0].base); cudaFree(pp[1].base);
+    cudaFree(mask_u.base); cudaFree(mask_v.base); cudaFree(solid.base);
     cudaFree(err_slots); cudaFree(step_slots); cudaFree(staging);
-    cudaFree(cg_r); cudaFree(cg_d); cudaFree(cg_partials); cudaFree(cg_scalars);
+    cudaFree(cg_r.base); cudaFree(cg_d.base); cudaFree(cg_partials); cudaFree(cg_scalars);
     if (h_cg) cudaFreeHost(h_cg);
     if (h_jres) cudaFreeHost(h_jres);
     if (h_step) cudaFreeHost(h_step);
@@ -156,6 +235,19 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
 
+  // rows [ja - kHalo, jb + kHalo] of a field with `rowlen` entries per row, zero-filled; 256 B of slack in
+  // front (16-byte halo of the first TMA strip) and 4 rows behind (prefetch of the register / bulk sweeps)
+  template <class T>
+  int falloc(Field<T>* f, size_t rowlen) {
+    const size_t front = 256 / sizeof(T);
+    const size_t count = front + (size_t)rows_alloc * rowlen + 4 * rowlen;
+    int rc;
+    if ((rc = dalloc(&f->base, count))) return rc;
+    f->rowlen = rowlen;
+    f->v = f->base + front - (long)(ja - kHalo) * (long)rowlen;
+    return CFD_OK;
+  }
+
   // Model::new, src/model.rs:219-299: zero fields, masks from the cylinder
   int init() override {
     int ndev = 0;
@@ -168,22 +260,24 @@ struct ModelImpl final : ModelBase {
       CFD_CUDA(cudaGetDevice(&device));
     }
     CFD_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (world > 1) {
+      CFD_NCCL_READY();
+      ncclUniqueId id;
+      memcpy(&id, opt.nccl_unique_id, sizeof id);
+      CFD_NCCL(nccl_api().CommInitRank(&comm, world, id, rank));
+    }
     int rc;
     for (int k = 0; k < 3; ++k) {
-      if ((rc = dalloc(&ubuf[k], n_u))) return rc;
-      if ((rc = dalloc(&vbuf[k], n_v))) return rc;
+      if ((rc = falloc(&ubuf[k], (size_t)nx + 1))) return rc;
+      if ((rc = falloc(&vbuf[k], (size_t)nx))) return rc;
     }
-    if ((rc = dalloc(&p, n_p))) return rc;
-    // slack around the p'-like buffers: the tuned sweeps stage rows with a 16-byte halo and prefetch up to
-    // 3 rows past row ny-1 without clamping; kFront elements (256 B) in front keep row 0 256-byte aligned
-    const size_t slack = 4 * (size_t)nx;
-    if ((rc = dalloc(&rhs_base, kFront + n_p + slack))) return rc;
-    if ((rc = dalloc(&pp_base[0], kFront + n_p + slack))) return rc;
-    if ((rc = dalloc(&pp_base[1], kFront + n_p + slack))) return rc;
-    rhs = rhs_base + kFront; pp[0] = pp_base[0] + kFront; pp[1] = pp_base[1] + kFront;
-    if ((rc = dalloc(&mask_u, n_u))) return rc;
-    if ((rc = dalloc(&mask_v, n_v))) return rc;
-    if ((rc = dalloc(&solid, n_p))) return rc;
+    if ((rc = falloc(&p, (size_t)nx))) return rc;
+    if ((rc = falloc(&rhs, (size_t)nx))) return rc;
+    if ((rc = falloc(&pp[0], (size_t)nx))) return rc;
+    if ((rc = falloc(&pp[1], (size_t)nx))) return rc;
+    if ((rc = falloc(&mask_u, (size_t)nx + 1))) return rc;
+    if ((rc = falloc(&mask_v, (size_t)nx))) return rc;
+    if ((rc = falloc(&solid, (size_t)nx))) return rc;
     if ((rc = dalloc(&err_slots, (size_t)kMaxSweepSlots))) return rc;
     if ((rc = dalloc(&step_slots, (size_t)4))) return rc;
     CFD_CUDA(cudaHostAlloc((void**)&h_jres, sizeof(cfdk::JacobiResult), cudaHostAllocMapped));
@@ -199,8 +293,9 @@ struct ModelImpl final : ModelBase {
     g.has_obstacle = grid.has_obstacle != 0;
     g.cavity = scenario == CFD_SCENARIO_CAVITY;
     g.dx = grid.dx; g.dy = grid.dy; g.cx = grid.center_x; g.cy = grid.center_y; g.radius = grid.radius;
-    dim3 blk(256), grd((nx + 1 + 255) / 256, ny + 1);
-    cfdk::k_build_masks<<<grd, blk, 0, stream>>>(g, solid, mask_u, mask_v);
+    const int mj_lo = ja, mj_hi = owns_top ? jb + 1 : jb;
+    dim3 blk(256), grd((nx + 1 + 255) / 256, mj_hi - mj_lo);
+    cfdk::k_build_masks<<<grd, blk, 0, stream>>>(g, solid.v, mask_u.v, mask_v.v, mj_lo, mj_hi);
     CFD_CUDA(cudaGetLastError());
     CFD_CUDA(cudaStreamSynchronize(stream));
     if ((rc = init_sweep_constants())) return rc;
@@ -209,7 +304,7 @@ struct ModelImpl final : ModelBase {
   }
 
   // 2-D tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point; libcuda is not linked)
-  int make_tensor_map(CUtensorMap* map, R* base, int box_cols) {
+  int make_tensor_map(CUtensorMap* map, R* first_row, int box_cols) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -221,12 +316,12 @@ struct ModelImpl final : ModelBase {
       if (!fn || q != cudaDriverEntryPointSuccess) return fail(CFD_ERR_CUDA, "cuTensorMapEncodeTiled not available");
       encode = (EncodeFn)fn;
     }
-    const cuuint64_t dims[2] = {(cuuint64_t)nx, (cuuint64_t)ny};
+    const cuuint64_t dims[2] = {(cuuint64_t)nx, (cuuint64_t)rows_alloc};
     const cuuint64_t strides[1] = {(cuuint64_t)nx * sizeof(R)};
     const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)cfdk::kChunkRows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(map, sizeof(R) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                              (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              (void*)first_row, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(CFD_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
@@ -234,7 +329,7 @@ struct ModelImpl final : ModelBase {
   }
 
   // divisors of the Jacobi update (src/model.rs:740-746) and, for fp64, their reciprocals refined by the
-  // same instruction sequence the compiler's division uses (cfdk::div_c); launch geometry of the sweep
+  // same instruction sequence the compiler's division uses (cfdk::div_fast); launch geometry of the sweep
   int init_sweep_constants() {
     div_dx_sq.y = dx * dx;                                      // :740
     div_dy_sq.y = dy * dy;                                      // :742
@@ -272,9 +367,10 @@ struct ModelImpl final : ModelBase {
     {
       using Ring = cfdk::SweepChunkRing<R>;
       int rc2;
-      if ((rc2 = make_tensor_map(&tmap_pp[0], pp[0], Ring::kPCols))) return rc2;
-      if ((rc2 = make_tensor_map(&tmap_pp[1], pp[1], Ring::kPCols))) return rc2;
-      if ((rc2 = make_tensor_map(&tmap_rhs, rhs, cfdk::kStripCols))) return rc2;
+      // the maps describe the LOCAL allocation: its row 0 is global row ja - kHalo
+      if ((rc2 = make_tensor_map(&tmap_pp[0], pp[0].row(ja - kHalo), Ring::kPCols))) return rc2;
+      if ((rc2 = make_tensor_map(&tmap_pp[1], pp[1].row(ja - kHalo), Ring::kPCols))) return rc2;
+      if ((rc2 = make_tensor_map(&tmap_rhs, rhs.row(ja - kHalo), cfdk::kStripCols))) return rc2;
       CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep4<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(Ring)));
       CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep5<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -299,16 +395,17 @@ struct ModelImpl final : ModelBase {
                                                              sizeof(cfdk::SweepChunkRing<R>)));
     if (per_sm < 1) per_sm = 1;
     const int resident = sms * per_sm;
-    const int rows = ny - 2;
+    const int rows = sweep_row_end() - sweep_row_begin();
     int rpb;
     if (opt.flags & (CFD_FLAG_REGISTER_SWEEP | CFD_FLAG_BULK_SWEEP)) {
       int gy = (resident + bx - 1) / bx;  // one wave
       if (gy > rows) gy = rows;
+      if (gy < 1) gy = 1;
       rpb = (rows + gy - 1) / gy;
       if (rpb < 8 && rows >= 8) rpb = 8;
     } else {
       // Tile height of the tensor-TMA sweeps.  SMs progress at visibly different rates (profiles/
-      // r1_sweep4.md: sm__cycles_active min 95k / max 194k at equal work), so the grid is cut into several
+      // r1_notes.md: sm__cycles_active min 95k / max 194k at equal work), so the grid is cut into several
       // waves of short tiles that the block scheduler hands out dynamically; 22 rows (+2 halo rows = six
       // 4-row TMA boxes exactly) measured best at 4096^2 (tools/tune_sweep.py).  Small grids get shorter
       // tiles so that every SM still has work.
@@ -326,18 +423,56 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
 
+  // interior pressure rows this rank sweeps / owned row ranges of the staggered fields
+  int sweep_row_begin() const { return ja > 1 ? ja : 1; }
+  int sweep_row_end() const { return jb < ny - 1 ? jb : ny - 1; }
+  int v_row_end() const { return owns_top ? jb + 1 : jb; }  // v rows [ja, v_row_end())
+
   cfdk::StepScalars<R> scalars(R dt_sub) const {
     cfdk::StepScalars<R> s;
     s.dx = dx; s.dy = dy; s.dt = dt_sub; s.nu = nu; s.nx = nx; s.ny = ny;
     return s;
   }
 
+  // ---- strip plumbing: NCCL send/recv of whole rows with the two neighbours, max-allreduce of scalars ----
+  ncclDataType_t nccl_real() const { return sizeof(R) == 8 ? ncclFloat64 : ncclFloat32; }
+
+  // refresh `down` halo rows below row `a` and `up` halo rows above row `b` of a field whose owned rows are
+  // [a, b): the lower neighbour owns [.., a), the upper one [b, ..)
+  int exchange_rows(const Field<R>& f, int a, int b, int down, int up, int send_down, int send_up) {
+    if (world == 1) return CFD_OK;
+    const size_t rl = f.rowlen;
+    CFD_NCCL(nccl_api().GroupStart());
+    if (rank > 0) {
+      if (send_down > 0) CFD_NCCL(nccl_api().Send(f.row(a), (size_t)send_down * rl, nccl_real(), rank - 1, comm, stream));
+      if (down > 0) CFD_NCCL(nccl_api().Recv(f.row(a - down), (size_t)down * rl, nccl_real(), rank - 1, comm, stream));
+    }
+    if (rank < world - 1) {
+      if (send_up > 0) CFD_NCCL(nccl_api().Send(f.row(b - send_up), (size_t)send_up * rl, nccl_real(), rank + 1, comm, stream));
+      if (up > 0) CFD_NCCL(nccl_api().Recv(f.row(b), (size_t)up * rl, nccl_real(), rank + 1, comm, stream));
+    }
+    CFD_NCCL(nccl_api().GroupEnd());
+    return CFD_OK;
+  }
+  // symmetric halo of depth d on a field with owned rows [a, b)
+  int exchange_halo(const Field<R>& f, int a, int b, int d) { return exchange_rows(f, a, b, d, d, d, d); }
+  // one row from above only (v* row jb feeds the divergence of row jb-1, src/model.rs:1430)
+  int fetch_row_above(const Field<R>& f, int a, int b) { return exchange_rows(f, a, b, 0, 1, 1, 0); }
+
+  int allreduce_max_u64(unsigned long long* d, size_t n) {
+    if (world == 1) return CFD_OK;
+    CFD_NCCL(nccl_api().AllReduce(d, d, n, ncclUint64, ncclMax, comm, stream));
+    return CFD_OK;
+  }
+
   // ---- one pressure solve: recompute_divergence (:1406-1440) + jacobi_pressure (:734-824) ----
-  int pressure_solve(R dt_sub, const R* us, const R* vs, int call_index, R* residual_out) {
+  int pressure_solve(R dt_sub, const Field<R>& us, const Field<R>& vs, int call_index, R* residual_out) {
     const int iters = opt.consts.jacobi_iterations;
+    int rc;
+    if ((rc = fetch_row_above(vs, ja, v_row_end()))) return rc;
     {
-      dim3 blk(256), grd((nx + 255) / 256, ny);
-      cfdk::k_divergence<R><<<grd, blk, 0, stream>>>(scalars(dt_sub), us, vs, rhs, 0, ny, err_slots, iters);
+      dim3 blk(256), grd((nx + 255) / 256, jb - ja);
+      cfdk::k_divergence<R><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, rhs.v, ja, jb, err_slots, iters);
       ++launches;
     }
     if (pressure_solver == CFD_SOLVER_CG) return cg_solve(dt_sub, call_index, residual_out);
@@ -349,34 +484,35 @@ struct ModelImpl final : ModelBase {
     c.one_minus_omega = R(1.0) - c.omega;                // :745
     c.tol = R(opt.consts.pressure_tolerance);
     c.nx = nx; c.ny = ny; c.cavity = scenario == CFD_SCENARIO_CAVITY;
+    c.row_begin = sweep_row_begin(); c.row_end = sweep_row_end();
+    const int rows = c.row_end - c.row_begin;
     CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index], stream));
-    if (opt.flags & CFD_FLAG_BASELINE_SWEEP) {
-      dim3 blk(256), grd((nx - 2 + 255) / 256, (ny - 2 + kJacobiRows - 1) / kJacobiRows);
-      for (int s = 0; s < iters; ++s) {
-        cfdk::k_jacobi_sweep<R, kJacobiRows><<<grd, blk, 0, stream>>>(c, pp[(ipp + s) & 1], rhs,
-                                                                      pp[(ipp + s + 1) & 1], err_slots, s);
-        ++launches;
-      }
-    } else {
-      cfdk::JacobiConsts2<R> c2;
-      c2.dx_sq = div_dx_sq; c2.dy_sq = div_dy_sq; c2.denom = div_denom;
-      c2.omega = c.omega; c2.one_minus_omega = c.one_minus_omega; c2.tol = c.tol;
-      c2.nx = nx; c2.ny = ny; c2.cavity = c.cavity; c2.rows_per_block = sweep_rows_per_block;
-      dim3 blk(128), grd((nx / 2 + 127) / 128, (ny - 2 + sweep_rows_per_block - 1) / sweep_rows_per_block);
-      for (int s = 0; s < iters; ++s) {
-        if (opt.flags & CFD_FLAG_REGISTER_SWEEP)
-          cfdk::k_jacobi_sweep2<R><<<grd, blk, 0, stream>>>(c2, pp[(ipp + s) & 1], rhs, pp[(ipp + s + 1) & 1],
-                                                            err_slots, s);
-        else if (opt.flags & CFD_FLAG_BULK_SWEEP)
-          cfdk::k_jacobi_sweep3<R><<<grd, blk, 0, stream>>>(c2, pp[(ipp + s) & 1], rhs, pp[(ipp + s + 1) & 1],
-                                                            err_slots, s);
-        else if (opt.flags & CFD_FLAG_SWEEP4)
-          cfdk::k_jacobi_sweep4<R><<<grd, blk, sizeof(cfdk::SweepChunkRing<R>), stream>>>(
-              c2, tmap_pp[(ipp + s) & 1], tmap_rhs, pp[(ipp + s + 1) & 1], err_slots, s);
-        else
-          cfdk::k_jacobi_sweep5<R><<<grd, blk, sizeof(cfdk::SweepChunkRing<R>), stream>>>(
-              c2, tmap_pp[(ipp + s) & 1], tmap_rhs, pp[(ipp + s + 1) & 1], err_slots, s);
-        ++launches;
+    cfdk::JacobiConsts2<R> c2;
+    c2.dx_sq = div_dx_sq; c2.dy_sq = div_dy_sq; c2.denom = div_denom;
+    c2.omega = c.omega; c2.one_minus_omega = c.one_minus_omega; c2.tol = c.tol;
+    c2.nx = nx; c2.ny = ny; c2.cavity = c.cavity; c2.rows_per_block = sweep_rows_per_block;
+    c2.row_begin = c.row_begin; c2.row_end = c.row_end; c2.row_shift = ja - kHalo;
+    const dim3 blk1(256), grd1((nx - 2 + 255) / 256, (rows + kJacobiRows - 1) / kJacobiRows);
+    const dim3 blk2(128), grd2((nx / 2 + 127) / 128, (rows + sweep_rows_per_block - 1) / sweep_rows_per_block);
+    const size_t ring_bytes = sizeof(cfdk::SweepChunkRing<R>);
+    for (int s = 0; s < iters; ++s) {
+      const int in = (ipp + s) & 1, out = in ^ 1;
+      if (opt.flags & CFD_FLAG_BASELINE_SWEEP)
+        cfdk::k_jacobi_sweep<R, kJacobiRows><<<grd1, blk1, 0, stream>>>(c, pp[in].v, rhs.v, pp[out].v, err_slots, s);
+      else if (opt.flags & CFD_FLAG_REGISTER_SWEEP)
+        cfdk::k_jacobi_sweep2<R><<<grd2, blk2, 0, stream>>>(c2, pp[in].v, rhs.v, pp[out].v, err_slots, s);
+      else if (opt.flags & CFD_FLAG_BULK_SWEEP)
+        cfdk::k_jacobi_sweep3<R><<<grd2, blk2, 0, stream>>>(c2, pp[in].v, rhs.v, pp[out].v, err_slots, s);
+      else if (opt.flags & CFD_FLAG_SWEEP4)
+        cfdk::k_jacobi_sweep4<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s);
+      else
+        cfdk::k_jacobi_sweep5<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s);
+      ++launches;
+      if (world > 1) {
+        // strips: the next sweep needs the neighbours' new boundary rows and the GLOBAL max|dp'| of this one.
+        // A rank that skipped the sweep (converged) still takes part; what it exchanges is never consumed.
+        if ((rc = exchange_halo(pp[out], ja, jb, 1))) return rc;
+        if ((rc = allreduce_max_u64(err_slots + s, 1))) return rc;
       }
     }
     cfdk::k_jacobi_finalize<R><<<1, 32, 0, stream>>>(err_slots, iters, c.tol, h_jres);
@@ -394,14 +530,15 @@ struct ModelImpl final : ModelBase {
 
   // EXTENSION, Mode C: conjugate gradients on the Jacobi iteration's own discrete problem (cfd_kernels.cuh)
   int cg_solve(R dt_sub, int call_index, R* residual_out) {
+    if (world > 1) return fail(CFD_ERR_UNSUPPORTED, "Mode C (CG) on strips is not available in this build");
     int rc;
     const dim3 blk(cfdk::kCgThreads);
     const dim3 g_all((nx + cfdk::kCgThreads - 1) / cfdk::kCgThreads, ny);
     const dim3 g_int((nx - 2 + cfdk::kCgThreads - 1) / cfdk::kCgThreads, ny - 2);
     const int n_all = (int)(g_all.x * g_all.y), n_int = (int)(g_int.x * g_int.y);
-    if (!cg_r) {
-      if ((rc = dalloc(&cg_r, n_p))) return rc;
-      if ((rc = dalloc(&cg_d, n_p))) return rc;
+    if (!cg_r.base) {
+      if ((rc = falloc(&cg_r, (size_t)nx))) return rc;
+      if ((rc = falloc(&cg_d, (size_t)nx))) return rc;
       if ((rc = dalloc(&cg_partials, (size_t)n_all))) return rc;
       if ((rc = dalloc(&cg_scalars, (size_t)1))) return rc;
       CFD_CUDA(cudaHostAlloc((void**)&h_cg, sizeof(cfdk::CgScalars), cudaHostAllocDefault));
@@ -410,15 +547,15 @@ struct ModelImpl final : ModelBase {
     c.dx_sq = dx * dx; c.dy_sq = dy * dy; c.dt = dt_sub; c.tol = R(opt.consts.cg_tolerance);
     c.n_unknowns = R((size_t)(nx - 2) * (size_t)(ny - 2));
     c.nx = nx; c.ny = ny; c.cavity = scenario == CFD_SCENARIO_CAVITY;
-    R* x = pp[ipp];
-    R* q = pp[ipp ^ 1];
+    R* x = pp[ipp].v;
+    R* q = pp[ipp ^ 1].v;
     cfdk::CgScalars init;
     memset(&init, 0, sizeof init);
     init.max_iterations = opt.consts.cg_max_iterations;
     *h_cg = init;
     CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index], stream));
     CFD_CUDA(cudaMemcpyAsync(cg_scalars, h_cg, sizeof init, cudaMemcpyHostToDevice, stream));
-    cfdk::k_cg_init<R><<<g_all, blk, 0, stream>>>(c, rhs, x, cg_r, cg_d, cg_partials);
+    cfdk::k_cg_init<R><<<g_all, blk, 0, stream>>>(c, rhs.v, x, cg_r.v, cg_d.v, cg_partials);
     cfdk::k_cg_reduce<R><<<1, 1024, 0, stream>>>(c, cg_scalars, cg_partials, n_all, 0);
     launches += 2;
     const int batch = 32;
@@ -427,11 +564,11 @@ struct ModelImpl final : ModelBase {
       CFD_CUDA(cudaStreamSynchronize(stream));
       if (h_cg->done) break;
       for (int it = 0; it < batch; ++it) {
-        cfdk::k_cg_apply<R><<<g_int, blk, 0, stream>>>(c, cg_scalars, cg_d, q, cg_partials);
+        cfdk::k_cg_apply<R><<<g_int, blk, 0, stream>>>(c, cg_scalars, cg_d.v, q, cg_partials);
         cfdk::k_cg_reduce<R><<<1, 1024, 0, stream>>>(c, cg_scalars, cg_partials, n_int, 1);
-        cfdk::k_cg_update<R><<<g_int, blk, 0, stream>>>(c, cg_scalars, cg_d, q, x, cg_r, cg_partials);
+        cfdk::k_cg_update<R><<<g_int, blk, 0, stream>>>(c, cg_scalars, cg_d.v, q, x, cg_r.v, cg_partials);
         cfdk::k_cg_reduce<R><<<1, 1024, 0, stream>>>(c, cg_scalars, cg_partials, n_int, 2);
-        cfdk::k_cg_direction<R><<<g_int, blk, 0, stream>>>(c, cg_scalars, cg_r, cg_d);
+        cfdk::k_cg_direction<R><<<g_int, blk, 0, stream>>>(c, cg_scalars, cg_r.v, cg_d.v);
         launches += 5;
       }
       CFD_CUDA(cudaGetLastError());
@@ -447,9 +584,11 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
 
-  int corrector(R dt_sub, const R* us, const R* vs, const R* uk, const R* vk, R* uo, R* vo) {
-    dim3 blk(256), grd((nx + 1 + 255) / 256, ny + 1);
-    cfdk::k_corrector<R><<<grd, blk, 0, stream>>>(scalars(dt_sub), us, vs, uk, vk, pp[ipp], uo, vo, p, 0, ny, ny + 1);
+  int corrector(R dt_sub, const Field<R>& us, const Field<R>& vs, const Field<R>& uk, const Field<R>& vk,
+                const Field<R>& uo, const Field<R>& vo) {
+    dim3 blk(256), grd((nx + 1 + 255) / 256, v_row_end() - ja);
+    cfdk::k_corrector<R><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, uk.v, vk.v, pp[ipp].v, uo.v, vo.v, p.v,
+                                                  ja, jb, v_row_end());
     ++launches;
     CFD_CUDA(cudaGetLastError());
     return CFD_OK;
@@ -474,17 +613,22 @@ struct ModelImpl final : ModelBase {
     last_K = 0;
     last_S = 0;
     int rc;
+    // strips: the predictor stencils reach two rows into the neighbours (second order)
+    if ((rc = exchange_halo(ubuf[X], ja, jb, kHalo))) return rc;
+    if ((rc = exchange_halo(vbuf[X], ja, v_row_end(), kHalo))) return rc;
     // ---- predictor (:538-670): reads u, v; writes the interior of u_star, v_star (the rest is carried state)
     {
       const auto s = scalars(dt_sub);
+      const int ju_lo = ja > 1 ? ja : 1, ju_hi = jb < ny - 1 ? jb : ny - 1;      // u rows 1..ny-2
+      const int jv_lo = ja > 1 ? ja : 1, jv_hi = v_row_end() < ny ? v_row_end() : ny;  // v rows 1..ny-1
       dim3 blk(256);
-      dim3 gu((nx + 255) / 256, ny - 2), gv((nx - 1 + 255) / 256, ny - 1);
+      dim3 gu((nx + 255) / 256, ju_hi - ju_lo), gv((nx - 1 + 255) / 256, jv_hi - jv_lo);
       if (velocity_scheme == CFD_SCHEME_SECOND_ORDER) {
-        cfdk::k_predict_u<R, true><<<gu, blk, 0, stream>>>(s, ubuf[X], vbuf[X], mask_u, ubuf[Y], 1, ny - 1);
-        cfdk::k_predict_v<R, true><<<gv, blk, 0, stream>>>(s, ubuf[X], vbuf[X], mask_v, vbuf[Y], 1, ny);
+        cfdk::k_predict_u<R, true><<<gu, blk, 0, stream>>>(s, ubuf[X].v, vbuf[X].v, mask_u.v, ubuf[Y].v, ju_lo, ju_hi);
+        cfdk::k_predict_v<R, true><<<gv, blk, 0, stream>>>(s, ubuf[X].v, vbuf[X].v, mask_v.v, vbuf[Y].v, jv_lo, jv_hi);
       } else {
-        cfdk::k_predict_u<R, false><<<gu, blk, 0, stream>>>(s, ubuf[X], vbuf[X], mask_u, ubuf[Y], 1, ny - 1);
-        cfdk::k_predict_v<R, false><<<gv, blk, 0, stream>>>(s, ubuf[X], vbuf[X], mask_v, vbuf[Y], 1, ny);
+        cfdk::k_predict_u<R, false><<<gu, blk, 0, stream>>>(s, ubuf[X].v, vbuf[X].v, mask_u.v, ubuf[Y].v, ju_lo, ju_hi);
+        cfdk::k_predict_v<R, false><<<gv, blk, 0, stream>>>(s, ubuf[X].v, vbuf[X].v, mask_v.v, vbuf[Y].v, jv_lo, jv_hi);
       }
       launches += 2;
       CFD_CUDA(cudaGetLastError());
@@ -510,15 +654,21 @@ struct ModelImpl final : ModelBase {
       b.parabolic = inlet_profile == CFD_INLET_PARABOLIC;
       b.cavity = scenario == CFD_SCENARIO_CAVITY;
       const int n = (nx > ny ? nx : ny) + 1;
-      cfdk::k_bc_edges<R><<<(n + 255) / 256, 256, 0, stream>>>(b, ubuf[cur], vbuf[cur], 0, ny, 1, 1);
-      dim3 blk(256), grd((nx + 255) / 256, ny);
-      cfdk::k_bc_solids<R><<<grd, blk, 0, stream>>>(nx, solid, ubuf[cur], vbuf[cur], 0, ny);
+      cfdk::k_bc_edges<R><<<(n + 255) / 256, 256, 0, stream>>>(b, ubuf[cur].v, vbuf[cur].v, ja, jb, owns_bottom ? 1 : 0,
+                                                              owns_top ? 1 : 0);
+      dim3 blk(256), grd((nx + 255) / 256, jb - ja);
+      cfdk::k_bc_solids<R><<<grd, blk, 0, stream>>>(nx, solid.v, ubuf[cur].v, vbuf[cur].v, ja, jb);
       launches += 2;
     }
-    // ---- residuals and CFL maxima (:333-348, :878-881)
+    // ---- residuals and CFL maxima (:333-348, :878-881) over the owned rows, then over the ranks
     CFD_CUDA(cudaMemsetAsync(step_slots, 0, 4 * sizeof(unsigned long long), stream));
-    cfdk::k_step_maxima<R><<<148 * 8, 256, 0, stream>>>(ubuf[cur], ubuf[X], n_u, vbuf[cur], vbuf[X], n_v, step_slots);
-    ++launches;
+    {
+      const size_t nu_own = (size_t)(jb - ja) * (nx + 1), nv_own = (size_t)(v_row_end() - ja) * nx;
+      cfdk::k_step_maxima<R><<<148 * 8, 256, 0, stream>>>(ubuf[cur].row(ja), ubuf[X].row(ja), nu_own, vbuf[cur].row(ja),
+                                                         vbuf[X].row(ja), nv_own, step_slots);
+      ++launches;
+    }
+    if ((rc = allreduce_max_u64(step_slots, 4))) return rc;
     CFD_CUDA(cudaMemcpyAsync(h_step, step_slots, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     CFD_CUDA(cudaEventRecord(ev_step1, stream));
     CFD_CUDA(cudaGetLastError());
@@ -591,24 +741,29 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
 
+  // owned parts of the three snapshot fields (whole fields when world == 1)
+  size_t own_p() const { return (size_t)(jb - ja) * nx; }
+  size_t own_u() const { return (size_t)(jb - ja) * (nx + 1); }
+  size_t own_v() const { return (size_t)(v_row_end() - ja) * nx; }
+
   // Model::get_snapshot, src/model.rs:1259-1267: p, u, v narrowed to f32 on the device, then D2H
   int get_snapshot(float* hp, float* hu, float* hv, float* hdt) override {
     CFD_CUDA(cudaSetDevice(device));
-    const size_t total = n_p + n_u + n_v;
+    const size_t np_ = own_p(), nu_ = own_u(), nv_ = own_v(), total = np_ + nu_ + nv_;
     int rc;
     if ((rc = ensure_staging(total * sizeof(float)))) return rc;
     float* d = (float*)staging;
     float* h = (float*)h_staging;
     const int grid_sz = 148 * 8;
-    if (hp) cfdk::k_to_f32<R><<<grid_sz, 256, 0, stream>>>(p, d, n_p);
-    if (hu) cfdk::k_to_f32<R><<<grid_sz, 256, 0, stream>>>(ubuf[iu], d + n_p, n_u);
-    if (hv) cfdk::k_to_f32<R><<<grid_sz, 256, 0, stream>>>(vbuf[iu], d + n_p + n_u, n_v);
+    if (hp) cfdk::k_to_f32<R><<<grid_sz, 256, 0, stream>>>(p.row(ja), d, np_);
+    if (hu) cfdk::k_to_f32<R><<<grid_sz, 256, 0, stream>>>(ubuf[iu].row(ja), d + np_, nu_);
+    if (hv) cfdk::k_to_f32<R><<<grid_sz, 256, 0, stream>>>(vbuf[iu].row(ja), d + np_ + nu_, nv_);
     CFD_CUDA(cudaGetLastError());
     CFD_CUDA(cudaMemcpyAsync(h, d, total * sizeof(float), cudaMemcpyDeviceToHost, stream));
     CFD_CUDA(cudaStreamSynchronize(stream));
-    if (hp) memcpy(hp, h, n_p * sizeof(float));
-    if (hu) memcpy(hu, h + n_p, n_u * sizeof(float));
-    if (hv) memcpy(hv, h + n_p + n_u, n_v * sizeof(float));
+    if (hp) memcpy(hp, h, np_ * sizeof(float));
+    if (hu) memcpy(hu, h + np_, nu_ * sizeof(float));
+    if (hv) memcpy(hv, h + np_ + nu_, nv_ * sizeof(float));
     if (hdt) *hdt = (float)dt;
     return CFD_OK;
   }
@@ -633,25 +788,26 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
 
+  // first owned entry and owned length of a real field
   R* real_field(int field, size_t* n) {
     switch (field) {
-      case CFD_FIELD_P: *n = n_p; return p;
-      case CFD_FIELD_U: *n = n_u; return ubuf[iu];
-      case CFD_FIELD_V: *n = n_v; return vbuf[iu];
-      case CFD_FIELD_U_STAR: *n = n_u; return ubuf[ius];
-      case CFD_FIELD_V_STAR: *n = n_v; return vbuf[ius];
-      case CFD_FIELD_RHS: *n = n_p; return rhs;
-      case CFD_FIELD_P_PRIME: *n = n_p; return pp[ipp];
+      case CFD_FIELD_P: *n = own_p(); return p.row(ja);
+      case CFD_FIELD_U: *n = own_u(); return ubuf[iu].row(ja);
+      case CFD_FIELD_V: *n = own_v(); return vbuf[iu].row(ja);
+      case CFD_FIELD_U_STAR: *n = own_u(); return ubuf[ius].row(ja);
+      case CFD_FIELD_V_STAR: *n = own_v(); return vbuf[ius].row(ja);
+      case CFD_FIELD_RHS: *n = own_p(); return rhs.row(ja);
+      case CFD_FIELD_P_PRIME: *n = own_p(); return pp[ipp].row(ja);
       // after a step the free buffer still holds the fields the step started from (u_old, v_old)
-      case CFD_FIELD_U_OLD: *n = n_u; return ubuf[ifree];
-      case CFD_FIELD_V_OLD: *n = n_v; return vbuf[ifree];
+      case CFD_FIELD_U_OLD: *n = own_u(); return ubuf[ifree].row(ja);
+      case CFD_FIELD_V_OLD: *n = own_v(); return vbuf[ifree].row(ja);
       default: *n = 0; return nullptr;
     }
   }
 
   int field_len(int field, uint64_t* len) override {
-    if (field == CFD_FIELD_MASK_U) { *len = n_u; return CFD_OK; }
-    if (field == CFD_FIELD_MASK_V) { *len = n_v; return CFD_OK; }
+    if (field == CFD_FIELD_MASK_U) { *len = own_u(); return CFD_OK; }
+    if (field == CFD_FIELD_MASK_V) { *len = own_v(); return CFD_OK; }
     size_t n;
     if (!real_field(field, &n)) return fail(CFD_ERR_INVALID_ARGUMENT, "unknown field id");
     *len = n;
@@ -667,7 +823,8 @@ struct ModelImpl final : ModelBase {
     if ((rc = ensure_staging(n64 * sizeof(double)))) return rc;
     double* d = (double*)staging;
     if (field == CFD_FIELD_MASK_U || field == CFD_FIELD_MASK_V) {
-      cfdk::k_u8_to_f64<<<148 * 8, 256, 0, stream>>>(field == CFD_FIELD_MASK_U ? mask_u : mask_v, d, (size_t)n64);
+      cfdk::k_u8_to_f64<<<148 * 8, 256, 0, stream>>>(field == CFD_FIELD_MASK_U ? mask_u.row(ja) : mask_v.row(ja), d,
+                                                     (size_t)n64);
     } else {
       size_t n;
       R* src = real_field(field, &n);
@@ -693,12 +850,14 @@ struct ModelImpl final : ModelBase {
     cfdk::k_from_f64<R><<<148 * 8, 256, 0, stream>>>((const double*)staging, dst, n);
     CFD_CUDA(cudaGetLastError());
     CFD_CUDA(cudaStreamSynchronize(stream));
+    // strips: p' halos are state too (they are refreshed only after a sweep)
+    if (field == CFD_FIELD_P_PRIME && (rc = exchange_halo(pp[ipp], ja, jb, 1))) return rc;
     return CFD_OK;
   }
 
   int rows(uint64_t* j0, uint64_t* j1) override {
-    *j0 = 0;
-    *j1 = (uint64_t)ny;
+    *j0 = (uint64_t)ja;
+    *j1 = (uint64_t)jb;
     return CFD_OK;
   }
 
@@ -745,7 +904,9 @@ int cfd_model_create_ex(const cfd_grid* grid, const cfd_params* params, const cf
   if (grid->nx > (1u << 30) || grid->ny > (1u << 30)) return fail(CFD_ERR_INVALID_ARGUMENT, "grid too large");
   if (!(grid->dx > 0.0f) || !(grid->dy > 0.0f)) return fail(CFD_ERR_INVALID_ARGUMENT, "grid: dx, dy must be positive");
   if (o.precision != 64 && o.precision != 32) return fail(CFD_ERR_INVALID_ARGUMENT, "precision must be 64 or 32");
-  if (o.world_size != 1) return fail(CFD_ERR_UNSUPPORTED, "world_size > 1 is not available in this build");
+  if (o.world_size < 1 || o.rank < 0 || o.rank >= o.world_size) return fail(CFD_ERR_INVALID_ARGUMENT, "rank / world_size out of range");
+  if (o.world_size > 1 && !o.nccl_unique_id) return fail(CFD_ERR_INVALID_ARGUMENT, "world_size > 1 needs nccl_unique_id");
+  if (o.world_size > 1 && grid->ny / (uint64_t)o.world_size < 4) return fail(CFD_ERR_INVALID_ARGUMENT, "strips need at least 4 rows per rank");
   if (o.consts.jacobi_iterations < 1 || o.consts.jacobi_iterations > kMaxSweepSlots)
     return fail(CFD_ERR_INVALID_ARGUMENT, "jacobi_iterations must be in 1..256");
   if (o.consts.outer_rounds < 0 || o.consts.outer_rounds > 1000) return fail(CFD_ERR_INVALID_ARGUMENT, "outer_rounds out of range");
@@ -832,8 +993,13 @@ int cfd_model_last_timing(cfd_model* m, double* step_ms, double* sweep_ms, uint6
 }
 
 int cfd_nccl_unique_id(void* out128) {
-  (void)out128;
-  return fail(CFD_ERR_UNSUPPORTED, "multi-GPU strips are not available in this build");
+  if (!out128) return fail(CFD_ERR_INVALID_ARGUMENT, "null out");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  CFD_NCCL_READY();
+  ncclUniqueId id;
+  CFD_NCCL(nccl_api().GetUniqueId(&id));
+  memcpy(out128, &id, sizeof id);
+  return CFD_OK;
 }
 
 int cfd_selftest_division(double divisor, uint64_t samples, uint64_t seed, int32_t mode, uint64_t* mismatches,

@@ -121,6 +121,22 @@ class Model:
         """`Model::new(grid, &params)` (src/model.rs:219)."""
         return cls(grid, params, **kw)
 
+    @classmethod
+    def strip(cls, grid: Grid, params: SimulationParams, rank: int, world_size: int, unique_id: bytes,
+              device: int = -1, precision: int = 64, flags: int = 0) -> "Model":
+        """One rank of a row-strip decomposition over `world_size` GPUs (one process per GPU).  `unique_id` is
+        the 128-byte id from `nccl_unique_id()` on rank 0, broadcast by the launcher.  Import torch BEFORE this
+        module in such processes, so that the process shares one libnccl.so.2."""
+        if len(unique_id) != 128:
+            raise CfdError(_abi.CFD_ERR_INVALID_ARGUMENT, "unique_id must be 128 bytes")
+        opts = default_options()
+        opts.precision, opts.device, opts.rank, opts.world_size, opts.flags = precision, device, rank, world_size, flags
+        buf = C.create_string_buffer(unique_id, 128)
+        opts.nccl_unique_id = C.cast(buf, C.c_void_p)
+        m = cls(grid, params, options=opts)
+        m._uid_buf = buf
+        return m
+
     # -- lifecycle ---------------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -153,10 +169,14 @@ class Model:
 
     def get_snapshot(self) -> SimSnapshot:
         """`Model::get_snapshot` (src/model.rs:1259-1267): owned f32 copies of p, u, v in reference layout."""
-        nx, ny = self.nx, self.ny
-        p = np.empty(nx * ny, dtype=np.float32)
-        u = np.empty((nx + 1) * ny, dtype=np.float32)
-        v = np.empty(nx * (ny + 1), dtype=np.float32)
+        n = C.c_uint64()
+        sizes = []
+        for fid in (_abi.FIELD_P, _abi.FIELD_U, _abi.FIELD_V):  # whole fields, or this rank's rows of a strip run
+            _check(self._lib, self._lib.cfd_model_field_len(self._handle(), fid, C.byref(n)))
+            sizes.append(int(n.value))
+        p = np.empty(sizes[0], dtype=np.float32)
+        u = np.empty(sizes[1], dtype=np.float32)
+        v = np.empty(sizes[2], dtype=np.float32)
         dt = C.c_float()
         _check(self._lib, self._lib.cfd_model_get_snapshot(self._handle(), p.ctypes.data, u.ctypes.data,
                                                            v.ctypes.data, C.byref(dt)))

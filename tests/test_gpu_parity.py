@@ -262,3 +262,21 @@ def test_mode_c_is_deterministic_run_to_run():
             m.update()
         outs.append((m.field(_abi.FIELD_U), m.field(_abi.FIELD_P), m.get_residuals().sweeps))
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
+
+
+def test_strips_over_nccl_are_bit_identical():
+    """world_size 2 (or more) strips against the single-domain model; needs >= 2 GPUs on the box
+    (`gpurun --gpus 2`), skipped on a single-GPU box."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = 2 if n < 4 else 4
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611",
+                        os.path.join(root, "tests", "mgpu_strip_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "strips ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
