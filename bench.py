@@ -203,17 +203,25 @@ def run_ours(args, w):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("cpu:gloo,cuda:nccl")
 
-    grid, params = make_grid(w), make_params(w)
+    # N > 1: WEAK scaling over row strips — every GPU owns a w.nx x w.ny strip of one tall channel
+    # (nx x N*ny cells, same dx = dy), halo rows and max-reductions over NCCL
+    from cfd_demo_b200.types import Cylinder, Grid
+    cyl = Cylinder(*w["cylinder"]) if w["cylinder"] else None
+    grid = Grid.uniform(w["nx"], w["ny"] * world, w["lx"], w["ly"] * world, cyl)
+    params = make_params(w)
     nx, ny = grid.nx, grid.ny
-    cells = nx * ny
-    from cfd_demo_b200.model import default_options
-    opts = default_options()
-    opts.device = local_rank
-    # NOTE multi-GPU: strip decomposition lands with cfd_model_create_ex(rank, world_size, nccl id); until then
-    # N > 1 runs N independent replicas of the same problem ("replicas only") and says so.
-    model = Model(grid, params, options=opts)
+    cells = nx * ny  # whole job
+    from cfd_demo_b200.model import default_options, nccl_unique_id
+    if world > 1:
+        uid = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        model = Model.strip(grid, params, rank, world, uid[0], device=local_rank)
+    else:
+        opts = default_options()
+        opts.device = local_rank
+        model = Model(grid, params, options=opts)
 
     def barrier():
         torch.cuda.synchronize()
@@ -261,7 +269,7 @@ def run_ours(args, w):
         model.update()
         res = model.get_residuals()       # device -> host: the step's residual scalars
         snap = model.get_snapshot()       # device -> host: p, u, v narrowed to f32 (SimSnapshot, src/model.rs:36-42)
-        d2h = snap.p.nbytes + snap.u.nbytes + snap.v.nbytes + 8 * 8
+        d2h = (snap.p.nbytes + snap.u.nbytes + snap.v.nbytes + 8 * 8) * world
         launches_e2e = model.last_timing()[2] + 3
     barrier()
     wall_e2e = time.perf_counter() - t1
@@ -272,13 +280,12 @@ def run_ours(args, w):
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     dev_s, wall_s, wall_e2e_s = [float(x) for x in times.tolist()]
-    replicas = world  # independent replicas until the strip decomposition is wired in
     steps = args.steps
-    value = replicas * cells * steps / dev_s
-    e2e_value = replicas * cells * steps / wall_e2e_s
+    value = cells * steps / dev_s
+    e2e_value = cells * steps / wall_e2e_s
     peak, peak_src = peak_hbm()
     sweep_us = sweep_ms * 1e3 / max(sweeps, 1)
-    algo_bytes = 3 * 8 * cells  # read p', rhs; write p'new
+    algo_bytes = 3 * 8 * cells // world  # per launch (one rank's strip): read p', rhs; write p'new
     achieved = algo_bytes / (sweep_us * 1e-6) / 1e9
     traffic = None
     try:
@@ -289,14 +296,15 @@ def run_ours(args, w):
     except Exception:
         pass
     k_per_step, s_per_step = solves / steps, sweeps / steps
-    step_bytes = 8 * cells * (8 + 10 * k_per_step + 3 * s_per_step) + 2 * cells
+    step_bytes = 8 * cells * (8 + 10 * k_per_step + 3 * s_per_step) + 2 * cells  # whole job
+    peak = peak * world
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # CPU port timed on rank 0 at N = 1 only
             from oracle import cpu_oracle
             cpu_oracle.build()
-            rounds = max(1, min(8, int(24.0 / (3.0 * cells / (4096.0 * 4096.0) + 1e-9))))
+            rounds = max(1, min(8, int(24.0 / (3.0 * w["nx"] * w["ny"] / (4096.0 * 4096.0) + 1e-9))))
             s = cpu_oracle_sample(w, 64, rounds)
             s32 = cpu_oracle_sample(w, 32, max(1, rounds // 2))
             cpu = {"value": s["cells"] / s["step_seconds"], "unit": "cell-updates/s", "cores": 1, "kind": "port",
@@ -311,13 +319,14 @@ def run_ours(args, w):
             "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
             "steps": steps, "warmup": args.warmup, "ms_per_step": dev_s * 1e3 / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "timesteps_per_s": replicas * steps / dev_s,
+            "timesteps_per_s": steps / dev_s,
             "wall_ms_per_step": wall_s * 1e3 / steps,
             "config": {"workload": w["desc"], "nx": nx, "ny": ny, "spinup_steps": w["spinup"],
                        "solves_per_step": k_per_step, "sweeps_per_step": s_per_step,
                        "l2": "every field (134 MB at 4096^2) is larger than L2 (126 MB); no flush needed",
                        "timing": "CUDA events on the model's stream around each update(), summed over K steps",
-                       "multi_gpu": "single domain" if world == 1 else f"{world} independent replicas (strips not wired in yet)"},
+                       "multi_gpu": "single domain" if world == 1 else
+                       f"{world} row strips of {w['nx']}x{w['ny']} cells each over NCCL (halo rows per sweep + max allreduce), weak scaling"},
             "step_algorithmic_gbs": step_bytes / (dev_s / steps) / 1e9,
             "step_frac_of_peak": step_bytes / (dev_s / steps) / 1e9 / peak,
             "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": 28, "d2h_bytes_per_step": d2h,
@@ -325,7 +334,8 @@ def run_ours(args, w):
                     "calls": "cfd_model_set_params + cfd_model_update + cfd_model_get_residuals + cfd_model_get_snapshot"},
             "gpu_launches": launches,
             "roofline": {"kernel": "cfdk::k_jacobi_sweep5<double> (one damped-Jacobi sweep incl. boundary update and max|dp'|)",
-                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "bound": "hbm", "achieved": achieved, "peak": peak / world, "unit": "GB/s",
+                         "frac": achieved / (peak / world),
                          "peak_source": peak_src, "traffic": traffic,
                          "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_us": sweep_us,
                          "launches_timed": sweeps,

@@ -182,6 +182,10 @@ struct ModelImpl final : ModelBase {
   int sweep_rows_per_block = 32;
   cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
   std::vector<cudaEvent_t> ev_sweep;  // pairs
+  // strips: communication stream + event ring for overlapping the halo exchange / max allreduce with the sweep
+  cudaStream_t comm_stream = nullptr;
+  static constexpr int kEvRing = 4;
+  cudaEvent_t ev_edge[kEvRing] = {}, ev_full[kEvRing] = {}, ev_halo[kEvRing] = {}, ev_max[kEvRing] = {};
   bool ready = false;
 
   ModelImpl(const cfd_grid& g, const cfd_params& prm, const cfd_options& o) : grid(g), opt(o) {
@@ -222,6 +226,13 @@ struct ModelImpl final : ModelBase {
     if (h_jres) cudaFreeHost(h_jres);
     if (h_step) cudaFreeHost(h_step);
     if (h_staging) cudaFreeHost(h_staging);
+    for (int k = 0; k < kEvRing; ++k) {
+      if (ev_edge[k]) cudaEventDestroy(ev_edge[k]);
+      if (ev_full[k]) cudaEventDestroy(ev_full[k]);
+      if (ev_halo[k]) cudaEventDestroy(ev_halo[k]);
+      if (ev_max[k]) cudaEventDestroy(ev_max[k]);
+    }
+    if (comm_stream) cudaStreamDestroy(comm_stream);
     if (ev_step0) cudaEventDestroy(ev_step0);
     if (ev_step1) cudaEventDestroy(ev_step1);
     for (auto e : ev_sweep) cudaEventDestroy(e);
@@ -261,6 +272,13 @@ struct ModelImpl final : ModelBase {
     }
     CFD_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (world > 1) {
+      CFD_CUDA(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+      for (int k = 0; k < kEvRing; ++k) {
+        CFD_CUDA(cudaEventCreateWithFlags(&ev_edge[k], cudaEventDisableTiming));
+        CFD_CUDA(cudaEventCreateWithFlags(&ev_full[k], cudaEventDisableTiming));
+        CFD_CUDA(cudaEventCreateWithFlags(&ev_halo[k], cudaEventDisableTiming));
+        CFD_CUDA(cudaEventCreateWithFlags(&ev_max[k], cudaEventDisableTiming));
+      }
       CFD_NCCL_READY();
       ncclUniqueId id;
       memcpy(&id, opt.nccl_unique_id, sizeof id);
@@ -439,8 +457,10 @@ struct ModelImpl final : ModelBase {
 
   // refresh `down` halo rows below row `a` and `up` halo rows above row `b` of a field whose owned rows are
   // [a, b): the lower neighbour owns [.., a), the upper one [b, ..)
-  int exchange_rows(const Field<R>& f, int a, int b, int down, int up, int send_down, int send_up) {
+  int exchange_rows(const Field<R>& f, int a, int b, int down, int up, int send_down, int send_up,
+                    cudaStream_t on = nullptr) {
     if (world == 1) return CFD_OK;
+    cudaStream_t stream = on ? on : this->stream;
     const size_t rl = f.rowlen;
     CFD_NCCL(nccl_api().GroupStart());
     if (rank > 0) {
@@ -455,12 +475,15 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
   // symmetric halo of depth d on a field with owned rows [a, b)
-  int exchange_halo(const Field<R>& f, int a, int b, int d) { return exchange_rows(f, a, b, d, d, d, d); }
+  int exchange_halo(const Field<R>& f, int a, int b, int d, cudaStream_t on = nullptr) {
+    return exchange_rows(f, a, b, d, d, d, d, on);
+  }
   // one row from above only (v* row jb feeds the divergence of row jb-1, src/model.rs:1430)
   int fetch_row_above(const Field<R>& f, int a, int b) { return exchange_rows(f, a, b, 0, 1, 1, 0); }
 
-  int allreduce_max_u64(unsigned long long* d, size_t n) {
+  int allreduce_max_u64(unsigned long long* d, size_t n, cudaStream_t on = nullptr) {
     if (world == 1) return CFD_OK;
+    cudaStream_t stream = on ? on : this->stream;
     CFD_NCCL(nccl_api().AllReduce(d, d, n, ncclUint64, ncclMax, comm, stream));
     return CFD_OK;
   }
@@ -492,27 +515,66 @@ struct ModelImpl final : ModelBase {
     c2.omega = c.omega; c2.one_minus_omega = c.one_minus_omega; c2.tol = c.tol;
     c2.nx = nx; c2.ny = ny; c2.cavity = c.cavity; c2.rows_per_block = sweep_rows_per_block;
     c2.row_begin = c.row_begin; c2.row_end = c.row_end; c2.row_shift = ja - kHalo;
+    c2.check_lag = 1;
     const dim3 blk1(256), grd1((nx - 2 + 255) / 256, (rows + kJacobiRows - 1) / kJacobiRows);
     const dim3 blk2(128), grd2((nx / 2 + 127) / 128, (rows + sweep_rows_per_block - 1) / sweep_rows_per_block);
     const size_t ring_bytes = sizeof(cfdk::SweepChunkRing<R>);
-    for (int s = 0; s < iters; ++s) {
-      const int in = (ipp + s) & 1, out = in ^ 1;
-      if (opt.flags & CFD_FLAG_BASELINE_SWEEP)
-        cfdk::k_jacobi_sweep<R, kJacobiRows><<<grd1, blk1, 0, stream>>>(c, pp[in].v, rhs.v, pp[out].v, err_slots, s);
-      else if (opt.flags & CFD_FLAG_REGISTER_SWEEP)
-        cfdk::k_jacobi_sweep2<R><<<grd2, blk2, 0, stream>>>(c2, pp[in].v, rhs.v, pp[out].v, err_slots, s);
-      else if (opt.flags & CFD_FLAG_BULK_SWEEP)
-        cfdk::k_jacobi_sweep3<R><<<grd2, blk2, 0, stream>>>(c2, pp[in].v, rhs.v, pp[out].v, err_slots, s);
-      else if (opt.flags & CFD_FLAG_SWEEP4)
-        cfdk::k_jacobi_sweep4<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s);
-      else
-        cfdk::k_jacobi_sweep5<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s);
-      ++launches;
-      if (world > 1) {
-        // strips: the next sweep needs the neighbours' new boundary rows and the GLOBAL max|dp'| of this one.
-        // A rank that skipped the sweep (converged) still takes part; what it exchanges is never consumed.
-        if ((rc = exchange_halo(pp[out], ja, jb, 1))) return rc;
-        if ((rc = allreduce_max_u64(err_slots + s, 1))) return rc;
+    const bool tuned_default = !(opt.flags & (CFD_FLAG_BASELINE_SWEEP | CFD_FLAG_REGISTER_SWEEP | CFD_FLAG_BULK_SWEEP | CFD_FLAG_SWEEP4));
+    const int edge = sweep_rows_per_block;  // rows of the two edge bands that are swept first
+    if (world > 1 && tuned_default && rows >= 3 * edge && (opt.flags & CFD_FLAG_OVERLAP_EXCHANGE)) {
+      // ---- strips, overlapped (opt-in): sweep the two edge bands, start the halo exchange on the communication
+      // stream, sweep the interior meanwhile; the max allreduce of sweep s runs during sweep s+1 (check_lag 2).
+      // Measured SLOWER than the in-stream form on 2 x B200 (196 vs 147 ms/step at 4096x8192): the sweep holds
+      // every SM's register file, so NCCL's own kernels cannot co-run and only add cross-stream latency
+      // (profiles/r1_notes.md).  Kept for A/B; the fix is peer-memory stores from the sweep itself.
+      c2.check_lag = 2;
+      for (int s = 0; s < iters; ++s) {
+        const int in = (ipp + s) & 1, out = in ^ 1, e = s % kEvRing;
+        if (s >= 1) CFD_CUDA(cudaStreamWaitEvent(stream, ev_halo[(s - 1) % kEvRing], 0));  // halos of this sweep's input
+        if (s >= 2) CFD_CUDA(cudaStreamWaitEvent(stream, ev_max[(s - 2) % kEvRing], 0));   // global max of sweep s-2
+        cfdk::JacobiConsts2<R> cb = c2, ct = c2, cm = c2;
+        cb.row_end = c2.row_begin + edge;
+        ct.row_begin = c2.row_end - edge;
+        cm.row_begin = cb.row_end; cm.row_end = ct.row_begin;
+        const dim3 g_edge(grd2.x, 1), g_mid(grd2.x, (cm.row_end - cm.row_begin + sweep_rows_per_block - 1) / sweep_rows_per_block);
+        cfdk::k_jacobi_sweep5<R><<<g_edge, blk2, ring_bytes, stream>>>(cb, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s);
+        cfdk::k_jacobi_sweep5<R><<<g_edge, blk2, ring_bytes, stream>>>(ct, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s);
+        CFD_CUDA(cudaEventRecord(ev_edge[e], stream));
+        cfdk::k_jacobi_sweep5<R><<<g_mid, blk2, ring_bytes, stream>>>(cm, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s);
+        CFD_CUDA(cudaEventRecord(ev_full[e], stream));
+        launches += 3;
+        CFD_CUDA(cudaStreamWaitEvent(comm_stream, ev_edge[e], 0));
+        if ((rc = exchange_halo(pp[out], ja, jb, 1, comm_stream))) return rc;
+        CFD_CUDA(cudaEventRecord(ev_halo[e], comm_stream));
+        CFD_CUDA(cudaStreamWaitEvent(comm_stream, ev_full[e], 0));
+        if ((rc = allreduce_max_u64(err_slots + s, 1, comm_stream))) return rc;
+        CFD_CUDA(cudaEventRecord(ev_max[e], comm_stream));
+      }
+      for (int k = 0; k < kEvRing && k < iters; ++k) {  // everything the communication stream still owes
+        CFD_CUDA(cudaStreamWaitEvent(stream, ev_halo[(iters - 1 - k) % kEvRing], 0));
+        CFD_CUDA(cudaStreamWaitEvent(stream, ev_max[(iters - 1 - k) % kEvRing], 0));
+      }
+    } else {
+      for (int s = 0; s < iters; ++s) {
+        const int in = (ipp + s) & 1, out = in ^ 1;
+        if (opt.flags & CFD_FLAG_BASELINE_SWEEP)
+          cfdk::k_jacobi_sweep<R, kJacobiRows><<<grd1, blk1, 0, stream>>>(c, pp[in].v, rhs.v, pp[out].v, err_slots, s);
+        else if (opt.flags & CFD_FLAG_REGISTER_SWEEP)
+          cfdk::k_jacobi_sweep2<R><<<grd2, blk2, 0, stream>>>(c2, pp[in].v, rhs.v, pp[out].v, err_slots, s);
+        else if (opt.flags & CFD_FLAG_BULK_SWEEP)
+          cfdk::k_jacobi_sweep3<R><<<grd2, blk2, 0, stream>>>(c2, pp[in].v, rhs.v, pp[out].v, err_slots, s);
+        else if (opt.flags & CFD_FLAG_SWEEP4)
+          cfdk::k_jacobi_sweep4<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s);
+        else
+          cfdk::k_jacobi_sweep5<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s);
+        ++launches;
+        if (world > 1) {
+          // strips, simple form: the next sweep needs the neighbours' new boundary rows and the GLOBAL max|dp'|
+          // of this one.  A rank that skipped the sweep (converged) still takes part; what it exchanges is
+          // never consumed.
+          if ((rc = exchange_halo(pp[out], ja, jb, 1))) return rc;
+          if ((rc = allreduce_max_u64(err_slots + s, 1))) return rc;
+        }
       }
     }
     cfdk::k_jacobi_finalize<R><<<1, 32, 0, stream>>>(err_slots, iters, c.tol, h_jres);
