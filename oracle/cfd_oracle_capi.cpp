@@ -80,6 +80,23 @@ double stage_t(Model<R>& m, int stage) {
 }
 }  // namespace
 
+// strip-decomposed run of the same algorithm (tests of the multi-rank design on CPU, e.g. over gloo): the model
+// keeps full-size arrays but computes only rows [ja, jb); the callbacks refresh halo rows / reduce scalars.
+typedef void (*cfdo_exchange_cb)(void* user, void* field, uint64_t row_len, uint64_t nrows, int below, int above,
+                                 int elem_bytes);
+typedef double (*cfdo_allreduce_cb)(void* user, double x, int op /* 0 max, 1 sum */);
+
+template <class R>
+static void set_strip_t(Model<R>& m, uint64_t ja, uint64_t jb, int owns_top, cfdo_exchange_cb ex, cfdo_allreduce_cb ar,
+                        void* user) {
+  m.ja = ja; m.jb = jb; m.owns_top = owns_top != 0;
+  m.hooks.exchange = [=](std::vector<R>& f, size_t row_len, size_t nrows, int below, int above) {
+    ex(user, f.data(), row_len, nrows, below, above, int(sizeof(R)));
+  };
+  m.hooks.allreduce_max = [=](R x) { return R(ar(user, double(x), 0)); };
+  m.hooks.allreduce_sum = [=](R x) { return R(ar(user, double(x), 1)); };
+}
+
 extern "C" {
 
 void cfd_solver_consts_default(cfd_solver_consts* out) { Model<double>::cfd_solver_consts_default_inline(out); }
@@ -153,6 +170,12 @@ void cfdo_set_scalars(void* hv, uint64_t simulation_step, double simulation_time
   } else {
     h->d->simulation_step = simulation_step; h->d->simulation_time = simulation_time; h->d->dt = dt;
   }
+}
+
+void cfdo_set_strip(void* hv, uint64_t ja, uint64_t jb, int owns_top, cfdo_exchange_cb ex, cfdo_allreduce_cb ar,
+                    void* user) {
+  auto* h = static_cast<Handle*>(hv);
+  if (h->f) set_strip_t(*h->f, ja, jb, owns_top, ex, ar, user); else set_strip_t(*h->d, ja, jb, owns_top, ex, ar, user);
 }
 
 uint64_t cfdo_total_sweeps(void* hv) {
