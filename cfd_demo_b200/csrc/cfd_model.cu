@@ -590,13 +590,27 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
 
-  // EXTENSION, Mode C: conjugate gradients on the Jacobi iteration's own discrete problem (cfd_kernels.cuh)
+  // EXTENSION, Mode C: conjugate gradients on the Jacobi iteration's own discrete problem (cfd_kernels.cuh).
+  // Strips: one halo row of the search direction per iteration, the two dot products sum-allreduced over NCCL.
+  int cg_reduce(const cfdk::CgConsts<R>& c, int n, int mode) {
+    if (world == 1) {
+      cfdk::k_cg_reduce<R><<<1, 1024, 0, stream>>>(c, cg_scalars, cg_partials, n, mode, 0);
+      ++launches;
+      return CFD_OK;
+    }
+    cfdk::k_cg_reduce<R><<<1, 1024, 0, stream>>>(c, cg_scalars, cg_partials, n, mode, 1);
+    CFD_NCCL(nccl_api().AllReduce(&cg_scalars->local_sum, &cg_scalars->local_sum, 1, ncclFloat64, ncclSum, comm, stream));
+    cfdk::k_cg_reduce<R><<<1, 32, 0, stream>>>(c, cg_scalars, cg_partials, n, mode, 2);
+    launches += 2;
+    return CFD_OK;
+  }
+
   int cg_solve(R dt_sub, int call_index, R* residual_out) {
-    if (world > 1) return fail(CFD_ERR_UNSUPPORTED, "Mode C (CG) on strips is not available in this build");
     int rc;
+    const int int_lo = sweep_row_begin(), int_hi = sweep_row_end();
     const dim3 blk(cfdk::kCgThreads);
-    const dim3 g_all((nx + cfdk::kCgThreads - 1) / cfdk::kCgThreads, ny);
-    const dim3 g_int((nx - 2 + cfdk::kCgThreads - 1) / cfdk::kCgThreads, ny - 2);
+    const dim3 g_all((nx + cfdk::kCgThreads - 1) / cfdk::kCgThreads, jb - ja);
+    const dim3 g_int((nx - 2 + cfdk::kCgThreads - 1) / cfdk::kCgThreads, int_hi - int_lo);
     const int n_all = (int)(g_all.x * g_all.y), n_int = (int)(g_int.x * g_int.y);
     if (!cg_r.base) {
       if ((rc = falloc(&cg_r, (size_t)nx))) return rc;
@@ -609,7 +623,9 @@ struct ModelImpl final : ModelBase {
     c.dx_sq = dx * dx; c.dy_sq = dy * dy; c.dt = dt_sub; c.tol = R(opt.consts.cg_tolerance);
     c.n_unknowns = R((size_t)(nx - 2) * (size_t)(ny - 2));
     c.nx = nx; c.ny = ny; c.cavity = scenario == CFD_SCENARIO_CAVITY;
-    R* x = pp[ipp].v;
+    c.own_lo = ja; c.own_hi = jb; c.int_lo = int_lo;
+    const Field<R>& xf = pp[ipp];
+    R* x = xf.v;
     R* q = pp[ipp ^ 1].v;
     cfdk::CgScalars init;
     memset(&init, 0, sizeof init);
@@ -618,26 +634,28 @@ struct ModelImpl final : ModelBase {
     CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index], stream));
     CFD_CUDA(cudaMemcpyAsync(cg_scalars, h_cg, sizeof init, cudaMemcpyHostToDevice, stream));
     cfdk::k_cg_init<R><<<g_all, blk, 0, stream>>>(c, rhs.v, x, cg_r.v, cg_d.v, cg_partials);
-    cfdk::k_cg_reduce<R><<<1, 1024, 0, stream>>>(c, cg_scalars, cg_partials, n_all, 0);
-    launches += 2;
+    ++launches;
+    if ((rc = cg_reduce(c, n_all, 0))) return rc;
     const int batch = 32;
     for (;;) {
       CFD_CUDA(cudaMemcpyAsync(h_cg, cg_scalars, sizeof init, cudaMemcpyDeviceToHost, stream));
       CFD_CUDA(cudaStreamSynchronize(stream));
       if (h_cg->done) break;
       for (int it = 0; it < batch; ++it) {
+        if ((rc = exchange_halo(cg_d, ja, jb, 1))) return rc;
         cfdk::k_cg_apply<R><<<g_int, blk, 0, stream>>>(c, cg_scalars, cg_d.v, q, cg_partials);
-        cfdk::k_cg_reduce<R><<<1, 1024, 0, stream>>>(c, cg_scalars, cg_partials, n_int, 1);
+        if ((rc = cg_reduce(c, n_int, 1))) return rc;
         cfdk::k_cg_update<R><<<g_int, blk, 0, stream>>>(c, cg_scalars, cg_d.v, q, x, cg_r.v, cg_partials);
-        cfdk::k_cg_reduce<R><<<1, 1024, 0, stream>>>(c, cg_scalars, cg_partials, n_int, 2);
+        if ((rc = cg_reduce(c, n_int, 2))) return rc;
         cfdk::k_cg_direction<R><<<g_int, blk, 0, stream>>>(c, cg_scalars, cg_r.v, cg_d.v);
-        launches += 5;
+        launches += 3;
       }
       CFD_CUDA(cudaGetLastError());
     }
     const int n_edge = (nx > ny ? nx : ny);
-    cfdk::k_cg_fill_boundary<R><<<(n_edge + 255) / 256, 256, 0, stream>>>(nx, ny, c.cavity, x);
+    cfdk::k_cg_fill_boundary<R><<<(n_edge + 255) / 256, 256, 0, stream>>>(nx, ny, c.cavity, x, ja, jb);
     ++launches;
+    if ((rc = exchange_halo(xf, ja, jb, 1))) return rc;  // the corrector reads p'[j-1] (src/model.rs:1380)
     CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index + 1], stream));
     CFD_CUDA(cudaGetLastError());
     last_S += (uint64_t)h_cg->iterations;

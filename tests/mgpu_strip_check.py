@@ -66,6 +66,40 @@ def main():
         strip.close()
         whole.close()
         dist.barrier()
+    # Mode C (CG): the dot products are sum-allreduced over the ranks, so parity is to a tolerance (1e-9 rel. L2)
+    from cfd_demo_b200.model import default_options
+    from cfd_demo_b200.types import PressureSolver, Scenario
+    import ctypes as C
+    for scenario, grid in ((Scenario.Channel, Grid.uniform(264, 96, 30.0, 10.0, Cylinder(7.5, 5.0, 0.75))),
+                           (Scenario.Cavity, Grid.uniform(128, 128, 1.0, 1.0, None))):
+        params = SimulationParams(dt=1e-3, viscosity=0.01, scenario=scenario, pressure_solver=PressureSolver.CG)
+        uid = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        opts = default_options()
+        opts.consts.cg_tolerance = 1e-13
+        opts.device, opts.rank, opts.world_size = local, rank, world
+        buf = C.create_string_buffer(uid[0], 128)
+        opts.nccl_unique_id = C.cast(buf, C.c_void_p)
+        strip = Model(grid, params, options=opts)
+        o1 = default_options()
+        o1.consts.cg_tolerance = 1e-13
+        o1.device = local
+        whole = Model(grid, params, options=o1)
+        ja, jb = strip.rows()
+        nx, ny = grid.nx, grid.ny
+        top = 1 if rank == world - 1 else 0
+        for s in range(10):
+            strip.update()
+            whole.update()
+        rs, rw = strip.get_residuals(), whole.get_residuals()
+        assert rs.jacobi_calls == rw.jacobi_calls == 2 and abs(rs.sweeps - rw.sweeps) <= 4, (rs, rw)
+        for fid, shape, hi in ((_abi.FIELD_P, (ny, nx), jb), (_abi.FIELD_U, (ny, nx + 1), jb), (_abi.FIELD_V, (ny + 1, nx), jb + top)):
+            a, b = strip.field(fid), whole.field(fid).reshape(shape)[ja:hi].ravel()
+            d = np.linalg.norm(a - b) / np.linalg.norm(b)
+            assert d <= 1e-9, (scenario, _abi.FIELD_NAMES[fid], d)
+        strip.close()
+        whole.close()
+        dist.barrier()
     if rank == 0:
         print(f"strips ok: {world} ranks bit-identical to the single-domain model on {len(cases)} cases")
     dist.destroy_process_group()
