@@ -27,7 +27,7 @@ FLAG_BASELINE_SWEEP = 2
 FLAG_REGISTER_SWEEP = 4
 FLAG_BULK_SWEEP = 8
 FLAG_SWEEP4 = 16
-FLAG_OVERLAP_EXCHANGE = 32
+FLAG_NCCL_EXCHANGE = 32
 
 
 class CfdGrid(C.Structure):

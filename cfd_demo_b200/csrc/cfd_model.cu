@@ -47,6 +47,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -67,11 +68,12 @@ NcclApi& nccl_api() {
       CFD_SYM(Send, "ncclSend");
       CFD_SYM(Recv, "ncclRecv");
       CFD_SYM(AllReduce, "ncclAllReduce");
+      CFD_SYM(AllGather, "ncclAllGather");
       CFD_SYM(GroupStart, "ncclGroupStart");
       CFD_SYM(GroupEnd, "ncclGroupEnd");
       CFD_SYM(GetErrorString, "ncclGetErrorString");
 #undef CFD_SYM
-      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.AllReduce &&
+      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.AllReduce && api.AllGather &&
                api.GroupStart && api.GroupEnd && api.GetErrorString;
     }
   }
@@ -182,10 +184,17 @@ struct ModelImpl final : ModelBase {
   int sweep_rows_per_block = 32;
   cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
   std::vector<cudaEvent_t> ev_sweep;  // pairs
-  // strips: communication stream + event ring for overlapping the halo exchange / max allreduce with the sweep
-  cudaStream_t comm_stream = nullptr;
-  static constexpr int kEvRing = 4;
-  cudaEvent_t ev_edge[kEvRing] = {}, ev_full[kEvRing] = {}, ev_halo[kEvRing] = {}, ev_max[kEvRing] = {};
+  // strips over peer memory (CUDA IPC): the neighbours' p' buffers and every rank's mailbox (cfd_kernels.cuh)
+  cfdk::Mailbox* mailbox = nullptr;              // this rank's, device memory
+  cfdk::Mailbox* peer_mailbox[cfdk::kMaxRanks] = {};
+  R* peer_pp_down[2] = {nullptr, nullptr};       // lower neighbour's pp[0], pp[1] (virtual origins)
+  R* peer_pp_up[2] = {nullptr, nullptr};
+  std::vector<void*> ipc_opened;
+  unsigned int* tickets = nullptr;               // [4][260]
+  unsigned long long solve_counter = 0;
+  unsigned long long* peer_trace = nullptr;
+  double dbg_work = 0, dbg_wait = 0, dbg_gap = 0, dbg_span = 0; unsigned long long dbg_n = 0, dbg_solves = 0;
+  bool peer_ready = false;
   bool ready = false;
 
   ModelImpl(const cfd_grid& g, const cfd_params& prm, const cfd_options& o) : grid(g), opt(o) {
@@ -226,13 +235,29 @@ struct ModelImpl final : ModelBase {
     if (h_jres) cudaFreeHost(h_jres);
     if (h_step) cudaFreeHost(h_step);
     if (h_staging) cudaFreeHost(h_staging);
-    for (int k = 0; k < kEvRing; ++k) {
-      if (ev_edge[k]) cudaEventDestroy(ev_edge[k]);
-      if (ev_full[k]) cudaEventDestroy(ev_full[k]);
-      if (ev_halo[k]) cudaEventDestroy(ev_halo[k]);
-      if (ev_max[k]) cudaEventDestroy(ev_max[k]);
+    if (tickets && getenv("CFD_PEER_DEBUG")) {
+      unsigned int h[16];
+      cudaMemcpy(h, tickets + 1040, sizeof h, cudaMemcpyDeviceToHost);
+      unsigned long long w0, w1;
+      memcpy(&w0, h + 8, 8); memcpy(&w1, h + 10, 8);
+      fprintf(stderr, "[cfd peer rank %d] halo waits %u, total %.3f ms (%.2f us each); last-block max waits %u, total %.3f ms\n",
+              rank, h[4], w0 / 1.9e6, h[4] ? w0 / 1.9e3 / h[4] : 0.0, h[5], w1 / 1.9e6);
     }
-    if (comm_stream) cudaStreamDestroy(comm_stream);
+    if (peer_trace) {
+      std::vector<unsigned long long> t(768);
+      cudaMemcpy(t.data(), peer_trace, 768 * 8, cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[cfd peer rank %d] saturated solves %llu: avg work %.1f us, exit wait %.1f us, gap %.1f us per sweep; avg solve span %.1f us\n",
+              rank, dbg_solves, dbg_n ? dbg_work / dbg_n : 0.0, dbg_n ? dbg_wait / dbg_n : 0.0, dbg_n ? dbg_gap / dbg_n : 0.0,
+              dbg_solves ? dbg_span / dbg_solves : 0.0);
+      fprintf(stderr, "[cfd peer rank %d] last solve, per sweep: start(+us since sweep 0) work_us exit_wait_us gap_to_next_us\n", rank);
+      for (int s2 = 0; s2 < 50; s2 += 1)
+        fprintf(stderr, "[cfd peer rank %d] s=%2d start %9.1f work %7.1f wait %6.1f gap %6.1f\n", rank, s2,
+                (t[s2] - t[0]) / 1e3, (t[256 + s2] - t[s2]) / 1e3, (t[512 + s2] - t[256 + s2]) / 1e3,
+                s2 < 49 ? ((double)t[s2 + 1] - (double)t[512 + s2]) / 1e3 : 0.0);
+      cudaFree(peer_trace);
+    }
+    for (void* ptr : ipc_opened) cudaIpcCloseMemHandle(ptr);
+    cudaFree(mailbox); cudaFree(tickets);
     if (ev_step0) cudaEventDestroy(ev_step0);
     if (ev_step1) cudaEventDestroy(ev_step1);
     for (auto e : ev_sweep) cudaEventDestroy(e);
@@ -272,13 +297,6 @@ struct ModelImpl final : ModelBase {
     }
     CFD_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (world > 1) {
-      CFD_CUDA(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
-      for (int k = 0; k < kEvRing; ++k) {
-        CFD_CUDA(cudaEventCreateWithFlags(&ev_edge[k], cudaEventDisableTiming));
-        CFD_CUDA(cudaEventCreateWithFlags(&ev_full[k], cudaEventDisableTiming));
-        CFD_CUDA(cudaEventCreateWithFlags(&ev_halo[k], cudaEventDisableTiming));
-        CFD_CUDA(cudaEventCreateWithFlags(&ev_max[k], cudaEventDisableTiming));
-      }
       CFD_NCCL_READY();
       ncclUniqueId id;
       memcpy(&id, opt.nccl_unique_id, sizeof id);
@@ -317,8 +335,87 @@ struct ModelImpl final : ModelBase {
     CFD_CUDA(cudaGetLastError());
     CFD_CUDA(cudaStreamSynchronize(stream));
     if ((rc = init_sweep_constants())) return rc;
+    if (world > 1 && !(opt.flags & CFD_FLAG_NCCL_EXCHANGE) && (rc = init_peer_memory())) return rc;
     ready = true;
     return CFD_OK;
+  }
+
+  // Map the neighbours' p' buffers and every rank's mailbox into this process (CUDA IPC; the 64-byte handles
+  // travel through one NCCL all-gather).  After this the sweep loop needs no NCCL call (k_jacobi_sweep5).
+  int init_peer_memory() {
+    if (world > cfdk::kMaxRanks) return fail(CFD_ERR_UNSUPPORTED, "peer-memory strips support at most 8 ranks");
+    int rc;
+    if ((rc = dalloc(&mailbox, (size_t)1))) return rc;
+    if ((rc = dalloc(&tickets, (size_t)4 * 260 + 16))) return rc;  // + diagnostics counters at [1044..1052)
+    if (getenv("CFD_PEER_DEBUG") && (rc = dalloc(&peer_trace, (size_t)3 * 256))) return rc;
+    CFD_CUDA(cudaStreamSynchronize(stream));
+    struct Handles { cudaIpcMemHandle_t pp0, pp1, box; };
+    static_assert(sizeof(Handles) == 192, "three 64-byte IPC handles");
+    std::vector<Handles> all((size_t)world);
+    Handles mine;
+    CFD_CUDA(cudaIpcGetMemHandle(&mine.pp0, pp[0].base));
+    CFD_CUDA(cudaIpcGetMemHandle(&mine.pp1, pp[1].base));
+    CFD_CUDA(cudaIpcGetMemHandle(&mine.box, mailbox));
+    unsigned char* d = nullptr;
+    CFD_CUDA(cudaMalloc((void**)&d, sizeof(Handles) * (size_t)(world + 1)));
+    CFD_CUDA(cudaMemcpyAsync(d, &mine, sizeof mine, cudaMemcpyHostToDevice, stream));
+    CFD_NCCL(nccl_api().AllGather(d, d + sizeof(Handles), sizeof(Handles), ncclChar, comm, stream));
+    CFD_CUDA(cudaMemcpyAsync(all.data(), d + sizeof(Handles), sizeof(Handles) * (size_t)world, cudaMemcpyDeviceToHost, stream));
+    CFD_CUDA(cudaStreamSynchronize(stream));
+    CFD_CUDA(cudaFree(d));
+    auto open = [&](const cudaIpcMemHandle_t& h, void** out) -> int {
+      CFD_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+      ipc_opened.push_back(*out);
+      return CFD_OK;
+    };
+    for (int r = 0; r < world; ++r) {
+      if (r == rank) { peer_mailbox[r] = mailbox; continue; }
+      void* ptr = nullptr;
+      if ((rc = open(all[(size_t)r].box, &ptr))) return rc;
+      peer_mailbox[r] = (cfdk::Mailbox*)ptr;
+    }
+    // a neighbour lays its buffers out exactly like this rank does (falloc): virtual origin = base + front -
+    // (its first owned row - kHalo) * nx
+    auto neighbour_origin = [&](void* base, int r) -> R* {
+      const int nb = ny / world, rem = ny % world;
+      const int ja_n = r * nb + (r < rem ? r : rem);
+      return (R*)base + kFront - (long)(ja_n - kHalo) * (long)nx;
+    };
+    if (rank > 0) {
+      void *b0 = nullptr, *b1 = nullptr;
+      if ((rc = open(all[(size_t)rank - 1].pp0, &b0))) return rc;
+      if ((rc = open(all[(size_t)rank - 1].pp1, &b1))) return rc;
+      peer_pp_down[0] = neighbour_origin(b0, rank - 1);
+      peer_pp_down[1] = neighbour_origin(b1, rank - 1);
+    }
+    if (rank < world - 1) {
+      void *b0 = nullptr, *b1 = nullptr;
+      if ((rc = open(all[(size_t)rank + 1].pp0, &b0))) return rc;
+      if ((rc = open(all[(size_t)rank + 1].pp1, &b1))) return rc;
+      peer_pp_up[0] = neighbour_origin(b0, rank + 1);
+      peer_pp_up[1] = neighbour_origin(b1, rank + 1);
+    }
+    peer_ready = true;
+    return CFD_OK;
+  }
+
+  cfdk::SweepPeer<R> sweep_peer(int out) const {
+    cfdk::SweepPeer<R> sp;
+    memset(&sp, 0, sizeof sp);
+    sp.rank = rank;
+    sp.world = 1;
+    if (!peer_ready) return sp;
+    sp.world = world;
+    sp.down_out = peer_pp_down[out];
+    sp.up_out = peer_pp_up[out];
+    sp.down_flag = rank > 0 ? &peer_mailbox[rank - 1]->halo_flag[1] : nullptr;
+    sp.up_flag = rank < world - 1 ? &peer_mailbox[rank + 1]->halo_flag[0] : nullptr;
+    sp.mine = mailbox;
+    for (int r = 0; r < world; ++r) sp.all[r] = peer_mailbox[r];
+    sp.tickets = tickets;
+    sp.stamp_base = solve_counter * 256ull;
+    sp.trace = peer_trace;
+    return sp;
   }
 
   // 2-D tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point; libcuda is not linked)
@@ -495,7 +592,7 @@ struct ModelImpl final : ModelBase {
     if ((rc = fetch_row_above(vs, ja, v_row_end()))) return rc;
     {
       dim3 blk(256), grd((nx + 255) / 256, jb - ja);
-      cfdk::k_divergence<R><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, rhs.v, ja, jb, err_slots, iters);
+      cfdk::k_divergence<R><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, rhs.v, ja, jb, err_slots, iters, tickets);
       ++launches;
     }
     if (pressure_solver == CFD_SOLVER_CG) return cg_solve(dt_sub, call_index, residual_out);
@@ -520,40 +617,19 @@ struct ModelImpl final : ModelBase {
     const dim3 blk2(128), grd2((nx / 2 + 127) / 128, (rows + sweep_rows_per_block - 1) / sweep_rows_per_block);
     const size_t ring_bytes = sizeof(cfdk::SweepChunkRing<R>);
     const bool tuned_default = !(opt.flags & (CFD_FLAG_BASELINE_SWEEP | CFD_FLAG_REGISTER_SWEEP | CFD_FLAG_BULK_SWEEP | CFD_FLAG_SWEEP4));
-    const int edge = sweep_rows_per_block;  // rows of the two edge bands that are swept first
-    if (world > 1 && tuned_default && rows >= 3 * edge && (opt.flags & CFD_FLAG_OVERLAP_EXCHANGE)) {
-      // ---- strips, overlapped (opt-in): sweep the two edge bands, start the halo exchange on the communication
-      // stream, sweep the interior meanwhile; the max allreduce of sweep s runs during sweep s+1 (check_lag 2).
-      // Measured SLOWER than the in-stream form on 2 x B200 (196 vs 147 ms/step at 4096x8192): the sweep holds
-      // every SM's register file, so NCCL's own kernels cannot co-run and only add cross-stream latency
-      // (profiles/r1_notes.md).  Kept for A/B; the fix is peer-memory stores from the sweep itself.
+    if (world > 1 && tuned_default && peer_ready) {
+      // ---- strips over peer memory: the sweep stores its edge rows into the neighbours' halos and publishes its
+      // max|dp'| to every rank's mailbox itself; convergence is checked two sweeps late (check_lag 2).
       c2.check_lag = 2;
+      ++solve_counter;
       for (int s = 0; s < iters; ++s) {
-        const int in = (ipp + s) & 1, out = in ^ 1, e = s % kEvRing;
-        if (s >= 1) CFD_CUDA(cudaStreamWaitEvent(stream, ev_halo[(s - 1) % kEvRing], 0));  // halos of this sweep's input
-        if (s >= 2) CFD_CUDA(cudaStreamWaitEvent(stream, ev_max[(s - 2) % kEvRing], 0));   // global max of sweep s-2
-        cfdk::JacobiConsts2<R> cb = c2, ct = c2, cm = c2;
-        cb.row_end = c2.row_begin + edge;
-        ct.row_begin = c2.row_end - edge;
-        cm.row_begin = cb.row_end; cm.row_end = ct.row_begin;
-        const dim3 g_edge(grd2.x, 1), g_mid(grd2.x, (cm.row_end - cm.row_begin + sweep_rows_per_block - 1) / sweep_rows_per_block);
-        cfdk::k_jacobi_sweep5<R><<<g_edge, blk2, ring_bytes, stream>>>(cb, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s);
-        cfdk::k_jacobi_sweep5<R><<<g_edge, blk2, ring_bytes, stream>>>(ct, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s);
-        CFD_CUDA(cudaEventRecord(ev_edge[e], stream));
-        cfdk::k_jacobi_sweep5<R><<<g_mid, blk2, ring_bytes, stream>>>(cm, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s);
-        CFD_CUDA(cudaEventRecord(ev_full[e], stream));
-        launches += 3;
-        CFD_CUDA(cudaStreamWaitEvent(comm_stream, ev_edge[e], 0));
-        if ((rc = exchange_halo(pp[out], ja, jb, 1, comm_stream))) return rc;
-        CFD_CUDA(cudaEventRecord(ev_halo[e], comm_stream));
-        CFD_CUDA(cudaStreamWaitEvent(comm_stream, ev_full[e], 0));
-        if ((rc = allreduce_max_u64(err_slots + s, 1, comm_stream))) return rc;
-        CFD_CUDA(cudaEventRecord(ev_max[e], comm_stream));
+        const int in = (ipp + s) & 1, out = in ^ 1;
+        cfdk::k_jacobi_sweep5<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s,
+                                                                      sweep_peer(out));
+        ++launches;
       }
-      for (int k = 0; k < kEvRing && k < iters; ++k) {  // everything the communication stream still owes
-        CFD_CUDA(cudaStreamWaitEvent(stream, ev_halo[(iters - 1 - k) % kEvRing], 0));
-        CFD_CUDA(cudaStreamWaitEvent(stream, ev_max[(iters - 1 - k) % kEvRing], 0));
-      }
+      cfdk::k_jacobi_finalize_peer<R><<<1, 32, 0, stream>>>(mailbox, world, solve_counter * 256ull, iters, c.tol, h_jres);
+      ++launches;
     } else {
       for (int s = 0; s < iters; ++s) {
         const int in = (ipp + s) & 1, out = in ^ 1;
@@ -566,7 +642,8 @@ struct ModelImpl final : ModelBase {
         else if (opt.flags & CFD_FLAG_SWEEP4)
           cfdk::k_jacobi_sweep4<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s);
         else
-          cfdk::k_jacobi_sweep5<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s);
+          cfdk::k_jacobi_sweep5<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s,
+                                                                        cfdk::SweepPeer<R>{});
         ++launches;
         if (world > 1) {
           // strips, simple form: the next sweep needs the neighbours' new boundary rows and the GLOBAL max|dp'|
@@ -577,12 +654,26 @@ struct ModelImpl final : ModelBase {
         }
       }
     }
-    cfdk::k_jacobi_finalize<R><<<1, 32, 0, stream>>>(err_slots, iters, c.tol, h_jres);
-    ++launches;
+    if (!(world > 1 && tuned_default && peer_ready)) {
+      cfdk::k_jacobi_finalize<R><<<1, 32, 0, stream>>>(err_slots, iters, c.tol, h_jres);
+      ++launches;
+    }
     CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index + 1], stream));
     CFD_CUDA(cudaGetLastError());
     CFD_CUDA(cudaStreamSynchronize(stream));
     const int ran = h_jres->sweeps;
+    if (peer_trace && ran == iters) {  // diagnostics: GPU-side timeline of this solve
+      std::vector<unsigned long long> t(768);
+      cudaMemcpy(t.data(), peer_trace, 768 * 8, cudaMemcpyDeviceToHost);
+      for (int s2 = 0; s2 < iters; ++s2) {
+        dbg_work += (t[256 + s2] - t[s2]) / 1e3;
+        dbg_wait += (t[512 + s2] - t[256 + s2]) / 1e3;
+        if (s2 + 1 < iters) dbg_gap += ((double)t[s2 + 1] - (double)t[512 + s2]) / 1e3;
+        ++dbg_n;
+      }
+      dbg_span += (t[512 + iters - 1] - t[0]) / 1e3;
+      ++dbg_solves;
+    }
     ipp = (ipp + ran) & 1;
     last_S += (uint64_t)ran;
     last_K += 1;
