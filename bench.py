@@ -219,7 +219,8 @@ def run_ours(args, w):
     if world > 1:
         uid = [nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
-        model = Model.strip(grid, params, rank, world, uid[0], device=local_rank)
+        model = Model.strip(grid, params, rank, world, uid[0], device=local_rank,
+                            flags=int(os.environ.get("CFD_BENCH_FLAGS", "0")))  # A/B hook (e.g. 32 = NCCL exchange)
     else:
         opts = default_options()
         opts.device = local_rank
