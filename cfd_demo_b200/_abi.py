@@ -28,6 +28,7 @@ FLAG_REGISTER_SWEEP = 4
 FLAG_BULK_SWEEP = 8
 FLAG_SWEEP4 = 16
 FLAG_NCCL_EXCHANGE = 32
+FLAG_TEMPORAL = 64
 
 
 class CfdGrid(C.Structure):

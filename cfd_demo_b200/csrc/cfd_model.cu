@@ -180,6 +180,8 @@ struct ModelImpl final : ModelBase {
   cfdk::CgScalars* cg_scalars = nullptr;   // device
   cfdk::CgScalars* h_cg = nullptr;         // pinned host copy
   CUtensorMap tmap_pp[2], tmap_rhs;  // 2-D tiled views of p' (ping, pong) and rhs for the tensor-TMA sweep
+  CUtensorMap tmap_rhs_halo;         // rhs with the same halo box as p' (two-sweep kernel)
+  int t2_rows_per_block = 20;        // tile height of the two-sweep kernel: rows + 4 halo rows = whole 4-row boxes
   cfdk::DivG<R> div_dx_sq, div_dy_sq, div_denom;  // divisors of the Jacobi update with hoisted reciprocals
   int sweep_rows_per_block = 32;
   cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
@@ -486,6 +488,9 @@ struct ModelImpl final : ModelBase {
       if ((rc2 = make_tensor_map(&tmap_pp[0], pp[0].row(ja - kHalo), Ring::kPCols))) return rc2;
       if ((rc2 = make_tensor_map(&tmap_pp[1], pp[1].row(ja - kHalo), Ring::kPCols))) return rc2;
       if ((rc2 = make_tensor_map(&tmap_rhs, rhs.row(ja - kHalo), cfdk::kStripCols))) return rc2;
+      if ((rc2 = make_tensor_map(&tmap_rhs_halo, rhs.row(ja - kHalo), Ring::kPCols))) return rc2;
+      CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep_t2<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(cfdk::SweepT2Ring<R>)));
       CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep4<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(Ring)));
       CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep5<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -533,6 +538,14 @@ struct ModelImpl final : ModelBase {
     if (const char* e = getenv("CFD_SWEEP_ROWS")) {  // tuning hook (tools/tune_sweep.py)
       const int v = atoi(e);
       if (v >= 2) rpb = v;
+    }
+    if (const char* e = getenv("CFD_T2_ROWS")) {
+      const int v = atoi(e);
+      if (v >= 4) t2_rows_per_block = v;
+    } else {
+      const long target_blocks = 4L * resident;
+      long want = ((long)rows * bx) / target_blocks;
+      t2_rows_per_block = want >= 20 ? 20 : (want >= 12 ? 12 : (want >= 8 ? 8 : 4));
     }
     sweep_rows_per_block = rpb;
     return CFD_OK;
@@ -613,11 +626,29 @@ struct ModelImpl final : ModelBase {
     c2.nx = nx; c2.ny = ny; c2.cavity = c.cavity; c2.rows_per_block = sweep_rows_per_block;
     c2.row_begin = c.row_begin; c2.row_end = c.row_end; c2.row_shift = ja - kHalo;
     c2.check_lag = 1;
+    c2.fix_pass = -1;
     const dim3 blk1(256), grd1((nx - 2 + 255) / 256, (rows + kJacobiRows - 1) / kJacobiRows);
     const dim3 blk2(128), grd2((nx / 2 + 127) / 128, (rows + sweep_rows_per_block - 1) / sweep_rows_per_block);
     const size_t ring_bytes = sizeof(cfdk::SweepChunkRing<R>);
     const bool tuned_default = !(opt.flags & (CFD_FLAG_BASELINE_SWEEP | CFD_FLAG_REGISTER_SWEEP | CFD_FLAG_BULK_SWEEP | CFD_FLAG_SWEEP4));
-    if (world > 1 && tuned_default && peer_ready) {
+    const bool use_t2 = world == 1 && tuned_default && (opt.flags & CFD_FLAG_TEMPORAL) && (iters % 2 == 0) &&
+                        rows >= 4;
+    if (use_t2) {
+      // ---- temporal blocking: two sweeps per pass over HBM (k_jacobi_sweep_t2), each pass followed by the
+      // conditional fix-up that restores the reference's stopping point when the FIRST sweep of a pass converged
+      cfdk::JacobiConsts2<R> ct = c2, cf = c2;
+      ct.rows_per_block = t2_rows_per_block;
+      const dim3 grd_t(grd2.x, (rows + t2_rows_per_block - 1) / t2_rows_per_block);
+      const size_t t2_bytes = sizeof(cfdk::SweepT2Ring<R>);
+      for (int pass = 0; pass < iters / 2; ++pass) {
+        const int in = (ipp + pass) & 1, out = in ^ 1, s = 2 * pass;
+        cfdk::k_jacobi_sweep_t2<R><<<grd_t, blk2, t2_bytes, stream>>>(ct, tmap_pp[in], tmap_rhs_halo, pp[out].v, err_slots, s);
+        cf.fix_pass = pass;
+        cfdk::k_jacobi_sweep5<R><<<grd2, blk2, ring_bytes, stream>>>(cf, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s,
+                                                                      cfdk::SweepPeer<R>{});
+        launches += 2;
+      }
+    } else if (world > 1 && tuned_default && peer_ready) {
       // ---- strips over peer memory: the sweep stores its edge rows into the neighbours' halos and publishes its
       // max|dp'| to every rank's mailbox itself; convergence is checked two sweeps late (check_lag 2).
       c2.check_lag = 2;
@@ -662,6 +693,7 @@ struct ModelImpl final : ModelBase {
     CFD_CUDA(cudaGetLastError());
     CFD_CUDA(cudaStreamSynchronize(stream));
     const int ran = h_jres->sweeps;
+    const int flips = use_t2 ? (ran + 1) / 2 : ran;  // buffer swaps performed: one per pass / per sweep
     if (peer_trace && ran == iters) {  // diagnostics: GPU-side timeline of this solve
       std::vector<unsigned long long> t(768);
       cudaMemcpy(t.data(), peer_trace, 768 * 8, cudaMemcpyDeviceToHost);
@@ -674,7 +706,7 @@ struct ModelImpl final : ModelBase {
       dbg_span += (t[512 + iters - 1] - t[0]) / 1e3;
       ++dbg_solves;
     }
-    ipp = (ipp + ran) & 1;
+    ipp = (ipp + flips) & 1;
     last_S += (uint64_t)ran;
     last_K += 1;
     *residual_out = (R)h_jres->last_error;
