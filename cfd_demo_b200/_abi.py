@@ -29,6 +29,7 @@ FLAG_BULK_SWEEP = 8
 FLAG_SWEEP4 = 16
 FLAG_NCCL_EXCHANGE = 32
 FLAG_TEMPORAL = 64
+FLAG_PERSISTENT_SWEEP = 128
 
 
 class CfdGrid(C.Structure):

@@ -184,6 +184,7 @@ struct ModelImpl final : ModelBase {
   int t2_rows_per_block = 20;        // tile height of the two-sweep kernel: rows + 4 halo rows = whole 4-row boxes
   cfdk::DivG<R> div_dx_sq, div_dy_sq, div_denom;  // divisors of the Jacobi update with hoisted reciprocals
   int sweep_rows_per_block = 32;
+  int sweep6_resident_blocks = 148 * 4;  // one wave of the persistent sweep
   cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
   std::vector<cudaEvent_t> ev_sweep;  // pairs
   // strips over peer memory (CUDA IPC): the neighbours' p' buffers and every rank's mailbox (cfd_kernels.cuh)
@@ -231,7 +232,7 @@ struct ModelImpl final : ModelBase {
     for (auto& f : vbuf) cudaFree(f.base);
     cudaFree(p.base); cudaFree(rhs.base); cudaFree(pp[0].base); cudaFree(pp[1].base);
     cudaFree(mask_u.base); cudaFree(mask_v.base); cudaFree(solid.base);
-    cudaFree(err_slots); cudaFree(step_slots); cudaFree(staging);
+    cudaFree(err_slots); cudaFree(step_slots); cudaFree(staging); cudaFree(tickets);
     cudaFree(cg_r.base); cudaFree(cg_d.base); cudaFree(cg_partials); cudaFree(cg_scalars);
     if (h_cg) cudaFreeHost(h_cg);
     if (h_jres) cudaFreeHost(h_jres);
@@ -259,7 +260,7 @@ struct ModelImpl final : ModelBase {
       cudaFree(peer_trace);
     }
     for (void* ptr : ipc_opened) cudaIpcCloseMemHandle(ptr);
-    cudaFree(mailbox); cudaFree(tickets);
+    cudaFree(mailbox);
     if (ev_step0) cudaEventDestroy(ev_step0);
     if (ev_step1) cudaEventDestroy(ev_step1);
     for (auto e : ev_sweep) cudaEventDestroy(e);
@@ -318,6 +319,8 @@ struct ModelImpl final : ModelBase {
     if ((rc = falloc(&solid, (size_t)nx))) return rc;
     if ((rc = dalloc(&err_slots, (size_t)kMaxSweepSlots))) return rc;
     if ((rc = dalloc(&step_slots, (size_t)4))) return rc;
+    // per-sweep tickets / stop flags / diagnostics (strips) and work counters (persistent sweep), cfd_kernels.cuh
+    if ((rc = dalloc(&tickets, (size_t)1400))) return rc;
     CFD_CUDA(cudaHostAlloc((void**)&h_jres, sizeof(cfdk::JacobiResult), cudaHostAllocMapped));
     CFD_CUDA(cudaHostAlloc((void**)&h_step, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
     CFD_CUDA(cudaEventCreate(&ev_step0));
@@ -348,7 +351,6 @@ struct ModelImpl final : ModelBase {
     if (world > cfdk::kMaxRanks) return fail(CFD_ERR_UNSUPPORTED, "peer-memory strips support at most 8 ranks");
     int rc;
     if ((rc = dalloc(&mailbox, (size_t)1))) return rc;
-    if ((rc = dalloc(&tickets, (size_t)4 * 260 + 16))) return rc;  // + diagnostics counters at [1044..1052)
     if (getenv("CFD_PEER_DEBUG") && (rc = dalloc(&peer_trace, (size_t)3 * 256))) return rc;
     CFD_CUDA(cudaStreamSynchronize(stream));
     struct Handles { cudaIpcMemHandle_t pp0, pp1, box; };
@@ -495,6 +497,13 @@ struct ModelImpl final : ModelBase {
                                     (int)sizeof(Ring)));
       CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep5<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(Ring)));
+      CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep6<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(Ring)));
+      int per_sm6 = 1;
+      CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm6, cfdk::k_jacobi_sweep6<R>, 128, sizeof(Ring)));
+      cudaDeviceProp prop6;
+      CFD_CUDA(cudaGetDeviceProperties(&prop6, device));
+      sweep6_resident_blocks = prop6.multiProcessorCount * (per_sm6 < 1 ? 1 : per_sm6);
     }
     // one thread per column pair, 128 threads per block; pick the rows per block so that the grid is a
     // whole number of waves of (SM count x resident blocks per SM)
@@ -631,6 +640,11 @@ struct ModelImpl final : ModelBase {
     const dim3 blk2(128), grd2((nx / 2 + 127) / 128, (rows + sweep_rows_per_block - 1) / sweep_rows_per_block);
     const size_t ring_bytes = sizeof(cfdk::SweepChunkRing<R>);
     const bool tuned_default = !(opt.flags & (CFD_FLAG_BASELINE_SWEEP | CFD_FLAG_REGISTER_SWEEP | CFD_FLAG_BULK_SWEEP | CFD_FLAG_SWEEP4));
+    const bool use6 = tuned_default && (opt.flags & CFD_FLAG_PERSISTENT_SWEEP);  // persistent warp-queue kernel (A/B)
+    const int n_units6 = ((nx + cfdk::kStripCols - 1) / cfdk::kStripCols) * ((rows + cfdk::kUnitRows - 1) / cfdk::kUnitRows);
+    int grid6 = (n_units6 + cfdk::kSweepWarps - 1) / cfdk::kSweepWarps;
+    if (grid6 > sweep6_resident_blocks) grid6 = sweep6_resident_blocks;
+    if (grid6 < 1) grid6 = 1;
     const bool use_t2 = world == 1 && tuned_default && (opt.flags & CFD_FLAG_TEMPORAL) && (iters % 2 == 0) &&
                         rows >= 4;
     if (use_t2) {
@@ -655,8 +669,12 @@ struct ModelImpl final : ModelBase {
       ++solve_counter;
       for (int s = 0; s < iters; ++s) {
         const int in = (ipp + s) & 1, out = in ^ 1;
-        cfdk::k_jacobi_sweep5<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s,
-                                                                      sweep_peer(out));
+        if (use6)
+          cfdk::k_jacobi_sweep6<R><<<grid6, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s,
+                                                                         sweep_peer(out), tickets + 1060 + s);
+        else
+          cfdk::k_jacobi_sweep5<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s,
+                                                                        sweep_peer(out));
         ++launches;
       }
       cfdk::k_jacobi_finalize_peer<R><<<1, 32, 0, stream>>>(mailbox, world, solve_counter * 256ull, iters, c.tol, h_jres);
@@ -672,6 +690,9 @@ struct ModelImpl final : ModelBase {
           cfdk::k_jacobi_sweep3<R><<<grd2, blk2, 0, stream>>>(c2, pp[in].v, rhs.v, pp[out].v, err_slots, s);
         else if (opt.flags & CFD_FLAG_SWEEP4)
           cfdk::k_jacobi_sweep4<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s);
+        else if (use6)
+          cfdk::k_jacobi_sweep6<R><<<grid6, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s,
+                                                                         cfdk::SweepPeer<R>{}, tickets + 1060 + s);
         else
           cfdk::k_jacobi_sweep5<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s,
                                                                         cfdk::SweepPeer<R>{});
