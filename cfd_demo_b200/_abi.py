@@ -1,7 +1,7 @@
 """ctypes mirror of include/cfd_b200.h (PODs and constants only; no library is loaded here)."""
 import ctypes as C
 
-CFD_ABI_VERSION = 1
+CFD_ABI_VERSION = 2
 
 CFD_OK = 0
 CFD_ERR_INVALID_ARGUMENT = 1
@@ -11,7 +11,7 @@ CFD_ERR_NCCL = 4
 
 SCHEME_FIRST_ORDER, SCHEME_SECOND_ORDER = 0, 1
 INLET_UNIFORM, INLET_PARABOLIC = 0, 1
-SOLVER_JACOBI, SOLVER_CG = 0, 1
+SOLVER_JACOBI, SOLVER_CG, SOLVER_MGCG = 0, 1, 2
 SCENARIO_CHANNEL, SCENARIO_CAVITY = 0, 1
 
 FIELD_P, FIELD_U, FIELD_V, FIELD_U_STAR, FIELD_V_STAR, FIELD_RHS, FIELD_P_PRIME = range(7)
@@ -49,7 +49,8 @@ class CfdSolverConsts(C.Structure):
     _fields_ = [("ramp_up_steps", C.c_int32), ("jacobi_iterations", C.c_int32),
                 ("outer_rounds", C.c_int32), ("cg_max_iterations", C.c_int32),
                 ("jacobi_omega", C.c_double), ("pressure_tolerance", C.c_double),
-                ("outer_tolerance", C.c_double), ("cfl", C.c_double), ("cg_tolerance", C.c_double)]
+                ("outer_tolerance", C.c_double), ("cfl", C.c_double), ("cg_tolerance", C.c_double),
+                ("mg_omega", C.c_double), ("mg_smoothing", C.c_int32), ("mg_reserved", C.c_int32)]
 
 
 class CfdOptions(C.Structure):

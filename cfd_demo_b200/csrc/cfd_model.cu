@@ -19,6 +19,7 @@
 
 #include "../../include/cfd_b200.h"
 #include "cfd_kernels.cuh"
+#include "cfd_mg.cuh"
 
 namespace {
 
@@ -103,6 +104,9 @@ void consts_default(cfd_solver_consts* c) {
   c->outer_tolerance = 1e-4;     // :721
   c->cfl = 0.2;                  // :885
   c->cg_tolerance = 1e-8;        // extension
+  c->mg_omega = 0.8;             // extension (MGCG)
+  c->mg_smoothing = 2;           // extension (MGCG)
+  c->mg_reserved = 0;
 }
 
 constexpr int kMaxSweepSlots = 256;
@@ -131,6 +135,7 @@ struct Field {
   T* base = nullptr;
   T* v = nullptr;
   size_t rowlen = 0;
+  size_t count = 0;  // entries allocated
   T* row(long j) const { return v + j * (long)rowlen; }
 };
 
@@ -179,6 +184,21 @@ struct ModelImpl final : ModelBase {
   double* cg_partials = nullptr;
   cfdk::CgScalars* cg_scalars = nullptr;   // device
   cfdk::CgScalars* h_cg = nullptr;         // pinned host copy
+  // Mode C fast path (MGCG) work space, allocated on first use (cfd_mg.cuh)
+  struct MgLevelHost {
+    int mx = 0, my = 0;
+    R* weights = nullptr;                      // WE, WW, CYW (mx each), WN, WS, CXH (my each)
+    R *e = nullptr, *rho = nullptr, *tmp = nullptr;  // (mx + 2) x (my + 2), ring of zeros; level 0 has none
+    R* cur = nullptr;                          // whichever of e / tmp holds the level's correction
+    cfdk::MgLevelDev<R> dev;
+  };
+  std::vector<MgLevelHost> mg;
+  Field<R> mg_rho, mg_d, mg_z[2];
+  CUtensorMap tmap_mg_z[2], tmap_mg_rho;
+  cfdk::MgScalars* mg_scalars = nullptr;  // device
+  cfdk::MgScalars* h_mg = nullptr;        // pinned host copy
+  double* mg_partials = nullptr;
+  unsigned long long* mg_err = nullptr;   // scratch max|dz| slot of the smoothing sweeps
   CUtensorMap tmap_pp[2], tmap_rhs;  // 2-D tiled views of p' (ping, pong) and rhs for the tensor-TMA sweep
   CUtensorMap tmap_rhs_halo;         // rhs with the same halo box as p' (two-sweep kernel)
   int t2_rows_per_block = 20;        // tile height of the two-sweep kernel: rows + 4 halo rows = whole 4-row boxes
@@ -234,6 +254,10 @@ struct ModelImpl final : ModelBase {
     cudaFree(mask_u.base); cudaFree(mask_v.base); cudaFree(solid.base);
     cudaFree(err_slots); cudaFree(step_slots); cudaFree(staging); cudaFree(tickets);
     cudaFree(cg_r.base); cudaFree(cg_d.base); cudaFree(cg_partials); cudaFree(cg_scalars);
+    for (auto& L : mg) { cudaFree(L.weights); cudaFree(L.e); cudaFree(L.rho); cudaFree(L.tmp); }
+    cudaFree(mg_rho.base); cudaFree(mg_d.base); cudaFree(mg_z[0].base); cudaFree(mg_z[1].base);
+    cudaFree(mg_scalars); cudaFree(mg_partials); cudaFree(mg_err);
+    if (h_mg) cudaFreeHost(h_mg);
     if (h_cg) cudaFreeHost(h_cg);
     if (h_jres) cudaFreeHost(h_jres);
     if (h_step) cudaFreeHost(h_step);
@@ -283,6 +307,7 @@ struct ModelImpl final : ModelBase {
     int rc;
     if ((rc = dalloc(&f->base, count))) return rc;
     f->rowlen = rowlen;
+    f->count = count;
     f->v = f->base + front - (long)(ja - kHalo) * (long)rowlen;
     return CFD_OK;
   }
@@ -618,6 +643,7 @@ struct ModelImpl final : ModelBase {
       ++launches;
     }
     if (pressure_solver == CFD_SOLVER_CG) return cg_solve(dt_sub, call_index, residual_out);
+    if (pressure_solver == CFD_SOLVER_MGCG) return mgcg_solve(dt_sub, call_index, residual_out);
     cfdk::JacobiConsts<R> c;
     c.dx_sq = dx * dx;                                   // :740
     c.dy_sq = dy * dy;                                   // :742
@@ -808,6 +834,199 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
 
+  // EXTENSION, Mode C fast path: CG preconditioned by one multigrid V-cycle (cfd_mg.cuh).  Level geometry is
+  // computed on the host in R precision with the same expressions as the oracle (mg_build_levels).
+  int mg_setup() {
+    if (world > 1) return fail(CFD_ERR_UNSUPPORTED, "MGCG runs on a single domain in this version (use CG on strips)");
+    const bool cavity = scenario == CFD_SCENARIO_CAVITY;
+    const R dx_sq = dx * dx, dy_sq = dy * dy;
+    std::vector<R> wx((size_t)nx - 2, R(1)), hy((size_t)ny - 2, R(1));
+    int rc;
+    for (;;) {
+      MgLevelHost L;
+      L.mx = (int)wx.size(); L.my = (int)hy.size();
+      const size_t mx = wx.size(), my = hy.size();
+      std::vector<R> hw(3 * mx + 3 * my, R(0));
+      R *WE = hw.data(), *WW = WE + mx, *CYW = WW + mx, *WN = CYW + mx, *WS = WN + my, *CXH = WS + my;
+      for (size_t i = 0; i < mx; ++i) {
+        if (i + 1 < mx) WE[i] = R(1) / (R(0.5) * (wx[i] + wx[i + 1]));
+        else if (!cavity) WE[i] = R(1) / (R(0.5) * wx[i] + R(0.5));
+        if (i > 0) WW[i] = R(1) / (R(0.5) * (wx[i - 1] + wx[i]));
+        CYW[i] = wx[i] / dy_sq;
+      }
+      for (size_t j = 0; j < my; ++j) {
+        if (j + 1 < my) WN[j] = R(1) / (R(0.5) * (hy[j] + hy[j + 1]));
+        if (j > 0) WS[j] = R(1) / (R(0.5) * (hy[j - 1] + hy[j]));
+        CXH[j] = hy[j] / dx_sq;
+      }
+      if ((rc = dalloc(&L.weights, hw.size()))) return rc;
+      CFD_CUDA(cudaMemcpyAsync(L.weights, hw.data(), hw.size() * sizeof(R), cudaMemcpyHostToDevice, stream));
+      CFD_CUDA(cudaStreamSynchronize(stream));  // hw goes out of scope
+      L.dev.mx = L.mx; L.dev.my = L.my;
+      L.dev.WE = L.weights; L.dev.WW = L.weights + mx; L.dev.CYW = L.weights + 2 * mx;
+      L.dev.WN = L.weights + 3 * mx; L.dev.WS = L.weights + 3 * mx + my; L.dev.CXH = L.weights + 3 * mx + 2 * my;
+      if (!mg.empty()) {
+        const size_t n = (mx + 2) * (my + 2);
+        if ((rc = dalloc(&L.e, n))) return rc;
+        if ((rc = dalloc(&L.rho, n))) return rc;
+        if ((rc = dalloc(&L.tmp, n))) return rc;
+      }
+      mg.push_back(L);
+      if (mx == 1 && my == 1) break;
+      auto pair_up = [](const std::vector<R>& w) {
+        std::vector<R> o((w.size() + 1) / 2, R(0));
+        for (size_t k = 0; k < o.size(); ++k) o[k] = w[2 * k] + (2 * k + 1 < w.size() ? w[2 * k + 1] : R(0));
+        return o;
+      };
+      wx = pair_up(wx);
+      hy = pair_up(hy);
+    }
+    if ((rc = falloc(&mg_rho, (size_t)nx))) return rc;
+    if ((rc = falloc(&mg_d, (size_t)nx))) return rc;
+    if ((rc = falloc(&mg_z[0], (size_t)nx))) return rc;
+    if ((rc = falloc(&mg_z[1], (size_t)nx))) return rc;
+    using Ring = cfdk::SweepChunkRing<R>;
+    if ((rc = make_tensor_map(&tmap_mg_z[0], mg_z[0].row(ja - kHalo), Ring::kPCols))) return rc;
+    if ((rc = make_tensor_map(&tmap_mg_z[1], mg_z[1].row(ja - kHalo), Ring::kPCols))) return rc;
+    if ((rc = make_tensor_map(&tmap_mg_rho, mg_rho.row(ja - kHalo), cfdk::kStripCols))) return rc;
+    if ((rc = dalloc(&mg_scalars, (size_t)1))) return rc;
+    if ((rc = dalloc(&mg_err, (size_t)kMaxSweepSlots))) return rc;
+    const size_t n_all = (size_t)((nx + cfdk::kMgThreads - 1) / cfdk::kMgThreads) * (size_t)ny;
+    if ((rc = dalloc(&mg_partials, n_all))) return rc;
+    CFD_CUDA(cudaHostAlloc((void**)&h_mg, sizeof(cfdk::MgScalars), cudaHostAllocDefault));
+    CFD_CUDA(cudaStreamSynchronize(stream));
+    return CFD_OK;
+  }
+
+  int mg_smoothing() const { return opt.consts.mg_smoothing < 1 ? 1 : opt.consts.mg_smoothing; }
+
+  // correction of level l >= 1 from its rho (result in mg[l].cur)
+  int mg_coarse_vcycle(int l) {
+    MgLevelHost& L = mg[(size_t)l];
+    const R omega = R(opt.consts.mg_omega);
+    const int nu_s = mg_smoothing();
+    const dim3 blk(cfdk::kMgThreads), grd((L.mx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, L.my);
+    R *a = L.e, *b = L.tmp;
+    if (L.mx == 1 && L.my == 1) {  // exact
+      cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, R(1), 1);
+      ++launches;
+      L.cur = b;
+      return CFD_OK;
+    }
+    for (int s = 0; s < nu_s; ++s) {
+      cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, omega, s == 0 ? 1 : 0);
+      ++launches;
+      std::swap(a, b);
+    }
+    MgLevelHost& C = mg[(size_t)l + 1];
+    const dim3 grd_c((C.mx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, C.my);
+    cfdk::k_mgc_restrict<R><<<grd_c, blk, 0, stream>>>(L.dev, a, L.rho, C.mx, C.my, C.rho);
+    ++launches;
+    int rc;
+    if ((rc = mg_coarse_vcycle(l + 1))) return rc;
+    cfdk::k_mgc_prolong<R><<<grd, blk, 0, stream>>>(L.mx, a, C.mx, C.cur);
+    ++launches;
+    for (int s = 0; s < nu_s; ++s) {
+      cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, omega, 0);
+      ++launches;
+      std::swap(a, b);
+    }
+    L.cur = a;
+    return CFD_OK;
+  }
+
+  // z <- V-cycle(rho); returns the index of the mg_z buffer holding z
+  int mg_precondition(const cfdk::MgFine<R>& c, int* z_index) {
+    const int nu_s = mg_smoothing();
+    cfdk::JacobiConsts2<R> c2;
+    c2.dx_sq = div_dx_sq; c2.dy_sq = div_dy_sq; c2.denom = div_denom;
+    c2.omega = R(opt.consts.mg_omega);
+    c2.one_minus_omega = R(1.0) - c2.omega;
+    c2.tol = R(0);
+    c2.nx = nx; c2.ny = ny; c2.cavity = c.cavity; c2.rows_per_block = sweep_rows_per_block;
+    c2.row_begin = 1; c2.row_end = ny - 1; c2.row_shift = ja - kHalo;
+    c2.check_lag = 1;
+    c2.fix_pass = -1;
+    const int rows = ny - 2;
+    const dim3 blk2(128), grd2((nx / 2 + 127) / 128, (rows + sweep_rows_per_block - 1) / sweep_rows_per_block);
+    const size_t ring_bytes = sizeof(cfdk::SweepChunkRing<R>);
+    int zc = 0;
+    auto smooth = [&]() {
+      cfdk::k_jacobi_sweep5<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_mg_z[zc], tmap_mg_rho, mg_z[zc ^ 1].v, mg_err, 0,
+                                                                    cfdk::SweepPeer<R>{});
+      ++launches;
+      zc ^= 1;
+    };
+    CFD_CUDA(cudaMemsetAsync(mg_z[0].base, 0, mg_z[0].count * sizeof(R), stream));
+    for (int s = 0; s < nu_s; ++s) smooth();
+    if (mg.size() > 1) {
+      MgLevelHost& C = mg[1];
+      const dim3 blk(cfdk::kMgThreads), grd_c((C.mx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, C.my);
+      const dim3 g_int((nx - 2 + cfdk::kMgThreads - 1) / cfdk::kMgThreads, ny - 2);
+      cfdk::k_mg_fine_restrict<R><<<grd_c, blk, 0, stream>>>(c, mg_z[zc].v, mg_rho.v, C.mx, C.my, C.rho);
+      ++launches;
+      int rc;
+      if ((rc = mg_coarse_vcycle(1))) return rc;
+      cfdk::k_mg_fine_prolong<R><<<g_int, blk, 0, stream>>>(c, mg_z[zc].v, C.mx, C.cur);
+      ++launches;
+    }
+    for (int s = 0; s < nu_s; ++s) smooth();
+    CFD_CUDA(cudaGetLastError());
+    *z_index = zc;
+    return CFD_OK;
+  }
+
+  int mgcg_solve(R dt_sub, int call_index, R* residual_out) {
+    int rc;
+    if (mg.empty() && (rc = mg_setup())) return rc;
+    cfdk::MgFine<R> c;
+    c.dx_sq = dx * dx; c.dy_sq = dy * dy; c.dt = dt_sub; c.tol = R(opt.consts.cg_tolerance);
+    c.n_unknowns = R((size_t)(nx - 2) * (size_t)(ny - 2));
+    c.nx = nx; c.ny = ny; c.cavity = scenario == CFD_SCENARIO_CAVITY;
+    const dim3 blk(cfdk::kMgThreads);
+    const dim3 g_all((nx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, ny);
+    const dim3 g_int((nx - 2 + cfdk::kMgThreads - 1) / cfdk::kMgThreads, ny - 2);
+    const int n_all = (int)(g_all.x * g_all.y), n_int = (int)(g_int.x * g_int.y);
+    const Field<R>& xf = pp[ipp];
+    R* x = xf.v;
+    R* w = pp[ipp ^ 1].v;
+    cfdk::MgScalars init;
+    memset(&init, 0, sizeof init);
+    init.max_iterations = opt.consts.cg_max_iterations;
+    *h_mg = init;
+    CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index], stream));
+    CFD_CUDA(cudaMemcpyAsync(mg_scalars, h_mg, sizeof init, cudaMemcpyHostToDevice, stream));
+    cfdk::k_mg_init<R><<<g_all, blk, 0, stream>>>(c, rhs.v, x, mg_rho.v, mg_d.v, mg_partials);
+    cfdk::k_mg_reduce<R><<<1, 1024, 0, stream>>>(c, mg_scalars, mg_partials, n_all, 0);
+    launches += 2;
+    for (;;) {
+      CFD_CUDA(cudaMemcpyAsync(h_mg, mg_scalars, sizeof init, cudaMemcpyDeviceToHost, stream));
+      CFD_CUDA(cudaStreamSynchronize(stream));
+      if (h_mg->done) break;
+      int zi = 0;
+      if ((rc = mg_precondition(c, &zi))) return rc;
+      const R* z = mg_z[zi].v;
+      cfdk::k_mg_dot<R><<<g_int, blk, 0, stream>>>(c, mg_rho.v, z, mg_partials);
+      cfdk::k_mg_reduce<R><<<1, 1024, 0, stream>>>(c, mg_scalars, mg_partials, n_int, 1);
+      cfdk::k_mg_direction<R><<<g_int, blk, 0, stream>>>(c, mg_scalars, z, mg_d.v);
+      cfdk::k_mg_apply<R><<<g_int, blk, 0, stream>>>(c, mg_d.v, w, mg_partials);
+      cfdk::k_mg_reduce<R><<<1, 1024, 0, stream>>>(c, mg_scalars, mg_partials, n_int, 2);
+      cfdk::k_mg_update<R><<<g_int, blk, 0, stream>>>(c, mg_scalars, mg_d.v, w, x, mg_rho.v, mg_partials);
+      cfdk::k_mg_reduce<R><<<1, 1024, 0, stream>>>(c, mg_scalars, mg_partials, n_int, 3);
+      launches += 7;
+      CFD_CUDA(cudaGetLastError());
+    }
+    const int n_edge = (nx > ny ? nx : ny);
+    cfdk::k_cg_fill_boundary<R><<<(n_edge + 255) / 256, 256, 0, stream>>>(nx, ny, c.cavity, x, ja, jb);
+    ++launches;
+    CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index + 1], stream));
+    CFD_CUDA(cudaGetLastError());
+    last_S += (uint64_t)h_mg->iterations;
+    last_K += 1;
+    *residual_out = (R)h_mg->measure;
+    return CFD_OK;
+  }
+
   int corrector(R dt_sub, const Field<R>& us, const Field<R>& vs, const Field<R>& uk, const Field<R>& vk,
                 const Field<R>& uo, const Field<R>& vo) {
     dim3 blk(256), grd((nx + 1 + 255) / 256, v_row_end() - ja);
@@ -938,8 +1157,10 @@ struct ModelImpl final : ModelBase {
 
   // Model::set_parameters, src/model.rs:1250-1257
   int set_params(const cfd_params& prm) override {
-    if (prm.pressure_solver != CFD_SOLVER_JACOBI && prm.pressure_solver != CFD_SOLVER_CG)
+    if (prm.pressure_solver < CFD_SOLVER_JACOBI || prm.pressure_solver > CFD_SOLVER_MGCG)
       return fail(CFD_ERR_INVALID_ARGUMENT, "pressure_solver out of range");
+    if (prm.pressure_solver == CFD_SOLVER_MGCG && world > 1)
+      return fail(CFD_ERR_UNSUPPORTED, "MGCG runs on a single domain in this version (use CG on strips)");
     nu = R(prm.viscosity);
     dt = R(prm.dt);
     target_inlet_velocity = R(prm.target_inlet_velocity);
@@ -1134,9 +1355,13 @@ int cfd_model_create_ex(const cfd_grid* grid, const cfd_params* params, const cf
   if (o.consts.jacobi_iterations < 1 || o.consts.jacobi_iterations > kMaxSweepSlots)
     return fail(CFD_ERR_INVALID_ARGUMENT, "jacobi_iterations must be in 1..256");
   if (o.consts.outer_rounds < 0 || o.consts.outer_rounds > 1000) return fail(CFD_ERR_INVALID_ARGUMENT, "outer_rounds out of range");
+  if (o.consts.mg_smoothing < 1 || o.consts.mg_smoothing > 16 || !(o.consts.mg_omega > 0.0) || !(o.consts.mg_omega <= 1.0))
+    return fail(CFD_ERR_INVALID_ARGUMENT, "mg_smoothing must be in 1..16 and mg_omega in (0, 1]");
+  if (params->pressure_solver == CFD_SOLVER_MGCG && o.world_size > 1)
+    return fail(CFD_ERR_UNSUPPORTED, "MGCG runs on a single domain in this version (use CG on strips)");
   if (params->velocity_scheme < 0 || params->velocity_scheme > 1 || params->inlet_profile < 0 ||
       params->inlet_profile > 1 || params->scenario < 0 || params->scenario > 1 || params->pressure_solver < 0 ||
-      params->pressure_solver > 1)
+      params->pressure_solver > CFD_SOLVER_MGCG)
     return fail(CFD_ERR_INVALID_ARGUMENT, "params: enum value out of range");
   std::unique_ptr<cfd_model> m(new cfd_model());
   if (o.precision == 32) m->impl.reset(new ModelImpl<float>(*grid, *params, o));

@@ -24,7 +24,7 @@
 namespace cfd {
 
 enum class VelocityScheme { FirstOrder = CFD_SCHEME_FIRST_ORDER, SecondOrder = CFD_SCHEME_SECOND_ORDER };
-enum class PressureSolver { Jacobi = CFD_SOLVER_JACOBI, CG = CFD_SOLVER_CG /* extension */ };
+enum class PressureSolver { Jacobi = CFD_SOLVER_JACOBI, CG = CFD_SOLVER_CG /* extension */, MGCG = CFD_SOLVER_MGCG /* extension */ };
 enum class InletProfile { Uniform = CFD_INLET_UNIFORM, Parabolic = CFD_INLET_PARABOLIC };
 enum class Scenario { Channel = CFD_SCENARIO_CHANNEL, Cavity = CFD_SCENARIO_CAVITY /* extension */ };
 

@@ -27,6 +27,7 @@ class VelocityScheme(enum.IntEnum):
 class PressureSolver(enum.IntEnum):
     Jacobi = _abi.SOLVER_JACOBI
     CG = _abi.SOLVER_CG  # extension
+    MGCG = _abi.SOLVER_MGCG  # extension: multigrid-preconditioned CG
 
 
 class InletProfile(enum.IntEnum):

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define CFD_ABI_VERSION 1
+#define CFD_ABI_VERSION 2
 
 /* ---- status codes ---------------------------------------------------------------------------- */
 #define CFD_OK 0
@@ -40,6 +40,9 @@ extern "C" {
 /* PressureSolver, src/model.rs:149-152 (Jacobi is the reference's only variant; CG is an extension) */
 #define CFD_SOLVER_JACOBI 0
 #define CFD_SOLVER_CG 1
+/* extension: conjugate gradients preconditioned by one geometric-multigrid V-cycle (Mode C);
+ * the damped-Jacobi sweep of the reference (src/model.rs:748-815) is its smoother on the finest level */
+#define CFD_SOLVER_MGCG 2
 /* Scenario: the reference hard-codes the channel (src/model.rs:807-815,827-875); cavity is an extension */
 #define CFD_SCENARIO_CHANNEL 0
 #define CFD_SCENARIO_CAVITY 1
@@ -85,7 +88,10 @@ typedef struct cfd_solver_consts {
   double pressure_tolerance;
   double outer_tolerance;
   double cfl;
-  double cg_tolerance;       /* extension: relative L2 of the Poisson residual */
+  double cg_tolerance;       /* extension (CG, MGCG): stop when dt * rms(Poisson residual) <= this */
+  double mg_omega;           /* extension (MGCG): damping of the Jacobi smoother, default 0.8 */
+  int32_t mg_smoothing;      /* extension (MGCG): pre- and post-smoothing sweeps per level, default 2 */
+  int32_t mg_reserved;
 } cfd_solver_consts;
 
 typedef struct cfd_options {

@@ -80,6 +80,16 @@ class Model {
   StripHooks<R> hooks;
   // CG work vectors (extension)
   std::vector<R> cg_r, cg_d, cg_q;
+  // multigrid-preconditioned CG work space (extension), see mgcg_pressure
+  struct MgLevel {
+    size_t mx = 0, my = 0;            // unknowns per direction
+    std::vector<R> wx, hy;            // cell widths / heights in finest-cell units
+    std::vector<R> WE, WW, CYW;       // per column: east / west link factors, wx / dy^2
+    std::vector<R> WN, WS, CXH;       // per row: north / south link factors, hy / dx^2
+    std::vector<R> e, rho, tmp;       // (mx + 2) x (my + 2) with a ring of zeros (levels >= 1)
+  };
+  std::vector<MgLevel> mg_levels;
+  std::vector<R> mg_rho, mg_d, mg_w, mg_z, mg_z2;
 
   // Model::new, src/model.rs:219-299
   Model(const cfd_grid& g, const cfd_params& prm, const cfd_solver_consts* c = nullptr) {
@@ -148,6 +158,9 @@ class Model {
     c->outer_tolerance = 1e-4;    // :721
     c->cfl = 0.2;                 // :885
     c->cg_tolerance = 1e-8;
+    c->mg_omega = 0.8;
+    c->mg_smoothing = 2;
+    c->mg_reserved = 0;
   }
 
   // Model::set_parameters, src/model.rs:1250-1257
@@ -236,6 +249,7 @@ class Model {
   R pressure_solve(R dt_sub) {
     last_jacobi_calls += 1;
     if (pressure_solver == CFD_SOLVER_CG) return cg_pressure(dt_sub);
+    if (pressure_solver == CFD_SOLVER_MGCG) return mgcg_pressure(dt_sub);
     return jacobi_pressure();
   }
 
@@ -675,6 +689,232 @@ class Model {
       ++it;
       last_sweeps += 1;
       total_sweeps += 1;
+    }
+    cg_fill_boundary(p_prime);
+    const R res = measure(rr);
+    last_pressure_residual = res;
+    return res;
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // EXTENSION (no reference counterpart; "Mode C" in DESIGN.md): conjugate gradients preconditioned by one
+  // geometric-multigrid V-cycle, on the same discrete problem as cg_pressure, in the reference's own sign
+  // convention: L x = rhs with (L x)[i,j] = ((xE - x) + (xW - x))/dx^2 + ((xN - x) + (xS - x))/dy^2 under the
+  // Jacobi boundary rules (mirror left / bottom / top, zero outlet column; cavity: mirror there too).
+  //  * Level 0 = the grid itself; its smoother is the reference's damped-Jacobi sweep (jacobi_sweep's
+  //    formula + jacobi_swap_and_bc's boundary update) with damping mg_omega.
+  //  * Level l+1 pairs the cells of level l per direction (a trailing single cell stays single when the
+  //    count is odd), down to 1 x 1.  Coarse operators are finite-volume discretisations on that
+  //    (non-uniform) tensor grid: a link between neighbours weighs (shared face) / (centre distance), in
+  //    finest-cell units; the outlet's zero sits half a finest cell beyond the last column.
+  //  * Transfer: residuals are summed over the (up to four) children, corrections are copied to them.
+  //  * V(n,n) with n = mg_smoothing damped-Jacobi sweeps before and after; the first sweep starts from zero.
+  // Same start (x = 0), stopping rule and return value as cg_pressure.
+  // ------------------------------------------------------------------------------------------------
+  void mg_build_levels() {
+    mg_levels.clear();
+    const R dx_sq = dx * dx, dy_sq = dy * dy;
+    std::vector<R> wx(nx - 2, R(1)), hy(ny - 2, R(1));
+    for (;;) {
+      MgLevel L;
+      L.mx = wx.size(); L.my = hy.size();
+      L.wx = wx; L.hy = hy;
+      L.WE.assign(L.mx, R(0)); L.WW.assign(L.mx, R(0)); L.CYW.assign(L.mx, R(0));
+      L.WN.assign(L.my, R(0)); L.WS.assign(L.my, R(0)); L.CXH.assign(L.my, R(0));
+      for (size_t i = 0; i < L.mx; ++i) {
+        if (i + 1 < L.mx) L.WE[i] = R(1) / (R(0.5) * (wx[i] + wx[i + 1]));
+        else if (scenario != CFD_SCENARIO_CAVITY) L.WE[i] = R(1) / (R(0.5) * wx[i] + R(0.5));
+        if (i > 0) L.WW[i] = R(1) / (R(0.5) * (wx[i - 1] + wx[i]));
+        L.CYW[i] = wx[i] / dy_sq;
+      }
+      for (size_t j = 0; j < L.my; ++j) {
+        if (j + 1 < L.my) L.WN[j] = R(1) / (R(0.5) * (hy[j] + hy[j + 1]));
+        if (j > 0) L.WS[j] = R(1) / (R(0.5) * (hy[j - 1] + hy[j]));
+        L.CXH[j] = hy[j] / dx_sq;
+      }
+      if (!mg_levels.empty()) {
+        const size_t n = (L.mx + 2) * (L.my + 2);
+        L.e.assign(n, R(0)); L.rho.assign(n, R(0)); L.tmp.assign(n, R(0));
+      }
+      mg_levels.push_back(std::move(L));
+      if (wx.size() == 1 && hy.size() == 1) break;
+      auto pair_up = [](const std::vector<R>& w) {
+        std::vector<R> o((w.size() + 1) / 2, R(0));
+        for (size_t k = 0; k < o.size(); ++k) o[k] = w[2 * k] + (2 * k + 1 < w.size() ? w[2 * k + 1] : R(0));
+        return o;
+      };
+      wx = pair_up(wx);
+      hy = pair_up(hy);
+    }
+  }
+
+  // one damped-Jacobi sweep of level 0: jacobi_sweep's formula on (in, rh) -> out, then the boundary update
+  void mg_fine_sweep(const std::vector<R>& in, const std::vector<R>& rh, std::vector<R>& out) {
+    const R omega = R(consts.mg_omega);
+    const R one_minus = R(1.0) - omega;
+    const R dx_sq = dx * dx, dy_sq = dy * dy;
+    const R denom = R(2.0) / (dx * dx) + R(2.0) / (dy * dy);
+    for (size_t j = 1; j + 1 < ny; ++j)
+      for (size_t i = 1; i < nx; ++i) {
+        const size_t idx = i + j * nx;
+        const R center = in[idx];
+        const R horizontal = (in[idx + 1] + in[idx - 1]) / dx_sq;
+        const R vertical = (in[idx + nx] + in[idx - nx]) / dy_sq;
+        const R p_update = (horizontal + vertical - rh[idx]) / denom;
+        out[idx] = omega * p_update + one_minus * center;
+      }
+    mg_fill_ring(out);
+  }
+  void mg_fill_ring(std::vector<R>& x) {  // jacobi_swap_and_bc's boundary update (rows, then columns)
+    for (size_t i = 0; i < nx; ++i) {
+      x[i] = x[i + nx];
+      x[i + (ny - 1) * nx] = x[i + (ny - 2) * nx];
+    }
+    for (size_t j = 0; j < ny; ++j) {
+      x[j * nx] = x[1 + j * nx];
+      x[(nx - 1) + j * nx] = scenario == CFD_SCENARIO_CAVITY ? x[(nx - 2) + j * nx] : R(0);
+    }
+  }
+  // (L x)[i,j] on an unknown, neighbours outside the unknowns replaced by the boundary rules
+  R mg_fine_apply(const std::vector<R>& x, size_t i, size_t j) const {
+    const R dx_sq = dx * dx, dy_sq = dy * dy;
+    const size_t idx = i + j * nx;
+    const R c = x[idx];
+    const R xe = (i == nx - 2) ? (scenario == CFD_SCENARIO_CAVITY ? c : R(0)) : x[idx + 1];
+    const R xw = (i == 1) ? c : x[idx - 1];
+    const R xn = (j == ny - 2) ? c : x[idx + nx];
+    const R xs = (j == 1) ? c : x[idx - nx];
+    return ((xe - c) + (xw - c)) / dx_sq + ((xn - c) + (xs - c)) / dy_sq;
+  }
+
+  static R mg_coarse_apply(const MgLevel& L, const std::vector<R>& e, size_t I, size_t J) {
+    const size_t W = L.mx + 2, idx = (I + 1) + (J + 1) * W;
+    const R c = e[idx];
+    return L.CXH[J] * (L.WE[I] * (e[idx + 1] - c) + L.WW[I] * (e[idx - 1] - c)) +
+           L.CYW[I] * (L.WN[J] * (e[idx + W] - c) + L.WS[J] * (e[idx - W] - c));
+  }
+  static void mg_coarse_sweep(const MgLevel& L, const std::vector<R>& in, const std::vector<R>& rho, std::vector<R>& out,
+                              R omega) {
+    const size_t W = L.mx + 2;
+    for (size_t J = 0; J < L.my; ++J)
+      for (size_t I = 0; I < L.mx; ++I) {
+        const size_t idx = (I + 1) + (J + 1) * W;
+        const R diag = L.CXH[J] * (L.WE[I] + L.WW[I]) + L.CYW[I] * (L.WN[J] + L.WS[J]);
+        const R c = in[idx];
+        out[idx] = diag > R(0) ? c + omega * ((mg_coarse_apply(L, in, I, J) - rho[idx]) / diag) : R(0);
+      }
+  }
+
+  // e <- approximately L_l^-1 rho on level l >= 1 (result in mg_levels[l].e)
+  void mg_coarse_vcycle(size_t l) {
+    MgLevel& L = mg_levels[l];
+    const R omega = R(consts.mg_omega);
+    const int nu_s = consts.mg_smoothing < 1 ? 1 : consts.mg_smoothing;
+    std::fill(L.e.begin(), L.e.end(), R(0));
+    if (L.mx == 1 && L.my == 1) {  // exact: e = -rho / diag (0 for the singular all-Neumann cavity)
+      mg_coarse_sweep(L, L.e, L.rho, L.tmp, R(1));
+      std::swap(L.e, L.tmp);
+      return;
+    }
+    for (int s = 0; s < nu_s; ++s) { mg_coarse_sweep(L, L.e, L.rho, L.tmp, omega); std::swap(L.e, L.tmp); }
+    MgLevel& C = mg_levels[l + 1];
+    const size_t WC = C.mx + 2, W = L.mx + 2;
+    for (size_t J = 0; J < C.my; ++J)
+      for (size_t I = 0; I < C.mx; ++I) {
+        R acc = R(0);
+        for (size_t b = 0; b < 2; ++b)
+          for (size_t a = 0; a < 2; ++a) {
+            const size_t i = 2 * I + a, j = 2 * J + b;
+            if (i < L.mx && j < L.my) acc += L.rho[(i + 1) + (j + 1) * W] - mg_coarse_apply(L, L.e, i, j);
+          }
+        C.rho[(I + 1) + (J + 1) * WC] = acc;
+      }
+    mg_coarse_vcycle(l + 1);
+    for (size_t j = 0; j < L.my; ++j)
+      for (size_t i = 0; i < L.mx; ++i) L.e[(i + 1) + (j + 1) * W] += C.e[(i / 2 + 1) + (j / 2 + 1) * WC];
+    for (int s = 0; s < nu_s; ++s) { mg_coarse_sweep(L, L.e, L.rho, L.tmp, omega); std::swap(L.e, L.tmp); }
+  }
+
+  // mg_z <- V-cycle applied to mg_rho
+  void mg_precondition() {
+    const int nu_s = consts.mg_smoothing < 1 ? 1 : consts.mg_smoothing;
+    std::fill(mg_z.begin(), mg_z.end(), R(0));
+    for (int s = 0; s < nu_s; ++s) { mg_fine_sweep(mg_z, mg_rho, mg_z2); std::swap(mg_z, mg_z2); }
+    if (mg_levels.size() > 1) {
+      MgLevel& C = mg_levels[1];
+      const size_t WC = C.mx + 2;
+      for (size_t J = 0; J < C.my; ++J)
+        for (size_t I = 0; I < C.mx; ++I) {
+          R acc = R(0);
+          for (size_t b = 0; b < 2; ++b)
+            for (size_t a = 0; a < 2; ++a) {
+              const size_t i = 1 + 2 * I + a, j = 1 + 2 * J + b;
+              if (i <= nx - 2 && j <= ny - 2) acc += mg_rho[i + j * nx] - mg_fine_apply(mg_z, i, j);
+            }
+          C.rho[(I + 1) + (J + 1) * WC] = acc;
+        }
+      mg_coarse_vcycle(1);
+      for (size_t j = 1; j + 1 < ny; ++j)
+        for (size_t i = 1; i + 1 < nx; ++i) mg_z[i + j * nx] += C.e[((i - 1) / 2 + 1) + ((j - 1) / 2 + 1) * WC];
+      mg_fill_ring(mg_z);
+    }
+    for (int s = 0; s < nu_s; ++s) { mg_fine_sweep(mg_z, mg_rho, mg_z2); std::swap(mg_z, mg_z2); }
+  }
+
+  R mgcg_pressure(R dt_sub) {
+    assert(!hooks.exchange && "MGCG is single-domain in this round");
+    const size_t n = nx * ny;
+    if (mg_levels.empty()) mg_build_levels();
+    if (mg_rho.size() != n) {
+      mg_rho.assign(n, R(0)); mg_d.assign(n, R(0)); mg_w.assign(n, R(0)); mg_z.assign(n, R(0)); mg_z2.assign(n, R(0));
+    }
+    const R n_unknowns = R((nx - 2) * (ny - 2));
+    const R tol = R(consts.cg_tolerance);
+    auto measure = [&](R rr_) { return dt_sub * std::sqrt(rr_ / n_unknowns); };
+    // dot products: row sums, then over rows (the CUDA path sums in another order -> tolerance parity)
+    auto dot = [&](const std::vector<R>& a, const std::vector<R>& b) {
+      R acc = 0;
+      for (size_t j = 1; j + 1 < ny; ++j) {
+        R row = 0;
+        for (size_t i = 1; i + 1 < nx; ++i) row += a[i + j * nx] * b[i + j * nx];
+        acc += row;
+      }
+      return acc;
+    };
+    std::fill(p_prime.begin(), p_prime.end(), R(0));
+    std::fill(mg_rho.begin(), mg_rho.end(), R(0));
+    std::fill(mg_d.begin(), mg_d.end(), R(0));
+    for (size_t j = 1; j + 1 < ny; ++j)
+      for (size_t i = 1; i + 1 < nx; ++i) mg_rho[i + j * nx] = rhs[i + j * nx];
+    R rr = dot(mg_rho, mg_rho);
+    int it = 0;
+    if (!(measure(rr) <= tol) && consts.cg_max_iterations > 0) {
+      mg_precondition();
+      R rz = dot(mg_rho, mg_z);
+      for (size_t k = 0; k < n; ++k) mg_d[k] = mg_z[k] + R(0) * mg_d[k];
+      for (;;) {
+        for (size_t j = 1; j + 1 < ny; ++j)
+          for (size_t i = 1; i + 1 < nx; ++i) mg_w[i + j * nx] = mg_fine_apply(mg_d, i, j);
+        const R dw = dot(mg_d, mg_w);
+        const R alpha = rz / dw;
+        for (size_t j = 1; j + 1 < ny; ++j)
+          for (size_t i = 1; i + 1 < nx; ++i) {
+            const size_t idx = i + j * nx;
+            p_prime[idx] = p_prime[idx] + alpha * mg_d[idx];
+            mg_rho[idx] = mg_rho[idx] - alpha * mg_w[idx];
+          }
+        rr = dot(mg_rho, mg_rho);
+        ++it;
+        last_sweeps += 1;
+        total_sweeps += 1;
+        if (measure(rr) <= tol || it >= consts.cg_max_iterations) break;
+        mg_precondition();
+        const R rz_new = dot(mg_rho, mg_z);
+        const R beta = rz_new / rz;
+        for (size_t j = 1; j + 1 < ny; ++j)
+          for (size_t i = 1; i + 1 < nx; ++i) mg_d[i + j * nx] = mg_z[i + j * nx] + beta * mg_d[i + j * nx];
+        rz = rz_new;
+      }
     }
     cg_fill_boundary(p_prime);
     const R res = measure(rr);

@@ -305,3 +305,70 @@ def test_full_size_saturated_step_bit_exact_2048():
     assert_fields_identical(gpu, cpu, STATE_FIELDS, "2048^2 saturated step")
     pp = gpu.field(_abi.FIELD_P_PRIME).reshape(2048, 2048)
     assert np.abs(pp[:, :-1]).min() > 0 and not pp[:, -1].any()  # dense: no untouched zero regions (outlet column is 0)
+
+
+@pytest.mark.parametrize("scenario", [Scenario.Channel, Scenario.Cavity])
+@pytest.mark.parametrize("shape", [(64, 64), (128, 93), (48, 6), (512, 512)])
+def test_mode_c_mgcg_matches_oracle_to_tolerance(scenario, shape):
+    """Mode C fast path (multigrid-preconditioned CG, an extension): smoother, transfers and coarse operators are
+    bit-identical to the oracle's, only the dot products are summed in another order -> tolerance parity
+    (north_star: relative L2 <= 1e-9 after N steps when both sides converge the Poisson solve to the same
+    residual; here dt*rms(r) <= 1e-12), same iteration counts."""
+    from cfd_demo_b200.model import default_options
+    from cfd_demo_b200.types import PressureSolver
+    from oracle.cpu_oracle import default_consts
+    nx, ny = shape
+    g = Grid.uniform(nx, ny, nx / 64.0, ny / 64.0, None) if scenario == Scenario.Cavity else channel_grid(nx, ny, lx=nx / 16.0, ly=ny / 16.0, cylinder=nx >= 64)
+    prm = SimulationParams(dt=1e-3, viscosity=0.01, scenario=scenario, pressure_solver=PressureSolver.MGCG,
+                           velocity_scheme=VelocityScheme.SecondOrder)
+    consts = default_consts()
+    consts.cg_tolerance = 1e-12
+    o = default_options()
+    o.consts = consts
+    gpu = Model(g, prm, options=o)
+    cpu = OracleModel(g, prm, precision=64, consts=consts)
+    for s in range(6 if nx >= 512 else 12):
+        gpu.update()
+        cpu.update()
+        rg, rc = gpu.get_residuals(), cpu.get_residuals()
+        assert rg.jacobi_calls == rc.jacobi_calls == 2
+        assert abs(rg.sweeps - rc.sweeps) <= 1 and rg.sweeps <= 20 and rg.f64["p"] <= 1e-12, (s, rg.sweeps, rc.sweeps)
+    for fid in (_abi.FIELD_U, _abi.FIELD_V, _abi.FIELD_P):
+        a, b = gpu.field(fid), cpu.field(fid)
+        assert np.isfinite(a).all() and np.abs(b).max() > 0
+        assert rel_l2(a, b) <= 1e-9, (_abi.FIELD_NAMES[fid], rel_l2(a, b))
+
+
+def test_mode_c_mgcg_first_vcycle_is_bit_identical():
+    """With cg_max_iterations = 1 the solve is ONE preconditioned step x = alpha * V(rhs): everything in V (the
+    reference's Jacobi sweep as smoother, restriction, coarse sweeps, prolongation) is order-free arithmetic, so
+    p' must agree with the oracle up to the single scalar alpha (two dot products)."""
+    from cfd_demo_b200.model import default_options
+    from cfd_demo_b200.types import PressureSolver
+    from oracle.cpu_oracle import default_consts
+    g = channel_grid(136, 61, lx=13.6, ly=6.1)
+    prm = SimulationParams(dt=1e-3, viscosity=0.01, pressure_solver=PressureSolver.MGCG)
+    consts = default_consts()
+    consts.cg_max_iterations = 1
+    consts.outer_rounds = 0
+    o = default_options()
+    o.consts = consts
+    gpu = Model(g, prm, options=o)
+    cpu = OracleModel(g, prm, precision=64, consts=consts)
+    for _ in range(3):
+        gpu.update()
+        cpu.update()
+    a, b = gpu.field(_abi.FIELD_P_PRIME), cpu.field(_abi.FIELD_P_PRIME)
+    k = np.argmax(np.abs(b))
+    ratio = a[k] / b[k]
+    assert abs(ratio - 1.0) < 1e-12
+    assert np.abs(a - ratio * b).max() <= 4e-16 * np.abs(b).max()
+
+
+def test_mgcg_rejects_strips_and_bad_constants():
+    from cfd_demo_b200.model import CfdError, default_options
+    from cfd_demo_b200.types import PressureSolver
+    o = default_options()
+    o.consts.mg_smoothing = 0
+    with pytest.raises(CfdError):
+        Model(box_grid(32), SimulationParams(pressure_solver=PressureSolver.MGCG), options=o)

@@ -193,3 +193,36 @@ def test_mode_c_cg_leaves_a_divergence_free_interior(scenario):
     # velocities BEFORE the boundary update are what the solve made divergence free; check rows/cols away from it
     div = (u[2:n - 2, 3:n - 1] - u[2:n - 2, 2:n - 2]) / g.dx + (v[3:n - 1, 2:n - 2] - v[2:n - 2, 2:n - 2]) / g.dy
     assert np.abs(div).max() < 1e-6 and np.abs(u).max() > 1e-3
+
+
+@pytest.mark.parametrize("scenario", [Scenario.Channel, Scenario.Cavity])
+@pytest.mark.parametrize("shape", [(64, 64), (48, 37), (40, 6)])
+def test_mode_c_mgcg_agrees_with_cg_and_needs_few_iterations(scenario, shape):
+    """Extension: multigrid-preconditioned CG solves the same discrete problem as CG (velocities agree to the
+    solver tolerance; the all-Neumann cavity pressure is defined up to a constant) in an (almost) grid-independent
+    handful of iterations, including odd unknown counts (trailing single-cell aggregates) and thin grids."""
+    from cfd_demo_b200.types import PressureSolver
+    nx, ny = shape
+    g = Grid.uniform(nx, ny, nx / 64.0, ny / 64.0, None) if scenario == Scenario.Cavity else channel_grid(nx, ny, lx=nx / 16.0, ly=ny / 16.0, cylinder=nx >= 48)
+    consts = default_consts()
+    consts.cg_tolerance = 1e-12
+    out = {}
+    for solver in (PressureSolver.CG, PressureSolver.MGCG):
+        prm = SimulationParams(dt=1e-3, viscosity=0.01, scenario=scenario, pressure_solver=solver)
+        m = OracleModel(g, prm, precision=64, consts=consts)
+        its = 0
+        for _ in range(8):
+            m.update()
+            r = m.get_residuals()
+            assert r.jacobi_calls == 2 and r.f64["p"] <= 1e-12
+            its = max(its, r.sweeps)
+        out[solver] = (m.field(_abi.FIELD_U), m.field(_abi.FIELD_V), m.field(_abi.FIELD_P), its)
+    cg, mg = out[PressureSolver.CG], out[PressureSolver.MGCG]
+    assert 0 < mg[3] <= 16 and mg[3] < cg[3], (mg[3], cg[3])
+    assert np.abs(cg[0]).max() > 1e-4
+    for k in range(2):
+        assert np.linalg.norm(cg[k] - mg[k]) <= 1e-8 * np.linalg.norm(cg[0]), k
+    dp = (cg[2] - mg[2]).reshape(ny, nx)[1:ny - 1, 1:nx - 1]
+    if scenario == Scenario.Cavity:
+        dp = dp - dp.mean()
+    assert np.abs(dp).max() <= 1e-7 * max(np.abs(cg[2]).max(), 1e-30) + 1e-12
