@@ -38,28 +38,109 @@ struct MgLevelDev {
 };
 
 constexpr int kMgThreads = 256;
+constexpr int kMgRows = 8;  // rows per block of the level-0 vector kernels
 
-// ---- level 0 vector kernels (grid: (ceil(nx / 256), ny) for init, (ceil((nx - 2) / 256), ny - 2) otherwise) ----
-
-// x = 0, d = 0, rho = rhs on the unknowns (0 on the ring), partial rho.rho per block
+// ---- level 0 vector kernels ----------------------------------------------------------------------------
+// A thread owns the aligned column pair (2t, 2t+1) (16-byte loads / stores; the ring columns 0 and nx-1 are
+// masked out) and walks kMgRows rows; grid = (ceil(nx / 512), ceil((ny - 2) / kMgRows)).  Dot products: every
+// thread accumulates its cells in a fixed order, a block reduces to ONE partial, and the block that finishes
+// last (ticket) sums the partials in index order and advances the CG scalars — deterministic, no extra launch.
 template <class R>
-__global__ void __launch_bounds__(kMgThreads) k_mg_init(MgFine<R> c, const R* __restrict__ rhs, R* __restrict__ x,
-                                                         R* __restrict__ rho, R* __restrict__ d,
-                                                         double* __restrict__ partials) {
-  __shared__ double s_red[kMgThreads / 32];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
-  double acc = 0.0;
-  if (i < c.nx) {
-    const size_t idx = (size_t)i + (size_t)j * c.nx;
-    const bool unknown = (i >= 1 && i <= c.nx - 2 && j >= 1 && j <= c.ny - 2);
-    const R b = unknown ? rhs[idx] : R(0);
-    x[idx] = R(0);
-    d[idx] = R(0);
-    rho[idx] = b;
-    acc = (double)(b * b);
+struct MgPair {
+  int c0, j0, j1;
+  bool v0, v1, any;
+};
+template <class R>
+__device__ __forceinline__ MgPair<R> mg_pair(const MgFine<R>& c) {
+  MgPair<R> p;
+  p.c0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  p.j0 = 1 + blockIdx.y * kMgRows;
+  p.j1 = min(p.j0 + kMgRows, c.ny - 1);
+  p.any = p.c0 < c.nx;
+  p.v0 = p.any && p.c0 >= 1;
+  p.v1 = p.any && p.c0 + 1 <= c.nx - 2;
+  return p;
+}
+
+// mode 0: rho.rho after init; 1: rho.z -> beta (0 before the first iteration); 2: d.w -> alpha;
+// 3: rho.rho after the update -> iteration count, stopping rule (same measure as k_cg_reduce)
+template <class R>
+__device__ __forceinline__ void mg_advance(const MgFine<R>& c, MgScalars* sc, double total, int mode) {
+  const R sum = (R)total;
+  if (mode == 1) {
+    sc->beta = sc->iterations == 0 ? 0.0 : (double)(sum / (R)sc->rz);
+    sc->rz = (double)sum;
+  } else if (mode == 2) {
+    sc->dw = (double)sum;
+    sc->alpha = (double)((R)sc->rz / sum);
+  } else {
+    if (mode == 3) sc->iterations += 1;
+    sc->rr = (double)sum;
+    const R measure = c.dt * (R)sqrt((double)(sum / c.n_unknowns));
+    sc->measure = (double)measure;
+    if (measure <= c.tol || sc->iterations >= sc->max_iterations) sc->done = 1;
   }
+}
+
+template <class R>
+__device__ __forceinline__ void mg_finish_dot(const MgFine<R>& c, MgScalars* sc, double* partials, unsigned* ticket,
+                                              double acc, int mode) {
+  __shared__ double s_red[kMgThreads / 32];
+  __shared__ int s_last;
+  const int n_blocks = (int)(gridDim.x * gridDim.y), bid = (int)(blockIdx.y * gridDim.x + blockIdx.x);
   const double t = block_sum<kMgThreads / 32>(acc, s_red);
-  if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = t;
+  if (threadIdx.x == 0) {
+    partials[bid] = t;
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == (unsigned)(n_blocks - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double a = 0.0;
+  for (int k = threadIdx.x; k < n_blocks; k += kMgThreads) a += __ldcg(partials + k);
+  const double total = block_sum<kMgThreads / 32>(a, s_red);
+  if (threadIdx.x == 0) {
+    mg_advance<R>(c, sc, total, mode);
+    *ticket = 0u;
+  }
+}
+
+// x = 0, d = 0 on the whole grid, rho = rhs on the unknowns (0 on the ring), rho.rho.
+// grid = (ceil(nx / 512), ceil(ny / kMgRows))
+template <class R>
+__global__ void __launch_bounds__(kMgThreads) k_mg_init(MgFine<R> c, MgScalars* __restrict__ sc,
+                                                         const R* __restrict__ rhs, R* __restrict__ x,
+                                                         R* __restrict__ rho, R* __restrict__ d,
+                                                         double* __restrict__ partials, unsigned* __restrict__ ticket) {
+  using V = typename Vec2<R>::type;
+  const int c0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int j0 = blockIdx.y * kMgRows, j1 = min(j0 + kMgRows, c.ny);
+  double acc = 0.0;
+  if (c0 < c.nx) {
+    V zero;
+    zero.x = R(0); zero.y = R(0);
+    for (int j = j0; j < j1; ++j) {
+      const size_t idx = (size_t)c0 + (size_t)j * c.nx;
+      const bool row_ok = j >= 1 && j <= c.ny - 2;
+      V b = *reinterpret_cast<const V*>(rhs + idx);
+      if (!(row_ok && c0 >= 1)) b.x = R(0);
+      if (!(row_ok && c0 + 1 <= c.nx - 2)) b.y = R(0);
+      *reinterpret_cast<V*>(x + idx) = zero;
+      *reinterpret_cast<V*>(d + idx) = zero;
+      *reinterpret_cast<V*>(rho + idx) = b;
+      acc += (double)(b.x * b.x);
+      acc += (double)(b.y * b.y);
+    }
+  }
+  mg_finish_dot<R>(c, sc, partials, ticket, acc, 0);
+}
+
+// (L x) on the unknowns of one column pair; l / r = the columns left / right of the pair, already replaced by the
+// boundary rules where the pair touches the ring (mirror; 0 at the channel outlet)
+template <class R>
+__device__ __forceinline__ R mg_lap(const MgFine<R>& c, R cc, R xe, R xw, R xn, R xs) {
+  return ((xe - cc) + (xw - cc)) / c.dx_sq + ((xn - cc) + (xs - cc)) / c.dy_sq;
 }
 
 template <class R>
@@ -70,99 +151,139 @@ __device__ __forceinline__ R mg_fine_apply(const MgFine<R>& c, const R* __restri
   const R xw = (i == 1) ? cc : x[idx - 1];
   const R xn = (j == c.ny - 2) ? cc : x[idx + c.nx];
   const R xs = (j == 1) ? cc : x[idx - c.nx];
-  return ((xe - cc) + (xw - cc)) / c.dx_sq + ((xn - cc) + (xs - cc)) / c.dy_sq;
+  return mg_lap<R>(c, cc, xe, xw, xn, xs);
 }
 
-// partial a.b over the unknowns
+// rho.z -> beta, rz
 template <class R>
-__global__ void __launch_bounds__(kMgThreads) k_mg_dot(MgFine<R> c, const R* __restrict__ a, const R* __restrict__ b,
-                                                        double* __restrict__ partials) {
-  __shared__ double s_red[kMgThreads / 32];
-  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y;
+__global__ void __launch_bounds__(kMgThreads) k_mg_dot(MgFine<R> c, MgScalars* __restrict__ sc, const R* __restrict__ a,
+                                                        const R* __restrict__ b, double* __restrict__ partials,
+                                                        unsigned* __restrict__ ticket, int mode) {
+  using V = typename Vec2<R>::type;
+  const MgPair<R> p = mg_pair<R>(c);
   double acc = 0.0;
-  if (i <= c.nx - 2) {
-    const size_t idx = (size_t)i + (size_t)j * c.nx;
-    acc = (double)(a[idx] * b[idx]);
+  if (p.any) {
+    for (int j = p.j0; j < p.j1; ++j) {
+      const size_t idx = (size_t)p.c0 + (size_t)j * c.nx;
+      const V av = *reinterpret_cast<const V*>(a + idx), bv = *reinterpret_cast<const V*>(b + idx);
+      if (p.v0) acc += (double)(av.x * bv.x);
+      if (p.v1) acc += (double)(av.y * bv.y);
+    }
   }
-  const double t = block_sum<kMgThreads / 32>(acc, s_red);
-  if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = t;
+  mg_finish_dot<R>(c, sc, partials, ticket, acc, mode);
 }
 
 // d = z + beta d
 template <class R>
 __global__ void __launch_bounds__(kMgThreads) k_mg_direction(MgFine<R> c, const MgScalars* __restrict__ sc,
                                                               const R* __restrict__ z, R* __restrict__ d) {
+  using V = typename Vec2<R>::type;
   const R beta = (R)sc->beta;
-  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y;
-  if (i <= c.nx - 2) {
-    const size_t idx = (size_t)i + (size_t)j * c.nx;
-    d[idx] = z[idx] + beta * d[idx];
+  const MgPair<R> p = mg_pair<R>(c);
+  if (!p.any) return;
+  for (int j = p.j0; j < p.j1; ++j) {
+    const size_t idx = (size_t)p.c0 + (size_t)j * c.nx;
+    const V zv = *reinterpret_cast<const V*>(z + idx);
+    V dv = *reinterpret_cast<const V*>(d + idx);
+    if (p.v0) dv.x = zv.x + beta * dv.x;
+    if (p.v1) dv.y = zv.y + beta * dv.y;
+    *reinterpret_cast<V*>(d + idx) = dv;
   }
 }
 
-// w = L d, partial d.w
+// w = L d, d.w -> alpha
 template <class R>
-__global__ void __launch_bounds__(kMgThreads) k_mg_apply(MgFine<R> c, const R* __restrict__ d, R* __restrict__ w,
-                                                          double* __restrict__ partials) {
-  __shared__ double s_red[kMgThreads / 32];
-  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y;
+__global__ void __launch_bounds__(kMgThreads) k_mg_apply(MgFine<R> c, MgScalars* __restrict__ sc, const R* __restrict__ d,
+                                                          R* __restrict__ w, double* __restrict__ partials,
+                                                          unsigned* __restrict__ ticket) {
+  using V = typename Vec2<R>::type;
+  const MgPair<R> p = mg_pair<R>(c);
   double acc = 0.0;
-  if (i <= c.nx - 2) {
-    const size_t idx = (size_t)i + (size_t)j * c.nx;
-    const R lw = mg_fine_apply<R>(c, d, i, j);
-    w[idx] = lw;
-    acc = (double)(d[idx] * lw);
+  if (p.any) {
+    const int nx = c.nx;
+    const R* col = d + p.c0;
+    V south = *reinterpret_cast<const V*>(col + (size_t)(p.j0 - 1) * nx);
+    V cen = *reinterpret_cast<const V*>(col + (size_t)p.j0 * nx);
+    for (int j = p.j0; j < p.j1; ++j) {
+      const size_t row = (size_t)j * nx;
+      const V north = *reinterpret_cast<const V*>(col + row + nx);
+      V out;
+      out.x = R(0); out.y = R(0);
+      if (p.v0) {
+        const R xw = (p.c0 == 1) ? cen.x : col[row - 1];
+        const R xe = (p.c0 == nx - 2) ? (c.cavity ? cen.x : R(0)) : cen.y;
+        const R xn = (j == c.ny - 2) ? cen.x : north.x, xs = (j == 1) ? cen.x : south.x;
+        out.x = mg_lap<R>(c, cen.x, xe, xw, xn, xs);
+        acc += (double)(cen.x * out.x);
+      }
+      if (p.v1) {
+        const R xw = (p.c0 + 1 == 1) ? cen.y : cen.x;
+        const R xe = (p.c0 + 1 == nx - 2) ? (c.cavity ? cen.y : R(0)) : col[row + 2];
+        const R xn = (j == c.ny - 2) ? cen.y : north.y, xs = (j == 1) ? cen.y : south.y;
+        out.y = mg_lap<R>(c, cen.y, xe, xw, xn, xs);
+        acc += (double)(cen.y * out.y);
+      }
+      *reinterpret_cast<V*>(w + p.c0 + row) = out;
+      south = cen;
+      cen = north;
+    }
   }
-  const double t = block_sum<kMgThreads / 32>(acc, s_red);
-  if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = t;
+  mg_finish_dot<R>(c, sc, partials, ticket, acc, 2);
 }
 
-// x += alpha d, rho -= alpha w, partial rho.rho
+// x += alpha d, rho -= alpha w, rho.rho -> iteration count, stopping rule
 template <class R>
-__global__ void __launch_bounds__(kMgThreads) k_mg_update(MgFine<R> c, const MgScalars* __restrict__ sc,
+__global__ void __launch_bounds__(kMgThreads) k_mg_update(MgFine<R> c, MgScalars* __restrict__ sc,
                                                            const R* __restrict__ d, const R* __restrict__ w,
                                                            R* __restrict__ x, R* __restrict__ rho,
-                                                           double* __restrict__ partials) {
-  __shared__ double s_red[kMgThreads / 32];
+                                                           double* __restrict__ partials, unsigned* __restrict__ ticket) {
+  using V = typename Vec2<R>::type;
   const R alpha = (R)sc->alpha;
-  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y;
+  const MgPair<R> p = mg_pair<R>(c);
   double acc = 0.0;
-  if (i <= c.nx - 2) {
-    const size_t idx = (size_t)i + (size_t)j * c.nx;
-    x[idx] = x[idx] + alpha * d[idx];
-    const R rn = rho[idx] - alpha * w[idx];
-    rho[idx] = rn;
-    acc = (double)(rn * rn);
+  if (p.any) {
+    for (int j = p.j0; j < p.j1; ++j) {
+      const size_t idx = (size_t)p.c0 + (size_t)j * c.nx;
+      const V dv = *reinterpret_cast<const V*>(d + idx), wv = *reinterpret_cast<const V*>(w + idx);
+      V xv = *reinterpret_cast<const V*>(x + idx), rv = *reinterpret_cast<const V*>(rho + idx);
+      if (p.v0) {
+        xv.x = xv.x + alpha * dv.x;
+        rv.x = rv.x - alpha * wv.x;
+        acc += (double)(rv.x * rv.x);
+      }
+      if (p.v1) {
+        xv.y = xv.y + alpha * dv.y;
+        rv.y = rv.y - alpha * wv.y;
+        acc += (double)(rv.y * rv.y);
+      }
+      *reinterpret_cast<V*>(x + idx) = xv;
+      *reinterpret_cast<V*>(rho + idx) = rv;
+    }
   }
-  const double t = block_sum<kMgThreads / 32>(acc, s_red);
-  if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = t;
+  mg_finish_dot<R>(c, sc, partials, ticket, acc, 3);
 }
 
-// one block: sums the per-block partials in a fixed order, then advances the scalars.
-// mode 0: rho.rho after init; 1: rho.z -> beta (0 before the first iteration); 2: d.w -> alpha;
-// 3: rho.rho after the update -> iteration count, stopping rule (same measure as k_cg_reduce)
+// First smoothing sweep of a V-cycle: the reference's Jacobi update (src/model.rs:788-793) applied to z = 0,
+//   z1 = omega * ((0 + 0 - rho) / denom) + (1 - omega) * 0,
+// and its boundary update (:807-815) — pointwise, so it needs neither the zero field nor the stencil.
 template <class R>
-__global__ void __launch_bounds__(1024) k_mg_reduce(MgFine<R> c, MgScalars* __restrict__ sc,
-                                                     const double* __restrict__ partials, int n, int mode) {
-  __shared__ double s_red[32];
-  double acc = 0.0;
-  for (int k = threadIdx.x; k < n; k += blockDim.x) acc += partials[k];
-  const double t = block_sum<32>(acc, s_red);
-  if (threadIdx.x == 0) {
-    const R sum = (R)t;
-    if (mode == 1) {
-      sc->beta = sc->iterations == 0 ? 0.0 : (double)(sum / (R)sc->rz);
-      sc->rz = (double)sum;
-    } else if (mode == 2) {
-      sc->dw = (double)sum;
-      sc->alpha = (double)((R)sc->rz / sum);
-    } else {
-      if (mode == 3) sc->iterations += 1;
-      sc->rr = (double)sum;
-      const R measure = c.dt * (R)sqrt((double)(sum / c.n_unknowns));
-      sc->measure = (double)measure;
-      if (measure <= c.tol || sc->iterations >= sc->max_iterations) sc->done = 1;
-    }
+__global__ void __launch_bounds__(kMgThreads) k_mg_first_sweep(MgFine<R> c, R omega, R one_minus_omega, R denom,
+                                                                const R* __restrict__ rho, R* __restrict__ z) {
+  using V = typename Vec2<R>::type;
+  const MgPair<R> p = mg_pair<R>(c);
+  if (!p.any) return;
+  const int nx = c.nx;
+  for (int j = p.j0; j < p.j1; ++j) {
+    const size_t idx = (size_t)p.c0 + (size_t)j * nx;
+    const V rv = *reinterpret_cast<const V*>(rho + idx);
+    V o;
+    o.x = omega * (((R(0) + R(0)) - rv.x) / denom) + one_minus_omega * R(0);
+    o.y = omega * (((R(0) + R(0)) - rv.y) / denom) + one_minus_omega * R(0);
+    if (p.c0 == 0) o.x = o.y;                             // p'[0,j] <- p'[1,j]
+    if (p.c0 == nx - 2) o.y = c.cavity ? o.x : R(0);      // outlet 0 / cavity mirror
+    *reinterpret_cast<V*>(z + idx) = o;
+    if (j == 1) *reinterpret_cast<V*>(z + p.c0) = o;                                   // bottom row <- row 1
+    if (j == c.ny - 2) *reinterpret_cast<V*>(z + p.c0 + (size_t)(c.ny - 1) * nx) = o;  // top row <- row ny-2
   }
 }
 
@@ -203,9 +324,11 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_fine_prolong(MgFine<R> c, R* 
 }
 
 // ---- coarse levels (l >= 1): fields (mx + 2) x (my + 2) with a ring of zeros ----
+// Per-cell operations, shared by the one-launch-per-operation kernels (large levels) and the single-block kernel
+// that runs the whole bottom of the V-cycle (k_mg_bottom).  Plain pointers: inside k_mg_bottom the fields are
+// written and re-read by the same launch, so no read-only (non-coherent) loads may be used on them.
 template <class R>
-__device__ __forceinline__ R mg_coarse_apply(const MgLevelDev<R>& L, const R* __restrict__ e, int I, int J, R cc,
-                                             bool zero_in) {
+__device__ __forceinline__ R mg_coarse_apply(const MgLevelDev<R>& L, const R* e, int I, int J, R cc, bool zero_in) {
   if (zero_in) cc = R(0);
   const size_t W = (size_t)L.mx + 2, idx = (size_t)(I + 1) + (size_t)(J + 1) * W;
   const R ee = zero_in ? R(0) : e[idx + 1], ew = zero_in ? R(0) : e[idx - 1];
@@ -213,28 +336,22 @@ __device__ __forceinline__ R mg_coarse_apply(const MgLevelDev<R>& L, const R* __
   return L.CXH[J] * (L.WE[I] * (ee - cc) + L.WW[I] * (ew - cc)) + L.CYW[I] * (L.WN[J] * (en - cc) + L.WS[J] * (es - cc));
 }
 
-// one damped-Jacobi sweep: out = in + omega * ((L in - rho) / diag)  (0 where the diagonal vanishes: the 1 x 1
-// level of the all-Neumann cavity); zero_in: `in` is taken as 0 without being read
+// one cell of a damped-Jacobi sweep: out = in + omega * ((L in - rho) / diag)  (0 where the diagonal vanishes: the
+// 1 x 1 level of the all-Neumann cavity); zero_in: `in` is taken as 0 without being read
 template <class R>
-__global__ void __launch_bounds__(kMgThreads) k_mgc_sweep(MgLevelDev<R> L, const R* __restrict__ in,
-                                                           const R* __restrict__ rho, R* __restrict__ out, R omega,
-                                                           int zero_in) {
-  const int I = blockIdx.x * blockDim.x + threadIdx.x, J = blockIdx.y;
-  if (I >= L.mx) return;
+__device__ __forceinline__ void mgc_sweep_cell(const MgLevelDev<R>& L, const R* in, const R* rho, R* out, R omega,
+                                               bool zero_in, int I, int J) {
   const size_t idx = (size_t)(I + 1) + (size_t)(J + 1) * ((size_t)L.mx + 2);
   const R diag = L.CXH[J] * (L.WE[I] + L.WW[I]) + L.CYW[I] * (L.WN[J] + L.WS[J]);
   const R cc = zero_in ? R(0) : in[idx];
-  const R le = mg_coarse_apply<R>(L, in, I, J, cc, zero_in != 0);
+  const R le = mg_coarse_apply<R>(L, in, I, J, cc, zero_in);
   out[idx] = diag > R(0) ? cc + omega * ((le - rho[idx]) / diag) : R(0);
 }
 
-// rho_{l+1}[I,J] = sum over the children of (rho_l - L_l e); one thread per cell of level l+1
+// rho_{l+1}[I,J] = sum over the children of (rho_l - L_l e)
 template <class R>
-__global__ void __launch_bounds__(kMgThreads) k_mgc_restrict(MgLevelDev<R> L, const R* __restrict__ e,
-                                                              const R* __restrict__ rho, int cmx, int cmy,
-                                                              R* __restrict__ crho) {
-  const int I = blockIdx.x * blockDim.x + threadIdx.x, J = blockIdx.y;
-  if (I >= cmx) return;
+__device__ __forceinline__ void mgc_restrict_cell(const MgLevelDev<R>& L, const R* e, const R* rho, int cmx, R* crho,
+                                                  int I, int J) {
   const size_t W = (size_t)L.mx + 2;
   R acc = R(0);
 #pragma unroll
@@ -250,13 +367,91 @@ __global__ void __launch_bounds__(kMgThreads) k_mgc_restrict(MgLevelDev<R> L, co
   crho[(size_t)(I + 1) + (size_t)(J + 1) * ((size_t)cmx + 2)] = acc;
 }
 
+template <class R>
+__global__ void __launch_bounds__(kMgThreads) k_mgc_sweep(MgLevelDev<R> L, const R* in, const R* rho, R* out, R omega,
+                                                           int zero_in) {
+  const int I = blockIdx.x * blockDim.x + threadIdx.x, J = blockIdx.y;
+  if (I < L.mx) mgc_sweep_cell<R>(L, in, rho, out, omega, zero_in != 0, I, J);
+}
+
+template <class R>
+__global__ void __launch_bounds__(kMgThreads) k_mgc_restrict(MgLevelDev<R> L, const R* e, const R* rho, int cmx,
+                                                              int cmy, R* crho) {
+  const int I = blockIdx.x * blockDim.x + threadIdx.x, J = blockIdx.y;
+  if (I < cmx) mgc_restrict_cell<R>(L, e, rho, cmx, crho, I, J);
+}
+
 // e_l += (correction of the parent); one thread per cell of level l
 template <class R>
-__global__ void __launch_bounds__(kMgThreads) k_mgc_prolong(int mx, R* __restrict__ e, int cmx, const R* __restrict__ ce) {
+__global__ void __launch_bounds__(kMgThreads) k_mgc_prolong(int mx, R* e, int cmx, const R* ce) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
   if (i >= mx) return;
   const size_t idx = (size_t)(i + 1) + (size_t)(j + 1) * ((size_t)mx + 2);
   e[idx] += ce[(size_t)(i / 2 + 1) + (size_t)(j / 2 + 1) * ((size_t)cmx + 2)];
+}
+
+// The bottom of the V-cycle in ONE launch: every level from the first one that fits 64 x 64 down to 1 x 1 and
+// back up, by a single block (the fields stay in L1/L2; phases are separated by __syncthreads).  Replaces ~45
+// launches of a few microseconds each.  lv[0].rho is the input, the correction ends up in lv[0].e.
+constexpr int kMgBottomMax = 8;
+constexpr int kMgBottomThreads = 1024;
+template <class R>
+struct MgBottomLevel {
+  MgLevelDev<R> dev;
+  R *e, *rho, *tmp;
+};
+template <class R>
+struct MgBottom {
+  int n, nu;
+  R omega;
+  MgBottomLevel<R> lv[kMgBottomMax];
+};
+
+template <class R>
+__global__ void __launch_bounds__(kMgBottomThreads) k_mg_bottom(const MgBottom<R> B) {
+  R* cur[kMgBottomMax];
+  R* oth[kMgBottomMax];
+  const int tid = threadIdx.x;
+  for (int l = 0; l < B.n; ++l) {
+    const MgBottomLevel<R>& L = B.lv[l];
+    const int mx = L.dev.mx, my = L.dev.my, cells = mx * my;
+    R *a = L.e, *b = L.tmp;
+    if (mx == 1 && my == 1) {  // exact
+      if (tid == 0) mgc_sweep_cell<R>(L.dev, a, L.rho, b, R(1), true, 0, 0);
+      cur[l] = b; oth[l] = a;
+      __syncthreads();
+      break;
+    }
+    for (int s = 0; s < B.nu; ++s) {
+      for (int k = tid; k < cells; k += kMgBottomThreads) mgc_sweep_cell<R>(L.dev, a, L.rho, b, B.omega, s == 0, k % mx, k / mx);
+      __syncthreads();
+      R* t = a; a = b; b = t;
+    }
+    cur[l] = a; oth[l] = b;
+    const MgBottomLevel<R>& C = B.lv[l + 1];
+    const int cmx = C.dev.mx, ccells = cmx * C.dev.my;
+    for (int k = tid; k < ccells; k += kMgBottomThreads) mgc_restrict_cell<R>(L.dev, a, L.rho, cmx, C.rho, k % cmx, k / cmx);
+    __syncthreads();
+  }
+  for (int l = B.n - 2; l >= 0; --l) {
+    const MgBottomLevel<R>& L = B.lv[l];
+    const int mx = L.dev.mx, my = L.dev.my, cells = mx * my;
+    const int cmx = B.lv[l + 1].dev.mx;
+    R *a = cur[l], *b = oth[l];
+    const R* ce = cur[l + 1];
+    for (int k = tid; k < cells; k += kMgBottomThreads) {
+      const int i = k % mx, j = k / mx;
+      a[(size_t)(i + 1) + (size_t)(j + 1) * ((size_t)mx + 2)] += ce[(size_t)(i / 2 + 1) + (size_t)(j / 2 + 1) * ((size_t)cmx + 2)];
+    }
+    __syncthreads();
+    for (int s = 0; s < B.nu; ++s) {
+      for (int k = tid; k < cells; k += kMgBottomThreads) mgc_sweep_cell<R>(L.dev, a, L.rho, b, B.omega, false, k % mx, k / mx);
+      __syncthreads();
+      R* t = a; a = b; b = t;
+    }
+    cur[l] = a; oth[l] = b;
+  }
+  // after nu + nu swaps the correction of a (non-trivial) level is back in its `e` buffer, where the caller expects it
 }
 
 }  // namespace cfdk

@@ -199,6 +199,9 @@ struct ModelImpl final : ModelBase {
   cfdk::MgScalars* h_mg = nullptr;        // pinned host copy
   double* mg_partials = nullptr;
   unsigned long long* mg_err = nullptr;   // scratch max|dz| slot of the smoothing sweeps
+  unsigned* mg_ticket = nullptr;          // last-block ticket of the fused dot-product reductions
+  int mg_bottom_level = 0;                // first level run by the single-block bottom kernel
+  cfdk::MgBottom<R> mg_bottom;
   CUtensorMap tmap_pp[2], tmap_rhs;  // 2-D tiled views of p' (ping, pong) and rhs for the tensor-TMA sweep
   CUtensorMap tmap_rhs_halo;         // rhs with the same halo box as p' (two-sweep kernel)
   int t2_rows_per_block = 20;        // tile height of the two-sweep kernel: rows + 4 halo rows = whole 4-row boxes
@@ -256,7 +259,7 @@ struct ModelImpl final : ModelBase {
     cudaFree(cg_r.base); cudaFree(cg_d.base); cudaFree(cg_partials); cudaFree(cg_scalars);
     for (auto& L : mg) { cudaFree(L.weights); cudaFree(L.e); cudaFree(L.rho); cudaFree(L.tmp); }
     cudaFree(mg_rho.base); cudaFree(mg_d.base); cudaFree(mg_z[0].base); cudaFree(mg_z[1].base);
-    cudaFree(mg_scalars); cudaFree(mg_partials); cudaFree(mg_err);
+    cudaFree(mg_scalars); cudaFree(mg_partials); cudaFree(mg_err); cudaFree(mg_ticket);
     if (h_mg) cudaFreeHost(h_mg);
     if (h_cg) cudaFreeHost(h_cg);
     if (h_jres) cudaFreeHost(h_jres);
@@ -891,8 +894,24 @@ struct ModelImpl final : ModelBase {
     if ((rc = make_tensor_map(&tmap_mg_rho, mg_rho.row(ja - kHalo), cfdk::kStripCols))) return rc;
     if ((rc = dalloc(&mg_scalars, (size_t)1))) return rc;
     if ((rc = dalloc(&mg_err, (size_t)kMaxSweepSlots))) return rc;
-    const size_t n_all = (size_t)((nx + cfdk::kMgThreads - 1) / cfdk::kMgThreads) * (size_t)ny;
+    if ((rc = dalloc(&mg_ticket, (size_t)4))) return rc;
+    const size_t n_all = (size_t)((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads)) *
+                         (size_t)((ny + cfdk::kMgRows - 1) / cfdk::kMgRows);
     if ((rc = dalloc(&mg_partials, n_all))) return rc;
+    // the bottom of the V-cycle (every level from the first that fits 64 x 64) runs in one single-block launch
+    mg_bottom_level = (int)mg.size() - 1;
+    for (int l = 1; l < (int)mg.size(); ++l)
+      if (mg[(size_t)l].mx <= 64 && mg[(size_t)l].my <= 64) { mg_bottom_level = l; break; }
+    if ((int)mg.size() - mg_bottom_level > cfdk::kMgBottomMax) return fail(CFD_ERR_UNSUPPORTED, "multigrid hierarchy too deep");
+    memset(&mg_bottom, 0, sizeof mg_bottom);
+    mg_bottom.n = (int)mg.size() - mg_bottom_level;
+    mg_bottom.nu = mg_smoothing();
+    mg_bottom.omega = R(opt.consts.mg_omega);
+    for (int k = 0; k < mg_bottom.n; ++k) {
+      const MgLevelHost& L = mg[(size_t)(mg_bottom_level + k)];
+      mg_bottom.lv[k].dev = L.dev;
+      mg_bottom.lv[k].e = L.e; mg_bottom.lv[k].rho = L.rho; mg_bottom.lv[k].tmp = L.tmp;
+    }
     CFD_CUDA(cudaHostAlloc((void**)&h_mg, sizeof(cfdk::MgScalars), cudaHostAllocDefault));
     CFD_CUDA(cudaStreamSynchronize(stream));
     return CFD_OK;
@@ -907,6 +926,12 @@ struct ModelImpl final : ModelBase {
     const int nu_s = mg_smoothing();
     const dim3 blk(cfdk::kMgThreads), grd((L.mx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, L.my);
     R *a = L.e, *b = L.tmp;
+    if (l == mg_bottom_level && !(opt.flags & CFD_FLAG_MG_NO_BOTTOM_KERNEL) && !(L.mx == 1 && L.my == 1)) {
+      cfdk::k_mg_bottom<R><<<1, cfdk::kMgBottomThreads, 0, stream>>>(mg_bottom);
+      ++launches;
+      L.cur = L.e;
+      return CFD_OK;
+    }
     if (L.mx == 1 && L.my == 1) {  // exact
       cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, R(1), 1);
       ++launches;
@@ -957,8 +982,15 @@ struct ModelImpl final : ModelBase {
       ++launches;
       zc ^= 1;
     };
-    CFD_CUDA(cudaMemsetAsync(mg_z[0].base, 0, mg_z[0].count * sizeof(R), stream));
-    for (int s = 0; s < nu_s; ++s) smooth();
+    {
+      // first sweep from z = 0: pointwise (k_mg_first_sweep) instead of a stencil sweep over a zero field
+      const dim3 g_vec((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads), (ny - 2 + cfdk::kMgRows - 1) / cfdk::kMgRows);
+      cfdk::k_mg_first_sweep<R><<<g_vec, cfdk::kMgThreads, 0, stream>>>(c, c2.omega, c2.one_minus_omega, div_denom.y,
+                                                                        mg_rho.v, mg_z[1].v);
+      ++launches;
+      zc = 1;
+    }
+    for (int s = 1; s < nu_s; ++s) smooth();
     if (mg.size() > 1) {
       MgLevelHost& C = mg[1];
       const dim3 blk(cfdk::kMgThreads), grd_c((C.mx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, C.my);
@@ -984,9 +1016,9 @@ struct ModelImpl final : ModelBase {
     c.n_unknowns = R((size_t)(nx - 2) * (size_t)(ny - 2));
     c.nx = nx; c.ny = ny; c.cavity = scenario == CFD_SCENARIO_CAVITY;
     const dim3 blk(cfdk::kMgThreads);
-    const dim3 g_all((nx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, ny);
-    const dim3 g_int((nx - 2 + cfdk::kMgThreads - 1) / cfdk::kMgThreads, ny - 2);
-    const int n_all = (int)(g_all.x * g_all.y), n_int = (int)(g_int.x * g_int.y);
+    const unsigned gx = (unsigned)((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads));
+    const dim3 g_all(gx, (ny + cfdk::kMgRows - 1) / cfdk::kMgRows);       // all rows (init)
+    const dim3 g_vec(gx, (ny - 2 + cfdk::kMgRows - 1) / cfdk::kMgRows);   // rows of unknowns
     const Field<R>& xf = pp[ipp];
     R* x = xf.v;
     R* w = pp[ipp ^ 1].v;
@@ -996,9 +1028,8 @@ struct ModelImpl final : ModelBase {
     *h_mg = init;
     CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index], stream));
     CFD_CUDA(cudaMemcpyAsync(mg_scalars, h_mg, sizeof init, cudaMemcpyHostToDevice, stream));
-    cfdk::k_mg_init<R><<<g_all, blk, 0, stream>>>(c, rhs.v, x, mg_rho.v, mg_d.v, mg_partials);
-    cfdk::k_mg_reduce<R><<<1, 1024, 0, stream>>>(c, mg_scalars, mg_partials, n_all, 0);
-    launches += 2;
+    cfdk::k_mg_init<R><<<g_all, blk, 0, stream>>>(c, mg_scalars, rhs.v, x, mg_rho.v, mg_d.v, mg_partials, mg_ticket);
+    launches += 1;
     for (;;) {
       CFD_CUDA(cudaMemcpyAsync(h_mg, mg_scalars, sizeof init, cudaMemcpyDeviceToHost, stream));
       CFD_CUDA(cudaStreamSynchronize(stream));
@@ -1006,14 +1037,11 @@ struct ModelImpl final : ModelBase {
       int zi = 0;
       if ((rc = mg_precondition(c, &zi))) return rc;
       const R* z = mg_z[zi].v;
-      cfdk::k_mg_dot<R><<<g_int, blk, 0, stream>>>(c, mg_rho.v, z, mg_partials);
-      cfdk::k_mg_reduce<R><<<1, 1024, 0, stream>>>(c, mg_scalars, mg_partials, n_int, 1);
-      cfdk::k_mg_direction<R><<<g_int, blk, 0, stream>>>(c, mg_scalars, z, mg_d.v);
-      cfdk::k_mg_apply<R><<<g_int, blk, 0, stream>>>(c, mg_d.v, w, mg_partials);
-      cfdk::k_mg_reduce<R><<<1, 1024, 0, stream>>>(c, mg_scalars, mg_partials, n_int, 2);
-      cfdk::k_mg_update<R><<<g_int, blk, 0, stream>>>(c, mg_scalars, mg_d.v, w, x, mg_rho.v, mg_partials);
-      cfdk::k_mg_reduce<R><<<1, 1024, 0, stream>>>(c, mg_scalars, mg_partials, n_int, 3);
-      launches += 7;
+      cfdk::k_mg_dot<R><<<g_vec, blk, 0, stream>>>(c, mg_scalars, mg_rho.v, z, mg_partials, mg_ticket, 1);
+      cfdk::k_mg_direction<R><<<g_vec, blk, 0, stream>>>(c, mg_scalars, z, mg_d.v);
+      cfdk::k_mg_apply<R><<<g_vec, blk, 0, stream>>>(c, mg_scalars, mg_d.v, w, mg_partials, mg_ticket);
+      cfdk::k_mg_update<R><<<g_vec, blk, 0, stream>>>(c, mg_scalars, mg_d.v, w, x, mg_rho.v, mg_partials, mg_ticket);
+      launches += 4;
       CFD_CUDA(cudaGetLastError());
     }
     const int n_edge = (nx > ny ? nx : ny);

@@ -111,6 +111,7 @@ typedef struct cfd_options {
 #define CFD_FLAG_NCCL_EXCHANGE 32u /* strips: NCCL send/recv + allreduce after every sweep instead of peer-memory stores (A/B) */
 #define CFD_FLAG_TEMPORAL 64u      /* two sweeps per HBM pass (k_jacobi_sweep_t2) instead of one per launch (A/B; slower, issue-bound) */
 #define CFD_FLAG_PERSISTENT_SWEEP 128u /* persistent warp-queue kernel (k_jacobi_sweep6) instead of one block per tile (A/B; slower) */
+#define CFD_FLAG_MG_NO_BOTTOM_KERNEL 256u /* MGCG: one launch per operation on every level instead of the single-block bottom kernel (A/B, cross-check) */
 #define CFD_FLAG_BULK_SWEEP 8u     /* row-by-row cp.async.bulk Jacobi kernel instead of the tensor-TMA one (A/B) */
 
 /* Residuals, src/model.rs:23-32.  f32 members mirror the reference; the trailing members are

@@ -372,3 +372,22 @@ def test_mgcg_rejects_strips_and_bad_constants():
     o.consts.mg_smoothing = 0
     with pytest.raises(CfdError):
         Model(box_grid(32), SimulationParams(pressure_solver=PressureSolver.MGCG), options=o)
+
+
+def test_mgcg_bottom_kernel_matches_per_level_launches():
+    """The single-block kernel that runs the bottom of the V-cycle performs the same per-cell arithmetic as one
+    launch per operation (CFD_FLAG_MG_NO_BOTTOM_KERNEL): complete state bit-identical."""
+    from cfd_demo_b200.model import default_options
+    from cfd_demo_b200.types import PressureSolver
+    g = channel_grid(264, 200, lx=26.4, ly=20.0)
+    prm = SimulationParams(dt=1e-3, viscosity=0.01, pressure_solver=PressureSolver.MGCG)
+    models = []
+    for flags in (0, 256):
+        o = default_options()
+        o.flags = flags
+        m = Model(g, prm, options=o)
+        for _ in range(6):
+            m.update()
+        models.append(m)
+    assert models[0].get_residuals().sweeps == models[1].get_residuals().sweeps > 0
+    assert_fields_identical(models[0], models[1], STATE_FIELDS, "bottom kernel vs per-level launches")
