@@ -3,13 +3,19 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-A "step" is one timestep of the BASELINE 4096x4096 workload (predictor, K pressure solves of <= 50 damped
-Jacobi sweeps each with the corrector after each, boundary conditions, residual / CFL reductions).  State is
-resident in HBM when the timed region starts.  Prints ONE JSON line (contract in the task description):
-`value` = cell-updates/s (= nx*ny*timesteps/s) of the whole job, `e2e` = the same metric through the C ABI
-with HOST buffers every step (set_params in, residuals + f32 snapshot out), `roofline` for the Jacobi sweep
-kernel from live CUDA-event timing, `cpu_baseline` = the CPU oracle (a C++ port of the reference, 1 core
-because the reference solver is single-threaded by construction, src/model.rs:1287) on a bounded sample.
+Default workload = the configuration BASELINE.json's metric is quoted on (configs[2]): lid-driven cavity, Re = 1000,
+4096 x 4096 cells, fp64, the pressure solve converged to dt * rms(residual) <= 1e-8 every step ("Mode C": conjugate
+gradients preconditioned by a multigrid V-cycle whose fine-level smoother is the reference's damped-Jacobi sweep
+kernel).  `--workload channel4096_modeR` is the reference's own algorithm (<= 50 Jacobi sweeps x <= 21 solves per
+step, never converged) in its dense saturated regime; with --gpus N > 1 that one runs as row strips over NVLink.
+
+A "step" is one timestep (predictor, K pressure solves with the corrector after each, boundary conditions,
+residual / CFL reductions).  State is resident in HBM when the timed region starts.  Prints ONE JSON line
+(contract in the task description): `value` = cell-updates/s (= nx*ny*timesteps/s) of the whole job, `e2e` = the
+same metric through the C ABI with HOST buffers every step (set_params in; residuals + the f32 snapshot of p, u, v
+out, into pinned memory), `roofline` for the Jacobi sweep kernel from live CUDA-event timing, `cpu_baseline` = the
+CPU oracle (a C++ port of the reference, 1 core because the reference solver is single-threaded by construction,
+src/model.rs:1287) on a bounded sample.
 
 `--impl reference` times that CPU port alone (the Rust reference cannot be built here: no Rust toolchain).
 """
@@ -33,17 +39,30 @@ import numpy as np  # noqa: E402
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 WORKLOADS = {
-    # name: (nx, ny, lx, ly, cylinder, params kwargs, spin-up steps to reach the dense saturated regime: until
-    # p' is non-zero everywhere the sweeps still hit the slow zero-dividend path; ~21 steps at 4096x4096, ~35 for
-    # the taller multi-GPU domains)
-    "channel4096_modeR": dict(nx=4096, ny=4096, lx=40.0, ly=40.0, cylinder=None, params={}, spinup=44,
+    # BASELINE.json configs[2] / SURVEY 8(d) config 3: cavity Re = 1000 at 4096^2, dt below the explicit diffusion
+    # limit dx^2 / (4 nu) = 1.49e-5, pressure solve converged to 1e-8 (Mode C, MGCG).  Spin-up runs through the
+    # reference's 100-step ramp of the driving velocity (src/model.rs:311-316).
+    "cavity4096_modeC": dict(kind="modeC", nx=4096, ny=4096, lx=1.0, ly=1.0, cylinder=None, spinup=110,
+                             params=dict(dt=1.0e-5, viscosity=1.0e-3, target_inlet_velocity=1.0, scenario=1,
+                                         pressure_solver=2),
+                             desc="lid-driven cavity Re=1000, 4096x4096, fp64, pressure solve converged to dt*rms(r) <= 1e-8 "
+                                  "every step (Mode C: CG preconditioned by a multigrid V(2,2)-cycle, the reference's "
+                                  "damped-Jacobi sweep kernel as fine-level smoother)"),
+    "cavity1024_modeC": dict(kind="modeC", nx=1024, ny=1024, lx=1.0, ly=1.0, cylinder=None, spinup=110,
+                             params=dict(dt=2.0e-5, viscosity=1.0e-2, target_inlet_velocity=1.0, scenario=1,
+                                         pressure_solver=2),
+                             desc="lid-driven cavity Re=100, 1024x1024, fp64, Mode C (MGCG), L2-resident regime"),
+    # the reference's own algorithm; spin-up until the dense saturated regime where every step runs K=21, S=1050
+    # (until p' is non-zero everywhere the sweeps still hit the slow zero-dividend path; ~21 steps at 4096x4096,
+    # ~35 for the taller multi-GPU domains)
+    "channel4096_modeR": dict(kind="modeR", nx=4096, ny=4096, lx=40.0, ly=40.0, cylinder=None, params={}, spinup=44,
                               desc="channel 4096x4096 (reference scenario), fp64, Mode R = the reference's damped "
                                    "Jacobi (<=50 sweeps) + <=20 outer re-corrections, dense saturated regime "
                                    "(K=21 solves, S=1050 sweeps per step)"),
-    "default800_modeR": dict(nx=800, ny=264, lx=30.0, ly=10.0, cylinder=(7.5, 5.0, 0.75), params={}, spinup=26,
+    "default800_modeR": dict(kind="modeR", nx=800, ny=264, lx=30.0, ly=10.0, cylinder=(7.5, 5.0, 0.75), params={}, spinup=26,
                              desc="reference default_grid() 800x264 + cylinder, Mode R"),
 }
-DEFAULT_WORKLOAD = "channel4096_modeR"
+DEFAULT_WORKLOAD = "cavity4096_modeC"
 
 
 def peak_hbm():
@@ -117,7 +136,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------
-# CPU side: the oracle port, timed on a bounded sample (one outer round = `u*<-u` copies + divergence +
+# CPU side, Mode R: the oracle port, timed on a bounded sample (one outer round = `u*<-u` copies + divergence +
 # 50-sweep Jacobi solve + corrector, src/model.rs:698-718) on dense synthetic fields of the workload's size.
 # A saturated timestep is 21 such rounds plus ~1 % of predictor / BC / reductions, which are timed once.
 # ---------------------------------------------------------------------------------------------------------
@@ -159,11 +178,11 @@ def cpu_oracle_sample(w, precision, rounds, rounds_per_step=21):
             "cells": nx * ny, "rounds": rounds, "cpu_seconds": sum(times) + t_misc}
 
 
-def run_reference(args, w):
-    """The reference arm: the CPU port of the reference (oracle), 1 core, bounded samples."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
+CPU_NOTE = ("C++ port of the reference (oracle/cfd_oracle.hpp); the Rust reference cannot be built here (no Rust "
+            "toolchain) and is single-threaded by construction (src/model.rs:1287)")
+
+
+def run_reference_mode_r(args, w):
     from oracle import cpu_oracle
     cpu_oracle.build()
     precision = 32 if args.ref_precision == 32 else 64
@@ -176,7 +195,7 @@ def run_reference(args, w):
     sample = (f"{s['rounds']} outer rounds (copies + divergence + {s['sweeps_per_round']:.0f}-sweep Jacobi solve + "
               f"corrector, src/model.rs:698-718) on dense synthetic {w['nx']}x{w['ny']} fields, median round "
               f"{s['t_round']:.3f} s, x21 rounds per saturated timestep + {s['t_misc']:.3f} s predictor/BC")
-    line = {
+    return {
         "impl": "reference", "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": s["step_seconds"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -184,13 +203,95 @@ def run_reference(args, w):
         "timesteps_per_s": 1.0 / s["step_seconds"],
         "config": {"workload": w["desc"], "nx": w["nx"], "ny": w["ny"], "solves_per_step": 21, "sweeps_per_step": 1050},
         "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": "port", "sample": sample,
-                         "host_cores": os.cpu_count(),
-                         "note": "C++ port of the reference (oracle/cfd_oracle.hpp); the Rust reference cannot be "
-                                 "built here (no Rust toolchain) and is single-threaded by construction"},
+                         "host_cores": os.cpu_count(), "note": CPU_NOTE},
         "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+
+
+def run_reference_mode_c(args, w):
+    """Mode C on the CPU port: the same workload from rest (the first two steps are trivial: the driving velocity
+    ramps up from 0, src/model.rs:311-316), W warm-up steps then up to K timed steps within a time budget."""
+    from oracle import cpu_oracle
+    from oracle.cpu_oracle import OracleModel
+    cpu_oracle.build()
+    precision = 32 if args.ref_precision == 32 else 64
+    grid, params = make_grid(w), make_params(w)
+    m = OracleModel(grid, params, precision=precision)
+    budget_s = float(os.environ.get("CFD_BENCH_REF_BUDGET_S", "150"))
+    t_begin = time.perf_counter()
+    for _ in range(max(args.warmup, 3)):
+        m.update()
+    times, iters = [], []
+    for _ in range(max(1, args.steps)):
+        t0 = time.perf_counter()
+        m.update()
+        times.append(time.perf_counter() - t0)
+        iters.append(m.get_residuals().sweeps)
+        if time.perf_counter() - t_begin + times[-1] > budget_s:
+            break
+    step_s = sum(times) / len(times)
+    value = grid.nx * grid.ny / step_s
+    sample = (f"{len(times)} timesteps of the same workload from rest after {max(args.warmup, 3)} warm-up steps "
+              f"(oracle<{'float' if precision == 32 else 'double'}>, MGCG iterations per step {iters}), mean {step_s:.3f} s/step")
+    return {
+        "impl": "reference", "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if precision == 32 else "f64", "data": "synthetic",
+        "timesteps_per_s": 1.0 / step_s, "steps_timed": len(times),
+        "config": {"workload": w["desc"], "nx": w["nx"], "ny": w["ny"], "solves_per_step": 2,
+                   "iterations_per_step": sum(iters) / len(iters)},
+        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count(), "note": CPU_NOTE},
+        "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def run_reference(args, w):
+    """The reference arm: the CPU port of the reference (oracle), 1 core, bounded samples; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    line = run_reference_mode_c(args, w) if w["kind"] == "modeC" else run_reference_mode_r(args, w)
     print(json.dumps(line), flush=True)
     return 0
+
+
+def cpu_baseline_mode_r(w, nx, ny):
+    rounds = max(1, min(8, int(24.0 / (3.0 * w["nx"] * w["ny"] / (4096.0 * 4096.0) + 1e-9))))
+    s = cpu_oracle_sample(w, 64, rounds)
+    s32 = cpu_oracle_sample(w, 32, max(1, rounds // 2))
+    return {"value": s["cells"] / s["step_seconds"], "unit": "cell-updates/s", "cores": 1, "kind": "port",
+            "host_cores": os.cpu_count(), "value_f32": s32["cells"] / s32["step_seconds"],
+            "sample": (f"oracle<double>: {s['rounds']} outer rounds (copies + divergence + "
+                       f"{s['sweeps_per_round']:.0f}-sweep Jacobi solve + corrector) on dense synthetic "
+                       f"{nx}x{ny} fields, median {s['t_round']:.3f} s/round, x21 rounds per saturated "
+                       f"timestep + {s['t_misc']:.3f} s predictor/BC; value_f32 = same with oracle<float> "
+                       f"(the reference's own precision)")}
+
+
+def cpu_baseline_mode_c(w, model):
+    """The GPU model's complete state after the timed region is loaded into the CPU oracle, which then computes the
+    SAME next timestep (the GPU does it too; iteration counts are compared)."""
+    from cfd_demo_b200 import _abi
+    from oracle.cpu_oracle import OracleModel
+    grid, params = make_grid(w), make_params(w)
+    cpu = OracleModel(grid, params, precision=64)
+    r0 = model.get_residuals()
+    for fid in (_abi.FIELD_P, _abi.FIELD_U, _abi.FIELD_V, _abi.FIELD_U_STAR, _abi.FIELD_V_STAR, _abi.FIELD_P_PRIME):
+        cpu.set_field(fid, model.field(fid))
+    cpu.set_scalars(r0.simulation_step, r0.f64["simulation_time"], r0.f64["dt"])
+    t0 = time.perf_counter()
+    cpu.update()
+    dt_cpu = time.perf_counter() - t0
+    model.update()
+    rc, rg = cpu.get_residuals(), model.get_residuals()
+    du = float(np.linalg.norm(cpu.field(_abi.FIELD_U) - model.field(_abi.FIELD_U)) /
+               max(np.linalg.norm(cpu.field(_abi.FIELD_U)), 1e-300))
+    return {"value": grid.nx * grid.ny / dt_cpu, "unit": "cell-updates/s", "cores": 1, "kind": "port",
+            "host_cores": os.cpu_count(),
+            "sample": (f"oracle<double>: ONE timestep (step {rc.simulation_step}) from the GPU model's state, {dt_cpu:.2f} s, "
+                       f"{rc.sweeps} MGCG iterations (GPU: {rg.sweeps}); relative L2 difference of u against the GPU's "
+                       f"same step: {du:.2e}")}
 
 
 def run_ours(args, w):
@@ -206,17 +307,20 @@ def run_ours(args, w):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("cpu:gloo,cuda:nccl")
-
-    # N > 1: WEAK scaling over row strips — every GPU owns a w.nx x w.ny strip of one tall channel
-    # (nx x N*ny cells, same dx = dy), halo rows and max-reductions over NCCL
+    mode_c = w["kind"] == "modeC"
+    # N > 1.  Mode R: WEAK scaling over row strips — every GPU owns a w.nx x w.ny strip of one tall channel
+    # (nx x N*ny cells, same dx = dy), halo rows and max-reductions over NVLink peer memory.
+    # Mode C (MGCG): the multigrid hierarchy does not shard yet -> N independent replicas of the workload.
+    strips = world > 1 and not mode_c
     from cfd_demo_b200.types import Cylinder, Grid
     cyl = Cylinder(*w["cylinder"]) if w["cylinder"] else None
-    grid = Grid.uniform(w["nx"], w["ny"] * world, w["lx"], w["ly"] * world, cyl)
+    ny_job = w["ny"] * world if strips else w["ny"]
+    grid = Grid.uniform(w["nx"], ny_job, w["lx"], w["ly"] * (world if strips else 1), cyl)
     params = make_params(w)
     nx, ny = grid.nx, grid.ny
-    cells = nx * ny  # whole job
+    cells = nx * ny * (1 if (strips or world == 1) else world)  # whole job
     from cfd_demo_b200.model import default_options, nccl_unique_id
-    if world > 1:
+    if strips:
         uid = [nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         model = Model.strip(grid, params, rank, world, uid[0], device=local_rank,
@@ -224,6 +328,7 @@ def run_ours(args, w):
     else:
         opts = default_options()
         opts.device = local_rank
+        opts.flags = int(os.environ.get("CFD_BENCH_FLAGS", "0"))
         model = Model(grid, params, options=opts)
 
     def barrier():
@@ -232,7 +337,8 @@ def run_ours(args, w):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # build the synthetic input: spin the flow up to the dense regime where every step saturates (K=21,S=1050)
+    # build the synthetic input on the device: spin the flow up (Mode R: to the dense regime where every step
+    # saturates at K=21, S=1050; Mode C: through the 100-step ramp of the lid velocity)
     spinup = int(os.environ.get("CFD_BENCH_SPINUP", w["spinup"]))
     for i in range(spinup):
         model.update()
@@ -240,6 +346,8 @@ def run_ours(args, w):
             r_, t_ = model.get_residuals(), model.last_timing()
             print(f"spinup {i + 1}: K {r_.jacobi_calls} S {r_.sweeps} step_ms {t_[0]:.2f} per-sweep us {t_[1] * 1e3 / max(r_.sweeps, 1):.1f}",
                   file=sys.stderr, flush=True)
+    if mode_c:
+        model.profile_smoother(True)  # CUDA-event pairs around the smoother launches (48 records per step)
     for _ in range(args.warmup):
         model.update()
 
@@ -254,7 +362,7 @@ def run_ours(args, w):
     # ---- timed region 1: K steps, state resident in HBM -------------------------------------------------
     barrier()
     t0 = time.perf_counter()
-    dev_ms, sweep_ms, sweeps, solves, launches = 0.0, 0.0, 0, 0, 0
+    dev_ms, sweep_ms, sweeps, solves, launches, smooth_ms, smooth_n = 0.0, 0.0, 0, 0, 0, 0.0, 0
     for _ in range(args.steps):
         model.update()
         s_ms, sw_ms, n_l = model.last_timing()
@@ -264,23 +372,37 @@ def run_ours(args, w):
         sweeps += r.sweeps
         solves += r.jacobi_calls
         launches += n_l
+        if mode_c:
+            a, b = model.last_smoother_timing()
+            smooth_ms += a
+            smooth_n += b
     barrier()
     wall = time.perf_counter() - t0
     if cudart is not None:
         cudart.cudaProfilerStop()
     # ---- timed region 2: the same K steps through the reference-facing calls with HOST buffers ------------
+    model.profile_smoother(False)
+    pinned = model.pinned_snapshot_buffers()
     barrier()
     t1 = time.perf_counter()
     d2h = 0
     for _ in range(args.steps):
-        model.set_parameters(params)      # host -> device: the 28-byte parameter block
+        model.set_parameters(params)         # host -> device: the 28-byte parameter block
         model.update()
-        res = model.get_residuals()       # device -> host: the step's residual scalars
-        snap = model.get_snapshot()       # device -> host: p, u, v narrowed to f32 (SimSnapshot, src/model.rs:36-42)
+        res = model.get_residuals()          # device -> host: the step's residual scalars
+        snap = model.get_snapshot(out=pinned)  # device -> host: p, u, v narrowed to f32 (SimSnapshot, src/model.rs:36-42)
         d2h = (snap.p.nbytes + snap.u.nbytes + snap.v.nbytes + 8 * 8) * world
-        launches_e2e = model.last_timing()[2] + 3
     barrier()
     wall_e2e = time.perf_counter() - t1
+    # the same with freshly allocated pageable buffers (what a caller holding plain Vec<f32>s gets)
+    t2 = time.perf_counter()
+    for _ in range(min(args.steps, 3)):
+        model.set_parameters(params)
+        model.update()
+        res = model.get_residuals()
+        snap = model.get_snapshot()
+    torch.cuda.synchronize()
+    wall_e2e_pageable = (time.perf_counter() - t2) / min(args.steps, 3)
     clocks = sampler.stop() if rank == 0 else None
 
     # max over ranks
@@ -292,62 +414,78 @@ def run_ours(args, w):
     value = cells * steps / dev_s
     e2e_value = cells * steps / wall_e2e_s
     peak, peak_src = peak_hbm()
-    sweep_us = sweep_ms * 1e3 / max(sweeps, 1)
-    algo_bytes = 3 * 8 * cells // world  # per launch (one rank's strip): read p', rhs; write p'new
+    rank_cells = nx * ny // world if strips else nx * ny
+    algo_bytes = 3 * 8 * rank_cells  # per launch (one rank's strip): read p', rhs; write p'new
+    if mode_c:
+        sweep_us = smooth_ms * 1e3 / max(smooth_n, 1)
+        roof_launches, roof_share = smooth_n, smooth_ms / max(dev_ms, 1e-9)
+        kernel_name = ("cfdk::k_jacobi_sweep5<double> (the reference's damped-Jacobi sweep incl. boundary update, here the "
+                       "fine-level smoother of the V-cycle: 3 launches per CG iteration)")
+    else:
+        sweep_us = sweep_ms * 1e3 / max(sweeps, 1)
+        roof_launches, roof_share = sweeps, sweep_ms / (dev_s * 1e3)
+        kernel_name = "cfdk::k_jacobi_sweep5<double> (one damped-Jacobi sweep incl. boundary update and max|dp'|)"
     achieved = algo_bytes / (sweep_us * 1e-6) / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_sweep_kernel.json")) as f:
             t = json.load(f)
-            if t.get("nx") == nx and t.get("ny") == ny:
+            if t.get("nx") == nx and t.get("ny") == rank_cells // nx:
                 traffic = t.get("dram_bytes_per_launch")
     except Exception:
         pass
     k_per_step, s_per_step = solves / steps, sweeps / steps
-    step_bytes = 8 * cells * (8 + 10 * k_per_step + 3 * s_per_step) + 2 * cells  # whole job
-    peak = peak * world
+    if mode_c:
+        # algorithmic bytes of a Mode C step: per CG iteration 28.5 s N on level 0 (first sweep
+        # 2, sweep 3, restriction 2.25, prolongation 2.25, 2 sweeps 6, rho.z 2, direction 3, L d 2, update 6) + 15.5 s N_l
+        # on every coarse level (sum N_l = N / 3); per solve 4 s N (init); per step 8 s N + 2 N + 10 s N per solve
+        step_bytes = (8 * nx * ny * (8 + 14 * k_per_step + (28.5 + 15.5 / 3.0) * s_per_step) + 2 * nx * ny) * \
+                     (world if not strips else 1)
+    else:
+        step_bytes = 8 * cells * (8 + 10 * k_per_step + 3 * s_per_step) + 2 * cells  # whole job
+    peak_job = peak * world
 
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:  # CPU port timed on rank 0 at N = 1 only
             from oracle import cpu_oracle
             cpu_oracle.build()
-            rounds = max(1, min(8, int(24.0 / (3.0 * w["nx"] * w["ny"] / (4096.0 * 4096.0) + 1e-9))))
-            s = cpu_oracle_sample(w, 64, rounds)
-            s32 = cpu_oracle_sample(w, 32, max(1, rounds // 2))
-            cpu = {"value": s["cells"] / s["step_seconds"], "unit": "cell-updates/s", "cores": 1, "kind": "port",
-                   "host_cores": os.cpu_count(),
-                   "value_f32": s32["cells"] / s32["step_seconds"],
-                   "sample": (f"oracle<double>: {s['rounds']} outer rounds (copies + divergence + "
-                              f"{s['sweeps_per_round']:.0f}-sweep Jacobi solve + corrector) on dense synthetic "
-                              f"{nx}x{ny} fields, median {s['t_round']:.3f} s/round, x21 rounds per saturated "
-                              f"timestep + {s['t_misc']:.3f} s predictor/BC; value_f32 = same with oracle<float> "
-                              f"(the reference's own precision)")}
+            cpu = cpu_baseline_mode_c(w, model) if mode_c else cpu_baseline_mode_r(w, nx, ny)
+        if world == 1:
+            multi = "single domain"
+        elif strips:
+            multi = (f"{world} row strips of {w['nx']}x{w['ny']} cells each, halo rows and max-reduction fused into the sweep "
+                     f"kernel over NVLink peer memory, weak scaling")
+        else:
+            multi = (f"{world} independent replicas of the workload, one per GPU (replicas only: the multigrid hierarchy of "
+                     f"Mode C does not shard in this version; strips: --workload channel4096_modeR)")
         line = {
             "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
             "steps": steps, "warmup": args.warmup, "ms_per_step": dev_s * 1e3 / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "timesteps_per_s": steps / dev_s,
+            "timesteps_per_s": steps / dev_s * (world if (world > 1 and not strips) else 1),
             "wall_ms_per_step": wall_s * 1e3 / steps,
             "config": {"workload": w["desc"], "nx": nx, "ny": ny, "spinup_steps": spinup,
-                       "solves_per_step": k_per_step, "sweeps_per_step": s_per_step,
+                       "solves_per_step": k_per_step,
+                       ("cg_iterations_per_step" if mode_c else "sweeps_per_step"): s_per_step,
                        "l2": "every field (134 MB at 4096^2) is larger than L2 (126 MB); no flush needed",
                        "timing": "CUDA events on the model's stream around each update(), summed over K steps",
-                       "multi_gpu": "single domain" if world == 1 else
-                       f"{world} row strips of {w['nx']}x{w['ny']} cells each over NCCL (halo rows per sweep + max allreduce), weak scaling"},
+                       "multi_gpu": multi},
             "step_algorithmic_gbs": step_bytes / (dev_s / steps) / 1e9,
-            "step_frac_of_peak": step_bytes / (dev_s / steps) / 1e9 / peak,
-            "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": 28, "d2h_bytes_per_step": d2h,
+            "step_frac_of_peak": step_bytes / (dev_s / steps) / 1e9 / peak_job,
+            "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": 28 * world, "d2h_bytes_per_step": d2h,
                     "ms_per_step": wall_e2e_s * 1e3 / steps,
-                    "calls": "cfd_model_set_params + cfd_model_update + cfd_model_get_residuals + cfd_model_get_snapshot"},
+                    "ms_per_step_pageable_destination": wall_e2e_pageable * 1e3,
+                    "calls": "cfd_model_set_params + cfd_model_update + cfd_model_get_residuals + cfd_model_get_snapshot "
+                             "(into cfd_host_alloc'ed pinned buffers)"},
             "gpu_launches": launches,
-            "roofline": {"kernel": "cfdk::k_jacobi_sweep5<double> (one damped-Jacobi sweep incl. boundary update and max|dp'|)",
-                         "bound": "hbm", "achieved": achieved, "peak": peak / world, "unit": "GB/s",
-                         "frac": achieved / (peak / world),
+            "roofline": {"kernel": kernel_name,
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": traffic,
                          "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_us": sweep_us,
-                         "launches_timed": sweeps,
-                         "share_of_step": sweep_ms / (dev_s * 1e3)},
+                         "launches_timed": roof_launches,
+                         "share_of_step": roof_share},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

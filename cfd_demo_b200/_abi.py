@@ -30,6 +30,7 @@ FLAG_SWEEP4 = 16
 FLAG_NCCL_EXCHANGE = 32
 FLAG_TEMPORAL = 64
 FLAG_PERSISTENT_SWEEP = 128
+FLAG_MG_NO_BOTTOM_KERNEL = 256
 
 
 class CfdGrid(C.Structure):

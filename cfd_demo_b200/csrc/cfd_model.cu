@@ -124,6 +124,8 @@ struct ModelBase {
   virtual int set_field_f64(int field, const double* in, uint64_t len) = 0;
   virtual int rows(uint64_t* j0, uint64_t* j1) = 0;
   virtual int last_timing(double* step_ms, double* sweep_ms, uint64_t* launches) = 0;
+  virtual int profile_smoother(int enable) = 0;
+  virtual int last_smoother_timing(double* ms, uint64_t* launches) = 0;
 };
 
 // One rotating / plain field: `base` is the allocation, `v` the VIRTUAL ORIGIN such that v[j * rowlen + i] is
@@ -179,6 +181,8 @@ struct ModelImpl final : ModelBase {
   size_t staging_bytes = 0;
   void* h_staging = nullptr;                 // pinned host scratch
   size_t h_staging_bytes = 0;
+  void* bounce[2] = {nullptr, nullptr};      // pinned bounce buffers for snapshots into pageable memory
+  cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
   // Mode C (CG) work space, allocated on first use
   Field<R> cg_r, cg_d;
   double* cg_partials = nullptr;
@@ -200,6 +204,12 @@ struct ModelImpl final : ModelBase {
   double* mg_partials = nullptr;
   unsigned long long* mg_err = nullptr;   // scratch max|dz| slot of the smoothing sweeps
   unsigned* mg_ticket = nullptr;          // last-block ticket of the fused dot-product reductions
+  // measurement hook: CUDA-event pairs around every k_jacobi_sweep5 launch of the MGCG smoother (bench.py roofline)
+  bool prof_smoother = false;
+  std::vector<cudaEvent_t> ev_prof;
+  size_t ev_prof_used = 0;
+  double last_prof_ms = 0;
+  uint64_t last_prof_launches = 0;
   int mg_bottom_level = 0;                // first level run by the single-block bottom kernel
   cfdk::MgBottom<R> mg_bottom;
   CUtensorMap tmap_pp[2], tmap_rhs;  // 2-D tiled views of p' (ping, pong) and rhs for the tensor-TMA sweep
@@ -265,6 +275,10 @@ struct ModelImpl final : ModelBase {
     if (h_jres) cudaFreeHost(h_jres);
     if (h_step) cudaFreeHost(h_step);
     if (h_staging) cudaFreeHost(h_staging);
+    for (int k = 0; k < 2; ++k) {
+      if (bounce[k]) cudaFreeHost(bounce[k]);
+      if (bounce_ev[k]) cudaEventDestroy(bounce_ev[k]);
+    }
     if (tickets && getenv("CFD_PEER_DEBUG")) {
       unsigned int h[16];
       cudaMemcpy(h, tickets + 1040, sizeof h, cudaMemcpyDeviceToHost);
@@ -291,6 +305,7 @@ struct ModelImpl final : ModelBase {
     if (ev_step0) cudaEventDestroy(ev_step0);
     if (ev_step1) cudaEventDestroy(ev_step1);
     for (auto e : ev_sweep) cudaEventDestroy(e);
+    for (auto e : ev_prof) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
   }
 
@@ -977,8 +992,19 @@ struct ModelImpl final : ModelBase {
     const size_t ring_bytes = sizeof(cfdk::SweepChunkRing<R>);
     int zc = 0;
     auto smooth = [&]() {
+      if (prof_smoother) {
+        if (ev_prof_used + 2 > ev_prof.size()) {
+          ev_prof.resize(ev_prof_used + 64, nullptr);
+          for (size_t k = ev_prof_used; k < ev_prof.size(); ++k) cudaEventCreate(&ev_prof[k]);
+        }
+        cudaEventRecord(ev_prof[ev_prof_used], stream);
+      }
       cfdk::k_jacobi_sweep5<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_mg_z[zc], tmap_mg_rho, mg_z[zc ^ 1].v, mg_err, 0,
                                                                     cfdk::SweepPeer<R>{});
+      if (prof_smoother) {
+        cudaEventRecord(ev_prof[ev_prof_used + 1], stream);
+        ev_prof_used += 2;
+      }
       ++launches;
       zc ^= 1;
     };
@@ -1071,6 +1097,7 @@ struct ModelImpl final : ModelBase {
     CFD_CUDA(cudaSetDevice(device));
     const auto t0 = std::chrono::steady_clock::now();
     launches = 0;
+    ev_prof_used = 0;
     CFD_CUDA(cudaEventRecord(ev_step0, stream));
     // u_old <- u, v_old <- v (:307-308): the current buffers simply stay untouched until the step ends
     const int X = iu, Y = ius, Z = ifree;
@@ -1179,6 +1206,12 @@ struct ModelImpl final : ModelBase {
       last_sweep_ms += ms;
     }
     last_launches = launches;
+    last_prof_ms = 0;
+    last_prof_launches = ev_prof_used / 2;
+    for (size_t k = 0; k + 1 < ev_prof_used; k += 2) {
+      CFD_CUDA(cudaEventElapsedTime(&ms, ev_prof[k], ev_prof[k + 1]));
+      last_prof_ms += ms;
+    }
     last_step_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();  // :378
     return CFD_OK;
   }
@@ -1219,24 +1252,64 @@ struct ModelImpl final : ModelBase {
   size_t own_u() const { return (size_t)(jb - ja) * (nx + 1); }
   size_t own_v() const { return (size_t)(v_row_end() - ja) * nx; }
 
+  // device -> host copy of `bytes` on the model's stream.  Pinned destinations (cudaHostAlloc / cudaHostRegister,
+  // e.g. cfd_host_alloc) are written by the copy engine directly; pageable ones go through two pinned bounce
+  // buffers so that the PCIe transfer of chunk k+1 overlaps the host memcpy of chunk k.
+  int copy_to_host(void* dst, const void* src_dev, size_t bytes) {
+    cudaPointerAttributes attr;
+    memset(&attr, 0, sizeof attr);
+    const cudaError_t qe = cudaPointerGetAttributes(&attr, dst);
+    if (qe != cudaSuccess) (void)cudaGetLastError();
+    if (qe == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+      CFD_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, stream));
+      return CFD_OK;
+    }
+    constexpr size_t kChunk = 8u << 20;
+    if (!bounce[0]) {
+      for (int k = 0; k < 2; ++k) {
+        CFD_CUDA(cudaHostAlloc(&bounce[k], kChunk, cudaHostAllocDefault));
+        CFD_CUDA(cudaEventCreateWithFlags(&bounce_ev[k], cudaEventDisableTiming));
+      }
+    }
+    const size_t n_chunks = (bytes + kChunk - 1) / kChunk;
+    auto issue = [&](size_t k) -> int {
+      const size_t off = k * kChunk, sz = bytes - off < kChunk ? bytes - off : kChunk;
+      CFD_CUDA(cudaMemcpyAsync(bounce[k & 1], (const char*)src_dev + off, sz, cudaMemcpyDeviceToHost, stream));
+      CFD_CUDA(cudaEventRecord(bounce_ev[k & 1], stream));
+      return CFD_OK;
+    };
+    int rc;
+    if (n_chunks && (rc = issue(0))) return rc;
+    for (size_t k = 0; k < n_chunks; ++k) {
+      if (k + 1 < n_chunks && (rc = issue(k + 1))) return rc;
+      CFD_CUDA(cudaEventSynchronize(bounce_ev[k & 1]));
+      const size_t off = k * kChunk, sz = bytes - off < kChunk ? bytes - off : kChunk;
+      memcpy((char*)dst + off, bounce[k & 1], sz);
+    }
+    return CFD_OK;
+  }
+
   // Model::get_snapshot, src/model.rs:1259-1267: p, u, v narrowed to f32 on the device, then D2H
   int get_snapshot(float* hp, float* hu, float* hv, float* hdt) override {
     CFD_CUDA(cudaSetDevice(device));
     const size_t np_ = own_p(), nu_ = own_u(), nv_ = own_v(), total = np_ + nu_ + nv_;
-    int rc;
-    if ((rc = ensure_staging(total * sizeof(float)))) return rc;
+    if (total * sizeof(float) > staging_bytes) {
+      cudaFree(staging);
+      staging = nullptr; staging_bytes = 0;
+      CFD_CUDA(cudaMalloc(&staging, total * sizeof(float)));
+      staging_bytes = total * sizeof(float);
+    }
     float* d = (float*)staging;
-    float* h = (float*)h_staging;
     const int grid_sz = 148 * 8;
     if (hp) cfdk::k_to_f32<R><<<grid_sz, 256, 0, stream>>>(p.row(ja), d, np_);
     if (hu) cfdk::k_to_f32<R><<<grid_sz, 256, 0, stream>>>(ubuf[iu].row(ja), d + np_, nu_);
     if (hv) cfdk::k_to_f32<R><<<grid_sz, 256, 0, stream>>>(vbuf[iu].row(ja), d + np_ + nu_, nv_);
     CFD_CUDA(cudaGetLastError());
-    CFD_CUDA(cudaMemcpyAsync(h, d, total * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    int rc;
+    if (hp && (rc = copy_to_host(hp, d, np_ * sizeof(float)))) return rc;
+    if (hu && (rc = copy_to_host(hu, d + np_, nu_ * sizeof(float)))) return rc;
+    if (hv && (rc = copy_to_host(hv, d + np_ + nu_, nv_ * sizeof(float)))) return rc;
     CFD_CUDA(cudaStreamSynchronize(stream));
-    if (hp) memcpy(hp, h, np_ * sizeof(float));
-    if (hu) memcpy(hu, h + np_, nu_ * sizeof(float));
-    if (hv) memcpy(hv, h + np_ + nu_, nv_ * sizeof(float));
     if (hdt) *hdt = (float)dt;
     return CFD_OK;
   }
@@ -1331,6 +1404,16 @@ struct ModelImpl final : ModelBase {
   int rows(uint64_t* j0, uint64_t* j1) override {
     *j0 = (uint64_t)ja;
     *j1 = (uint64_t)jb;
+    return CFD_OK;
+  }
+
+  int profile_smoother(int enable) override {
+    prof_smoother = enable != 0;
+    return CFD_OK;
+  }
+  int last_smoother_timing(double* ms, uint64_t* n) override {
+    if (ms) *ms = last_prof_ms;
+    if (n) *n = last_prof_launches;
     return CFD_OK;
   }
 
@@ -1469,6 +1552,16 @@ int cfd_model_last_timing(cfd_model* m, double* step_ms, double* sweep_ms, uint6
   return m->impl->last_timing(step_ms, sweep_ms, kernel_launches);
 }
 
+int cfd_model_profile_smoother(cfd_model* m, int32_t enable) {
+  CFD_CHECK_MODEL(m);
+  return m->impl->profile_smoother(enable);
+}
+
+int cfd_model_last_smoother_timing(cfd_model* m, double* ms, uint64_t* launches) {
+  CFD_CHECK_MODEL(m);
+  return m->impl->last_smoother_timing(ms, launches);
+}
+
 int cfd_nccl_unique_id(void* out128) {
   if (!out128) return fail(CFD_ERR_INVALID_ARGUMENT, "null out");
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
@@ -1495,6 +1588,17 @@ int cfd_selftest_division(double divisor, uint64_t samples, uint64_t seed, int32
   *mismatches = h[0];
   if (fast_path_taken) *fast_path_taken = h[1];
   return CFD_OK;
+}
+
+int cfd_host_alloc(uint64_t bytes, void** out) {
+  if (!out) return fail(CFD_ERR_INVALID_ARGUMENT, "null out");
+  *out = nullptr;
+  CFD_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return CFD_OK;
+}
+
+void cfd_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
 }
 
 const char* cfd_last_error(void) { return g_last_error.c_str(); }

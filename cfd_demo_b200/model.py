@@ -64,6 +64,11 @@ def load_library():
     lib.cfd_model_rows.argtypes = [C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
     lib.cfd_model_last_timing.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double), P(C.c_uint64)]
     lib.cfd_nccl_unique_id.argtypes = [C.c_void_p]
+    lib.cfd_model_profile_smoother.argtypes = [C.c_void_p, C.c_int32]
+    lib.cfd_model_last_smoother_timing.argtypes = [C.c_void_p, P(C.c_double), P(C.c_uint64)]
+    lib.cfd_host_alloc.argtypes = [C.c_uint64, P(C.c_void_p)]
+    lib.cfd_host_free.argtypes = [C.c_void_p]
+    lib.cfd_host_free.restype = None
     lib.cfd_selftest_division.argtypes = [C.c_double, C.c_uint64, C.c_uint64, C.c_int32, P(C.c_uint64),
                                           P(C.c_uint64)]
     if lib.cfd_abi_version() != _abi.CFD_ABI_VERSION:
@@ -81,6 +86,30 @@ def default_options() -> _abi.CfdOptions:
     o = _abi.CfdOptions()
     load_library().cfd_options_default(C.byref(o))
     return o
+
+
+class PinnedBuffer:
+    """Page-locked host memory (cfd_host_alloc) viewed as a numpy array; snapshots into it skip the bounce copy."""
+
+    def __init__(self, count: int, dtype=np.float32):
+        self._lib = load_library()
+        self._ptr = C.c_void_p()
+        nbytes = int(count) * np.dtype(dtype).itemsize
+        _check(self._lib, self._lib.cfd_host_alloc(nbytes, C.byref(self._ptr)))
+        raw = (C.c_char * max(nbytes, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(raw, dtype=dtype, count=int(count))
+
+    def close(self):
+        if self._ptr:
+            self.array = None
+            self._lib.cfd_host_free(self._ptr)
+            self._ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def nccl_unique_id() -> bytes:
@@ -167,16 +196,28 @@ class Model:
         p = params.to_c()
         _check(self._lib, self._lib.cfd_model_set_params(self._handle(), C.byref(p)))
 
-    def get_snapshot(self) -> SimSnapshot:
-        """`Model::get_snapshot` (src/model.rs:1259-1267): owned f32 copies of p, u, v in reference layout."""
+    def snapshot_sizes(self):
         n = C.c_uint64()
         sizes = []
         for fid in (_abi.FIELD_P, _abi.FIELD_U, _abi.FIELD_V):  # whole fields, or this rank's rows of a strip run
             _check(self._lib, self._lib.cfd_model_field_len(self._handle(), fid, C.byref(n)))
             sizes.append(int(n.value))
-        p = np.empty(sizes[0], dtype=np.float32)
-        u = np.empty(sizes[1], dtype=np.float32)
-        v = np.empty(sizes[2], dtype=np.float32)
+        return sizes
+
+    def pinned_snapshot_buffers(self):
+        """Three page-locked f32 buffers sized for `get_snapshot(out=...)`."""
+        return [PinnedBuffer(n, np.float32) for n in self.snapshot_sizes()]
+
+    def get_snapshot(self, out=None) -> SimSnapshot:
+        """`Model::get_snapshot` (src/model.rs:1259-1267): owned f32 copies of p, u, v in reference layout.
+        `out` = three preallocated buffers (`pinned_snapshot_buffers()`) to fill instead of new arrays."""
+        if out is not None:
+            p, u, v = (b.array if isinstance(b, PinnedBuffer) else b for b in out)
+        else:
+            sizes = self.snapshot_sizes()
+            p = np.empty(sizes[0], dtype=np.float32)
+            u = np.empty(sizes[1], dtype=np.float32)
+            v = np.empty(sizes[2], dtype=np.float32)
         dt = C.c_float()
         _check(self._lib, self._lib.cfd_model_get_snapshot(self._handle(), p.ctypes.data, u.ctypes.data,
                                                            v.ctypes.data, C.byref(dt)))
@@ -208,6 +249,14 @@ class Model:
         j0, j1 = C.c_uint64(), C.c_uint64()
         _check(self._lib, self._lib.cfd_model_rows(self._handle(), C.byref(j0), C.byref(j1)))
         return int(j0.value), int(j1.value)
+
+    def profile_smoother(self, enable: bool):
+        _check(self._lib, self._lib.cfd_model_profile_smoother(self._handle(), 1 if enable else 0))
+
+    def last_smoother_timing(self):
+        ms, n = C.c_double(), C.c_uint64()
+        _check(self._lib, self._lib.cfd_model_last_smoother_timing(self._handle(), C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
 
     def last_timing(self):
         step_ms, sweep_ms, launches = C.c_double(), C.c_double(), C.c_uint64()

@@ -155,6 +155,11 @@ int cfd_model_set_params(cfd_model* m, const cfd_params* params);
  * Caller-allocated, reference layout: p nx*ny, u (nx+1)*ny, v nx*(ny+1); any pointer may be NULL.
  * With world_size > 1 each rank receives its own rows only (see cfd_model_rows). */
 int cfd_model_get_snapshot(cfd_model* m, float* p, float* u, float* v, float* dt);
+/* Page-locked host memory for snapshot buffers (no reference counterpart: `SimSnapshot` owns plain Vec<f32>).
+ * cfd_model_get_snapshot detects pinned destinations and lets the copy engine write them directly; pageable
+ * destinations are served through pinned bounce buffers (chunked, PCIe transfer overlapped with the memcpy). */
+int cfd_host_alloc(uint64_t bytes, void** out);
+void cfd_host_free(void* ptr);
 /* Model::get_residuals(&self), src/model.rs:1269-1280. */
 int cfd_model_get_residuals(cfd_model* m, cfd_residuals* out);
 /* Parity harness: any field (CFD_FIELD_*) widened to double, reference layout. */
@@ -169,6 +174,11 @@ int cfd_model_rows(cfd_model* m, uint64_t* j0, uint64_t* j1);
 /* Device time in ms of the last cfd_model_update / update_n, and of the Jacobi sweeps inside it,
  * both from CUDA events on the model's own stream. */
 int cfd_model_last_timing(cfd_model* m, double* step_ms, double* sweep_ms, uint64_t* kernel_launches);
+
+/* MGCG: bracket every launch of the fine-level smoother (k_jacobi_sweep5) with CUDA events on the model's stream;
+ * cfd_model_last_smoother_timing returns their summed duration and count for the last cfd_model_update. */
+int cfd_model_profile_smoother(cfd_model* m, int32_t enable);
+int cfd_model_last_smoother_timing(cfd_model* m, double* ms, uint64_t* launches);
 
 /* Self-test of the hot kernels' exact division by a loop-invariant divisor (cfdk::div_c): draws `samples`
  * dividends (mode 0 random bit patterns, 1 moderate magnitudes, 2 near representable quotients, 3 near

@@ -43,14 +43,15 @@ def test_struct_layouts_match_the_header(lib):
     # sizes follow from the header's member lists (natural alignment)
     assert C.sizeof(_abi.CfdGrid) == 48
     assert C.sizeof(_abi.CfdParams) == 28
-    assert C.sizeof(_abi.CfdSolverConsts) == 56
-    assert C.sizeof(_abi.CfdOptions) == 32 + 56
+    assert C.sizeof(_abi.CfdSolverConsts) == 72
+    assert C.sizeof(_abi.CfdOptions) == 32 + 72
     assert C.sizeof(_abi.CfdResiduals) == 8 + 5 * 4 + 4 + 8 + 3 * 8 + 5 * 8
     o = model.default_options()
     assert (o.precision, o.device, o.rank, o.world_size) == (64, -1, 0, 1)
     c = o.consts
     assert (c.ramp_up_steps, c.jacobi_iterations, c.outer_rounds) == (100, 50, 20)
     assert (c.jacobi_omega, c.pressure_tolerance, c.outer_tolerance, c.cfl) == (0.75, 1e-4, 1e-4, 0.2)
+    assert (c.cg_tolerance, c.mg_omega, c.mg_smoothing) == (1e-8, 0.8, 2)
 
 
 def test_argument_validation_needs_no_gpu(lib):
