@@ -15,11 +15,11 @@ SOLVER_JACOBI, SOLVER_CG, SOLVER_MGCG = 0, 1, 2
 SCENARIO_CHANNEL, SCENARIO_CAVITY = 0, 1
 
 FIELD_P, FIELD_U, FIELD_V, FIELD_U_STAR, FIELD_V_STAR, FIELD_RHS, FIELD_P_PRIME = range(7)
-FIELD_U_OLD, FIELD_V_OLD, FIELD_MASK_U, FIELD_MASK_V = 7, 8, 9, 10
+FIELD_U_OLD, FIELD_V_OLD, FIELD_MASK_U, FIELD_MASK_V, FIELD_MG_GUESS = 7, 8, 9, 10, 11
 FIELD_NAMES = {
     FIELD_P: "p", FIELD_U: "u", FIELD_V: "v", FIELD_U_STAR: "u_star", FIELD_V_STAR: "v_star",
     FIELD_RHS: "rhs", FIELD_P_PRIME: "p_prime", FIELD_U_OLD: "u_old", FIELD_V_OLD: "v_old",
-    FIELD_MASK_U: "mask_u", FIELD_MASK_V: "mask_v",
+    FIELD_MASK_U: "mask_u", FIELD_MASK_V: "mask_v", FIELD_MG_GUESS: "mg_guess",
 }
 
 FLAG_NO_GRAPH = 1
@@ -51,7 +51,7 @@ class CfdSolverConsts(C.Structure):
                 ("outer_rounds", C.c_int32), ("cg_max_iterations", C.c_int32),
                 ("jacobi_omega", C.c_double), ("pressure_tolerance", C.c_double),
                 ("outer_tolerance", C.c_double), ("cfl", C.c_double), ("cg_tolerance", C.c_double),
-                ("mg_omega", C.c_double), ("mg_smoothing", C.c_int32), ("mg_reserved", C.c_int32)]
+                ("mg_omega", C.c_double), ("mg_smoothing", C.c_int32), ("mg_warm_start", C.c_int32)]
 
 
 class CfdOptions(C.Structure):

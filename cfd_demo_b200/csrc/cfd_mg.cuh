@@ -106,36 +106,6 @@ __device__ __forceinline__ void mg_finish_dot(const MgFine<R>& c, MgScalars* sc,
   }
 }
 
-// x = 0, d = 0 on the whole grid, rho = rhs on the unknowns (0 on the ring), rho.rho.
-// grid = (ceil(nx / 512), ceil(ny / kMgRows))
-template <class R>
-__global__ void __launch_bounds__(kMgThreads) k_mg_init(MgFine<R> c, MgScalars* __restrict__ sc,
-                                                         const R* __restrict__ rhs, R* __restrict__ x,
-                                                         R* __restrict__ rho, R* __restrict__ d,
-                                                         double* __restrict__ partials, unsigned* __restrict__ ticket) {
-  using V = typename Vec2<R>::type;
-  const int c0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-  const int j0 = blockIdx.y * kMgRows, j1 = min(j0 + kMgRows, c.ny);
-  double acc = 0.0;
-  if (c0 < c.nx) {
-    V zero;
-    zero.x = R(0); zero.y = R(0);
-    for (int j = j0; j < j1; ++j) {
-      const size_t idx = (size_t)c0 + (size_t)j * c.nx;
-      const bool row_ok = j >= 1 && j <= c.ny - 2;
-      V b = *reinterpret_cast<const V*>(rhs + idx);
-      if (!(row_ok && c0 >= 1)) b.x = R(0);
-      if (!(row_ok && c0 + 1 <= c.nx - 2)) b.y = R(0);
-      *reinterpret_cast<V*>(x + idx) = zero;
-      *reinterpret_cast<V*>(d + idx) = zero;
-      *reinterpret_cast<V*>(rho + idx) = b;
-      acc += (double)(b.x * b.x);
-      acc += (double)(b.y * b.y);
-    }
-  }
-  mg_finish_dot<R>(c, sc, partials, ticket, acc, 0);
-}
-
 // (L x) on the unknowns of one column pair; l / r = the columns left / right of the pair, already replaced by the
 // boundary rules where the pair touches the ring (mirror; 0 at the channel outlet)
 template <class R>
@@ -152,6 +122,43 @@ __device__ __forceinline__ R mg_fine_apply(const MgFine<R>& c, const R* __restri
   const R xn = (j == c.ny - 2) ? cc : x[idx + c.nx];
   const R xs = (j == 1) ? cc : x[idx - c.nx];
   return mg_lap<R>(c, cc, xe, xw, xn, xs);
+}
+
+// x = guess (or 0), d = 0 on the whole grid, rho = rhs - L x on the unknowns (0 on the ring), rho.rho.
+// grid = (ceil(nx / 512), ceil(ny / kMgRows))
+template <class R>
+__global__ void __launch_bounds__(kMgThreads) k_mg_init(MgFine<R> c, MgScalars* __restrict__ sc,
+                                                         const R* __restrict__ rhs, const R* __restrict__ guess,
+                                                         R* __restrict__ x, R* __restrict__ rho, R* __restrict__ d,
+                                                         double* __restrict__ partials, unsigned* __restrict__ ticket) {
+  using V = typename Vec2<R>::type;
+  const int c0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int j0 = blockIdx.y * kMgRows, j1 = min(j0 + kMgRows, c.ny);
+  double acc = 0.0;
+  if (c0 < c.nx) {
+    V zero;
+    zero.x = R(0); zero.y = R(0);
+    for (int j = j0; j < j1; ++j) {
+      const size_t idx = (size_t)c0 + (size_t)j * c.nx;
+      const bool row_ok = j >= 1 && j <= c.ny - 2;
+      const bool ok0 = row_ok && c0 >= 1, ok1 = row_ok && c0 + 1 <= c.nx - 2;
+      V b = *reinterpret_cast<const V*>(rhs + idx);
+      V x0 = zero;
+      if (guess != nullptr) {
+        x0 = *reinterpret_cast<const V*>(guess + idx);
+        if (ok0) b.x = b.x - mg_fine_apply<R>(c, guess, c0, j);
+        if (ok1) b.y = b.y - mg_fine_apply<R>(c, guess, c0 + 1, j);
+      }
+      if (!ok0) b.x = R(0);
+      if (!ok1) b.y = R(0);
+      *reinterpret_cast<V*>(x + idx) = x0;
+      *reinterpret_cast<V*>(d + idx) = zero;
+      *reinterpret_cast<V*>(rho + idx) = b;
+      acc += (double)(b.x * b.x);
+      acc += (double)(b.y * b.y);
+    }
+  }
+  mg_finish_dot<R>(c, sc, partials, ticket, acc, 0);
 }
 
 // rho.z -> beta, rz

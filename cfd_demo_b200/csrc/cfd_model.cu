@@ -106,7 +106,7 @@ void consts_default(cfd_solver_consts* c) {
   c->cg_tolerance = 1e-8;        // extension
   c->mg_omega = 0.8;             // extension (MGCG)
   c->mg_smoothing = 2;           // extension (MGCG)
-  c->mg_reserved = 0;
+  c->mg_warm_start = 1;          // extension (MGCG)
 }
 
 constexpr int kMaxSweepSlots = 256;
@@ -198,6 +198,7 @@ struct ModelImpl final : ModelBase {
   };
   std::vector<MgLevelHost> mg;
   Field<R> mg_rho, mg_d, mg_z[2];
+  Field<R> mg_guess;  // p' of the previous step's first solve (warm start; carried state)
   CUtensorMap tmap_mg_z[2], tmap_mg_rho;
   cfdk::MgScalars* mg_scalars = nullptr;  // device
   cfdk::MgScalars* h_mg = nullptr;        // pinned host copy
@@ -268,7 +269,7 @@ struct ModelImpl final : ModelBase {
     cudaFree(err_slots); cudaFree(step_slots); cudaFree(staging); cudaFree(tickets);
     cudaFree(cg_r.base); cudaFree(cg_d.base); cudaFree(cg_partials); cudaFree(cg_scalars);
     for (auto& L : mg) { cudaFree(L.weights); cudaFree(L.e); cudaFree(L.rho); cudaFree(L.tmp); }
-    cudaFree(mg_rho.base); cudaFree(mg_d.base); cudaFree(mg_z[0].base); cudaFree(mg_z[1].base);
+    cudaFree(mg_rho.base); cudaFree(mg_d.base); cudaFree(mg_guess.base); cudaFree(mg_z[0].base); cudaFree(mg_z[1].base);
     cudaFree(mg_scalars); cudaFree(mg_partials); cudaFree(mg_err); cudaFree(mg_ticket);
     if (h_mg) cudaFreeHost(h_mg);
     if (h_cg) cudaFreeHost(h_cg);
@@ -903,6 +904,7 @@ struct ModelImpl final : ModelBase {
     if ((rc = falloc(&mg_d, (size_t)nx))) return rc;
     if ((rc = falloc(&mg_z[0], (size_t)nx))) return rc;
     if ((rc = falloc(&mg_z[1], (size_t)nx))) return rc;
+    if ((rc = falloc(&mg_guess, (size_t)nx))) return rc;
     using Ring = cfdk::SweepChunkRing<R>;
     if ((rc = make_tensor_map(&tmap_mg_z[0], mg_z[0].row(ja - kHalo), Ring::kPCols))) return rc;
     if ((rc = make_tensor_map(&tmap_mg_z[1], mg_z[1].row(ja - kHalo), Ring::kPCols))) return rc;
@@ -1054,7 +1056,11 @@ struct ModelImpl final : ModelBase {
     *h_mg = init;
     CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index], stream));
     CFD_CUDA(cudaMemcpyAsync(mg_scalars, h_mg, sizeof init, cudaMemcpyHostToDevice, stream));
-    cfdk::k_mg_init<R><<<g_all, blk, 0, stream>>>(c, mg_scalars, rhs.v, x, mg_rho.v, mg_d.v, mg_partials, mg_ticket);
+    // first solve of a step: start from the p' the first solve of the previous step ended with (mg_warm_start)
+    const bool first_solve = call_index == 0;
+    const bool warm = first_solve && opt.consts.mg_warm_start != 0;
+    cfdk::k_mg_init<R><<<g_all, blk, 0, stream>>>(c, mg_scalars, rhs.v, warm ? mg_guess.v : nullptr, x, mg_rho.v, mg_d.v,
+                                                  mg_partials, mg_ticket);
     launches += 1;
     for (;;) {
       CFD_CUDA(cudaMemcpyAsync(h_mg, mg_scalars, sizeof init, cudaMemcpyDeviceToHost, stream));
@@ -1073,6 +1079,8 @@ struct ModelImpl final : ModelBase {
     const int n_edge = (nx > ny ? nx : ny);
     cfdk::k_cg_fill_boundary<R><<<(n_edge + 255) / 256, 256, 0, stream>>>(nx, ny, c.cavity, x, ja, jb);
     ++launches;
+    if (first_solve)
+      CFD_CUDA(cudaMemcpyAsync(mg_guess.row(0), xf.row(0), n_p * sizeof(R), cudaMemcpyDeviceToDevice, stream));
     CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index + 1], stream));
     CFD_CUDA(cudaGetLastError());
     last_S += (uint64_t)h_mg->iterations;
@@ -1347,6 +1355,10 @@ struct ModelImpl final : ModelBase {
       // after a step the free buffer still holds the fields the step started from (u_old, v_old)
       case CFD_FIELD_U_OLD: *n = own_u(); return ubuf[ifree].row(ja);
       case CFD_FIELD_V_OLD: *n = own_v(); return vbuf[ifree].row(ja);
+      case CFD_FIELD_MG_GUESS:
+        if (!mg_guess.base && (world > 1 || mg_setup() != CFD_OK)) { *n = 0; return nullptr; }
+        *n = own_p();
+        return mg_guess.row(ja);
       default: *n = 0; return nullptr;
     }
   }

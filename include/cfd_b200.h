@@ -59,7 +59,8 @@ extern "C" {
 #define CFD_FIELD_V_OLD 8
 #define CFD_FIELD_MASK_U 9  /* 0/1 as double */
 #define CFD_FIELD_MASK_V 10 /* 0/1 as double */
-#define CFD_FIELD_COUNT 11
+#define CFD_FIELD_MG_GUESS 11 /* MGCG extension: p' of the previous step's first solve (the warm start; carried state) */
+#define CFD_FIELD_COUNT 12
 
 /* ---- PODs ---------------------------------------------------------------------------------------- */
 /* Grid + Option<Cylinder>, src/model.rs:121-139 */
@@ -91,7 +92,9 @@ typedef struct cfd_solver_consts {
   double cg_tolerance;       /* extension (CG, MGCG): stop when dt * rms(Poisson residual) <= this */
   double mg_omega;           /* extension (MGCG): damping of the Jacobi smoother, default 0.8 */
   int32_t mg_smoothing;      /* extension (MGCG): pre- and post-smoothing sweeps per level, default 2 */
-  int32_t mg_reserved;
+  int32_t mg_warm_start;     /* extension (MGCG): 1 (default) = the first solve of a step starts from the p' the first
+                              * solve of the previous step ended with — like the reference's Jacobi, which never resets
+                              * p' (src/model.rs:734-824); re-correction solves and 0 = start from p' = 0 */
 } cfd_solver_consts;
 
 typedef struct cfd_options {

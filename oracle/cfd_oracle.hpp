@@ -90,6 +90,7 @@ class Model {
   };
   std::vector<MgLevel> mg_levels;
   std::vector<R> mg_rho, mg_d, mg_w, mg_z, mg_z2;
+  std::vector<R> mg_guess;  // p' of the previous step's first solve (warm start; carried state)
 
   // Model::new, src/model.rs:219-299
   Model(const cfd_grid& g, const cfd_params& prm, const cfd_solver_consts* c = nullptr) {
@@ -146,6 +147,7 @@ class Model {
     scenario = prm.scenario;
     u_old = u; v_old = v; u_star = u; v_star = v;
     rhs.assign(size_p, R(0)); p_prime.assign(size_p, R(0)); p_prime_new.assign(size_p, R(0));
+    mg_guess.assign(size_p, R(0));
   }
 
   static void cfd_solver_consts_default_inline(cfd_solver_consts* c) {
@@ -160,7 +162,7 @@ class Model {
     c->cg_tolerance = 1e-8;
     c->mg_omega = 0.8;
     c->mg_smoothing = 2;
-    c->mg_reserved = 0;
+    c->mg_warm_start = 1;
   }
 
   // Model::set_parameters, src/model.rs:1250-1257
@@ -709,7 +711,10 @@ class Model {
   //    finest-cell units; the outlet's zero sits half a finest cell beyond the last column.
   //  * Transfer: residuals are summed over the (up to four) children, corrections are copied to them.
   //  * V(n,n) with n = mg_smoothing damped-Jacobi sweeps before and after; the first sweep starts from zero.
-  // Same start (x = 0), stopping rule and return value as cg_pressure.
+  // Stopping rule and return value as cg_pressure.  Start: the FIRST solve of a timestep starts from the p' the
+  // first solve of the previous timestep ended with (mg_warm_start; the reference's Jacobi never resets p' either,
+  // src/model.rs:734-824 — p' is the full pressure of this non-incremental projection and varies slowly in time);
+  // the re-correction solves of the outer loop (:696-724), whose solution is ~0, start from 0.
   // ------------------------------------------------------------------------------------------------
   void mg_build_levels() {
     mg_levels.clear();
@@ -881,11 +886,14 @@ class Model {
       }
       return acc;
     };
-    std::fill(p_prime.begin(), p_prime.end(), R(0));
+    const bool first_solve = last_jacobi_calls == 1;  // pressure_solve() counted this call already
+    const bool warm = consts.mg_warm_start != 0 && first_solve;
+    if (warm) p_prime = mg_guess; else std::fill(p_prime.begin(), p_prime.end(), R(0));
     std::fill(mg_rho.begin(), mg_rho.end(), R(0));
     std::fill(mg_d.begin(), mg_d.end(), R(0));
     for (size_t j = 1; j + 1 < ny; ++j)
-      for (size_t i = 1; i + 1 < nx; ++i) mg_rho[i + j * nx] = rhs[i + j * nx];
+      for (size_t i = 1; i + 1 < nx; ++i)
+        mg_rho[i + j * nx] = warm ? rhs[i + j * nx] - mg_fine_apply(p_prime, i, j) : rhs[i + j * nx];
     R rr = dot(mg_rho, mg_rho);
     int it = 0;
     if (!(measure(rr) <= tol) && consts.cg_max_iterations > 0) {
@@ -917,6 +925,7 @@ class Model {
       }
     }
     cg_fill_boundary(p_prime);
+    if (first_solve) mg_guess = p_prime;
     const R res = measure(rr);
     last_pressure_residual = res;
     return res;

@@ -30,6 +30,7 @@ std::vector<R>* field_ptr(Model<R>& m, int field) {
     case CFD_FIELD_P_PRIME: return &m.p_prime;
     case CFD_FIELD_U_OLD: return &m.u_old;
     case CFD_FIELD_V_OLD: return &m.v_old;
+    case CFD_FIELD_MG_GUESS: return &m.mg_guess;
     default: return nullptr;
   }
 }

@@ -351,6 +351,7 @@ def test_mode_c_mgcg_first_vcycle_is_bit_identical():
     consts = default_consts()
     consts.cg_max_iterations = 1
     consts.outer_rounds = 0
+    consts.mg_warm_start = 0
     o = default_options()
     o.consts = consts
     gpu = Model(g, prm, options=o)
@@ -391,3 +392,47 @@ def test_mgcg_bottom_kernel_matches_per_level_launches():
         models.append(m)
     assert models[0].get_residuals().sweeps == models[1].get_residuals().sweeps > 0
     assert_fields_identical(models[0], models[1], STATE_FIELDS, "bottom kernel vs per-level launches")
+
+
+def test_mgcg_warm_start_state_restarts_in_the_oracle():
+    """The warm start (p' of the previous step's first solve, CFD_FIELD_MG_GUESS) is carried state: load the GPU's
+    complete state into the oracle after a spin-up and compute one more step on both sides — same iteration count
+    (far fewer than a cold start needs), fields within the Mode C tolerance; and a cold-start model converges to the
+    same velocities."""
+    from cfd_demo_b200.model import default_options
+    from cfd_demo_b200.types import PressureSolver
+    from oracle.cpu_oracle import default_consts
+    n = 256
+    g = Grid.uniform(n, n, 1.0, 1.0, None)
+    nu = 1e-3
+    prm = SimulationParams(dt=0.02 * (1.0 / n) ** 2 / nu, viscosity=nu, scenario=Scenario.Cavity,
+                           pressure_solver=PressureSolver.MGCG)
+    consts = default_consts()
+    consts.ramp_up_steps = 5
+    its = {}
+    models = {}
+    for warm in (1, 0):
+        consts.mg_warm_start = warm
+        o = default_options()
+        o.consts = consts
+        m = Model(g, prm, options=o)
+        for _ in range(40):
+            m.update()
+        its[warm] = m.get_residuals().sweeps
+        models[warm] = m
+    assert 0 < its[1] < its[0], its
+    assert rel_l2(models[1].field(_abi.FIELD_U), models[0].field(_abi.FIELD_U)) < 1e-6
+    consts.mg_warm_start = 1
+    gpu = models[1]
+    cpu = OracleModel(g, prm, precision=64, consts=consts)
+    r0 = gpu.get_residuals()
+    for fid in (_abi.FIELD_P, _abi.FIELD_U, _abi.FIELD_V, _abi.FIELD_U_STAR, _abi.FIELD_V_STAR, _abi.FIELD_P_PRIME,
+                _abi.FIELD_MG_GUESS):
+        cpu.set_field(fid, gpu.field(fid))
+    cpu.set_scalars(r0.simulation_step, r0.f64["simulation_time"], r0.f64["dt"])
+    gpu.update()
+    cpu.update()
+    rg, rc = gpu.get_residuals(), cpu.get_residuals()
+    assert rg.sweeps == rc.sweeps == its[1] and rg.jacobi_calls == rc.jacobi_calls == 2
+    for fid in (_abi.FIELD_U, _abi.FIELD_V, _abi.FIELD_P, _abi.FIELD_MG_GUESS):
+        assert rel_l2(gpu.field(fid), cpu.field(fid)) <= 1e-9, _abi.FIELD_NAMES[fid]
