@@ -19,17 +19,6 @@
 
 namespace cfdk {
 
-struct MgScalars {
-  double rr, rz, dw, alpha, beta, measure;
-  int done, iterations, max_iterations, pad;
-};
-
-template <class R>
-struct MgFine {
-  R dx_sq, dy_sq, dt, tol, n_unknowns;
-  int nx, ny, cavity;
-};
-
 template <class R>
 struct MgLevelDev {
   int mx, my;               // unknowns per direction; fields are (mx + 2) x (my + 2)
@@ -60,50 +49,6 @@ __device__ __forceinline__ MgPair<R> mg_pair(const MgFine<R>& c) {
   p.v0 = p.any && p.c0 >= 1;
   p.v1 = p.any && p.c0 + 1 <= c.nx - 2;
   return p;
-}
-
-// mode 0: rho.rho after init; 1: rho.z -> beta (0 before the first iteration); 2: d.w -> alpha;
-// 3: rho.rho after the update -> iteration count, stopping rule (same measure as k_cg_reduce)
-template <class R>
-__device__ __forceinline__ void mg_advance(const MgFine<R>& c, MgScalars* sc, double total, int mode) {
-  const R sum = (R)total;
-  if (mode == 1) {
-    sc->beta = sc->iterations == 0 ? 0.0 : (double)(sum / (R)sc->rz);
-    sc->rz = (double)sum;
-  } else if (mode == 2) {
-    sc->dw = (double)sum;
-    sc->alpha = (double)((R)sc->rz / sum);
-  } else {
-    if (mode == 3) sc->iterations += 1;
-    sc->rr = (double)sum;
-    const R measure = c.dt * (R)sqrt((double)(sum / c.n_unknowns));
-    sc->measure = (double)measure;
-    if (measure <= c.tol || sc->iterations >= sc->max_iterations) sc->done = 1;
-  }
-}
-
-template <class R>
-__device__ __forceinline__ void mg_finish_dot(const MgFine<R>& c, MgScalars* sc, double* partials, unsigned* ticket,
-                                              double acc, int mode) {
-  __shared__ double s_red[kMgThreads / 32];
-  __shared__ int s_last;
-  const int n_blocks = (int)(gridDim.x * gridDim.y), bid = (int)(blockIdx.y * gridDim.x + blockIdx.x);
-  const double t = block_sum<kMgThreads / 32>(acc, s_red);
-  if (threadIdx.x == 0) {
-    partials[bid] = t;
-    __threadfence();
-    s_last = atomicAdd(ticket, 1u) == (unsigned)(n_blocks - 1);
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  double a = 0.0;
-  for (int k = threadIdx.x; k < n_blocks; k += kMgThreads) a += __ldcg(partials + k);
-  const double total = block_sum<kMgThreads / 32>(a, s_red);
-  if (threadIdx.x == 0) {
-    mg_advance<R>(c, sc, total, mode);
-    *ticket = 0u;
-  }
 }
 
 // (L x) on the unknowns of one column pair; l / r = the columns left / right of the pair, already replaced by the
@@ -158,10 +103,13 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_init(MgFine<R> c, MgScalars* 
       acc += (double)(b.y * b.y);
     }
   }
-  mg_finish_dot<R>(c, sc, partials, ticket, acc, 0);
+  mg_finish_dot<R, kMgThreads>(c, sc, partials, ticket, acc, 0);
 }
 
-// rho.z -> beta, rz
+// The kernels below load every row of their tile before they compute (fully unrolled, rows past the tile's end
+// predicated off): with one row in flight per thread they were latency-bound at ~3 TB/s.
+
+// a.b over the unknowns -> mg_advance(mode)
 template <class R>
 __global__ void __launch_bounds__(kMgThreads) k_mg_dot(MgFine<R> c, MgScalars* __restrict__ sc, const R* __restrict__ a,
                                                         const R* __restrict__ b, double* __restrict__ partials,
@@ -170,75 +118,90 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_dot(MgFine<R> c, MgScalars* _
   const MgPair<R> p = mg_pair<R>(c);
   double acc = 0.0;
   if (p.any) {
-    for (int j = p.j0; j < p.j1; ++j) {
+    V av[kMgRows], bv[kMgRows];
+#pragma unroll
+    for (int r = 0; r < kMgRows; ++r) {
+      const int j = min(p.j0 + r, c.ny - 2);
       const size_t idx = (size_t)p.c0 + (size_t)j * c.nx;
-      const V av = *reinterpret_cast<const V*>(a + idx), bv = *reinterpret_cast<const V*>(b + idx);
-      if (p.v0) acc += (double)(av.x * bv.x);
-      if (p.v1) acc += (double)(av.y * bv.y);
+      av[r] = *reinterpret_cast<const V*>(a + idx);
+      bv[r] = *reinterpret_cast<const V*>(b + idx);
+    }
+#pragma unroll
+    for (int r = 0; r < kMgRows; ++r) {
+      if (p.j0 + r < p.j1) {
+        if (p.v0) acc += (double)(av[r].x * bv[r].x);
+        if (p.v1) acc += (double)(av[r].y * bv[r].y);
+      }
     }
   }
-  mg_finish_dot<R>(c, sc, partials, ticket, acc, mode);
+  mg_finish_dot<R, kMgThreads>(c, sc, partials, ticket, acc, mode);
 }
 
-// d = z + beta d
+// d_new = z + beta d_old and w = L d_new in one pass (d_new goes to its own buffer: neighbours still read d_old),
+// d_new.w -> alpha.  Tiles of kMgDirRows rows; grid = (ceil(nx / 512), ceil((ny - 2) / kMgDirRows)).
+constexpr int kMgDirRows = 4;
 template <class R>
-__global__ void __launch_bounds__(kMgThreads) k_mg_direction(MgFine<R> c, const MgScalars* __restrict__ sc,
-                                                              const R* __restrict__ z, R* __restrict__ d) {
+__global__ void __launch_bounds__(kMgThreads) k_mg_dir_apply(MgFine<R> c, MgScalars* __restrict__ sc,
+                                                              const R* __restrict__ z, const R* __restrict__ d_old,
+                                                              R* __restrict__ d_new, R* __restrict__ w,
+                                                              double* __restrict__ partials, unsigned* __restrict__ ticket) {
   using V = typename Vec2<R>::type;
   const R beta = (R)sc->beta;
-  const MgPair<R> p = mg_pair<R>(c);
-  if (!p.any) return;
-  for (int j = p.j0; j < p.j1; ++j) {
-    const size_t idx = (size_t)p.c0 + (size_t)j * c.nx;
-    const V zv = *reinterpret_cast<const V*>(z + idx);
-    V dv = *reinterpret_cast<const V*>(d + idx);
-    if (p.v0) dv.x = zv.x + beta * dv.x;
-    if (p.v1) dv.y = zv.y + beta * dv.y;
-    *reinterpret_cast<V*>(d + idx) = dv;
-  }
-}
-
-// w = L d, d.w -> alpha
-template <class R>
-__global__ void __launch_bounds__(kMgThreads) k_mg_apply(MgFine<R> c, MgScalars* __restrict__ sc, const R* __restrict__ d,
-                                                          R* __restrict__ w, double* __restrict__ partials,
-                                                          unsigned* __restrict__ ticket) {
-  using V = typename Vec2<R>::type;
-  const MgPair<R> p = mg_pair<R>(c);
+  const int nx = c.nx;
+  const int c0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int j0 = 1 + blockIdx.y * kMgDirRows, j1 = min(j0 + kMgDirRows, c.ny - 1);
+  const bool any = c0 < nx, v0 = any && c0 >= 1, v1 = any && c0 + 1 <= nx - 2;
   double acc = 0.0;
-  if (p.any) {
-    const int nx = c.nx;
-    const R* col = d + p.c0;
-    V south = *reinterpret_cast<const V*>(col + (size_t)(p.j0 - 1) * nx);
-    V cen = *reinterpret_cast<const V*>(col + (size_t)p.j0 * nx);
-    for (int j = p.j0; j < p.j1; ++j) {
+  if (any) {
+    V dn[kMgDirRows + 2];            // d_new of the own pair on rows j0-1 .. j0+kMgDirRows
+    R dl[kMgDirRows], dr[kMgDirRows];  // d_new left / right of the pair on the tile's rows
+    const int cl = max(c0 - 1, 0), cr = min(c0 + 2, nx - 1);
+#pragma unroll
+    for (int m = 0; m < kMgDirRows + 2; ++m) {
+      const int j = min(j0 - 1 + m, c.ny - 1);
+      const size_t idx = (size_t)c0 + (size_t)j * nx;
+      const V zv = *reinterpret_cast<const V*>(z + idx), dv = *reinterpret_cast<const V*>(d_old + idx);
+      dn[m].x = zv.x + beta * dv.x;
+      dn[m].y = zv.y + beta * dv.y;
+    }
+#pragma unroll
+    for (int r = 0; r < kMgDirRows; ++r) {
+      const int j = min(j0 + r, c.ny - 2);
       const size_t row = (size_t)j * nx;
-      const V north = *reinterpret_cast<const V*>(col + row + nx);
-      V out;
-      out.x = R(0); out.y = R(0);
-      if (p.v0) {
-        const R xw = (p.c0 == 1) ? cen.x : col[row - 1];
-        const R xe = (p.c0 == nx - 2) ? (c.cavity ? cen.x : R(0)) : cen.y;
-        const R xn = (j == c.ny - 2) ? cen.x : north.x, xs = (j == 1) ? cen.x : south.x;
-        out.x = mg_lap<R>(c, cen.x, xe, xw, xn, xs);
-        acc += (double)(cen.x * out.x);
+      dl[r] = z[row + cl] + beta * d_old[row + cl];
+      dr[r] = z[row + cr] + beta * d_old[row + cr];
+    }
+#pragma unroll
+    for (int r = 0; r < kMgDirRows; ++r) {
+      const int j = j0 + r;
+      if (j < j1) {
+        const V cen = dn[r + 1], south = dn[r], north = dn[r + 2];
+        V out;
+        out.x = R(0); out.y = R(0);
+        if (v0) {
+          const R xw = (c0 == 1) ? cen.x : dl[r];
+          const R xe = (c0 == nx - 2) ? (c.cavity ? cen.x : R(0)) : cen.y;
+          const R xn = (j == c.ny - 2) ? cen.x : north.x, xs = (j == 1) ? cen.x : south.x;
+          out.x = mg_lap<R>(c, cen.x, xe, xw, xn, xs);
+          acc += (double)(cen.x * out.x);
+        }
+        if (v1) {
+          const R xw = (c0 + 1 == 1) ? cen.y : cen.x;
+          const R xe = (c0 + 1 == nx - 2) ? (c.cavity ? cen.y : R(0)) : dr[r];
+          const R xn = (j == c.ny - 2) ? cen.y : north.y, xs = (j == 1) ? cen.y : south.y;
+          out.y = mg_lap<R>(c, cen.y, xe, xw, xn, xs);
+          acc += (double)(cen.y * out.y);
+        }
+        *reinterpret_cast<V*>(d_new + c0 + (size_t)j * nx) = cen;
+        *reinterpret_cast<V*>(w + c0 + (size_t)j * nx) = out;
       }
-      if (p.v1) {
-        const R xw = (p.c0 + 1 == 1) ? cen.y : cen.x;
-        const R xe = (p.c0 + 1 == nx - 2) ? (c.cavity ? cen.y : R(0)) : col[row + 2];
-        const R xn = (j == c.ny - 2) ? cen.y : north.y, xs = (j == 1) ? cen.y : south.y;
-        out.y = mg_lap<R>(c, cen.y, xe, xw, xn, xs);
-        acc += (double)(cen.y * out.y);
-      }
-      *reinterpret_cast<V*>(w + p.c0 + row) = out;
-      south = cen;
-      cen = north;
     }
   }
-  mg_finish_dot<R>(c, sc, partials, ticket, acc, 2);
+  mg_finish_dot<R, kMgThreads>(c, sc, partials, ticket, acc, 2);
 }
 
-// x += alpha d, rho -= alpha w, rho.rho -> iteration count, stopping rule
+// x += alpha d, rho -= alpha w, rho.rho -> iteration count, stopping rule.  Tiles of kMgUpdRows rows.
+constexpr int kMgUpdRows = 4;
 template <class R>
 __global__ void __launch_bounds__(kMgThreads) k_mg_update(MgFine<R> c, MgScalars* __restrict__ sc,
                                                            const R* __restrict__ d, const R* __restrict__ w,
@@ -246,28 +209,59 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_update(MgFine<R> c, MgScalars
                                                            double* __restrict__ partials, unsigned* __restrict__ ticket) {
   using V = typename Vec2<R>::type;
   const R alpha = (R)sc->alpha;
-  const MgPair<R> p = mg_pair<R>(c);
+  const int c0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int j0 = 1 + blockIdx.y * kMgUpdRows, j1 = min(j0 + kMgUpdRows, c.ny - 1);
+  const bool any = c0 < c.nx, v0 = any && c0 >= 1, v1 = any && c0 + 1 <= c.nx - 2;
   double acc = 0.0;
-  if (p.any) {
-    for (int j = p.j0; j < p.j1; ++j) {
-      const size_t idx = (size_t)p.c0 + (size_t)j * c.nx;
-      const V dv = *reinterpret_cast<const V*>(d + idx), wv = *reinterpret_cast<const V*>(w + idx);
-      V xv = *reinterpret_cast<const V*>(x + idx), rv = *reinterpret_cast<const V*>(rho + idx);
-      if (p.v0) {
-        xv.x = xv.x + alpha * dv.x;
-        rv.x = rv.x - alpha * wv.x;
-        acc += (double)(rv.x * rv.x);
+  if (any) {
+    V dv[kMgUpdRows], wv[kMgUpdRows], xv[kMgUpdRows], rv[kMgUpdRows];
+#pragma unroll
+    for (int r = 0; r < kMgUpdRows; ++r) {
+      const int j = min(j0 + r, c.ny - 2);
+      const size_t idx = (size_t)c0 + (size_t)j * c.nx;
+      dv[r] = *reinterpret_cast<const V*>(d + idx);
+      wv[r] = *reinterpret_cast<const V*>(w + idx);
+      xv[r] = *reinterpret_cast<const V*>(x + idx);
+      rv[r] = *reinterpret_cast<const V*>(rho + idx);
+    }
+#pragma unroll
+    for (int r = 0; r < kMgUpdRows; ++r) {
+      const int j = j0 + r;
+      if (j < j1) {
+        if (v0) {
+          xv[r].x = xv[r].x + alpha * dv[r].x;
+          rv[r].x = rv[r].x - alpha * wv[r].x;
+          acc += (double)(rv[r].x * rv[r].x);
+        }
+        if (v1) {
+          xv[r].y = xv[r].y + alpha * dv[r].y;
+          rv[r].y = rv[r].y - alpha * wv[r].y;
+          acc += (double)(rv[r].y * rv[r].y);
+        }
+        const size_t idx = (size_t)c0 + (size_t)j * c.nx;
+        *reinterpret_cast<V*>(x + idx) = xv[r];
+        *reinterpret_cast<V*>(rho + idx) = rv[r];
       }
-      if (p.v1) {
-        xv.y = xv.y + alpha * dv.y;
-        rv.y = rv.y - alpha * wv.y;
-        acc += (double)(rv.y * rv.y);
-      }
-      *reinterpret_cast<V*>(x + idx) = xv;
-      *reinterpret_cast<V*>(rho + idx) = rv;
     }
   }
-  mg_finish_dot<R>(c, sc, partials, ticket, acc, 3);
+  mg_finish_dot<R, kMgThreads>(c, sc, partials, ticket, acc, 3);
+}
+
+// end of a step's first solve (mg_warm_start 2): next start vector = 2 x - last, last = x; whole grid, grid-stride
+template <class R>
+__global__ void __launch_bounds__(kMgThreads) k_mg_extrapolate(const R* __restrict__ x, R* __restrict__ last,
+                                                                R* __restrict__ guess, size_t n) {
+  using V = typename Vec2<R>::type;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n / 2; k += stride) {
+    const V xv = reinterpret_cast<const V*>(x)[k];
+    const V lv = reinterpret_cast<const V*>(last)[k];
+    V g;
+    g.x = R(2) * xv.x - lv.x;
+    g.y = R(2) * xv.y - lv.y;
+    reinterpret_cast<V*>(guess)[k] = g;
+    reinterpret_cast<V*>(last)[k] = xv;
+  }
 }
 
 // First smoothing sweep of a V-cycle: the reference's Jacobi update (src/model.rs:788-793) applied to z = 0,
@@ -280,17 +274,23 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_first_sweep(MgFine<R> c, R om
   const MgPair<R> p = mg_pair<R>(c);
   if (!p.any) return;
   const int nx = c.nx;
-  for (int j = p.j0; j < p.j1; ++j) {
-    const size_t idx = (size_t)p.c0 + (size_t)j * nx;
-    const V rv = *reinterpret_cast<const V*>(rho + idx);
-    V o;
-    o.x = omega * (((R(0) + R(0)) - rv.x) / denom) + one_minus_omega * R(0);
-    o.y = omega * (((R(0) + R(0)) - rv.y) / denom) + one_minus_omega * R(0);
-    if (p.c0 == 0) o.x = o.y;                             // p'[0,j] <- p'[1,j]
-    if (p.c0 == nx - 2) o.y = c.cavity ? o.x : R(0);      // outlet 0 / cavity mirror
-    *reinterpret_cast<V*>(z + idx) = o;
-    if (j == 1) *reinterpret_cast<V*>(z + p.c0) = o;                                   // bottom row <- row 1
-    if (j == c.ny - 2) *reinterpret_cast<V*>(z + p.c0 + (size_t)(c.ny - 1) * nx) = o;  // top row <- row ny-2
+  V rv[kMgRows];
+#pragma unroll
+  for (int r = 0; r < kMgRows; ++r)
+    rv[r] = *reinterpret_cast<const V*>(rho + p.c0 + (size_t)min(p.j0 + r, c.ny - 2) * nx);
+#pragma unroll
+  for (int r = 0; r < kMgRows; ++r) {
+    const int j = p.j0 + r;
+    if (j < p.j1) {
+      V o;
+      o.x = omega * (((R(0) + R(0)) - rv[r].x) / denom) + one_minus_omega * R(0);
+      o.y = omega * (((R(0) + R(0)) - rv[r].y) / denom) + one_minus_omega * R(0);
+      if (p.c0 == 0) o.x = o.y;                             // p'[0,j] <- p'[1,j]
+      if (p.c0 == nx - 2) o.y = c.cavity ? o.x : R(0);      // outlet 0 / cavity mirror
+      *reinterpret_cast<V*>(z + p.c0 + (size_t)j * nx) = o;
+      if (j == 1) *reinterpret_cast<V*>(z + p.c0) = o;                                   // bottom row <- row 1
+      if (j == c.ny - 2) *reinterpret_cast<V*>(z + p.c0 + (size_t)(c.ny - 1) * nx) = o;  // top row <- row ny-2
+    }
   }
 }
 

@@ -106,7 +106,7 @@ void consts_default(cfd_solver_consts* c) {
   c->cg_tolerance = 1e-8;        // extension
   c->mg_omega = 0.8;             // extension (MGCG)
   c->mg_smoothing = 2;           // extension (MGCG)
-  c->mg_warm_start = 1;          // extension (MGCG)
+  c->mg_warm_start = 2;          // extension (MGCG)
 }
 
 constexpr int kMaxSweepSlots = 256;
@@ -197,9 +197,11 @@ struct ModelImpl final : ModelBase {
     cfdk::MgLevelDev<R> dev;
   };
   std::vector<MgLevelHost> mg;
-  Field<R> mg_rho, mg_d, mg_z[2];
-  Field<R> mg_guess;  // p' of the previous step's first solve (warm start; carried state)
-  CUtensorMap tmap_mg_z[2], tmap_mg_rho;
+  Field<R> mg_rho, mg_b[3];  // mg_b: the search direction d and the two smoothing buffers of z, roles rotate
+  int mg_id = 0;             // index of the buffer that holds d
+  Field<R> mg_guess;  // start vector of the next step's first solve (carried state)
+  Field<R> mg_last;   // p' the last first-solve ended with (carried state, mg_warm_start 2)
+  CUtensorMap tmap_mg_b[3], tmap_mg_rho;
   cfdk::MgScalars* mg_scalars = nullptr;  // device
   cfdk::MgScalars* h_mg = nullptr;        // pinned host copy
   double* mg_partials = nullptr;
@@ -269,7 +271,8 @@ struct ModelImpl final : ModelBase {
     cudaFree(err_slots); cudaFree(step_slots); cudaFree(staging); cudaFree(tickets);
     cudaFree(cg_r.base); cudaFree(cg_d.base); cudaFree(cg_partials); cudaFree(cg_scalars);
     for (auto& L : mg) { cudaFree(L.weights); cudaFree(L.e); cudaFree(L.rho); cudaFree(L.tmp); }
-    cudaFree(mg_rho.base); cudaFree(mg_d.base); cudaFree(mg_guess.base); cudaFree(mg_z[0].base); cudaFree(mg_z[1].base);
+    cudaFree(mg_rho.base); cudaFree(mg_guess.base); cudaFree(mg_last.base);
+    for (auto& f : mg_b) cudaFree(f.base);
     cudaFree(mg_scalars); cudaFree(mg_partials); cudaFree(mg_err); cudaFree(mg_ticket);
     if (h_mg) cudaFreeHost(h_mg);
     if (h_cg) cudaFreeHost(h_cg);
@@ -901,20 +904,26 @@ struct ModelImpl final : ModelBase {
       hy = pair_up(hy);
     }
     if ((rc = falloc(&mg_rho, (size_t)nx))) return rc;
-    if ((rc = falloc(&mg_d, (size_t)nx))) return rc;
-    if ((rc = falloc(&mg_z[0], (size_t)nx))) return rc;
-    if ((rc = falloc(&mg_z[1], (size_t)nx))) return rc;
+    for (auto& f : mg_b)
+      if ((rc = falloc(&f, (size_t)nx))) return rc;
     if ((rc = falloc(&mg_guess, (size_t)nx))) return rc;
+    if ((rc = falloc(&mg_last, (size_t)nx))) return rc;
     using Ring = cfdk::SweepChunkRing<R>;
-    if ((rc = make_tensor_map(&tmap_mg_z[0], mg_z[0].row(ja - kHalo), Ring::kPCols))) return rc;
-    if ((rc = make_tensor_map(&tmap_mg_z[1], mg_z[1].row(ja - kHalo), Ring::kPCols))) return rc;
+    for (int k = 0; k < 3; ++k)
+      if ((rc = make_tensor_map(&tmap_mg_b[k], mg_b[k].row(ja - kHalo), Ring::kPCols))) return rc;
+    CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep5<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(Ring)));
     if ((rc = make_tensor_map(&tmap_mg_rho, mg_rho.row(ja - kHalo), cfdk::kStripCols))) return rc;
     if ((rc = dalloc(&mg_scalars, (size_t)1))) return rc;
     if ((rc = dalloc(&mg_err, (size_t)kMaxSweepSlots))) return rc;
     if ((rc = dalloc(&mg_ticket, (size_t)4))) return rc;
-    const size_t n_all = (size_t)((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads)) *
-                         (size_t)((ny + cfdk::kMgRows - 1) / cfdk::kMgRows);
-    if ((rc = dalloc(&mg_partials, n_all))) return rc;
+    {
+      // one partial per block of the largest grid that ends in a dot product: the 4-row vector tiles, or the sweep
+      const size_t gx = (size_t)((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads));
+      const size_t n_vec = gx * (size_t)((ny + 3) / 4 + 1);
+      const size_t n_sweep = (size_t)((nx / 2 + 127) / 128) * (size_t)((ny - 2 + sweep_rows_per_block - 1) / sweep_rows_per_block);
+      if ((rc = dalloc(&mg_partials, n_vec > n_sweep ? n_vec : n_sweep))) return rc;
+    }
     // the bottom of the V-cycle (every level from the first that fits 64 x 64) runs in one single-block launch
     mg_bottom_level = (int)mg.size() - 1;
     for (int l = 1; l < (int)mg.size(); ++l)
@@ -977,7 +986,8 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
 
-  // z <- V-cycle(rho); returns the index of the mg_z buffer holding z
+  // z <- V-cycle(rho), smoothing between the two mg_b buffers that do not hold d; the last smoothing sweep also
+  // accumulates rho.z (-> beta).  Returns the index of the buffer holding z.
   int mg_precondition(const cfdk::MgFine<R>& c, int* z_index) {
     const int nu_s = mg_smoothing();
     cfdk::JacobiConsts2<R> c2;
@@ -992,8 +1002,11 @@ struct ModelImpl final : ModelBase {
     const int rows = ny - 2;
     const dim3 blk2(128), grd2((nx / 2 + 127) / 128, (rows + sweep_rows_per_block - 1) / sweep_rows_per_block);
     const size_t ring_bytes = sizeof(cfdk::SweepChunkRing<R>);
-    int zc = 0;
-    auto smooth = [&]() {
+    const int za = (mg_id + 1) % 3, zb = (mg_id + 2) % 3;
+    int zc = za, zo = zb;  // current / other smoothing buffer
+    cfdk::SweepDot<R> dot;
+    dot.c = c; dot.sc = mg_scalars; dot.partials = mg_partials; dot.ticket = mg_ticket;
+    auto smooth = [&](bool with_dot) {
       if (prof_smoother) {
         if (ev_prof_used + 2 > ev_prof.size()) {
           ev_prof.resize(ev_prof_used + 64, nullptr);
@@ -1001,36 +1014,39 @@ struct ModelImpl final : ModelBase {
         }
         cudaEventRecord(ev_prof[ev_prof_used], stream);
       }
-      cfdk::k_jacobi_sweep5<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_mg_z[zc], tmap_mg_rho, mg_z[zc ^ 1].v, mg_err, 0,
-                                                                    cfdk::SweepPeer<R>{});
+      if (with_dot)
+        cfdk::k_jacobi_sweep5<R, true><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_mg_b[zc], tmap_mg_rho, mg_b[zo].v, mg_err, 0,
+                                                                           cfdk::SweepPeer<R>{}, dot);
+      else
+        cfdk::k_jacobi_sweep5<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_mg_b[zc], tmap_mg_rho, mg_b[zo].v, mg_err, 0,
+                                                                      cfdk::SweepPeer<R>{});
       if (prof_smoother) {
         cudaEventRecord(ev_prof[ev_prof_used + 1], stream);
         ev_prof_used += 2;
       }
       ++launches;
-      zc ^= 1;
+      std::swap(zc, zo);
     };
     {
       // first sweep from z = 0: pointwise (k_mg_first_sweep) instead of a stencil sweep over a zero field
       const dim3 g_vec((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads), (ny - 2 + cfdk::kMgRows - 1) / cfdk::kMgRows);
       cfdk::k_mg_first_sweep<R><<<g_vec, cfdk::kMgThreads, 0, stream>>>(c, c2.omega, c2.one_minus_omega, div_denom.y,
-                                                                        mg_rho.v, mg_z[1].v);
+                                                                        mg_rho.v, mg_b[zc].v);
       ++launches;
-      zc = 1;
     }
-    for (int s = 1; s < nu_s; ++s) smooth();
+    for (int s = 1; s < nu_s; ++s) smooth(false);
     if (mg.size() > 1) {
       MgLevelHost& C = mg[1];
       const dim3 blk(cfdk::kMgThreads), grd_c((C.mx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, C.my);
       const dim3 g_int((nx - 2 + cfdk::kMgThreads - 1) / cfdk::kMgThreads, ny - 2);
-      cfdk::k_mg_fine_restrict<R><<<grd_c, blk, 0, stream>>>(c, mg_z[zc].v, mg_rho.v, C.mx, C.my, C.rho);
+      cfdk::k_mg_fine_restrict<R><<<grd_c, blk, 0, stream>>>(c, mg_b[zc].v, mg_rho.v, C.mx, C.my, C.rho);
       ++launches;
       int rc;
       if ((rc = mg_coarse_vcycle(1))) return rc;
-      cfdk::k_mg_fine_prolong<R><<<g_int, blk, 0, stream>>>(c, mg_z[zc].v, C.mx, C.cur);
+      cfdk::k_mg_fine_prolong<R><<<g_int, blk, 0, stream>>>(c, mg_b[zc].v, C.mx, C.cur);
       ++launches;
     }
-    for (int s = 0; s < nu_s; ++s) smooth();
+    for (int s = 0; s < nu_s; ++s) smooth(s == nu_s - 1);
     CFD_CUDA(cudaGetLastError());
     *z_index = zc;
     return CFD_OK;
@@ -1046,7 +1062,8 @@ struct ModelImpl final : ModelBase {
     const dim3 blk(cfdk::kMgThreads);
     const unsigned gx = (unsigned)((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads));
     const dim3 g_all(gx, (ny + cfdk::kMgRows - 1) / cfdk::kMgRows);       // all rows (init)
-    const dim3 g_vec(gx, (ny - 2 + cfdk::kMgRows - 1) / cfdk::kMgRows);   // rows of unknowns
+    const dim3 g_dir(gx, (ny - 2 + cfdk::kMgDirRows - 1) / cfdk::kMgDirRows);  // rows of unknowns, 4-row tiles
+    const dim3 g_upd(gx, (ny - 2 + cfdk::kMgUpdRows - 1) / cfdk::kMgUpdRows);
     const Field<R>& xf = pp[ipp];
     R* x = xf.v;
     R* w = pp[ipp ^ 1].v;
@@ -1059,8 +1076,8 @@ struct ModelImpl final : ModelBase {
     // first solve of a step: start from the p' the first solve of the previous step ended with (mg_warm_start)
     const bool first_solve = call_index == 0;
     const bool warm = first_solve && opt.consts.mg_warm_start != 0;
-    cfdk::k_mg_init<R><<<g_all, blk, 0, stream>>>(c, mg_scalars, rhs.v, warm ? mg_guess.v : nullptr, x, mg_rho.v, mg_d.v,
-                                                  mg_partials, mg_ticket);
+    cfdk::k_mg_init<R><<<g_all, blk, 0, stream>>>(c, mg_scalars, rhs.v, warm ? mg_guess.v : nullptr, x, mg_rho.v,
+                                                  mg_b[mg_id].v, mg_partials, mg_ticket);
     launches += 1;
     for (;;) {
       CFD_CUDA(cudaMemcpyAsync(h_mg, mg_scalars, sizeof init, cudaMemcpyDeviceToHost, stream));
@@ -1068,19 +1085,26 @@ struct ModelImpl final : ModelBase {
       if (h_mg->done) break;
       int zi = 0;
       if ((rc = mg_precondition(c, &zi))) return rc;
-      const R* z = mg_z[zi].v;
-      cfdk::k_mg_dot<R><<<g_vec, blk, 0, stream>>>(c, mg_scalars, mg_rho.v, z, mg_partials, mg_ticket, 1);
-      cfdk::k_mg_direction<R><<<g_vec, blk, 0, stream>>>(c, mg_scalars, z, mg_d.v);
-      cfdk::k_mg_apply<R><<<g_vec, blk, 0, stream>>>(c, mg_scalars, mg_d.v, w, mg_partials, mg_ticket);
-      cfdk::k_mg_update<R><<<g_vec, blk, 0, stream>>>(c, mg_scalars, mg_d.v, w, x, mg_rho.v, mg_partials, mg_ticket);
-      launches += 4;
+      // rho.z (-> beta) came out of the V-cycle's last sweep; d_new goes to the smoothing buffer that is free now
+      const int dn = 3 - mg_id - zi;
+      cfdk::k_mg_dir_apply<R><<<g_dir, blk, 0, stream>>>(c, mg_scalars, mg_b[zi].v, mg_b[mg_id].v, mg_b[dn].v, w, mg_partials,
+                                                         mg_ticket);
+      mg_id = dn;
+      cfdk::k_mg_update<R><<<g_upd, blk, 0, stream>>>(c, mg_scalars, mg_b[mg_id].v, w, x, mg_rho.v, mg_partials, mg_ticket);
+      launches += 2;
       CFD_CUDA(cudaGetLastError());
     }
     const int n_edge = (nx > ny ? nx : ny);
     cfdk::k_cg_fill_boundary<R><<<(n_edge + 255) / 256, 256, 0, stream>>>(nx, ny, c.cavity, x, ja, jb);
     ++launches;
-    if (first_solve)
-      CFD_CUDA(cudaMemcpyAsync(mg_guess.row(0), xf.row(0), n_p * sizeof(R), cudaMemcpyDeviceToDevice, stream));
+    if (first_solve) {
+      if (opt.consts.mg_warm_start == 2) {
+        cfdk::k_mg_extrapolate<R><<<148 * 8, cfdk::kMgThreads, 0, stream>>>(xf.row(0), mg_last.row(0), mg_guess.row(0), n_p);
+        ++launches;
+      } else {
+        CFD_CUDA(cudaMemcpyAsync(mg_guess.row(0), xf.row(0), n_p * sizeof(R), cudaMemcpyDeviceToDevice, stream));
+      }
+    }
     CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index + 1], stream));
     CFD_CUDA(cudaGetLastError());
     last_S += (uint64_t)h_mg->iterations;
@@ -1356,9 +1380,10 @@ struct ModelImpl final : ModelBase {
       case CFD_FIELD_U_OLD: *n = own_u(); return ubuf[ifree].row(ja);
       case CFD_FIELD_V_OLD: *n = own_v(); return vbuf[ifree].row(ja);
       case CFD_FIELD_MG_GUESS:
+      case CFD_FIELD_MG_LAST:
         if (!mg_guess.base && (world > 1 || mg_setup() != CFD_OK)) { *n = 0; return nullptr; }
         *n = own_p();
-        return mg_guess.row(ja);
+        return field == CFD_FIELD_MG_GUESS ? mg_guess.row(ja) : mg_last.row(ja);
       default: *n = 0; return nullptr;
     }
   }
@@ -1478,7 +1503,7 @@ int cfd_model_create_ex(const cfd_grid* grid, const cfd_params* params, const cf
   if (o.consts.jacobi_iterations < 1 || o.consts.jacobi_iterations > kMaxSweepSlots)
     return fail(CFD_ERR_INVALID_ARGUMENT, "jacobi_iterations must be in 1..256");
   if (o.consts.outer_rounds < 0 || o.consts.outer_rounds > 1000) return fail(CFD_ERR_INVALID_ARGUMENT, "outer_rounds out of range");
-  if (o.consts.mg_smoothing < 1 || o.consts.mg_smoothing > 16 || !(o.consts.mg_omega > 0.0) || !(o.consts.mg_omega <= 1.0))
+  if (o.consts.mg_warm_start < 0 || o.consts.mg_warm_start > 2 || o.consts.mg_smoothing < 1 || o.consts.mg_smoothing > 16 || !(o.consts.mg_omega > 0.0) || !(o.consts.mg_omega <= 1.0))
     return fail(CFD_ERR_INVALID_ARGUMENT, "mg_smoothing must be in 1..16 and mg_omega in (0, 1]");
   if (params->pressure_solver == CFD_SOLVER_MGCG && o.world_size > 1)
     return fail(CFD_ERR_UNSUPPORTED, "MGCG runs on a single domain in this version (use CG on strips)");

@@ -59,8 +59,9 @@ extern "C" {
 #define CFD_FIELD_V_OLD 8
 #define CFD_FIELD_MASK_U 9  /* 0/1 as double */
 #define CFD_FIELD_MASK_V 10 /* 0/1 as double */
-#define CFD_FIELD_MG_GUESS 11 /* MGCG extension: p' of the previous step's first solve (the warm start; carried state) */
-#define CFD_FIELD_COUNT 12
+#define CFD_FIELD_MG_GUESS 11 /* MGCG extension: start vector of the next step's first solve (carried state) */
+#define CFD_FIELD_MG_LAST 12  /* MGCG extension: p' the last first-solve ended with (carried state, mg_warm_start 2) */
+#define CFD_FIELD_COUNT 13
 
 /* ---- PODs ---------------------------------------------------------------------------------------- */
 /* Grid + Option<Cylinder>, src/model.rs:121-139 */
@@ -92,9 +93,11 @@ typedef struct cfd_solver_consts {
   double cg_tolerance;       /* extension (CG, MGCG): stop when dt * rms(Poisson residual) <= this */
   double mg_omega;           /* extension (MGCG): damping of the Jacobi smoother, default 0.8 */
   int32_t mg_smoothing;      /* extension (MGCG): pre- and post-smoothing sweeps per level, default 2 */
-  int32_t mg_warm_start;     /* extension (MGCG): 1 (default) = the first solve of a step starts from the p' the first
-                              * solve of the previous step ended with — like the reference's Jacobi, which never resets
-                              * p' (src/model.rs:734-824); re-correction solves and 0 = start from p' = 0 */
+  int32_t mg_warm_start;     /* extension (MGCG), start vector of the FIRST solve of a step: 1 = the p' the first solve
+                              * of the previous step ended with — like the reference's Jacobi, which never resets p'
+                              * (src/model.rs:734-824); 2 (default) = linear extrapolation in time from the last two,
+                              * 2 p'_n - p'_(n-1) (the JS twin's "extrapolated initial guess", index.html:262-270);
+                              * 0 and every re-correction solve = start from p' = 0 */
 } cfd_solver_consts;
 
 typedef struct cfd_options {

@@ -90,7 +90,8 @@ class Model {
   };
   std::vector<MgLevel> mg_levels;
   std::vector<R> mg_rho, mg_d, mg_w, mg_z, mg_z2;
-  std::vector<R> mg_guess;  // p' of the previous step's first solve (warm start; carried state)
+  std::vector<R> mg_guess;  // start vector of the next step's first solve (carried state)
+  std::vector<R> mg_last;   // p' the last first-solve ended with (carried state, mg_warm_start 2)
 
   // Model::new, src/model.rs:219-299
   Model(const cfd_grid& g, const cfd_params& prm, const cfd_solver_consts* c = nullptr) {
@@ -148,6 +149,7 @@ class Model {
     u_old = u; v_old = v; u_star = u; v_star = v;
     rhs.assign(size_p, R(0)); p_prime.assign(size_p, R(0)); p_prime_new.assign(size_p, R(0));
     mg_guess.assign(size_p, R(0));
+    mg_last.assign(size_p, R(0));
   }
 
   static void cfd_solver_consts_default_inline(cfd_solver_consts* c) {
@@ -162,7 +164,7 @@ class Model {
     c->cg_tolerance = 1e-8;
     c->mg_omega = 0.8;
     c->mg_smoothing = 2;
-    c->mg_warm_start = 1;
+    c->mg_warm_start = 2;
   }
 
   // Model::set_parameters, src/model.rs:1250-1257
@@ -711,10 +713,12 @@ class Model {
   //    finest-cell units; the outlet's zero sits half a finest cell beyond the last column.
   //  * Transfer: residuals are summed over the (up to four) children, corrections are copied to them.
   //  * V(n,n) with n = mg_smoothing damped-Jacobi sweeps before and after; the first sweep starts from zero.
-  // Stopping rule and return value as cg_pressure.  Start: the FIRST solve of a timestep starts from the p' the
-  // first solve of the previous timestep ended with (mg_warm_start; the reference's Jacobi never resets p' either,
-  // src/model.rs:734-824 — p' is the full pressure of this non-incremental projection and varies slowly in time);
-  // the re-correction solves of the outer loop (:696-724), whose solution is ~0, start from 0.
+  // Stopping rule and return value as cg_pressure.  Start: the FIRST solve of a timestep starts from mg_guess —
+  // the p' the first solve of the previous timestep ended with (mg_warm_start 1; the reference's Jacobi never
+  // resets p' either, src/model.rs:734-824 — p' is the full pressure of this non-incremental projection and varies
+  // slowly in time), or its linear extrapolation in time 2 p'_n - p'_(n-1) (mg_warm_start 2, default; the JS
+  // twin's "extrapolated initial guess", index.html:262-270).  The re-correction solves of the outer loop
+  // (:696-724), whose solution is ~0, start from 0.
   // ------------------------------------------------------------------------------------------------
   void mg_build_levels() {
     mg_levels.clear();
@@ -925,7 +929,16 @@ class Model {
       }
     }
     cg_fill_boundary(p_prime);
-    if (first_solve) mg_guess = p_prime;
+    if (first_solve) {
+      if (consts.mg_warm_start == 2) {
+        for (size_t k = 0; k < n; ++k) {
+          mg_guess[k] = R(2) * p_prime[k] - mg_last[k];
+          mg_last[k] = p_prime[k];
+        }
+      } else {
+        mg_guess = p_prime;
+      }
+    }
     const R res = measure(rr);
     last_pressure_residual = res;
     return res;

@@ -31,6 +31,7 @@ std::vector<R>* field_ptr(Model<R>& m, int field) {
     case CFD_FIELD_U_OLD: return &m.u_old;
     case CFD_FIELD_V_OLD: return &m.v_old;
     case CFD_FIELD_MG_GUESS: return &m.mg_guess;
+    case CFD_FIELD_MG_LAST: return &m.mg_last;
     default: return nullptr;
   }
 }

@@ -427,12 +427,12 @@ def test_mgcg_warm_start_state_restarts_in_the_oracle():
     cpu = OracleModel(g, prm, precision=64, consts=consts)
     r0 = gpu.get_residuals()
     for fid in (_abi.FIELD_P, _abi.FIELD_U, _abi.FIELD_V, _abi.FIELD_U_STAR, _abi.FIELD_V_STAR, _abi.FIELD_P_PRIME,
-                _abi.FIELD_MG_GUESS):
+                _abi.FIELD_MG_GUESS, _abi.FIELD_MG_LAST):
         cpu.set_field(fid, gpu.field(fid))
     cpu.set_scalars(r0.simulation_step, r0.f64["simulation_time"], r0.f64["dt"])
     gpu.update()
     cpu.update()
     rg, rc = gpu.get_residuals(), cpu.get_residuals()
     assert rg.sweeps == rc.sweeps == its[1] and rg.jacobi_calls == rc.jacobi_calls == 2
-    for fid in (_abi.FIELD_U, _abi.FIELD_V, _abi.FIELD_P, _abi.FIELD_MG_GUESS):
+    for fid in (_abi.FIELD_U, _abi.FIELD_V, _abi.FIELD_P, _abi.FIELD_MG_GUESS, _abi.FIELD_MG_LAST):
         assert rel_l2(gpu.field(fid), cpu.field(fid)) <= 1e-9, _abi.FIELD_NAMES[fid]
