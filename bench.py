@@ -404,6 +404,19 @@ def run_ours(args, w):
         snap = model.get_snapshot()
     torch.cuda.synchronize()
     wall_e2e_pageable = (time.perf_counter() - t2) / min(args.steps, 3)
+    # and with the UI's colour map computed on the device: one nx*ny RGBA image instead of 3 fields
+    wall_e2e_image = None
+    if world == 1 or not strips:
+        from cfd_demo_b200.model import PinnedBuffer
+        img_buf = PinnedBuffer(nx * ny * 4, np.uint8)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        for _ in range(min(args.steps, 5)):
+            model.set_parameters(params)
+            model.update()
+            res = model.get_residuals()
+            model.render_rgba(1, out=img_buf)
+        wall_e2e_image = (time.perf_counter() - t3) / min(args.steps, 5)
     clocks = sampler.stop() if rank == 0 else None
 
     # max over ranks
@@ -477,6 +490,7 @@ def run_ours(args, w):
             "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": 28 * world, "d2h_bytes_per_step": d2h,
                     "ms_per_step": wall_e2e_s * 1e3 / steps,
                     "ms_per_step_pageable_destination": wall_e2e_pageable * 1e3,
+                    "ms_per_step_rgba_image_instead": None if wall_e2e_image is None else wall_e2e_image * 1e3,
                     "calls": "cfd_model_set_params + cfd_model_update + cfd_model_get_residuals + cfd_model_get_snapshot "
                              "(into cfd_host_alloc'ed pinned buffers)"},
             "gpu_launches": launches,

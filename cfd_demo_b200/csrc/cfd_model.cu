@@ -124,6 +124,7 @@ struct ModelBase {
   virtual int set_field_f64(int field, const double* in, uint64_t len) = 0;
   virtual int rows(uint64_t* j0, uint64_t* j1) = 0;
   virtual int last_timing(double* step_ms, double* sweep_ms, uint64_t* launches) = 0;
+  virtual int render(int mode, unsigned char* rgba, float* min_out, float* max_out) = 0;
   virtual int profile_smoother(int enable) = 0;
   virtual int last_smoother_timing(double* ms, uint64_t* launches) = 0;
 };
@@ -1346,6 +1347,38 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
 
+  // The UI's colour map (src/app.rs:235-404) on the device: nx x ny RGBA pixels into `rgba` (host memory)
+  int render(int mode, unsigned char* rgba, float* min_out, float* max_out) override {
+    if (world > 1) return fail(CFD_ERR_UNSUPPORTED, "render: single domain only in this version");
+    if (mode < 0 || mode > 2) return fail(CFD_ERR_INVALID_ARGUMENT, "render: mode must be 0 (pressure), 1 (velocity) or 2 (vorticity)");
+    CFD_CUDA(cudaSetDevice(device));
+    const size_t bytes = n_p * 4 + 16;
+    if (bytes > staging_bytes) {
+      cudaFree(staging);
+      staging = nullptr; staging_bytes = 0;
+      CFD_CUDA(cudaMalloc(&staging, bytes));
+      staging_bytes = bytes;
+    }
+    unsigned* slots = (unsigned*)((char*)staging + n_p * 4);
+    const unsigned init[2] = {0xff800000u /* key of +inf */, 0x007fffffu /* key of -inf */};
+    CFD_CUDA(cudaMemcpyAsync(slots, init, sizeof init, cudaMemcpyHostToDevice, stream));
+    cfdk::RenderGeom g;
+    g.nx = nx; g.ny = ny; g.mode = mode; g.has_obstacle = grid.has_obstacle != 0;
+    g.dx = grid.dx; g.dy = grid.dy; g.cx = grid.center_x; g.cy = grid.center_y; g.radius = grid.radius;
+    const dim3 blk(256), grd((nx + 255) / 256, ny);
+    cfdk::k_render_minmax<R><<<grd, blk, 0, stream>>>(g, p.v, ubuf[iu].v, vbuf[iu].v, slots);
+    cfdk::k_render_pixels<R><<<grd, blk, 0, stream>>>(g, p.v, ubuf[iu].v, vbuf[iu].v, slots, (uchar4*)staging);
+    CFD_CUDA(cudaGetLastError());
+    unsigned h_slots[2];
+    CFD_CUDA(cudaMemcpyAsync(h_slots, slots, sizeof h_slots, cudaMemcpyDeviceToHost, stream));
+    int rc;
+    if (rgba && (rc = copy_to_host(rgba, staging, n_p * 4))) return rc;
+    CFD_CUDA(cudaStreamSynchronize(stream));
+    if (min_out) *min_out = cfdk::f32_from_order_key(h_slots[0]);
+    if (max_out) *max_out = cfdk::f32_from_order_key(h_slots[1]);
+    return CFD_OK;
+  }
+
   // Model::get_residuals, src/model.rs:1269-1280
   int get_residuals(cfd_residuals* out) override {
     out->simulation_step = simulation_step;
@@ -1552,6 +1585,11 @@ int cfd_model_set_params(cfd_model* m, const cfd_params* params) {
 int cfd_model_get_snapshot(cfd_model* m, float* p, float* u, float* v, float* dt) {
   CFD_CHECK_MODEL(m);
   return m->impl->get_snapshot(p, u, v, dt);
+}
+
+int cfd_model_render_rgba(cfd_model* m, int32_t mode, uint8_t* rgba, float* min_out, float* max_out) {
+  CFD_CHECK_MODEL(m);
+  return m->impl->render(mode, rgba, min_out, max_out);
 }
 
 int cfd_model_get_residuals(cfd_model* m, cfd_residuals* out) {

@@ -58,6 +58,7 @@ def load_library():
     lib.cfd_model_set_params.argtypes = [C.c_void_p, P(_abi.CfdParams)]
     lib.cfd_model_get_snapshot.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, P(C.c_float)]
     lib.cfd_model_get_residuals.argtypes = [C.c_void_p, P(_abi.CfdResiduals)]
+    lib.cfd_model_render_rgba.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, P(C.c_float), P(C.c_float)]
     lib.cfd_model_field_len.argtypes = [C.c_void_p, C.c_int32, P(C.c_uint64)]
     lib.cfd_model_get_field_f64.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64]
     lib.cfd_model_set_field_f64.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64]
@@ -222,6 +223,16 @@ class Model:
         _check(self._lib, self._lib.cfd_model_get_snapshot(self._handle(), p.ctypes.data, u.ctypes.data,
                                                            v.ctypes.data, C.byref(dt)))
         return SimSnapshot(p=p, u=u, v=v, dt=float(dt.value), paused=False)
+
+    def render_rgba(self, mode: int, out=None):
+        """The UI's colour map (src/app.rs:235-404) computed on the device: (ny, nx, 4) uint8 RGBA, plus the (min, max)
+        of the mapped quantity.  mode 0 pressure, 1 velocity magnitude, 2 vorticity."""
+        if out is None:
+            out = np.empty(self.nx * self.ny * 4, dtype=np.uint8)
+        arr = out.array if isinstance(out, PinnedBuffer) else out
+        lo, hi = C.c_float(), C.c_float()
+        _check(self._lib, self._lib.cfd_model_render_rgba(self._handle(), int(mode), arr.ctypes.data, C.byref(lo), C.byref(hi)))
+        return arr.reshape(self.ny, self.nx, 4), float(lo.value), float(hi.value)
 
     def get_residuals(self) -> Residuals:
         """`Model::get_residuals` (src/model.rs:1269-1280)."""

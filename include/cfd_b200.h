@@ -166,6 +166,15 @@ int cfd_model_get_snapshot(cfd_model* m, float* p, float* u, float* v, float* dt
  * destinations are served through pinned bounce buffers (chunked, PCIe transfer overlapped with the memcpy). */
 int cfd_host_alloc(uint64_t bytes, void** out);
 void cfd_host_free(void* ptr);
+/* The UI's colour map of a snapshot (src/app.rs:235-404: pressure :238-279, velocity magnitude :281-330, vorticity
+ * :332-398; min/max normalisation :247-249, red-blue ramp, grey cylinder overlay :262-268) computed on the device from
+ * the f32-narrowed fields: nx*ny RGBA pixels (egui::Color32::from_rgb), row j of the image = row j of the grid, into
+ * caller-allocated host memory (pinned or pageable).  mode: 0 pressure, 1 velocity, 2 vorticity.  min_out / max_out
+ * (may be NULL) receive the normalisation range BEFORE the `max = min + 1` adjustment.  Single domain only. */
+#define CFD_RENDER_PRESSURE 0
+#define CFD_RENDER_VELOCITY 1
+#define CFD_RENDER_VORTICITY 2
+int cfd_model_render_rgba(cfd_model* m, int32_t mode, uint8_t* rgba, float* min_out, float* max_out);
 /* Model::get_residuals(&self), src/model.rs:1269-1280. */
 int cfd_model_get_residuals(cfd_model* m, cfd_residuals* out);
 /* Parity harness: any field (CFD_FIELD_*) widened to double, reference layout. */
