@@ -309,10 +309,12 @@ def run_ours(args, w):
     if world > 1:
         dist.init_process_group("cpu:gloo,cuda:nccl")
     mode_c = w["kind"] == "modeC"
-    # N > 1.  Mode R: WEAK scaling over row strips — every GPU owns a w.nx x w.ny strip of one tall channel
-    # (nx x N*ny cells, same dx = dy), halo rows and max-reductions over NVLink peer memory.
-    # Mode C (MGCG): the multigrid hierarchy does not shard yet -> N independent replicas of the workload.
-    strips = world > 1 and not mode_c
+    # N > 1: WEAK scaling over row strips — every GPU owns a w.nx x w.ny strip of one tall domain (nx x N*ny cells, same
+    # dx = dy).  Mode R: halo rows and max-reductions fused into the sweep kernel over NVLink peer memory.  Mode C
+    # (MGCG): level 0 and coarse levels 1-2 in strips (NCCL halo row after every sweep, sum-allreduce per dot
+    # product), level 3 gathered, the rest of the hierarchy replicated.
+    # CFD_BENCH_REPLICAS=1: N independent replicas of the single-GPU workload instead (no data-path collective).
+    strips = world > 1 and os.environ.get("CFD_BENCH_REPLICAS") != "1"
     from cfd_demo_b200.types import Cylinder, Grid
     cyl = Cylinder(*w["cylinder"]) if w["cylinder"] else None
     ny_job = w["ny"] * world if strips else w["ny"]
@@ -332,7 +334,19 @@ def run_ours(args, w):
         opts.flags = int(os.environ.get("CFD_BENCH_FLAGS", "0"))
         model = Model(grid, params, options=opts)
 
+    # multi-rank runs: a rank that dies leaves the others waiting in a collective; abort instead of hanging the box
+    progress = {"t": time.time()}
+    if world > 1:
+        def watchdog():
+            while True:
+                time.sleep(5.0)
+                if time.time() - progress["t"] > float(os.environ.get("CFD_BENCH_WATCHDOG_S", "240")):
+                    print(f"bench.py rank {rank}: no progress for too long, aborting", file=sys.stderr, flush=True)
+                    os._exit(3)
+        threading.Thread(target=watchdog, daemon=True).start()
+
     def barrier():
+        progress["t"] = time.time()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -343,6 +357,7 @@ def run_ours(args, w):
     spinup = int(os.environ.get("CFD_BENCH_SPINUP", w["spinup"]))
     for i in range(spinup):
         model.update()
+        progress["t"] = time.time()
         if os.environ.get("CFD_BENCH_VERBOSE") and rank == 0:
             r_, t_ = model.get_residuals(), model.last_timing()
             print(f"spinup {i + 1}: K {r_.jacobi_calls} S {r_.sweeps} step_ms {t_[0]:.2f} per-sweep us {t_[1] * 1e3 / max(r_.sweeps, 1):.1f}",
@@ -366,6 +381,7 @@ def run_ours(args, w):
     dev_ms, sweep_ms, sweeps, solves, launches, smooth_ms, smooth_n = 0.0, 0.0, 0, 0, 0, 0.0, 0
     for _ in range(args.steps):
         model.update()
+        progress["t"] = time.time()
         s_ms, sw_ms, n_l = model.last_timing()
         r = model.get_residuals()
         dev_ms += s_ms
@@ -467,12 +483,15 @@ def run_ours(args, w):
             cpu = cpu_baseline_mode_c(w, model) if mode_c else cpu_baseline_mode_r(w, nx, ny)
         if world == 1:
             multi = "single domain"
-        elif strips:
+        elif strips and not mode_c:
             multi = (f"{world} row strips of {w['nx']}x{w['ny']} cells each, halo rows and max-reduction fused into the sweep "
                      f"kernel over NVLink peer memory, weak scaling")
+        elif strips:
+            multi = (f"{world} row strips of {w['nx']}x{w['ny']} cells each (one {nx}x{ny} cavity), weak scaling: multigrid levels 0-2 in "
+                     f"strips with an NCCL halo row after every sweep, level 3 gathered and the rest replicated, dot products "
+                     f"sum-allreduced")
         else:
-            multi = (f"{world} independent replicas of the workload, one per GPU (replicas only: the multigrid hierarchy of "
-                     f"Mode C does not shard in this version; strips: --workload channel4096_modeR)")
+            multi = f"{world} independent replicas of the workload, one per GPU (CFD_BENCH_REPLICAS=1)"
         line = {
             "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
             "steps": steps, "warmup": args.warmup, "ms_per_step": dev_s * 1e3 / steps, "higher_is_better": True,

@@ -43,8 +43,8 @@ template <class R>
 __device__ __forceinline__ MgPair<R> mg_pair(const MgFine<R>& c) {
   MgPair<R> p;
   p.c0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-  p.j0 = 1 + blockIdx.y * kMgRows;
-  p.j1 = min(p.j0 + kMgRows, c.ny - 1);
+  p.j0 = c.row_lo + blockIdx.y * kMgRows;
+  p.j1 = min(p.j0 + kMgRows, c.row_hi);
   p.any = p.c0 < c.nx;
   p.v0 = p.any && p.c0 >= 1;
   p.v1 = p.any && p.c0 + 1 <= c.nx - 2;
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_init(MgFine<R> c, MgScalars* 
                                                          double* __restrict__ partials, unsigned* __restrict__ ticket) {
   using V = typename Vec2<R>::type;
   const int c0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-  const int j0 = blockIdx.y * kMgRows, j1 = min(j0 + kMgRows, c.ny);
+  const int j0 = c.init_lo + blockIdx.y * kMgRows, j1 = min(j0 + kMgRows, c.init_hi);
   double acc = 0.0;
   if (c0 < c.nx) {
     V zero;
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_dot(MgFine<R> c, MgScalars* _
     V av[kMgRows], bv[kMgRows];
 #pragma unroll
     for (int r = 0; r < kMgRows; ++r) {
-      const int j = min(p.j0 + r, c.ny - 2);
+      const int j = min(p.j0 + r, c.row_hi - 1);
       const size_t idx = (size_t)p.c0 + (size_t)j * c.nx;
       av[r] = *reinterpret_cast<const V*>(a + idx);
       bv[r] = *reinterpret_cast<const V*>(b + idx);
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_dir_apply(MgFine<R> c, MgScal
   const R beta = (R)sc->beta;
   const int nx = c.nx;
   const int c0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-  const int j0 = 1 + blockIdx.y * kMgDirRows, j1 = min(j0 + kMgDirRows, c.ny - 1);
+  const int j0 = c.row_lo + blockIdx.y * kMgDirRows, j1 = min(j0 + kMgDirRows, c.row_hi);
   const bool any = c0 < nx, v0 = any && c0 >= 1, v1 = any && c0 + 1 <= nx - 2;
   double acc = 0.0;
   if (any) {
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_dir_apply(MgFine<R> c, MgScal
     const int cl = max(c0 - 1, 0), cr = min(c0 + 2, nx - 1);
 #pragma unroll
     for (int m = 0; m < kMgDirRows + 2; ++m) {
-      const int j = min(j0 - 1 + m, c.ny - 1);
+      const int j = min(j0 - 1 + m, c.row_hi);  // row_hi is the ring / halo row above the owned unknowns
       const size_t idx = (size_t)c0 + (size_t)j * nx;
       const V zv = *reinterpret_cast<const V*>(z + idx), dv = *reinterpret_cast<const V*>(d_old + idx);
       dn[m].x = zv.x + beta * dv.x;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_dir_apply(MgFine<R> c, MgScal
     }
 #pragma unroll
     for (int r = 0; r < kMgDirRows; ++r) {
-      const int j = min(j0 + r, c.ny - 2);
+      const int j = min(j0 + r, c.row_hi - 1);
       const size_t row = (size_t)j * nx;
       dl[r] = z[row + cl] + beta * d_old[row + cl];
       dr[r] = z[row + cr] + beta * d_old[row + cr];
@@ -210,14 +210,14 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_update(MgFine<R> c, MgScalars
   using V = typename Vec2<R>::type;
   const R alpha = (R)sc->alpha;
   const int c0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-  const int j0 = 1 + blockIdx.y * kMgUpdRows, j1 = min(j0 + kMgUpdRows, c.ny - 1);
+  const int j0 = c.row_lo + blockIdx.y * kMgUpdRows, j1 = min(j0 + kMgUpdRows, c.row_hi);
   const bool any = c0 < c.nx, v0 = any && c0 >= 1, v1 = any && c0 + 1 <= c.nx - 2;
   double acc = 0.0;
   if (any) {
     V dv[kMgUpdRows], wv[kMgUpdRows], xv[kMgUpdRows], rv[kMgUpdRows];
 #pragma unroll
     for (int r = 0; r < kMgUpdRows; ++r) {
-      const int j = min(j0 + r, c.ny - 2);
+      const int j = min(j0 + r, c.row_hi - 1);
       const size_t idx = (size_t)c0 + (size_t)j * c.nx;
       dv[r] = *reinterpret_cast<const V*>(d + idx);
       wv[r] = *reinterpret_cast<const V*>(w + idx);
@@ -245,6 +245,12 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_update(MgFine<R> c, MgScalars
     }
   }
   mg_finish_dot<R, kMgThreads>(c, sc, partials, ticket, acc, 3);
+}
+
+// strips: advance the CG scalars from the sum-allreduced local_sum (the single-domain kernels do this themselves)
+template <class R>
+__global__ void k_mg_advance(MgFine<R> c, MgScalars* __restrict__ sc, int mode) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) mg_advance<R>(c, sc, sc->local_sum, mode);
 }
 
 // end of a step's first solve (mg_warm_start 2): next start vector = 2 x - last, last = x; whole grid, grid-stride
@@ -277,7 +283,7 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_first_sweep(MgFine<R> c, R om
   V rv[kMgRows];
 #pragma unroll
   for (int r = 0; r < kMgRows; ++r)
-    rv[r] = *reinterpret_cast<const V*>(rho + p.c0 + (size_t)min(p.j0 + r, c.ny - 2) * nx);
+    rv[r] = *reinterpret_cast<const V*>(rho + p.c0 + (size_t)min(p.j0 + r, c.row_hi - 1) * nx);
 #pragma unroll
   for (int r = 0; r < kMgRows; ++r) {
     const int j = p.j0 + r;
@@ -299,9 +305,9 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_first_sweep(MgFine<R> c, R om
 // rho_1[I,J] = sum over the children of (rho - L z); one thread per coarse cell
 template <class R>
 __global__ void __launch_bounds__(kMgThreads) k_mg_fine_restrict(MgFine<R> c, const R* __restrict__ z,
-                                                                  const R* __restrict__ rho, int cmx, int cmy,
+                                                                  const R* __restrict__ rho, int cmx, int c_lo,
                                                                   R* __restrict__ crho) {
-  const int I = blockIdx.x * blockDim.x + threadIdx.x, J = blockIdx.y;
+  const int I = blockIdx.x * blockDim.x + threadIdx.x, J = c_lo + blockIdx.y;  // grid.y = owned rows of level 1
   if (I >= cmx) return;
   R acc = R(0);
 #pragma unroll
@@ -318,8 +324,9 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_fine_restrict(MgFine<R> c, co
 // never read by a stencil on the unknowns and are left alone).  One thread per unknown.
 template <class R>
 __global__ void __launch_bounds__(kMgThreads) k_mg_fine_prolong(MgFine<R> c, R* __restrict__ z, int cmx,
-                                                                 const R* __restrict__ ce) {
-  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y;
+                                                                 const R* __restrict__ ce, int j_lo) {
+  // grid.y = rows handled: the owned unknown rows plus, on strips, the neighbours' edge rows (halo)
+  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = j_lo + blockIdx.y;
   if (i > c.nx - 2) return;
   const size_t idx = (size_t)i + (size_t)j * c.nx;
   const R v = z[idx] + ce[(size_t)((i - 1) / 2 + 1) + (size_t)((j - 1) / 2 + 1) * (cmx + 2)];
@@ -376,22 +383,22 @@ __device__ __forceinline__ void mgc_restrict_cell(const MgLevelDev<R>& L, const 
 
 template <class R>
 __global__ void __launch_bounds__(kMgThreads) k_mgc_sweep(MgLevelDev<R> L, const R* in, const R* rho, R* out, R omega,
-                                                           int zero_in) {
-  const int I = blockIdx.x * blockDim.x + threadIdx.x, J = blockIdx.y;
+                                                           int zero_in, int row_lo) {
+  const int I = blockIdx.x * blockDim.x + threadIdx.x, J = row_lo + blockIdx.y;
   if (I < L.mx) mgc_sweep_cell<R>(L, in, rho, out, omega, zero_in != 0, I, J);
 }
 
 template <class R>
 __global__ void __launch_bounds__(kMgThreads) k_mgc_restrict(MgLevelDev<R> L, const R* e, const R* rho, int cmx,
-                                                              int cmy, R* crho) {
-  const int I = blockIdx.x * blockDim.x + threadIdx.x, J = blockIdx.y;
+                                                              int c_lo, R* crho) {
+  const int I = blockIdx.x * blockDim.x + threadIdx.x, J = c_lo + blockIdx.y;
   if (I < cmx) mgc_restrict_cell<R>(L, e, rho, cmx, crho, I, J);
 }
 
 // e_l += (correction of the parent); one thread per cell of level l
 template <class R>
-__global__ void __launch_bounds__(kMgThreads) k_mgc_prolong(int mx, R* e, int cmx, const R* ce) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+__global__ void __launch_bounds__(kMgThreads) k_mgc_prolong(int mx, R* e, int cmx, const R* ce, int row_lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = row_lo + blockIdx.y;
   if (i >= mx) return;
   const size_t idx = (size_t)(i + 1) + (size_t)(j + 1) * ((size_t)mx + 2);
   e[idx] += ce[(size_t)(i / 2 + 1) + (size_t)(j / 2 + 1) * ((size_t)cmx + 2)];

@@ -49,6 +49,7 @@ struct NcclApi {
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -70,11 +71,12 @@ NcclApi& nccl_api() {
       CFD_SYM(Recv, "ncclRecv");
       CFD_SYM(AllReduce, "ncclAllReduce");
       CFD_SYM(AllGather, "ncclAllGather");
+      CFD_SYM(Broadcast, "ncclBroadcast");
       CFD_SYM(GroupStart, "ncclGroupStart");
       CFD_SYM(GroupEnd, "ncclGroupEnd");
       CFD_SYM(GetErrorString, "ncclGetErrorString");
 #undef CFD_SYM
-      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.AllReduce && api.AllGather &&
+      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.AllReduce && api.AllGather && api.Broadcast &&
                api.GroupStart && api.GroupEnd && api.GetErrorString;
     }
   }
@@ -141,6 +143,18 @@ struct Field {
   size_t count = 0;  // entries allocated
   T* row(long j) const { return v + j * (long)rowlen; }
 };
+
+// Row strips: rank r owns array rows [strip_row_start(r), strip_row_start(r + 1)).  Interior boundaries sit at
+// 1 + (a multiple of kStripAlign) so that the unknown rows (array row - 1) of a strip pair up within the strip on the
+// first three multigrid levels (cfd_mg.cuh); any partition gives bit-identical Mode R results.
+constexpr int kStripAlign = 8;
+inline int strip_row_start(int ny, int world, int r) {
+  if (r <= 0) return 0;
+  if (r >= world) return ny;
+  const long unknowns = (long)ny - 2;
+  const long b = (r * unknowns / world) / kStripAlign * kStripAlign;
+  return (int)(1 + b);
+}
 
 constexpr int kHalo = 2;  // rows: the second-order predictor reaches j +- 2 (src/model.rs:999, 1044, 1195, 1239)
 
@@ -253,9 +267,8 @@ struct ModelImpl final : ModelBase {
     scenario = prm.scenario;
     rank = o.rank;
     world = o.world_size;
-    const int base = ny / world, rem = ny % world;
-    ja = rank * base + (rank < rem ? rank : rem);
-    jb = ja + base + (rank < rem ? 1 : 0);
+    ja = strip_row_start(ny, world, rank);
+    jb = strip_row_start(ny, world, rank + 1);
     owns_bottom = rank == 0;
     owns_top = rank == world - 1;
     rows_alloc = (jb - ja) + 2 * kHalo + 1;
@@ -429,8 +442,7 @@ struct ModelImpl final : ModelBase {
     // a neighbour lays its buffers out exactly like this rank does (falloc): virtual origin = base + front -
     // (its first owned row - kHalo) * nx
     auto neighbour_origin = [&](void* base, int r) -> R* {
-      const int nb = ny / world, rem = ny % world;
-      const int ja_n = r * nb + (r < rem ? r : rem);
+      const int ja_n = strip_row_start(ny, world, r);
       return (R*)base + kFront - (long)(ja_n - kHalo) * (long)nx;
     };
     if (rank > 0) {
@@ -860,7 +872,6 @@ struct ModelImpl final : ModelBase {
   // EXTENSION, Mode C fast path: CG preconditioned by one multigrid V-cycle (cfd_mg.cuh).  Level geometry is
   // computed on the host in R precision with the same expressions as the oracle (mg_build_levels).
   int mg_setup() {
-    if (world > 1) return fail(CFD_ERR_UNSUPPORTED, "MGCG runs on a single domain in this version (use CG on strips)");
     const bool cavity = scenario == CFD_SCENARIO_CAVITY;
     const R dx_sq = dx * dx, dy_sq = dy * dy;
     std::vector<R> wx((size_t)nx - 2, R(1)), hy((size_t)ny - 2, R(1));
@@ -930,6 +941,7 @@ struct ModelImpl final : ModelBase {
     for (int l = 1; l < (int)mg.size(); ++l)
       if (mg[(size_t)l].mx <= 64 && mg[(size_t)l].my <= 64) { mg_bottom_level = l; break; }
     if ((int)mg.size() - mg_bottom_level > cfdk::kMgBottomMax) return fail(CFD_ERR_UNSUPPORTED, "multigrid hierarchy too deep");
+    mg_ld = world > 1 ? (mg_bottom_level - 1 < 2 ? mg_bottom_level - 1 : 2) : -1;
     memset(&mg_bottom, 0, sizeof mg_bottom);
     mg_bottom.n = (int)mg.size() - mg_bottom_level;
     mg_bottom.nu = mg_smoothing();
@@ -946,13 +958,71 @@ struct ModelImpl final : ModelBase {
 
   int mg_smoothing() const { return opt.consts.mg_smoothing < 1 ? 1 : opt.consts.mg_smoothing; }
 
+  // ---- strips (world > 1): level 0 lives in row strips like every other field; coarse levels are allocated in full
+  // on every rank.  Levels 1..mg_ld are computed in strips too (each rank its own rows, one halo row exchanged after
+  // every sweep); level mg_ld + 1 is gathered and everything below runs replicated on every rank (identical values,
+  // no further communication).  The aligned partition (strip_row_start) makes the cells of a strip pair up within
+  // the strip on levels 0..2.
+  int mg_ld = -1;  // last coarse level computed in strips (-1: none / single domain)
+  // owned rows [lo, hi) of level l, in unknown-row numbering of that level, for rank r
+  int lvl_lo(int l, int r) const {
+    const int a = strip_row_start(ny, world, r);
+    return ((a > 1 ? a : 1) - 1) >> l;
+  }
+  int lvl_hi(int l, int r) const {
+    if (r == world - 1) return mg[(size_t)l].my;
+    return (strip_row_start(ny, world, r + 1) - 1) >> l;
+  }
+  bool lvl_dist(int l) const { return world > 1 && l <= mg_ld; }
+
+  // one halo row each way of a coarse-level field (row pitch mx + 2; unknown row J is array row J + 1)
+  int exchange_level(R* f, int l) {
+    const size_t pitch = (size_t)mg[(size_t)l].mx + 2;
+    const int lo = lvl_lo(l, rank), hi = lvl_hi(l, rank);
+    CFD_NCCL(nccl_api().GroupStart());
+    if (rank > 0) {
+      CFD_NCCL(nccl_api().Send(f + (size_t)(lo + 1) * pitch, pitch, nccl_real(), rank - 1, comm, stream));
+      CFD_NCCL(nccl_api().Recv(f + (size_t)lo * pitch, pitch, nccl_real(), rank - 1, comm, stream));
+    }
+    if (rank < world - 1) {
+      CFD_NCCL(nccl_api().Send(f + (size_t)hi * pitch, pitch, nccl_real(), rank + 1, comm, stream));
+      CFD_NCCL(nccl_api().Recv(f + (size_t)(hi + 1) * pitch, pitch, nccl_real(), rank + 1, comm, stream));
+    }
+    CFD_NCCL(nccl_api().GroupEnd());
+    return CFD_OK;
+  }
+  // every rank receives every rank's rows of a level-l field (one in-place broadcast per owner, grouped)
+  int gather_level(R* f, int l) {
+    const size_t pitch = (size_t)mg[(size_t)l].mx + 2;
+    CFD_NCCL(nccl_api().GroupStart());
+    for (int r = 0; r < world; ++r) {
+      const int lo = lvl_lo(l, r), hi = lvl_hi(l, r);
+      if (hi <= lo) continue;
+      R* rows = f + (size_t)(lo + 1) * pitch;
+      CFD_NCCL(nccl_api().Broadcast(rows, rows, (size_t)(hi - lo) * pitch, nccl_real(), r, comm, stream));
+    }
+    CFD_NCCL(nccl_api().GroupEnd());
+    return CFD_OK;
+  }
+  // strips: finish a dot product whose rank-local sum sits in mg_scalars->local_sum
+  int mg_finish_strips(const cfdk::MgFine<R>& c, int mode) {
+    if (world == 1) return CFD_OK;
+    CFD_NCCL(nccl_api().AllReduce(&mg_scalars->local_sum, &mg_scalars->local_sum, 1, ncclFloat64, ncclSum, comm, stream));
+    cfdk::k_mg_advance<R><<<1, 32, 0, stream>>>(c, mg_scalars, mode);
+    ++launches;
+    return CFD_OK;
+  }
+
   // correction of level l >= 1 from its rho (result in mg[l].cur)
   int mg_coarse_vcycle(int l) {
     MgLevelHost& L = mg[(size_t)l];
     const R omega = R(opt.consts.mg_omega);
     const int nu_s = mg_smoothing();
-    const dim3 blk(cfdk::kMgThreads), grd((L.mx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, L.my);
+    const bool dist = lvl_dist(l);
+    const int lo = dist ? lvl_lo(l, rank) : 0, hi = dist ? lvl_hi(l, rank) : L.my;
+    const dim3 blk(cfdk::kMgThreads), grd((L.mx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, hi - lo);
     R *a = L.e, *b = L.tmp;
+    int rc;
     if (l == mg_bottom_level && !(opt.flags & CFD_FLAG_MG_NO_BOTTOM_KERNEL) && !(L.mx == 1 && L.my == 1)) {
       cfdk::k_mg_bottom<R><<<1, cfdk::kMgBottomThreads, 0, stream>>>(mg_bottom);
       ++launches;
@@ -960,31 +1030,50 @@ struct ModelImpl final : ModelBase {
       return CFD_OK;
     }
     if (L.mx == 1 && L.my == 1) {  // exact
-      cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, R(1), 1);
+      cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, R(1), 1, 0);
       ++launches;
       L.cur = b;
       return CFD_OK;
     }
     for (int s = 0; s < nu_s; ++s) {
-      cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, omega, s == 0 ? 1 : 0);
+      cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, omega, s == 0 ? 1 : 0, lo);
       ++launches;
       std::swap(a, b);
+      if (dist && (rc = exchange_level(a, l))) return rc;
     }
     MgLevelHost& C = mg[(size_t)l + 1];
-    const dim3 grd_c((C.mx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, C.my);
-    cfdk::k_mgc_restrict<R><<<grd_c, blk, 0, stream>>>(L.dev, a, L.rho, C.mx, C.my, C.rho);
+    const int c_lo = dist ? lvl_lo(l + 1, rank) : 0, c_hi = dist ? lvl_hi(l + 1, rank) : C.my;
+    const dim3 grd_c((C.mx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, c_hi - c_lo);
+    cfdk::k_mgc_restrict<R><<<grd_c, blk, 0, stream>>>(L.dev, a, L.rho, C.mx, c_lo, C.rho);
     ++launches;
-    int rc;
+    if (dist && !lvl_dist(l + 1) && (rc = gather_level(C.rho, l + 1))) return rc;
     if ((rc = mg_coarse_vcycle(l + 1))) return rc;
-    cfdk::k_mgc_prolong<R><<<grd, blk, 0, stream>>>(L.mx, a, C.mx, C.cur);
-    ++launches;
+    {
+      // strips: also correct the neighbours' edge rows (halo), from the parent's halo rows
+      const int p_lo = dist ? (lo > 0 ? lo - 1 : 0) : 0, p_hi = dist ? (hi < L.my ? hi + 1 : L.my) : L.my;
+      const dim3 grd_p((L.mx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, p_hi - p_lo);
+      cfdk::k_mgc_prolong<R><<<grd_p, blk, 0, stream>>>(L.mx, a, C.mx, C.cur, p_lo);
+      ++launches;
+    }
     for (int s = 0; s < nu_s; ++s) {
-      cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, omega, 0);
+      cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, omega, 0, lo);
       ++launches;
       std::swap(a, b);
+      if (dist && (rc = exchange_level(a, l))) return rc;
     }
     L.cur = a;
     return CFD_OK;
+  }
+
+  cfdk::MgFine<R> mg_fine(R dt_sub) const {
+    cfdk::MgFine<R> c;
+    c.dx_sq = dx * dx; c.dy_sq = dy * dy; c.dt = dt_sub; c.tol = R(opt.consts.cg_tolerance);
+    c.n_unknowns = R((size_t)(nx - 2) * (size_t)(ny - 2));
+    c.nx = nx; c.ny = ny; c.cavity = scenario == CFD_SCENARIO_CAVITY;
+    c.row_lo = sweep_row_begin(); c.row_hi = sweep_row_end();
+    c.init_lo = ja; c.init_hi = jb;
+    c.defer = world > 1 ? 1 : 0;
+    return c;
   }
 
   // z <- V-cycle(rho), smoothing between the two mg_b buffers that do not hold d; the last smoothing sweep also
@@ -997,17 +1086,18 @@ struct ModelImpl final : ModelBase {
     c2.one_minus_omega = R(1.0) - c2.omega;
     c2.tol = R(0);
     c2.nx = nx; c2.ny = ny; c2.cavity = c.cavity; c2.rows_per_block = sweep_rows_per_block;
-    c2.row_begin = 1; c2.row_end = ny - 1; c2.row_shift = ja - kHalo;
+    c2.row_begin = c.row_lo; c2.row_end = c.row_hi; c2.row_shift = ja - kHalo;
     c2.check_lag = 1;
     c2.fix_pass = -1;
-    const int rows = ny - 2;
+    const int rows = c.row_hi - c.row_lo;
     const dim3 blk2(128), grd2((nx / 2 + 127) / 128, (rows + sweep_rows_per_block - 1) / sweep_rows_per_block);
     const size_t ring_bytes = sizeof(cfdk::SweepChunkRing<R>);
     const int za = (mg_id + 1) % 3, zb = (mg_id + 2) % 3;
     int zc = za, zo = zb;  // current / other smoothing buffer
+    int rc;
     cfdk::SweepDot<R> dot;
     dot.c = c; dot.sc = mg_scalars; dot.partials = mg_partials; dot.ticket = mg_ticket;
-    auto smooth = [&](bool with_dot) {
+    auto smooth = [&](bool with_dot) -> int {
       if (prof_smoother) {
         if (ev_prof_used + 2 > ev_prof.size()) {
           ev_prof.resize(ev_prof_used + 64, nullptr);
@@ -1027,27 +1117,36 @@ struct ModelImpl final : ModelBase {
       }
       ++launches;
       std::swap(zc, zo);
+      return exchange_halo(mg_b[zc], ja, jb, 1);  // strips: the neighbours' new edge rows (no-op on one GPU)
     };
     {
       // first sweep from z = 0: pointwise (k_mg_first_sweep) instead of a stencil sweep over a zero field
-      const dim3 g_vec((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads), (ny - 2 + cfdk::kMgRows - 1) / cfdk::kMgRows);
+      const dim3 g_vec((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads), (rows + cfdk::kMgRows - 1) / cfdk::kMgRows);
       cfdk::k_mg_first_sweep<R><<<g_vec, cfdk::kMgThreads, 0, stream>>>(c, c2.omega, c2.one_minus_omega, div_denom.y,
                                                                         mg_rho.v, mg_b[zc].v);
       ++launches;
+      if ((rc = exchange_halo(mg_b[zc], ja, jb, 1))) return rc;
     }
-    for (int s = 1; s < nu_s; ++s) smooth(false);
+    for (int s = 1; s < nu_s; ++s)
+      if ((rc = smooth(false))) return rc;
     if (mg.size() > 1) {
       MgLevelHost& C = mg[1];
-      const dim3 blk(cfdk::kMgThreads), grd_c((C.mx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, C.my);
-      const dim3 g_int((nx - 2 + cfdk::kMgThreads - 1) / cfdk::kMgThreads, ny - 2);
-      cfdk::k_mg_fine_restrict<R><<<grd_c, blk, 0, stream>>>(c, mg_b[zc].v, mg_rho.v, C.mx, C.my, C.rho);
+      const int c_lo = world > 1 ? lvl_lo(1, rank) : 0, c_hi = world > 1 ? lvl_hi(1, rank) : C.my;
+      const dim3 blk(cfdk::kMgThreads), grd_c((C.mx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, c_hi - c_lo);
+      cfdk::k_mg_fine_restrict<R><<<grd_c, blk, 0, stream>>>(c, mg_b[zc].v, mg_rho.v, C.mx, c_lo, C.rho);
       ++launches;
-      int rc;
+      if (world > 1 && !lvl_dist(1) && (rc = gather_level(C.rho, 1))) return rc;
       if ((rc = mg_coarse_vcycle(1))) return rc;
-      cfdk::k_mg_fine_prolong<R><<<g_int, blk, 0, stream>>>(c, mg_b[zc].v, C.mx, C.cur);
+      // strips: also correct the neighbours' edge rows (halo) of z, from the parent's halo rows
+      const int p_lo = world > 1 && c.row_lo > 1 ? c.row_lo - 1 : c.row_lo;
+      const int p_hi = world > 1 && c.row_hi < ny - 1 ? c.row_hi + 1 : c.row_hi;
+      const dim3 g_int((nx - 2 + cfdk::kMgThreads - 1) / cfdk::kMgThreads, p_hi - p_lo);
+      cfdk::k_mg_fine_prolong<R><<<g_int, blk, 0, stream>>>(c, mg_b[zc].v, C.mx, C.cur, p_lo);
       ++launches;
     }
-    for (int s = 0; s < nu_s; ++s) smooth(s == nu_s - 1);
+    for (int s = 0; s < nu_s; ++s)
+      if ((rc = smooth(s == nu_s - 1))) return rc;
+    if ((rc = mg_finish_strips(c, 1))) return rc;
     CFD_CUDA(cudaGetLastError());
     *z_index = zc;
     return CFD_OK;
@@ -1056,15 +1155,13 @@ struct ModelImpl final : ModelBase {
   int mgcg_solve(R dt_sub, int call_index, R* residual_out) {
     int rc;
     if (mg.empty() && (rc = mg_setup())) return rc;
-    cfdk::MgFine<R> c;
-    c.dx_sq = dx * dx; c.dy_sq = dy * dy; c.dt = dt_sub; c.tol = R(opt.consts.cg_tolerance);
-    c.n_unknowns = R((size_t)(nx - 2) * (size_t)(ny - 2));
-    c.nx = nx; c.ny = ny; c.cavity = scenario == CFD_SCENARIO_CAVITY;
+    const cfdk::MgFine<R> c = mg_fine(dt_sub);
     const dim3 blk(cfdk::kMgThreads);
     const unsigned gx = (unsigned)((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads));
-    const dim3 g_all(gx, (ny + cfdk::kMgRows - 1) / cfdk::kMgRows);       // all rows (init)
-    const dim3 g_dir(gx, (ny - 2 + cfdk::kMgDirRows - 1) / cfdk::kMgDirRows);  // rows of unknowns, 4-row tiles
-    const dim3 g_upd(gx, (ny - 2 + cfdk::kMgUpdRows - 1) / cfdk::kMgUpdRows);
+    const int rows = c.row_hi - c.row_lo;
+    const dim3 g_all(gx, (jb - ja + cfdk::kMgRows - 1) / cfdk::kMgRows);            // every owned row (init)
+    const dim3 g_dir(gx, (rows + cfdk::kMgDirRows - 1) / cfdk::kMgDirRows);         // owned rows of unknowns, 4-row tiles
+    const dim3 g_upd(gx, (rows + cfdk::kMgUpdRows - 1) / cfdk::kMgUpdRows);
     const Field<R>& xf = pp[ipp];
     R* x = xf.v;
     R* w = pp[ipp ^ 1].v;
@@ -1074,12 +1171,14 @@ struct ModelImpl final : ModelBase {
     *h_mg = init;
     CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index], stream));
     CFD_CUDA(cudaMemcpyAsync(mg_scalars, h_mg, sizeof init, cudaMemcpyHostToDevice, stream));
-    // first solve of a step: start from the p' the first solve of the previous step ended with (mg_warm_start)
+    // first solve of a step: start from mg_guess (mg_warm_start); its stencil needs the neighbours' edge rows
     const bool first_solve = call_index == 0;
     const bool warm = first_solve && opt.consts.mg_warm_start != 0;
+    if (warm && (rc = exchange_halo(mg_guess, ja, jb, 1))) return rc;
     cfdk::k_mg_init<R><<<g_all, blk, 0, stream>>>(c, mg_scalars, rhs.v, warm ? mg_guess.v : nullptr, x, mg_rho.v,
                                                   mg_b[mg_id].v, mg_partials, mg_ticket);
     launches += 1;
+    if ((rc = mg_finish_strips(c, 0))) return rc;
     for (;;) {
       CFD_CUDA(cudaMemcpyAsync(h_mg, mg_scalars, sizeof init, cudaMemcpyDeviceToHost, stream));
       CFD_CUDA(cudaStreamSynchronize(stream));
@@ -1091,19 +1190,23 @@ struct ModelImpl final : ModelBase {
       cfdk::k_mg_dir_apply<R><<<g_dir, blk, 0, stream>>>(c, mg_scalars, mg_b[zi].v, mg_b[mg_id].v, mg_b[dn].v, w, mg_partials,
                                                          mg_ticket);
       mg_id = dn;
+      if ((rc = mg_finish_strips(c, 2))) return rc;
+      if ((rc = exchange_halo(mg_b[mg_id], ja, jb, 1))) return rc;  // strips: d's edge rows for the next L d
       cfdk::k_mg_update<R><<<g_upd, blk, 0, stream>>>(c, mg_scalars, mg_b[mg_id].v, w, x, mg_rho.v, mg_partials, mg_ticket);
       launches += 2;
+      if ((rc = mg_finish_strips(c, 3))) return rc;
       CFD_CUDA(cudaGetLastError());
     }
     const int n_edge = (nx > ny ? nx : ny);
     cfdk::k_cg_fill_boundary<R><<<(n_edge + 255) / 256, 256, 0, stream>>>(nx, ny, c.cavity, x, ja, jb);
     ++launches;
+    if ((rc = exchange_halo(xf, ja, jb, 1))) return rc;  // the corrector reads p'[j-1] (src/model.rs:1380)
     if (first_solve) {
       if (opt.consts.mg_warm_start == 2) {
-        cfdk::k_mg_extrapolate<R><<<148 * 8, cfdk::kMgThreads, 0, stream>>>(xf.row(0), mg_last.row(0), mg_guess.row(0), n_p);
+        cfdk::k_mg_extrapolate<R><<<148 * 8, cfdk::kMgThreads, 0, stream>>>(xf.row(ja), mg_last.row(ja), mg_guess.row(ja), own_p());
         ++launches;
       } else {
-        CFD_CUDA(cudaMemcpyAsync(mg_guess.row(0), xf.row(0), n_p * sizeof(R), cudaMemcpyDeviceToDevice, stream));
+        CFD_CUDA(cudaMemcpyAsync(mg_guess.row(ja), xf.row(ja), own_p() * sizeof(R), cudaMemcpyDeviceToDevice, stream));
       }
     }
     CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index + 1], stream));
@@ -1253,8 +1356,6 @@ struct ModelImpl final : ModelBase {
   int set_params(const cfd_params& prm) override {
     if (prm.pressure_solver < CFD_SOLVER_JACOBI || prm.pressure_solver > CFD_SOLVER_MGCG)
       return fail(CFD_ERR_INVALID_ARGUMENT, "pressure_solver out of range");
-    if (prm.pressure_solver == CFD_SOLVER_MGCG && world > 1)
-      return fail(CFD_ERR_UNSUPPORTED, "MGCG runs on a single domain in this version (use CG on strips)");
     nu = R(prm.viscosity);
     dt = R(prm.dt);
     target_inlet_velocity = R(prm.target_inlet_velocity);
@@ -1414,7 +1515,7 @@ struct ModelImpl final : ModelBase {
       case CFD_FIELD_V_OLD: *n = own_v(); return vbuf[ifree].row(ja);
       case CFD_FIELD_MG_GUESS:
       case CFD_FIELD_MG_LAST:
-        if (!mg_guess.base && (world > 1 || mg_setup() != CFD_OK)) { *n = 0; return nullptr; }
+        if (!mg_guess.base && mg_setup() != CFD_OK) { *n = 0; return nullptr; }
         *n = own_p();
         return field == CFD_FIELD_MG_GUESS ? mg_guess.row(ja) : mg_last.row(ja);
       default: *n = 0; return nullptr;
@@ -1532,14 +1633,12 @@ int cfd_model_create_ex(const cfd_grid* grid, const cfd_params* params, const cf
   if (o.precision != 64 && o.precision != 32) return fail(CFD_ERR_INVALID_ARGUMENT, "precision must be 64 or 32");
   if (o.world_size < 1 || o.rank < 0 || o.rank >= o.world_size) return fail(CFD_ERR_INVALID_ARGUMENT, "rank / world_size out of range");
   if (o.world_size > 1 && !o.nccl_unique_id) return fail(CFD_ERR_INVALID_ARGUMENT, "world_size > 1 needs nccl_unique_id");
-  if (o.world_size > 1 && grid->ny / (uint64_t)o.world_size < 4) return fail(CFD_ERR_INVALID_ARGUMENT, "strips need at least 4 rows per rank");
+  if (o.world_size > 1 && grid->ny / (uint64_t)o.world_size < 16) return fail(CFD_ERR_INVALID_ARGUMENT, "strips need at least 16 rows per rank");
   if (o.consts.jacobi_iterations < 1 || o.consts.jacobi_iterations > kMaxSweepSlots)
     return fail(CFD_ERR_INVALID_ARGUMENT, "jacobi_iterations must be in 1..256");
   if (o.consts.outer_rounds < 0 || o.consts.outer_rounds > 1000) return fail(CFD_ERR_INVALID_ARGUMENT, "outer_rounds out of range");
   if (o.consts.mg_warm_start < 0 || o.consts.mg_warm_start > 2 || o.consts.mg_smoothing < 1 || o.consts.mg_smoothing > 16 || !(o.consts.mg_omega > 0.0) || !(o.consts.mg_omega <= 1.0))
     return fail(CFD_ERR_INVALID_ARGUMENT, "mg_smoothing must be in 1..16 and mg_omega in (0, 1]");
-  if (params->pressure_solver == CFD_SOLVER_MGCG && o.world_size > 1)
-    return fail(CFD_ERR_UNSUPPORTED, "MGCG runs on a single domain in this version (use CG on strips)");
   if (params->velocity_scheme < 0 || params->velocity_scheme > 1 || params->inlet_profile < 0 ||
       params->inlet_profile > 1 || params->scenario < 0 || params->scenario > 1 || params->pressure_solver < 0 ||
       params->pressure_solver > CFD_SOLVER_MGCG)

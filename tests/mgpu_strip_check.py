@@ -17,6 +17,17 @@ from cfd_demo_b200.types import Cylinder, Grid, InletProfile, SimulationParams, 
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    log_dir = os.environ.get("CFD_STRIP_LOG_DIR")  # per-rank progress log (a failing rank leaves the others waiting in NCCL)
+    log = open(os.path.join(log_dir, f"strip_check_rank{rank}.log"), "w") if log_dir else None
+
+    def progress(msg):
+        if log:
+            log.write(msg + "\n")
+            log.flush()
+    import faulthandler
+    if log:
+        faulthandler.enable(log)
+        sys.excepthook = lambda t, v, tb: (progress("EXCEPTION " + repr(v)), sys.__excepthook__(t, v, tb))
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")
     uid = [nccl_unique_id() if rank == 0 else None]
@@ -65,14 +76,25 @@ def main():
         assert rw.sweeps > 30
         strip.close()
         whole.close()
+        progress(f"mode R case {ci} ok")
         dist.barrier()
     # Mode C (CG): the dot products are sum-allreduced over the ranks, so parity is to a tolerance (1e-9 rel. L2)
     from cfd_demo_b200.model import default_options
     from cfd_demo_b200.types import PressureSolver, Scenario
     import ctypes as C
-    for scenario, grid in ((Scenario.Channel, Grid.uniform(264, 96, 30.0, 10.0, Cylinder(7.5, 5.0, 0.75))),
-                           (Scenario.Cavity, Grid.uniform(128, 128, 1.0, 1.0, None))):
-        params = SimulationParams(dt=1e-3, viscosity=0.01, scenario=scenario, pressure_solver=PressureSolver.CG)
+    # (solver, scenario, grid, steps).  MGCG: level 0 and the first coarse levels run in strips (one halo row after every
+    # sweep), the rest of the hierarchy is gathered and replicated; 128^2 gathers level 1 already, 520 x 264 runs
+    # levels 1 and 2 in strips and gathers level 3.
+    mode_c = [
+        (PressureSolver.CG, Scenario.Channel, Grid.uniform(264, 96, 30.0, 10.0, Cylinder(7.5, 5.0, 0.75)), 10),
+        (PressureSolver.CG, Scenario.Cavity, Grid.uniform(128, 128, 1.0, 1.0, None), 10),
+        (PressureSolver.MGCG, Scenario.Cavity, Grid.uniform(128, 128, 1.0, 1.0, None), 10),
+        (PressureSolver.MGCG, Scenario.Channel, Grid.uniform(264, 96, 26.4, 9.6, Cylinder(6.6, 4.8, 0.72)), 10),
+        (PressureSolver.MGCG, Scenario.Cavity, Grid.uniform(520, 264, 520 / 256.0, 264 / 256.0, None), 8),
+        (PressureSolver.MGCG, Scenario.Channel, Grid.uniform(1040, 600, 10.4, 6.0, Cylinder(2.6, 3.0, 0.45)), 8),
+    ]
+    for solver, scenario, grid, n_steps in mode_c:
+        params = SimulationParams(dt=1e-3, viscosity=0.01, scenario=scenario, pressure_solver=solver)
         uid = [nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         opts = default_options()
@@ -88,15 +110,20 @@ def main():
         ja, jb = strip.rows()
         nx, ny = grid.nx, grid.ny
         top = 1 if rank == world - 1 else 0
-        for s in range(10):
+        progress(f"mode C {solver.name} {scenario.name} {grid.nx}x{grid.ny}: rows {ja}..{jb}")
+        for s in range(n_steps):
             strip.update()
+            progress(f"  step {s} strip done: {strip.get_residuals().sweeps} iterations")
             whole.update()
-        rs, rw = strip.get_residuals(), whole.get_residuals()
-        assert rs.jacobi_calls == rw.jacobi_calls == 2 and abs(rs.sweeps - rw.sweeps) <= 4, (rs, rw)
+            rs, rw = strip.get_residuals(), whole.get_residuals()
+            slack = 4 if solver == PressureSolver.CG else 1
+            assert rs.jacobi_calls == rw.jacobi_calls == 2 and abs(rs.sweeps - rw.sweeps) <= slack, (solver, s, rs, rw)
+        assert rw.sweeps > 0
         for fid, shape, hi in ((_abi.FIELD_P, (ny, nx), jb), (_abi.FIELD_U, (ny, nx + 1), jb), (_abi.FIELD_V, (ny + 1, nx), jb + top)):
             a, b = strip.field(fid), whole.field(fid).reshape(shape)[ja:hi].ravel()
             d = np.linalg.norm(a - b) / np.linalg.norm(b)
-            assert d <= 1e-9, (scenario, _abi.FIELD_NAMES[fid], d)
+            progress(f"  {_abi.FIELD_NAMES[fid]} rel l2 {d:.3e}")
+            assert d <= 1e-9, (solver, scenario, _abi.FIELD_NAMES[fid], d)
         strip.close()
         whole.close()
         dist.barrier()
