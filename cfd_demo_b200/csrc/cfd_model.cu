@@ -1721,6 +1721,14 @@ int cfd_model_rows(cfd_model* m, uint64_t* j0, uint64_t* j1) {
   return m->impl->rows(j0, j1);
 }
 
+int cfd_strip_rows(uint64_t ny, int32_t world_size, int32_t rank, uint64_t* j0, uint64_t* j1) {
+  if (!j0 || !j1 || world_size < 1 || rank < 0 || rank >= world_size || ny < 4 || ny > (1u << 30))
+    return fail(CFD_ERR_INVALID_ARGUMENT, "cfd_strip_rows: bad argument");
+  *j0 = (uint64_t)strip_row_start((int)ny, world_size, rank);
+  *j1 = (uint64_t)strip_row_start((int)ny, world_size, rank + 1);
+  return CFD_OK;
+}
+
 int cfd_model_last_timing(cfd_model* m, double* step_ms, double* sweep_ms, uint64_t* kernel_launches) {
   CFD_CHECK_MODEL(m);
   return m->impl->last_timing(step_ms, sweep_ms, kernel_launches);

@@ -63,6 +63,7 @@ def load_library():
     lib.cfd_model_get_field_f64.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64]
     lib.cfd_model_set_field_f64.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64]
     lib.cfd_model_rows.argtypes = [C.c_void_p, P(C.c_uint64), P(C.c_uint64)]
+    lib.cfd_strip_rows.argtypes = [C.c_uint64, C.c_int32, C.c_int32, P(C.c_uint64), P(C.c_uint64)]
     lib.cfd_model_last_timing.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double), P(C.c_uint64)]
     lib.cfd_nccl_unique_id.argtypes = [C.c_void_p]
     lib.cfd_model_profile_smoother.argtypes = [C.c_void_p, C.c_int32]
@@ -111,6 +112,14 @@ class PinnedBuffer:
             self.close()
         except Exception:
             pass
+
+
+def strip_rows(ny: int, world_size: int, rank: int):
+    """Rows [j0, j1) of pressure cells that `rank` of `world_size` owns (the library's strip partition)."""
+    lib = load_library()
+    j0, j1 = C.c_uint64(), C.c_uint64()
+    _check(lib, lib.cfd_strip_rows(int(ny), int(world_size), int(rank), C.byref(j0), C.byref(j1)))
+    return int(j0.value), int(j1.value)
 
 
 def nccl_unique_id() -> bytes:

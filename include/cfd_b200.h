@@ -110,7 +110,7 @@ typedef struct cfd_options {
   cfd_solver_consts consts;
 } cfd_options;
 
-#define CFD_FLAG_NO_GRAPH 1u      /* launch kernels directly instead of replaying the captured step graph */
+#define CFD_FLAG_NO_GRAPH 1u      /* reserved: no effect in this version (every kernel is launched directly) */
 #define CFD_FLAG_BASELINE_SWEEP 2u /* simple one-column-per-thread Jacobi kernel, compiler divisions (cross-check) */
 #define CFD_FLAG_REGISTER_SWEEP 4u /* register-prefetch Jacobi kernel instead of the TMA-staged one (A/B) */
 #define CFD_FLAG_SWEEP4 16u        /* one-row-per-step tensor-TMA Jacobi kernel instead of the row-pair one (A/B) */
@@ -184,6 +184,10 @@ int cfd_model_get_field_f64(cfd_model* m, int32_t field, double* out, uint64_t l
 int cfd_model_set_field_f64(cfd_model* m, int32_t field, const double* in, uint64_t len);
 /* Rows [j0, j1) of pressure cells owned by this rank (whole grid when world_size == 1). */
 int cfd_model_rows(cfd_model* m, uint64_t* j0, uint64_t* j1);
+/* The strip partition itself (pure host arithmetic, no device needed): rows [j0, j1) of rank `rank` of `world_size`
+ * for a grid of ny rows.  Interior boundaries sit at 1 + (a multiple of 8), so that the unknown rows of a strip pair
+ * up within the strip on the first three multigrid levels (MGCG on strips). */
+int cfd_strip_rows(uint64_t ny, int32_t world_size, int32_t rank, uint64_t* j0, uint64_t* j1);
 
 /* ---- measurement hooks (bench.py / profiles; no reference counterpart) ------------------------------- */
 /* Device time in ms of the last cfd_model_update / update_n, and of the Jacobi sweeps inside it,
