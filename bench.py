@@ -48,6 +48,12 @@ WORKLOADS = {
                              desc="lid-driven cavity Re=1000, 4096x4096, fp64, pressure solve converged to dt*rms(r) <= 1e-8 "
                                   "every step (Mode C: CG preconditioned by a multigrid V(2,2)-cycle, the reference's "
                                   "damped-Jacobi sweep kernel as fine-level smoother)"),
+    # BASELINE.json configs[4]: the 16384^2 cavity; with --gpus N the SAME grid is cut into N strips (strong scaling)
+    "cavity16384_modeC": dict(kind="modeC", nx=16384, ny=16384, lx=1.0, ly=1.0, cylinder=None, spinup=110, strong=True,
+                              params=dict(dt=0.6e-6, viscosity=1.0e-3, target_inlet_velocity=1.0, scenario=1,
+                                          pressure_solver=2),
+                              desc="lid-driven cavity Re=1000, 16384x16384, fp64, Mode C (MGCG) converged to dt*rms(r) <= 1e-8, "
+                                   "strong scaling (the same grid on every GPU count)"),
     "cavity1024_modeC": dict(kind="modeC", nx=1024, ny=1024, lx=1.0, ly=1.0, cylinder=None, spinup=110,
                              params=dict(dt=2.0e-5, viscosity=1.0e-2, target_inlet_velocity=1.0, scenario=1,
                                          pressure_solver=2),
@@ -317,8 +323,10 @@ def run_ours(args, w):
     strips = world > 1 and os.environ.get("CFD_BENCH_REPLICAS") != "1"
     from cfd_demo_b200.types import Cylinder, Grid
     cyl = Cylinder(*w["cylinder"]) if w["cylinder"] else None
-    ny_job = w["ny"] * world if strips else w["ny"]
-    grid = Grid.uniform(w["nx"], ny_job, w["lx"], w["ly"] * (world if strips else 1), cyl)
+    strong = bool(w.get("strong")) and strips
+    weak = strips and not strong
+    ny_job = w["ny"] * world if weak else w["ny"]
+    grid = Grid.uniform(w["nx"], ny_job, w["lx"], w["ly"] * (world if weak else 1), cyl)
     params = make_params(w)
     nx, ny = grid.nx, grid.ny
     cells = nx * ny * (1 if (strips or world == 1) else world)  # whole job
@@ -487,7 +495,7 @@ def run_ours(args, w):
             multi = (f"{world} row strips of {w['nx']}x{w['ny']} cells each, halo rows and max-reduction fused into the sweep "
                      f"kernel over NVLink peer memory, weak scaling")
         elif strips:
-            multi = (f"{world} row strips of {w['nx']}x{w['ny']} cells each (one {nx}x{ny} cavity), weak scaling: multigrid levels 0-2 in "
+            multi = (f"{world} row strips of one {nx}x{ny} cavity, {'strong' if strong else 'weak'} scaling: multigrid levels 0-2 in "
                      f"strips with an NCCL halo row after every sweep, level 3 gathered and the rest replicated, dot products "
                      f"sum-allreduced")
         else:
@@ -495,7 +503,7 @@ def run_ours(args, w):
         line = {
             "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
             "steps": steps, "warmup": args.warmup, "ms_per_step": dev_s * 1e3 / steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "timesteps_per_s": steps / dev_s * (world if (world > 1 and not strips) else 1),
             "wall_ms_per_step": wall_s * 1e3 / steps,
             "config": {"workload": w["desc"], "nx": nx, "ny": ny, "spinup_steps": spinup,

@@ -146,8 +146,8 @@ struct Field {
 
 // Row strips: rank r owns array rows [strip_row_start(r), strip_row_start(r + 1)).  Interior boundaries sit at
 // 1 + (a multiple of kStripAlign) so that the unknown rows (array row - 1) of a strip pair up within the strip on the
-// first three multigrid levels (cfd_mg.cuh); any partition gives bit-identical Mode R results.
-constexpr int kStripAlign = 8;
+// first four multigrid levels (cfd_mg.cuh); any partition gives bit-identical Mode R results.
+constexpr int kStripAlign = 16;
 inline int strip_row_start(int ny, int world, int r) {
   if (r <= 0) return 0;
   if (r >= world) return ny;
@@ -941,7 +941,7 @@ struct ModelImpl final : ModelBase {
     for (int l = 1; l < (int)mg.size(); ++l)
       if (mg[(size_t)l].mx <= 64 && mg[(size_t)l].my <= 64) { mg_bottom_level = l; break; }
     if ((int)mg.size() - mg_bottom_level > cfdk::kMgBottomMax) return fail(CFD_ERR_UNSUPPORTED, "multigrid hierarchy too deep");
-    mg_ld = world > 1 ? (mg_bottom_level - 1 < 2 ? mg_bottom_level - 1 : 2) : -1;
+    mg_ld = world > 1 ? (mg_bottom_level - 1 < 3 ? mg_bottom_level - 1 : 3) : -1;
     memset(&mg_bottom, 0, sizeof mg_bottom);
     mg_bottom.n = (int)mg.size() - mg_bottom_level;
     mg_bottom.nu = mg_smoothing();
@@ -962,7 +962,7 @@ struct ModelImpl final : ModelBase {
   // on every rank.  Levels 1..mg_ld are computed in strips too (each rank its own rows, one halo row exchanged after
   // every sweep); level mg_ld + 1 is gathered and everything below runs replicated on every rank (identical values,
   // no further communication).  The aligned partition (strip_row_start) makes the cells of a strip pair up within
-  // the strip on levels 0..2.
+  // the strip on levels 0..3.
   int mg_ld = -1;  // last coarse level computed in strips (-1: none / single domain)
   // owned rows [lo, hi) of level l, in unknown-row numbering of that level, for rank r
   int lvl_lo(int l, int r) const {
@@ -1633,7 +1633,7 @@ int cfd_model_create_ex(const cfd_grid* grid, const cfd_params* params, const cf
   if (o.precision != 64 && o.precision != 32) return fail(CFD_ERR_INVALID_ARGUMENT, "precision must be 64 or 32");
   if (o.world_size < 1 || o.rank < 0 || o.rank >= o.world_size) return fail(CFD_ERR_INVALID_ARGUMENT, "rank / world_size out of range");
   if (o.world_size > 1 && !o.nccl_unique_id) return fail(CFD_ERR_INVALID_ARGUMENT, "world_size > 1 needs nccl_unique_id");
-  if (o.world_size > 1 && grid->ny / (uint64_t)o.world_size < 16) return fail(CFD_ERR_INVALID_ARGUMENT, "strips need at least 16 rows per rank");
+  if (o.world_size > 1 && (grid->ny - 2) / (uint64_t)o.world_size < 17) return fail(CFD_ERR_INVALID_ARGUMENT, "strips need at least 17 unknown rows per rank");
   if (o.consts.jacobi_iterations < 1 || o.consts.jacobi_iterations > kMaxSweepSlots)
     return fail(CFD_ERR_INVALID_ARGUMENT, "jacobi_iterations must be in 1..256");
   if (o.consts.outer_rounds < 0 || o.consts.outer_rounds > 1000) return fail(CFD_ERR_INVALID_ARGUMENT, "outer_rounds out of range");

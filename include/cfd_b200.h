@@ -185,8 +185,8 @@ int cfd_model_set_field_f64(cfd_model* m, int32_t field, const double* in, uint6
 /* Rows [j0, j1) of pressure cells owned by this rank (whole grid when world_size == 1). */
 int cfd_model_rows(cfd_model* m, uint64_t* j0, uint64_t* j1);
 /* The strip partition itself (pure host arithmetic, no device needed): rows [j0, j1) of rank `rank` of `world_size`
- * for a grid of ny rows.  Interior boundaries sit at 1 + (a multiple of 8), so that the unknown rows of a strip pair
- * up within the strip on the first three multigrid levels (MGCG on strips). */
+ * for a grid of ny rows.  Interior boundaries sit at 1 + (a multiple of 16), so that the unknown rows of a strip pair
+ * up within the strip on the first four multigrid levels (MGCG on strips). */
 int cfd_strip_rows(uint64_t ny, int32_t world_size, int32_t rank, uint64_t* j0, uint64_t* j1);
 
 /* ---- measurement hooks (bench.py / profiles; no reference counterpart) ------------------------------- */

@@ -84,7 +84,7 @@ def main():
     import ctypes as C
     # (solver, scenario, grid, steps).  MGCG: level 0 and the first coarse levels run in strips (one halo row after every
     # sweep), the rest of the hierarchy is gathered and replicated; 128^2 gathers level 1 already, 520 x 264 runs
-    # levels 1 and 2 in strips and gathers level 3.
+    # levels 1 and 2 in strips and gathers level 3, 2056 x 1100 runs levels 1-3 in strips.
     mode_c = [
         (PressureSolver.CG, Scenario.Channel, Grid.uniform(264, 96, 30.0, 10.0, Cylinder(7.5, 5.0, 0.75)), 10),
         (PressureSolver.CG, Scenario.Cavity, Grid.uniform(128, 128, 1.0, 1.0, None), 10),
@@ -92,6 +92,7 @@ def main():
         (PressureSolver.MGCG, Scenario.Channel, Grid.uniform(264, 96, 26.4, 9.6, Cylinder(6.6, 4.8, 0.72)), 10),
         (PressureSolver.MGCG, Scenario.Cavity, Grid.uniform(520, 264, 520 / 256.0, 264 / 256.0, None), 8),
         (PressureSolver.MGCG, Scenario.Channel, Grid.uniform(1040, 600, 10.4, 6.0, Cylinder(2.6, 3.0, 0.45)), 8),
+        (PressureSolver.MGCG, Scenario.Cavity, Grid.uniform(2056, 1100, 2056 / 1024.0, 1100 / 1024.0, None), 5),
     ]
     for solver, scenario, grid, n_steps in mode_c:
         params = SimulationParams(dt=1e-3, viscosity=0.01, scenario=scenario, pressure_solver=solver)

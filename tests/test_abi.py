@@ -97,25 +97,25 @@ def test_cpp_host_mirror_builds_and_fails_loudly_without_gpu(lib):
 
 
 @pytest.mark.parametrize("ny,world", [(96, 2), (41, 2), (264, 4), (4096, 8), (32768, 8), (16384, 3), (600, 2), (100, 5)])
-def test_strip_partition_is_contiguous_and_pairs_up_on_three_multigrid_levels(lib, ny, world):
+def test_strip_partition_is_contiguous_and_pairs_up_on_four_multigrid_levels(lib, ny, world):
     """Host logic of the N > 1 path (no GPU needed): the strips tile [0, ny) without gaps, rank 0 / the last rank own
-    the ring rows, and every interior boundary sits at array row 1 + 8k — so the unknown rows (array row - 1) of a strip
-    are closed under the pairing (2J, 2J+1) -> J on multigrid levels 0, 1 and 2 (restriction and prolongation of the
+    the ring rows, and every interior boundary sits at array row 1 + 16k — so the unknown rows (array row - 1) of a strip
+    are closed under the pairing (2J, 2J+1) -> J on multigrid levels 0 to 3 (restriction and prolongation of the
     MGCG strips then need no communication)."""
     rows = [model.strip_rows(ny, world, r) for r in range(world)]
     assert rows[0][0] == 0 and rows[-1][1] == ny
     for (a0, a1), (b0, b1) in zip(rows, rows[1:]):
         assert a1 == b0 and a1 > a0
     sizes = [b - a for a, b in rows]
-    assert min(sizes) >= 8 and max(sizes) - min(sizes) <= 16 + 2
+    assert min(sizes) >= 16 and max(sizes) - min(sizes) <= 32 + 2
     for a, _ in rows[1:]:
-        assert (a - 1) % 8 == 0
-    # closure: for every level l <= 2, each level-(l+1) row has all its children in one strip
+        assert (a - 1) % 16 == 0
+    # closure: for every level l <= 3, each level-(l+1) row has all its children in one strip
     owner = np.zeros(ny - 2, dtype=int)
     for r, (a, b) in enumerate(rows):
         owner[max(a, 1) - 1:min(b, ny - 1) - 1] = r
     cur = owner
-    for _ in range(3):
+    for _ in range(4):
         n = len(cur)
         pairs = cur[:n - n % 2].reshape(-1, 2)
         assert (pairs[:, 0] == pairs[:, 1]).all()
