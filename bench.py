@@ -284,7 +284,7 @@ def cpu_baseline_mode_c(w, model):
     cpu = OracleModel(grid, params, precision=64)
     r0 = model.get_residuals()
     for fid in (_abi.FIELD_P, _abi.FIELD_U, _abi.FIELD_V, _abi.FIELD_U_STAR, _abi.FIELD_V_STAR, _abi.FIELD_P_PRIME,
-                _abi.FIELD_MG_GUESS, _abi.FIELD_MG_LAST):
+                _abi.FIELD_MG_GUESS, _abi.FIELD_MG_LAST, _abi.FIELD_MG_LAST2):
         cpu.set_field(fid, model.field(fid))
     cpu.set_scalars(r0.simulation_step, r0.f64["simulation_time"], r0.f64["dt"])
     t0 = time.perf_counter()

@@ -247,6 +247,25 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_update(MgFine<R> c, MgScalars
   mg_finish_dot<R, kMgThreads>(c, sc, partials, ticket, acc, 3);
 }
 
+// end of a step's first solve (mg_warm_start 3): next start vector = 3 x - 3 last + last2, last2 = last, last = x
+template <class R>
+__global__ void __launch_bounds__(kMgThreads) k_mg_extrapolate2(const R* __restrict__ x, R* __restrict__ last,
+                                                                 R* __restrict__ last2, R* __restrict__ guess, size_t n) {
+  using V = typename Vec2<R>::type;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n / 2; k += stride) {
+    const V xv = reinterpret_cast<const V*>(x)[k];
+    const V lv = reinterpret_cast<const V*>(last)[k];
+    const V mv = reinterpret_cast<const V*>(last2)[k];
+    V g;
+    g.x = R(3) * xv.x - R(3) * lv.x + mv.x;
+    g.y = R(3) * xv.y - R(3) * lv.y + mv.y;
+    reinterpret_cast<V*>(guess)[k] = g;
+    reinterpret_cast<V*>(last2)[k] = lv;
+    reinterpret_cast<V*>(last)[k] = xv;
+  }
+}
+
 // strips: advance the CG scalars from the sum-allreduced local_sum (the single-domain kernels do this themselves)
 template <class R>
 __global__ void k_mg_advance(MgFine<R> c, MgScalars* __restrict__ sc, int mode) {

@@ -108,7 +108,7 @@ void consts_default(cfd_solver_consts* c) {
   c->cg_tolerance = 1e-8;        // extension
   c->mg_omega = 0.8;             // extension (MGCG)
   c->mg_smoothing = 2;           // extension (MGCG)
-  c->mg_warm_start = 2;          // extension (MGCG)
+  c->mg_warm_start = 3;          // extension (MGCG)
 }
 
 constexpr int kMaxSweepSlots = 256;
@@ -216,6 +216,7 @@ struct ModelImpl final : ModelBase {
   int mg_id = 0;             // index of the buffer that holds d
   Field<R> mg_guess;  // start vector of the next step's first solve (carried state)
   Field<R> mg_last;   // p' the last first-solve ended with (carried state, mg_warm_start 2)
+  Field<R> mg_last2;  // the one before that (carried state, mg_warm_start 3)
   CUtensorMap tmap_mg_b[3], tmap_mg_rho;
   cfdk::MgScalars* mg_scalars = nullptr;  // device
   cfdk::MgScalars* h_mg = nullptr;        // pinned host copy
@@ -285,7 +286,7 @@ struct ModelImpl final : ModelBase {
     cudaFree(err_slots); cudaFree(step_slots); cudaFree(staging); cudaFree(tickets);
     cudaFree(cg_r.base); cudaFree(cg_d.base); cudaFree(cg_partials); cudaFree(cg_scalars);
     for (auto& L : mg) { cudaFree(L.weights); cudaFree(L.e); cudaFree(L.rho); cudaFree(L.tmp); }
-    cudaFree(mg_rho.base); cudaFree(mg_guess.base); cudaFree(mg_last.base);
+    cudaFree(mg_rho.base); cudaFree(mg_guess.base); cudaFree(mg_last.base); cudaFree(mg_last2.base);
     for (auto& f : mg_b) cudaFree(f.base);
     cudaFree(mg_scalars); cudaFree(mg_partials); cudaFree(mg_err); cudaFree(mg_ticket);
     if (h_mg) cudaFreeHost(h_mg);
@@ -920,6 +921,7 @@ struct ModelImpl final : ModelBase {
       if ((rc = falloc(&f, (size_t)nx))) return rc;
     if ((rc = falloc(&mg_guess, (size_t)nx))) return rc;
     if ((rc = falloc(&mg_last, (size_t)nx))) return rc;
+    if ((rc = falloc(&mg_last2, (size_t)nx))) return rc;
     using Ring = cfdk::SweepChunkRing<R>;
     for (int k = 0; k < 3; ++k)
       if ((rc = make_tensor_map(&tmap_mg_b[k], mg_b[k].row(ja - kHalo), Ring::kPCols))) return rc;
@@ -1202,7 +1204,11 @@ struct ModelImpl final : ModelBase {
     ++launches;
     if ((rc = exchange_halo(xf, ja, jb, 1))) return rc;  // the corrector reads p'[j-1] (src/model.rs:1380)
     if (first_solve) {
-      if (opt.consts.mg_warm_start == 2) {
+      if (opt.consts.mg_warm_start == 3) {
+        cfdk::k_mg_extrapolate2<R><<<148 * 8, cfdk::kMgThreads, 0, stream>>>(xf.row(ja), mg_last.row(ja), mg_last2.row(ja),
+                                                                            mg_guess.row(ja), own_p());
+        ++launches;
+      } else if (opt.consts.mg_warm_start == 2) {
         cfdk::k_mg_extrapolate<R><<<148 * 8, cfdk::kMgThreads, 0, stream>>>(xf.row(ja), mg_last.row(ja), mg_guess.row(ja), own_p());
         ++launches;
       } else {
@@ -1515,9 +1521,10 @@ struct ModelImpl final : ModelBase {
       case CFD_FIELD_V_OLD: *n = own_v(); return vbuf[ifree].row(ja);
       case CFD_FIELD_MG_GUESS:
       case CFD_FIELD_MG_LAST:
+      case CFD_FIELD_MG_LAST2:
         if (!mg_guess.base && mg_setup() != CFD_OK) { *n = 0; return nullptr; }
         *n = own_p();
-        return field == CFD_FIELD_MG_GUESS ? mg_guess.row(ja) : mg_last.row(ja);
+        return field == CFD_FIELD_MG_GUESS ? mg_guess.row(ja) : (field == CFD_FIELD_MG_LAST ? mg_last.row(ja) : mg_last2.row(ja));
       default: *n = 0; return nullptr;
     }
   }
@@ -1637,7 +1644,7 @@ int cfd_model_create_ex(const cfd_grid* grid, const cfd_params* params, const cf
   if (o.consts.jacobi_iterations < 1 || o.consts.jacobi_iterations > kMaxSweepSlots)
     return fail(CFD_ERR_INVALID_ARGUMENT, "jacobi_iterations must be in 1..256");
   if (o.consts.outer_rounds < 0 || o.consts.outer_rounds > 1000) return fail(CFD_ERR_INVALID_ARGUMENT, "outer_rounds out of range");
-  if (o.consts.mg_warm_start < 0 || o.consts.mg_warm_start > 2 || o.consts.mg_smoothing < 1 || o.consts.mg_smoothing > 16 || !(o.consts.mg_omega > 0.0) || !(o.consts.mg_omega <= 1.0))
+  if (o.consts.mg_warm_start < 0 || o.consts.mg_warm_start > 3 || o.consts.mg_smoothing < 1 || o.consts.mg_smoothing > 16 || !(o.consts.mg_omega > 0.0) || !(o.consts.mg_omega <= 1.0))
     return fail(CFD_ERR_INVALID_ARGUMENT, "mg_smoothing must be in 1..16 and mg_omega in (0, 1]");
   if (params->velocity_scheme < 0 || params->velocity_scheme > 1 || params->inlet_profile < 0 ||
       params->inlet_profile > 1 || params->scenario < 0 || params->scenario > 1 || params->pressure_solver < 0 ||

@@ -61,7 +61,8 @@ extern "C" {
 #define CFD_FIELD_MASK_V 10 /* 0/1 as double */
 #define CFD_FIELD_MG_GUESS 11 /* MGCG extension: start vector of the next step's first solve (carried state) */
 #define CFD_FIELD_MG_LAST 12  /* MGCG extension: p' the last first-solve ended with (carried state, mg_warm_start 2) */
-#define CFD_FIELD_COUNT 13
+#define CFD_FIELD_MG_LAST2 13 /* MGCG extension: the one before that (carried state, mg_warm_start 3) */
+#define CFD_FIELD_COUNT 14
 
 /* ---- PODs ---------------------------------------------------------------------------------------- */
 /* Grid + Option<Cylinder>, src/model.rs:121-139 */
@@ -95,8 +96,9 @@ typedef struct cfd_solver_consts {
   int32_t mg_smoothing;      /* extension (MGCG): pre- and post-smoothing sweeps per level, default 2 */
   int32_t mg_warm_start;     /* extension (MGCG), start vector of the FIRST solve of a step: 1 = the p' the first solve
                               * of the previous step ended with — like the reference's Jacobi, which never resets p'
-                              * (src/model.rs:734-824); 2 (default) = linear extrapolation in time from the last two,
+                              * (src/model.rs:734-824); 2 = linear extrapolation in time from the last two,
                               * 2 p'_n - p'_(n-1) (the JS twin's "extrapolated initial guess", index.html:262-270);
+                              * 3 (default) = quadratic, 3 p'_n - 3 p'_(n-1) + p'_(n-2);
                               * 0 and every re-correction solve = start from p' = 0 */
 } cfd_solver_consts;
 

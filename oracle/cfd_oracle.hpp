@@ -92,6 +92,7 @@ class Model {
   std::vector<R> mg_rho, mg_d, mg_w, mg_z, mg_z2;
   std::vector<R> mg_guess;  // start vector of the next step's first solve (carried state)
   std::vector<R> mg_last;   // p' the last first-solve ended with (carried state, mg_warm_start 2)
+  std::vector<R> mg_last2;  // the one before that (carried state, mg_warm_start 3)
 
   // Model::new, src/model.rs:219-299
   Model(const cfd_grid& g, const cfd_params& prm, const cfd_solver_consts* c = nullptr) {
@@ -150,6 +151,7 @@ class Model {
     rhs.assign(size_p, R(0)); p_prime.assign(size_p, R(0)); p_prime_new.assign(size_p, R(0));
     mg_guess.assign(size_p, R(0));
     mg_last.assign(size_p, R(0));
+    mg_last2.assign(size_p, R(0));
   }
 
   static void cfd_solver_consts_default_inline(cfd_solver_consts* c) {
@@ -164,7 +166,7 @@ class Model {
     c->cg_tolerance = 1e-8;
     c->mg_omega = 0.8;
     c->mg_smoothing = 2;
-    c->mg_warm_start = 2;
+    c->mg_warm_start = 3;
   }
 
   // Model::set_parameters, src/model.rs:1250-1257
@@ -716,8 +718,9 @@ class Model {
   // Stopping rule and return value as cg_pressure.  Start: the FIRST solve of a timestep starts from mg_guess —
   // the p' the first solve of the previous timestep ended with (mg_warm_start 1; the reference's Jacobi never
   // resets p' either, src/model.rs:734-824 — p' is the full pressure of this non-incremental projection and varies
-  // slowly in time), or its linear extrapolation in time 2 p'_n - p'_(n-1) (mg_warm_start 2, default; the JS
-  // twin's "extrapolated initial guess", index.html:262-270).  The re-correction solves of the outer loop
+  // slowly in time), or its linear extrapolation in time 2 p'_n - p'_(n-1) (mg_warm_start 2; the JS twin's
+  // "extrapolated initial guess", index.html:262-270), or the quadratic one 3 p'_n - 3 p'_(n-1) + p'_(n-2)
+  // (mg_warm_start 3, default).  The re-correction solves of the outer loop
   // (:696-724), whose solution is ~0, start from 0.
   // ------------------------------------------------------------------------------------------------
   void mg_build_levels() {
@@ -930,7 +933,13 @@ class Model {
     }
     cg_fill_boundary(p_prime);
     if (first_solve) {
-      if (consts.mg_warm_start == 2) {
+      if (consts.mg_warm_start == 3) {  // quadratic extrapolation 3 p'_n - 3 p'_(n-1) + p'_(n-2)
+        for (size_t k = 0; k < n; ++k) {
+          mg_guess[k] = R(3) * p_prime[k] - R(3) * mg_last[k] + mg_last2[k];
+          mg_last2[k] = mg_last[k];
+          mg_last[k] = p_prime[k];
+        }
+      } else if (consts.mg_warm_start == 2) {
         for (size_t k = 0; k < n; ++k) {
           mg_guess[k] = R(2) * p_prime[k] - mg_last[k];
           mg_last[k] = p_prime[k];

@@ -32,6 +32,7 @@ std::vector<R>* field_ptr(Model<R>& m, int field) {
     case CFD_FIELD_V_OLD: return &m.v_old;
     case CFD_FIELD_MG_GUESS: return &m.mg_guess;
     case CFD_FIELD_MG_LAST: return &m.mg_last;
+    case CFD_FIELD_MG_LAST2: return &m.mg_last2;
     default: return nullptr;
   }
 }

@@ -52,7 +52,7 @@ def test_struct_layouts_match_the_header(lib):
     c = o.consts
     assert (c.ramp_up_steps, c.jacobi_iterations, c.outer_rounds) == (100, 50, 20)
     assert (c.jacobi_omega, c.pressure_tolerance, c.outer_tolerance, c.cfl) == (0.75, 1e-4, 1e-4, 0.2)
-    assert (c.cg_tolerance, c.mg_omega, c.mg_smoothing, c.mg_warm_start) == (1e-8, 0.8, 2, 2)
+    assert (c.cg_tolerance, c.mg_omega, c.mg_smoothing, c.mg_warm_start) == (1e-8, 0.8, 2, 3)
 
 
 def test_argument_validation_needs_no_gpu(lib):

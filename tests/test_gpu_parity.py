@@ -395,7 +395,7 @@ def test_mgcg_bottom_kernel_matches_per_level_launches():
 
 
 def test_mgcg_warm_start_state_restarts_in_the_oracle():
-    """The warm start (p' of the previous step's first solve, CFD_FIELD_MG_GUESS) is carried state: load the GPU's
+    """The start vector (extrapolated from the previous steps' first-solve results: CFD_FIELD_MG_GUESS / _LAST / _LAST2) is carried state: load the GPU's
     complete state into the oracle after a spin-up and compute one more step on both sides — same iteration count
     (far fewer than a cold start needs), fields within the Mode C tolerance; and a cold-start model converges to the
     same velocities."""
@@ -411,7 +411,7 @@ def test_mgcg_warm_start_state_restarts_in_the_oracle():
     consts.ramp_up_steps = 5
     its = {}
     models = {}
-    for warm in (1, 0):
+    for warm in (3, 0):
         consts.mg_warm_start = warm
         o = default_options()
         o.consts = consts
@@ -420,19 +420,19 @@ def test_mgcg_warm_start_state_restarts_in_the_oracle():
             m.update()
         its[warm] = m.get_residuals().sweeps
         models[warm] = m
-    assert 0 < its[1] < its[0], its
-    assert rel_l2(models[1].field(_abi.FIELD_U), models[0].field(_abi.FIELD_U)) < 1e-6
-    consts.mg_warm_start = 1
-    gpu = models[1]
+    assert 0 < its[3] < its[0], its
+    assert rel_l2(models[3].field(_abi.FIELD_U), models[0].field(_abi.FIELD_U)) < 1e-6
+    consts.mg_warm_start = 3
+    gpu = models[3]
     cpu = OracleModel(g, prm, precision=64, consts=consts)
     r0 = gpu.get_residuals()
     for fid in (_abi.FIELD_P, _abi.FIELD_U, _abi.FIELD_V, _abi.FIELD_U_STAR, _abi.FIELD_V_STAR, _abi.FIELD_P_PRIME,
-                _abi.FIELD_MG_GUESS, _abi.FIELD_MG_LAST):
+                _abi.FIELD_MG_GUESS, _abi.FIELD_MG_LAST, _abi.FIELD_MG_LAST2):
         cpu.set_field(fid, gpu.field(fid))
     cpu.set_scalars(r0.simulation_step, r0.f64["simulation_time"], r0.f64["dt"])
     gpu.update()
     cpu.update()
     rg, rc = gpu.get_residuals(), cpu.get_residuals()
-    assert rg.sweeps == rc.sweeps == its[1] and rg.jacobi_calls == rc.jacobi_calls == 2
-    for fid in (_abi.FIELD_U, _abi.FIELD_V, _abi.FIELD_P, _abi.FIELD_MG_GUESS, _abi.FIELD_MG_LAST):
+    assert rg.sweeps == rc.sweeps and abs(rg.sweeps - its[3]) <= 1 and rg.jacobi_calls == rc.jacobi_calls == 2
+    for fid in (_abi.FIELD_U, _abi.FIELD_V, _abi.FIELD_P, _abi.FIELD_MG_GUESS, _abi.FIELD_MG_LAST, _abi.FIELD_MG_LAST2):
         assert rel_l2(gpu.field(fid), cpu.field(fid)) <= 1e-9, _abi.FIELD_NAMES[fid]
