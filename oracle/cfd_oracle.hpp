@@ -48,6 +48,8 @@ struct StripHooks {
   std::function<void(std::vector<R>& field, size_t row_len, size_t nrows, int below, int above)> exchange;
   std::function<R(R)> allreduce_max;
   std::function<R(R)> allreduce_sum;
+  // every rank contributes rows [lo, hi) of `field` (nrows rows of row_len) and receives everybody else's
+  std::function<void(std::vector<R>& field, size_t row_len, size_t nrows, size_t lo, size_t hi)> gather_rows;
 };
 
 template <class R>
@@ -760,13 +762,15 @@ class Model {
     }
   }
 
-  // one damped-Jacobi sweep of level 0: jacobi_sweep's formula on (in, rh) -> out, then the boundary update
+  // one damped-Jacobi sweep of level 0: jacobi_sweep's formula on (in, rh) -> out over the owned rows, then the
+  // boundary update (and, on strips, the neighbours' new edge rows)
   void mg_fine_sweep(const std::vector<R>& in, const std::vector<R>& rh, std::vector<R>& out) {
     const R omega = R(consts.mg_omega);
     const R one_minus = R(1.0) - omega;
     const R dx_sq = dx * dx, dy_sq = dy * dy;
     const R denom = R(2.0) / (dx * dx) + R(2.0) / (dy * dy);
-    for (size_t j = 1; j + 1 < ny; ++j)
+    const size_t j_lo = std::max<size_t>(1, ja), j_hi = std::min(ny - 1, jb);
+    for (size_t j = j_lo; j < j_hi; ++j)
       for (size_t i = 1; i < nx; ++i) {
         const size_t idx = i + j * nx;
         const R center = in[idx];
@@ -779,13 +783,14 @@ class Model {
   }
   void mg_fill_ring(std::vector<R>& x) {  // jacobi_swap_and_bc's boundary update (rows, then columns)
     for (size_t i = 0; i < nx; ++i) {
-      x[i] = x[i + nx];
-      x[i + (ny - 1) * nx] = x[i + (ny - 2) * nx];
+      if (ja == 0) x[i] = x[i + nx];
+      if (jb == ny) x[i + (ny - 1) * nx] = x[i + (ny - 2) * nx];
     }
-    for (size_t j = 0; j < ny; ++j) {
+    for (size_t j = ja; j < jb; ++j) {
       x[j * nx] = x[1 + j * nx];
       x[(nx - 1) + j * nx] = scenario == CFD_SCENARIO_CAVITY ? x[(nx - 2) + j * nx] : R(0);
     }
+    if (hooks.exchange) hooks.exchange(x, nx, ny, 1, 1);
   }
   // (L x)[i,j] on an unknown, neighbours outside the unknowns replaced by the boundary rules
   R mg_fine_apply(const std::vector<R>& x, size_t i, size_t j) const {
@@ -847,15 +852,21 @@ class Model {
     for (int s = 0; s < nu_s; ++s) { mg_coarse_sweep(L, L.e, L.rho, L.tmp, omega); std::swap(L.e, L.tmp); }
   }
 
-  // mg_z <- V-cycle applied to mg_rho
+  // mg_z <- V-cycle applied to mg_rho.  Strips (hooks set): level 0 is computed on the owned rows with one halo row
+  // refreshed after every sweep; the residual of level 1 is gathered on every rank and the coarse levels run
+  // replicated (the CUDA path keeps three more levels in strips — same per-cell arithmetic either way).  The strip
+  // boundaries must pair up the unknown rows (the library's aligned partition, cfd_strip_rows).
   void mg_precondition() {
     const int nu_s = consts.mg_smoothing < 1 ? 1 : consts.mg_smoothing;
+    const size_t j_lo = std::max<size_t>(1, ja), j_hi = std::min(ny - 1, jb);
     std::fill(mg_z.begin(), mg_z.end(), R(0));
     for (int s = 0; s < nu_s; ++s) { mg_fine_sweep(mg_z, mg_rho, mg_z2); std::swap(mg_z, mg_z2); }
     if (mg_levels.size() > 1) {
       MgLevel& C = mg_levels[1];
       const size_t WC = C.mx + 2;
-      for (size_t J = 0; J < C.my; ++J)
+      const size_t c_lo = (j_lo - 1) / 2, c_hi = (jb >= ny) ? C.my : (j_hi - 1) / 2;
+      assert(((j_lo - 1) % 2 == 0) && (jb >= ny || (j_hi - 1) % 2 == 0) && "strip boundaries must pair up the unknown rows");
+      for (size_t J = c_lo; J < c_hi; ++J)
         for (size_t I = 0; I < C.mx; ++I) {
           R acc = R(0);
           for (size_t b = 0; b < 2; ++b)
@@ -865,8 +876,9 @@ class Model {
             }
           C.rho[(I + 1) + (J + 1) * WC] = acc;
         }
+      if (hooks.gather_rows) hooks.gather_rows(C.rho, WC, C.my + 2, c_lo + 1, c_hi + 1);
       mg_coarse_vcycle(1);
-      for (size_t j = 1; j + 1 < ny; ++j)
+      for (size_t j = j_lo; j < j_hi; ++j)
         for (size_t i = 1; i + 1 < nx; ++i) mg_z[i + j * nx] += C.e[((i - 1) / 2 + 1) + ((j - 1) / 2 + 1) * WC];
       mg_fill_ring(mg_z);
     }
@@ -874,31 +886,34 @@ class Model {
   }
 
   R mgcg_pressure(R dt_sub) {
-    assert(!hooks.exchange && "MGCG is single-domain in this round");
+    assert((!hooks.exchange || hooks.gather_rows) && "MGCG on strips needs the gather hook");
     const size_t n = nx * ny;
     if (mg_levels.empty()) mg_build_levels();
     if (mg_rho.size() != n) {
       mg_rho.assign(n, R(0)); mg_d.assign(n, R(0)); mg_w.assign(n, R(0)); mg_z.assign(n, R(0)); mg_z2.assign(n, R(0));
     }
+    const size_t j_lo = std::max<size_t>(1, ja), j_hi = std::min(ny - 1, jb);  // owned rows of unknowns
     const R n_unknowns = R((nx - 2) * (ny - 2));
     const R tol = R(consts.cg_tolerance);
     auto measure = [&](R rr_) { return dt_sub * std::sqrt(rr_ / n_unknowns); };
-    // dot products: row sums, then over rows (the CUDA path sums in another order -> tolerance parity)
+    // dot products: row sums, then over the owned rows, then over the ranks (the CUDA path sums in another order
+    // -> tolerance parity)
     auto dot = [&](const std::vector<R>& a, const std::vector<R>& b) {
       R acc = 0;
-      for (size_t j = 1; j + 1 < ny; ++j) {
+      for (size_t j = j_lo; j < j_hi; ++j) {
         R row = 0;
         for (size_t i = 1; i + 1 < nx; ++i) row += a[i + j * nx] * b[i + j * nx];
         acc += row;
       }
-      return acc;
+      return hooks.allreduce_sum ? hooks.allreduce_sum(acc) : acc;
     };
     const bool first_solve = last_jacobi_calls == 1;  // pressure_solve() counted this call already
     const bool warm = consts.mg_warm_start != 0 && first_solve;
     if (warm) p_prime = mg_guess; else std::fill(p_prime.begin(), p_prime.end(), R(0));
+    if (warm && hooks.exchange) hooks.exchange(p_prime, nx, ny, 1, 1);
     std::fill(mg_rho.begin(), mg_rho.end(), R(0));
     std::fill(mg_d.begin(), mg_d.end(), R(0));
-    for (size_t j = 1; j + 1 < ny; ++j)
+    for (size_t j = j_lo; j < j_hi; ++j)
       for (size_t i = 1; i + 1 < nx; ++i)
         mg_rho[i + j * nx] = warm ? rhs[i + j * nx] - mg_fine_apply(p_prime, i, j) : rhs[i + j * nx];
     R rr = dot(mg_rho, mg_rho);
@@ -908,11 +923,12 @@ class Model {
       R rz = dot(mg_rho, mg_z);
       for (size_t k = 0; k < n; ++k) mg_d[k] = mg_z[k] + R(0) * mg_d[k];
       for (;;) {
-        for (size_t j = 1; j + 1 < ny; ++j)
+        if (hooks.exchange) hooks.exchange(mg_d, nx, ny, 1, 1);
+        for (size_t j = j_lo; j < j_hi; ++j)
           for (size_t i = 1; i + 1 < nx; ++i) mg_w[i + j * nx] = mg_fine_apply(mg_d, i, j);
         const R dw = dot(mg_d, mg_w);
         const R alpha = rz / dw;
-        for (size_t j = 1; j + 1 < ny; ++j)
+        for (size_t j = j_lo; j < j_hi; ++j)
           for (size_t i = 1; i + 1 < nx; ++i) {
             const size_t idx = i + j * nx;
             p_prime[idx] = p_prime[idx] + alpha * mg_d[idx];
@@ -926,7 +942,7 @@ class Model {
         mg_precondition();
         const R rz_new = dot(mg_rho, mg_z);
         const R beta = rz_new / rz;
-        for (size_t j = 1; j + 1 < ny; ++j)
+        for (size_t j = j_lo; j < j_hi; ++j)
           for (size_t i = 1; i + 1 < nx; ++i) mg_d[i + j * nx] = mg_z[i + j * nx] + beta * mg_d[i + j * nx];
         rz = rz_new;
       }

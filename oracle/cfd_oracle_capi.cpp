@@ -88,6 +88,15 @@ double stage_t(Model<R>& m, int stage) {
 typedef void (*cfdo_exchange_cb)(void* user, void* field, uint64_t row_len, uint64_t nrows, int below, int above,
                                  int elem_bytes);
 typedef double (*cfdo_allreduce_cb)(void* user, double x, int op /* 0 max, 1 sum */);
+typedef void (*cfdo_gather_cb)(void* user, void* field, uint64_t row_len, uint64_t nrows, uint64_t lo, uint64_t hi,
+                               int elem_bytes);
+
+template <class R>
+static void set_gather_t(Model<R>& m, cfdo_gather_cb cb, void* user) {
+  m.hooks.gather_rows = [=](std::vector<R>& f, size_t row_len, size_t nrows, size_t lo, size_t hi) {
+    cb(user, f.data(), row_len, nrows, lo, hi, int(sizeof(R)));
+  };
+}
 
 template <class R>
 static void set_strip_t(Model<R>& m, uint64_t ja, uint64_t jb, int owns_top, cfdo_exchange_cb ex, cfdo_allreduce_cb ar,
@@ -179,6 +188,11 @@ void cfdo_set_strip(void* hv, uint64_t ja, uint64_t jb, int owns_top, cfdo_excha
                     void* user) {
   auto* h = static_cast<Handle*>(hv);
   if (h->f) set_strip_t(*h->f, ja, jb, owns_top, ex, ar, user); else set_strip_t(*h->d, ja, jb, owns_top, ex, ar, user);
+}
+
+void cfdo_set_gather(void* hv, cfdo_gather_cb cb, void* user) {
+  auto* h = static_cast<Handle*>(hv);
+  if (h->f) set_gather_t(*h->f, cb, user); else set_gather_t(*h->d, cb, user);
 }
 
 uint64_t cfdo_total_sweeps(void* hv) {

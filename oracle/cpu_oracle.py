@@ -20,6 +20,7 @@ _LIBS = {}
 
 EXCHANGE_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int)
 ALLREDUCE_CB = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_double, C.c_int)
+GATHER_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int)
 
 
 def build(force: bool = False) -> None:
@@ -57,6 +58,7 @@ def _load(checked: bool = False):
     lib.cfdo_stage.argtypes = [C.c_void_p, C.c_int]
     lib.cfdo_set_scalars.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_double]
     lib.cfdo_set_strip.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, EXCHANGE_CB, ALLREDUCE_CB, C.c_void_p]
+    lib.cfdo_set_gather.argtypes = [C.c_void_p, GATHER_CB, C.c_void_p]
     lib.cfdo_total_sweeps.restype = C.c_uint64
     lib.cfdo_total_sweeps.argtypes = [C.c_void_p]
     lib.cfd_solver_consts_default.argtypes = [C.POINTER(_abi.CfdSolverConsts)]
@@ -129,11 +131,12 @@ class OracleModel:
     def set_scalars(self, simulation_step: int, simulation_time: float, dt: float):
         self._lib.cfdo_set_scalars(self._h, int(simulation_step), float(simulation_time), float(dt))
 
-    def set_strip(self, ja: int, jb: int, owns_top: bool, exchange, allreduce):
+    def set_strip(self, ja: int, jb: int, owns_top: bool, exchange, allreduce, gather=None):
         """Restrict the model to rows [ja, jb) of a strip decomposition.  `exchange(field2d, ja, jb, below, above)`
         gets a writable (nrows, row_len) numpy view and must refresh `below` halo rows under ja and `above` over
         jb (sending the mirror-image rows to the neighbours); `allreduce(x, op)` reduces a float over the ranks
-        (op 0 = max, 1 = sum)."""
+        (op 0 = max, 1 = sum); `gather(field2d, lo, hi)` (needed by MGCG) contributes rows [lo, hi) of a writable
+        (nrows, row_len) view and must fill in every other rank's rows."""
         def _ex(_user, ptr, row_len, nrows, below, above, elem_bytes):
             dtype = np.float32 if elem_bytes == 4 else np.float64
             buf = (C.c_char * (row_len * nrows * elem_bytes)).from_address(ptr)
@@ -144,6 +147,14 @@ class OracleModel:
 
         self._cb = (EXCHANGE_CB(_ex), ALLREDUCE_CB(_ar))  # keep the thunks alive
         self._lib.cfdo_set_strip(self._h, int(ja), int(jb), 1 if owns_top else 0, self._cb[0], self._cb[1], None)
+        if gather is not None:
+            def _ga(_user, ptr, row_len, nrows, lo, hi, elem_bytes):
+                dtype = np.float32 if elem_bytes == 4 else np.float64
+                buf = (C.c_char * (row_len * nrows * elem_bytes)).from_address(ptr)
+                gather(np.frombuffer(buf, dtype=dtype).reshape(nrows, row_len), int(lo), int(hi))
+
+            self._cb_gather = GATHER_CB(_ga)
+            self._lib.cfdo_set_gather(self._h, self._cb_gather, None)
 
     def total_sweeps(self) -> int:
         return int(self._lib.cfdo_total_sweeps(self._h))

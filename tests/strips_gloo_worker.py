@@ -13,6 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cfd_demo_b200 import _abi  # noqa: E402
 from cfd_demo_b200.types import (Cylinder, Grid, InletProfile, PressureSolver, Scenario, SimulationParams,  # noqa: E402
                                  VelocityScheme)
+from cfd_demo_b200.model import strip_rows  # noqa: E402  (host-only partition query; no GPU needed)
 from oracle.cpu_oracle import OracleModel, default_consts  # noqa: E402
 
 
@@ -50,6 +51,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX if op == 0 else dist.ReduceOp.SUM)
         return float(t[0])
 
+    def gather(f, lo, hi):
+        parts = [None] * world
+        dist.all_gather_object(parts, (lo, hi, f[lo:hi].copy()))
+        for r, (a, b, rows) in enumerate(parts):
+            if r != rank:
+                f[a:b] = rows
+
     cyl = Cylinder(7.5, 5.0, 0.75)
     cg = default_consts()
     cg.cg_tolerance = 1e-13
@@ -61,18 +69,27 @@ def main():
          SimulationParams(dt=1e-3, viscosity=0.01, scenario=Scenario.Cavity), 64, None, 10, True),
         ("modeC channel", Grid.uniform(48, 32, 30.0, 10.0, cyl),
          SimulationParams(dt=1e-3, viscosity=0.01, pressure_solver=PressureSolver.CG), 64, cg, 8, False),
+        # multigrid-preconditioned CG on strips: level 0 in strips, level-1 residual gathered, coarse levels replicated;
+        # the strips are the library's aligned partition (cfd_strip_rows), which pairs up the unknown rows
+        ("modeC mgcg cavity", Grid.uniform(64, 120, 64 / 64.0, 120 / 64.0, None),
+         SimulationParams(dt=1e-3, viscosity=0.01, scenario=Scenario.Cavity, pressure_solver=PressureSolver.MGCG), 64, cg, 8, False),
+        ("modeC mgcg channel", Grid.uniform(96, 103, 9.6, 10.3, Cylinder(2.4, 5.0, 0.9)),
+         SimulationParams(dt=1e-3, viscosity=0.01, pressure_solver=PressureSolver.MGCG), 64, cg, 8, False),
     ]
     for name, grid, params, precision, consts, steps, exact in cases:
         nx, ny = grid.nx, grid.ny
-        ja, jb = split_rows(ny, rank, world)
+        mgcg = params.pressure_solver == PressureSolver.MGCG
+        ja, jb = strip_rows(ny, world, rank) if mgcg else split_rows(ny, rank, world)
         top = rank == world - 1
         strip = OracleModel(grid, params, precision=precision, consts=consts)
-        strip.set_strip(ja, jb, top, exchange, allreduce)
+        strip.set_strip(ja, jb, top, exchange, allreduce, gather)
         whole = OracleModel(grid, params, precision=precision, consts=consts)
         for s in range(steps):
             strip.update()
             whole.update()
             rs, rw = strip.get_residuals(), whole.get_residuals()
+            if mgcg:
+                assert rs.jacobi_calls == rw.jacobi_calls == 2 and abs(rs.sweeps - rw.sweeps) <= 1, (name, s, rs.sweeps, rw.sweeps)
             if exact:
                 assert (rs.jacobi_calls, rs.sweeps) == (rw.jacobi_calls, rw.sweeps), (name, s)
                 for k in ("dt", "p", "u", "v"):
