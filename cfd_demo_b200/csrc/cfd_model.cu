@@ -561,7 +561,7 @@ struct ModelImpl final : ModelBase {
       CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep6<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(Ring)));
       int per_sm6 = 1;
-      CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm6, cfdk::k_jacobi_sweep6<R>, 128, sizeof(Ring)));
+      CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm6, cfdk::k_jacobi_sweep6<R>, cfdk::kSweepWarps * 32, sizeof(Ring)));
       cudaDeviceProp prop6;
       CFD_CUDA(cudaGetDeviceProperties(&prop6, device));
       sweep6_resident_blocks = prop6.multiProcessorCount * (per_sm6 < 1 ? 1 : per_sm6);
@@ -571,24 +571,26 @@ struct ModelImpl final : ModelBase {
     cudaDeviceProp prop;
     CFD_CUDA(cudaGetDeviceProperties(&prop, device));
     const int sms = prop.multiProcessorCount;
-    const int bx = (nx / 2 + 127) / 128;
+    const int kSweepThreads = cfdk::kSweepWarps * 32;
+    const int bx = (nx / 2 + kSweepThreads - 1) / kSweepThreads;
     int per_sm = 4;
     if (opt.flags & CFD_FLAG_REGISTER_SWEEP)
       CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep2<R>, 128, 0));
     else if (opt.flags & CFD_FLAG_BULK_SWEEP)
-      CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep3<R>, 128, 0));
+      CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep3<R>, kSweepThreads, 0));
     else if (opt.flags & CFD_FLAG_SWEEP4)
-      CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep4<R>, 128,
+      CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep4<R>, kSweepThreads,
                                                              sizeof(cfdk::SweepChunkRing<R>)));
     else
-      CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep5<R>, 128,
+      CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep5<R>, kSweepThreads,
                                                              sizeof(cfdk::SweepChunkRing<R>)));
     if (per_sm < 1) per_sm = 1;
     const int resident = sms * per_sm;
     const int rows = sweep_row_end() - sweep_row_begin();
     int rpb;
     if (opt.flags & (CFD_FLAG_REGISTER_SWEEP | CFD_FLAG_BULK_SWEEP)) {
-      int gy = (resident + bx - 1) / bx;  // one wave
+      const int bxw = (opt.flags & CFD_FLAG_REGISTER_SWEEP) ? (nx / 2 + 127) / 128 : bx;  // sweep2 keeps 128-thread blocks
+      int gy = (resident + bxw - 1) / bxw;  // one wave
       if (gy > rows) gy = rows;
       if (gy < 1) gy = 1;
       rpb = (rows + gy - 1) / gy;
@@ -699,7 +701,8 @@ struct ModelImpl final : ModelBase {
     c2.check_lag = 1;
     c2.fix_pass = -1;
     const dim3 blk1(256), grd1((nx - 2 + 255) / 256, (rows + kJacobiRows - 1) / kJacobiRows);
-    const dim3 blk2(128), grd2((nx / 2 + 127) / 128, (rows + sweep_rows_per_block - 1) / sweep_rows_per_block);
+    const int kSweepThreads = cfdk::kSweepWarps * 32;
+    const dim3 blk2(kSweepThreads), grd2((nx / 2 + kSweepThreads - 1) / kSweepThreads, (rows + sweep_rows_per_block - 1) / sweep_rows_per_block);
     const size_t ring_bytes = sizeof(cfdk::SweepChunkRing<R>);
     const bool tuned_default = !(opt.flags & (CFD_FLAG_BASELINE_SWEEP | CFD_FLAG_REGISTER_SWEEP | CFD_FLAG_BULK_SWEEP | CFD_FLAG_SWEEP4));
     const bool use6 = tuned_default && (opt.flags & CFD_FLAG_PERSISTENT_SWEEP);  // persistent warp-queue kernel (A/B)
@@ -747,7 +750,8 @@ struct ModelImpl final : ModelBase {
         if (opt.flags & CFD_FLAG_BASELINE_SWEEP)
           cfdk::k_jacobi_sweep<R, kJacobiRows><<<grd1, blk1, 0, stream>>>(c, pp[in].v, rhs.v, pp[out].v, err_slots, s);
         else if (opt.flags & CFD_FLAG_REGISTER_SWEEP)
-          cfdk::k_jacobi_sweep2<R><<<grd2, blk2, 0, stream>>>(c2, pp[in].v, rhs.v, pp[out].v, err_slots, s);
+          cfdk::k_jacobi_sweep2<R><<<dim3((nx / 2 + 127) / 128, grd2.y), dim3(128), 0, stream>>>(c2, pp[in].v, rhs.v, pp[out].v,
+                                                                                               err_slots, s);  // fixed 128-thread blocks
         else if (opt.flags & CFD_FLAG_BULK_SWEEP)
           cfdk::k_jacobi_sweep3<R><<<grd2, blk2, 0, stream>>>(c2, pp[in].v, rhs.v, pp[out].v, err_slots, s);
         else if (opt.flags & CFD_FLAG_SWEEP4)
@@ -935,7 +939,7 @@ struct ModelImpl final : ModelBase {
       // one partial per block of the largest grid that ends in a dot product: the 4-row vector tiles, or the sweep
       const size_t gx = (size_t)((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads));
       const size_t n_vec = gx * (size_t)((ny + 3) / 4 + 1);
-      const size_t n_sweep = (size_t)((nx / 2 + 127) / 128) * (size_t)((ny - 2 + sweep_rows_per_block - 1) / sweep_rows_per_block);
+      const size_t n_sweep = (size_t)((nx / 2 + cfdk::kSweepWarps * 32 - 1) / (cfdk::kSweepWarps * 32)) * (size_t)((ny - 2 + sweep_rows_per_block - 1) / sweep_rows_per_block);
       if ((rc = dalloc(&mg_partials, n_vec > n_sweep ? n_vec : n_sweep))) return rc;
     }
     // the bottom of the V-cycle (every level from the first that fits 64 x 64) runs in one single-block launch
@@ -1092,7 +1096,8 @@ struct ModelImpl final : ModelBase {
     c2.check_lag = 1;
     c2.fix_pass = -1;
     const int rows = c.row_hi - c.row_lo;
-    const dim3 blk2(128), grd2((nx / 2 + 127) / 128, (rows + sweep_rows_per_block - 1) / sweep_rows_per_block);
+    const int kSweepThreads = cfdk::kSweepWarps * 32;
+    const dim3 blk2(kSweepThreads), grd2((nx / 2 + kSweepThreads - 1) / kSweepThreads, (rows + sweep_rows_per_block - 1) / sweep_rows_per_block);
     const size_t ring_bytes = sizeof(cfdk::SweepChunkRing<R>);
     const int za = (mg_id + 1) % 3, zb = (mg_id + 2) % 3;
     int zc = za, zo = zb;  // current / other smoothing buffer

@@ -24,7 +24,7 @@ from . import _abi
 from .types import Grid, Residuals, SimSnapshot, SimulationParams
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcfd_b200.so")
+LIB_PATH = os.environ.get("CFD_B200_LIB") or os.path.join(_HERE, "libcfd_b200.so")  # override: A/B builds (tools/)
 _lib = None
 
 

@@ -151,8 +151,8 @@ void cfd_model_destroy(cfd_model* m);
 /* ---- stepping -------------------------------------------------------------------------------------- */
 /* Model::update(&mut self), src/model.rs:304-379: exactly one timestep, synchronous. */
 int cfd_model_update(cfd_model* m);
-/* Extension: n timesteps with no host round trip between them (dt control stays on the device).
- * Equivalent to n calls of cfd_model_update. */
+/* Extension: n timesteps in one FFI call (saves the per-call binding overhead; in this version it is exactly n calls of
+ * cfd_model_update, convergence scalars and dt control still pass through the host between steps). */
 int cfd_model_update_n(cfd_model* m, uint64_t n);
 /* Model::set_parameters(&mut self, &params), src/model.rs:1250-1257 (`scenario` is ignored here, as
  * the reference has no such parameter to change). */
