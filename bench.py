@@ -335,7 +335,7 @@ def run_ours(args, w):
         uid = [nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         model = Model.strip(grid, params, rank, world, uid[0], device=local_rank,
-                            flags=int(os.environ.get("CFD_BENCH_FLAGS", "0")))  # A/B hook (e.g. 32 = NCCL exchange)
+                            flags=int(os.environ.get("CFD_BENCH_FLAGS", "0")))  # A/B hook (e.g. 512 = peer-memory exchange)
     else:
         opts = default_options()
         opts.device = local_rank
@@ -492,8 +492,10 @@ def run_ours(args, w):
         if world == 1:
             multi = "single domain"
         elif strips and not mode_c:
-            multi = (f"{world} row strips of {w['nx']}x{w['ny']} cells each, halo rows and max-reduction fused into the sweep "
-                     f"kernel over NVLink peer memory, weak scaling")
+            peer = int(os.environ.get("CFD_BENCH_FLAGS", "0")) & 512
+            multi = (f"{world} row strips of {w['nx']}x{w['ny']} cells each, weak scaling, " +
+                     ("halo rows and max-reduction fused into the sweep kernel over NVLink peer memory (CFD_BENCH_FLAGS=512)"
+                      if peer else "NCCL halo rows + max-allreduce after every sweep (CFD_BENCH_FLAGS=512: fused peer-memory path)"))
         elif strips:
             multi = (f"{world} row strips of one {nx}x{ny} cavity, {'strong' if strong else 'weak'} scaling: multigrid levels 0-2 in "
                      f"strips with an NCCL halo row after every sweep, level 3 gathered and the rest replicated, dot products "

@@ -31,6 +31,7 @@ FLAG_NCCL_EXCHANGE = 32
 FLAG_TEMPORAL = 64
 FLAG_PERSISTENT_SWEEP = 128
 FLAG_MG_NO_BOTTOM_KERNEL = 256
+FLAG_PEER_EXCHANGE = 512
 
 
 class CfdGrid(C.Structure):

