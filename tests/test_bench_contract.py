@@ -1,0 +1,47 @@
+"""bench.py's reference arm (the CPU port, no GPU needed) prints ONE JSON line with the keys the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_reference(workload, extra_env=None):
+    env = dict(os.environ, CFD_BENCH_REF_BUDGET_S="20", OMP_NUM_THREADS="1")
+    env.update(extra_env or {})
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", workload,
+                        "--steps", "2", "--warmup", "3"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    return json.loads(lines[0])
+
+
+def test_reference_arm_mode_c_line(oracle_built):
+    d = run_reference("cavity1024_modeC")
+    assert d["impl"] == "reference" and d["metric"] == "cell_updates_per_s" and d["unit"] == "cell-updates/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert d["value"] > 0 and abs(d["value"] - 1024 * 1024 / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == d["value"] and "MGCG iterations" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("lid-driven cavity") and d["config"]["iterations_per_step"] > 0
+
+
+def test_reference_arm_is_rank_zero_only(oracle_built):
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_default_workload_is_the_baseline_config():
+    sys.path.insert(0, ROOT)
+    import bench
+    w = bench.WORKLOADS[bench.DEFAULT_WORKLOAD]
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    assert "4096" in base["metric"] and "cavity Re=1000 on 4096" in base["configs"][2]
+    assert (w["nx"], w["ny"], w["kind"]) == (4096, 4096, "modeC") and w["params"]["scenario"] == 1
+    assert abs(1.0 * 1.0 / w["params"]["viscosity"] - 1000.0) < 1e-6          # Re = U L / nu
+    assert w["params"]["dt"] < (1.0 / 4096) ** 2 / (4 * w["params"]["viscosity"])  # explicit diffusion limit
