@@ -34,6 +34,8 @@ extern "C" {
     fn cfd_model_set_params(m: *mut CfdModel, params: *const CfdParams) -> c_int;
     fn cfd_model_get_snapshot(m: *mut CfdModel, p: *mut f32, u: *mut f32, v: *mut f32, dt: *mut f32) -> c_int;
     fn cfd_model_get_residuals(m: *mut CfdModel, out: *mut CfdResiduals) -> c_int;
+    /// extension: the UI's colour map (src/app.rs:235-404) computed on the device; mode 0 pressure, 1 velocity, 2 vorticity
+    fn cfd_model_render_rgba(m: *mut CfdModel, mode: i32, rgba: *mut u8, min_out: *mut f32, max_out: *mut f32) -> c_int;
     fn cfd_last_error() -> *const c_char;
 }
 
@@ -114,6 +116,14 @@ impl Model {
         let mut dt = 0.0f32;
         check(unsafe { cfd_model_get_snapshot(self.handle, p.as_mut_ptr(), u.as_mut_ptr(), v.as_mut_ptr(), &mut dt) });
         SimSnapshot { p, u, v, dt, paused: false }
+    }
+    /// Extension (not in the reference): the finished `nx x ny` RGBA image of app.rs:235-404 for
+    /// `egui::ColorImage::from_rgba_unmultiplied([nx, ny], &rgba)` — one third of the bytes of a snapshot and no
+    /// per-pixel work on the UI thread.  `mode`: 0 pressure, 1 velocity magnitude, 2 vorticity.
+    pub fn render_rgba(&self, mode: i32) -> Vec<u8> {
+        let mut rgba = vec![0u8; self.grid.nx * self.grid.ny * 4];
+        check(unsafe { cfd_model_render_rgba(self.handle, mode, rgba.as_mut_ptr(), std::ptr::null_mut(), std::ptr::null_mut()) });
+        rgba
     }
     pub fn get_residuals(&self) -> Residuals {
         let mut r = CfdResiduals::default();
