@@ -8,7 +8,8 @@
 // PARITY UNPINNED: the reference has no tests, golden vectors or fixtures for model.rs
 // and no Rust toolchain exists in this environment, so this restatement could not be checked against
 // outputs of the reference itself.  It is pinned only by known answers that follow from reading the
-// code (tests/test_oracle_kat.py) and by an independent numpy restatement (oracle/numpy_restatement.py).
+// code (tests/test_oracle_kat.py) and by an independent numpy restatement (oracle/numpy_restatement.py, both velocity
+// schemes) that must agree with it bit for bit in f32 and f64.
 //
 // Faithfulness rules: flat row-major indexing exactly as the Rust (so the
 // "next row" wrap-around reads of the last 8-lane chunk happen naturally), the same 8-lane chunk /

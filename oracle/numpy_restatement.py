@@ -1,5 +1,5 @@
 """numpy_restatement.py — a SECOND, independently written CPU restatement of the reference hot path (TEST
-INFRASTRUCTURE, not product code): `Model::update` of src/model.rs for the FirstOrder scheme, written row-vectorised in
+INFRASTRUCTURE, not product code): `Model::update` of src/model.rs, written row-vectorised in
 numpy straight from the Rust source, with the dtype as a parameter (float32 = the reference's arithmetic).
 
 Purpose: cross-check the C++ oracle (cfd_oracle.hpp), which was transliterated loop by loop.  The two share no code
@@ -7,8 +7,9 @@ and are structured differently (whole rows here, 8-lane chunks + scalar tails th
 requires them to agree bit for bit.  PARITY UNPINNED all the same: neither has been compared with outputs of the
 Rust reference (no Rust toolchain here, no golden vectors in the reference).
 
-Scope: nx % 8 == 0 (the reference panics otherwise), FirstOrder scheme (:540-552, :590-632), both inlet
-profiles, optional cylinder.  Every numpy expression keeps the Rust association; numpy evaluates each elementwise
+Scope: nx % 8 == 0 (the reference panics otherwise, SURVEY N1), both velocity schemes (FirstOrder :540-552, :590-632;
+SecondOrder :553-579, :634-669 with the scalar face functions :911-1053, :1098-1248), both inlet profiles, optional
+cylinder.  Every numpy expression keeps the Rust association; numpy evaluates each elementwise
 operation as a single IEEE op of the array dtype (no FMA).  Flat indexing is kept (`u[i + j*(nx+1)]`) so that the
 reference's reads past the end of a row land in the next row exactly as in the Rust.
 """
@@ -28,7 +29,8 @@ class NumpyModel:
         self.dt, self.nu = T(f(params.dt)), T(f(params.viscosity))            # :265-266
         self.target = T(f(params.target_inlet_velocity))
         self.parabolic = int(params.inlet_profile) == 1
-        assert int(params.velocity_scheme) == 0 and int(params.pressure_solver) == 0 and int(params.scenario) == 0
+        assert int(params.pressure_solver) == 0 and int(params.scenario) == 0
+        self.second = int(params.velocity_scheme) == 1
         self.current = T(0)
         self.step, self.ramp, self.time = 0, 100, T(0)                        # :267-269
         self.u = np.zeros((nx + 1) * ny, dtype)                               # :223-229
@@ -57,21 +59,44 @@ class NumpyModel:
         self.last_p = self.last_u = self.last_v = T(0)
         self.K = self.S = 0
 
-    # ---- predictor, FirstOrder (:540-552 + :382-436; :590-632 + :439-521) ----
+    @staticmethod
+    def _g(a, idx):
+        """gather with clamped indices: np.where evaluates both branches, the Rust only the one it takes"""
+        return a[np.clip(idx, 0, a.size - 1)]
+
+    # ---- predictor (:538-580 + :382-436; :586-670 + :439-521) ----
     def predictor_u(self, dt):
         nx, ny, W, T = self.nx, self.ny, self.nx + 1, self.T
-        u, v = self.u, self.v
+        u, v, g = self.u, self.v, self._g
         i = np.arange(1, nx + 1)                    # chunks 1, 9, ... cover columns 1..nx when nx % 8 == 0
         for j in range(1, ny - 1):
             idx = i + j * W
             v_n, v_s = v[i + (j + 1) * nx], v[i + j * nx]                     # get_v_north / south :1056-1069
             uc = u[idx]
-            u_n = np.where(v_n >= 0, uc, u[idx + W])                          # :966-981
-            u_s = np.where(v_s >= 0, u[idx - W], uc)                          # :1011-1026
             ur = u[idx + 1]
-            u_e = np.where((uc + ur) * T(0.5) >= 0, uc, ur)                   # :893-908
             ul = u[idx - 1]
-            u_w = np.where((ul + uc) * T(0.5) >= 0, ul, uc)                   # :929-941
+            if self.second:                                                   # scalar face functions, per column (:564-569)
+                h, q = T(0.5), T(1.5)
+                vn_s = h * (v[(i - 1) + (j + 1) * nx] + v[i + (j + 1) * nx])  # get_v_north_scalar :984-989 (i > 0)
+                un_pos = (q * uc - h * u[idx - W]) if j > 1 else uc           # :992-1008
+                far = i + (j + 2) * W
+                un_neg = np.where((far < u.size) & (j < ny - 1), q * u[idx + W] - h * g(u, far), u[idx + W])
+                u_n = np.where(vn_s >= 0, un_pos, un_neg)
+                vs_s = h * (v[(i - 1) + j * nx] + v[i + j * nx])              # get_v_south_scalar :1029-1034
+                us_pos = (q * u[idx - W] - h * g(u, idx - 2 * W)) if j > 1 else u[idx - W]      # :1037-1053
+                us_neg = q * uc - h * u[idx + W]                              # j < ny always
+                u_s = np.where(vs_s >= 0, us_pos, us_neg)
+                ue_pos = np.where(i > 1, q * uc - h * ul, uc)                 # :911-926
+                ue_neg = np.where(((idx + 2) < u.size) & (i < nx - 1), q * ur - h * g(u, idx + 2), ur)
+                u_e = np.where(uc >= 0, ue_pos, ue_neg)
+                uw_pos = np.where(i > 2, q * ul - h * g(u, idx - 2), ul)      # :944-963
+                uw_neg = np.where(i < nx, q * uc - h * ur, uc)
+                u_w = np.where(ul >= 0, uw_pos, uw_neg)
+            else:
+                u_n = np.where(v_n >= 0, uc, u[idx + W])                      # :966-981
+                u_s = np.where(v_s >= 0, u[idx - W], uc)                      # :1011-1026
+                u_e = np.where((uc + ur) * T(0.5) >= 0, uc, ur)               # :893-908
+                u_w = np.where((ul + uc) * T(0.5) >= 0, ul, uc)               # :929-941
             conv = (u_e * u_e - u_w * u_w) / self.dx + (v_n * u_n - v_s * u_s) / self.dy      # :408-415
             lap = (ur - T(2) * uc + ul) / (self.dx * self.dx) + (u[idx + W] - T(2) * uc + u[idx - W]) / (self.dy * self.dy)
             res = uc + dt * (-conv + self.nu * lap)                           # :433
@@ -79,16 +104,36 @@ class NumpyModel:
 
     def predictor_v(self, dt):
         nx, ny, W, T = self.nx, self.ny, self.nx + 1, self.T
-        u, v = self.u, self.v
+        u, v, g = self.u, self.v, self._g
         i = np.arange(1, nx)                        # body chunks + the scalar tail reach column nx-1 (:591-620)
         for j in range(1, ny):
             idx = i + j * nx
             ue, uw = u[i + 1 + j * W], u[i + j * W]                           # :600-601, :622-626
             vc, vn_, vs_ = v[idx], v[idx + nx], v[idx - nx]
-            v_n = np.where((vc + vn_) * T(0.5) >= 0, vc, vn_)                 # :1163-1185
-            v_s = np.where((vc + vs_) * T(0.5) >= 0, vs_, vc)                 # :1207-1229
-            v_e = np.where(ue >= 0, vc, v[idx + 1])                           # :1073-1095
-            v_w = np.where(uw >= 0, v[idx - 1], vc)                           # :1116-1142
+            if self.second:
+                h, q = T(0.5), T(1.5)
+                ve_pos = q * vc - h * v[idx - 1]                              # :1098-1113 (i > 0)
+                ve_neg = np.where(((idx + 2) < v.size) & (i < nx - 2), q * v[idx + 1] - h * g(v, idx + 2), v[idx + 1])
+                v_e = np.where(ue >= 0, ve_pos, ve_neg)
+                vw_pos = np.where(i > 1, q * v[idx - 1] - h * g(v, idx - 2), v[idx - 1])       # :1145-1160
+                vw_neg = np.where(i < nx - 1, q * vc - h * v[idx + 1], vc)
+                v_w = np.where(uw >= 0, vw_pos, vw_neg)
+                vn_pos = (q * vc - h * vs_) if j > 1 else vc                  # :1188-1204
+                far = i + (j + 2) * nx
+                vn_neg = np.where((far < v.size) & (j < ny - 1), q * vn_ - h * g(v, far), vn_)
+                v_n = np.where(h * (vc + vn_) >= 0, vn_pos, vn_neg)
+                vs_pos = (q * vs_ - h * g(v, idx - 2 * nx)) if j > 1 else vs_ # :1232-1248
+                vs_neg = q * vc - h * vn_                                     # j < ny always
+                v_s = np.where(h * (vs_ + vc) >= 0, vs_pos, vs_neg)
+                # the lane of column nx-1 keeps zero fluxes (`break` at :647-650) but is still written (:456-496)
+                last = i >= nx - 1
+                z = T(0)
+                ue, uw, v_e, v_w, v_n, v_s = (np.where(last, z, a) for a in (ue, uw, v_e, v_w, v_n, v_s))
+            else:
+                v_n = np.where((vc + vn_) * T(0.5) >= 0, vc, vn_)             # :1163-1185
+                v_s = np.where((vc + vs_) * T(0.5) >= 0, vs_, vc)             # :1207-1229
+                v_e = np.where(ue >= 0, vc, v[idx + 1])                       # :1073-1095
+                v_w = np.where(uw >= 0, v[idx - 1], vc)                       # :1116-1142
             conv = (ue * v_e - uw * v_w) / self.dx + (v_n * v_n - v_s * v_s) / self.dy        # :501-505
             lap = (v[idx + 1] - T(2) * vc + v[idx - 1]) / (self.dx * self.dx) + (vn_ - T(2) * vc + vs_) / (self.dy * self.dy)
             res = vc + dt * (-conv + self.nu * lap)

@@ -229,7 +229,7 @@ def test_mode_c_mgcg_agrees_with_cg_and_needs_few_iterations(scenario, shape):
 
 
 @pytest.mark.parametrize("precision", [32, 64])
-@pytest.mark.parametrize("case", ["default_grid", "parabolic_small"])
+@pytest.mark.parametrize("case", ["default_grid", "parabolic_small", "second_order_default_grid", "second_order_small"])
 def test_cpp_oracle_agrees_bit_for_bit_with_the_independent_numpy_restatement(precision, case):
     """Two restatements of src/model.rs written independently and structured differently (C++: 8-lane chunks and
     scalar tails, loop by loop; numpy: whole rows, straight from the Rust) must produce identical bits: every state
@@ -238,6 +238,13 @@ def test_cpp_oracle_agrees_bit_for_bit_with_the_independent_numpy_restatement(pr
     from oracle.numpy_restatement import NumpyModel
     if case == "default_grid":
         g, prm, steps = default_grid(), SimulationParams(), 11
+    elif case == "second_order_default_grid":
+        g, prm, steps = default_grid(), SimulationParams(velocity_scheme=VelocityScheme.SecondOrder), 11
+    elif case == "second_order_small":
+        g = channel_grid(48, 19)
+        prm = SimulationParams(velocity_scheme=VelocityScheme.SecondOrder, inlet_profile=InletProfile.Parabolic, dt=0.02,
+                               viscosity=1e-3)
+        steps = 60
     else:
         g = channel_grid(40, 21)
         prm, steps = SimulationParams(inlet_profile=InletProfile.Parabolic, dt=0.02, viscosity=1e-3), 60
