@@ -366,7 +366,7 @@ def test_mode_c_mgcg_first_vcycle_is_bit_identical():
     assert np.abs(a - ratio * b).max() <= 4e-16 * np.abs(b).max()
 
 
-def test_mgcg_rejects_strips_and_bad_constants():
+def test_mgcg_rejects_bad_constants():
     from cfd_demo_b200.model import CfdError, default_options
     from cfd_demo_b200.types import PressureSolver
     o = default_options()
