@@ -436,3 +436,32 @@ def test_mgcg_warm_start_state_restarts_in_the_oracle():
     assert rg.sweeps == rc.sweeps and abs(rg.sweeps - its[3]) <= 1 and rg.jacobi_calls == rc.jacobi_calls == 2
     for fid in (_abi.FIELD_U, _abi.FIELD_V, _abi.FIELD_P, _abi.FIELD_MG_GUESS, _abi.FIELD_MG_LAST, _abi.FIELD_MG_LAST2):
         assert rel_l2(gpu.field(fid), cpu.field(fid)) <= 1e-9, _abi.FIELD_NAMES[fid]
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+def test_nan_and_inf_propagate_exactly_like_the_oracle(precision):
+    """A blown-up run "just shows NaNs" in the reference (no NaN checks); its reductions fold with
+    f32::max, which ignores NaN (:338, :795-798, :879-880).  Poison one interior velocity with NaN and one with +inf:
+    the NaN / inf pattern of every state field, the residuals and the solver counters must match the oracle for as
+    long as the front spreads (this also drives the sweep through its out-of-line true-division path)."""
+    g = channel_grid(64, 24)
+    prm = SimulationParams()
+    gpu, cpu = Model(g, prm, precision=precision), OracleModel(g, prm, precision=precision)
+    for _ in range(8):
+        gpu.update()
+        cpu.update()
+    u = gpu.field(_abi.FIELD_U)
+    u[10 * 65 + 20] = np.nan
+    u[15 * 65 + 40] = np.inf
+    for m in (gpu, cpu):
+        m.set_field(_abi.FIELD_U, u)
+    for s in range(4):
+        gpu.update()
+        cpu.update()
+        rg, rc = gpu.get_residuals(), cpu.get_residuals()
+        assert (rg.jacobi_calls, rg.sweeps) == (rc.jacobi_calls, rc.sweeps), s
+        for k in ("dt", "p", "u", "v"):
+            a, b = rg.f64[k], rc.f64[k]
+            assert a == b or (np.isnan(a) and np.isnan(b)), (s, k, a, b)
+        assert_fields_identical(gpu, cpu, STATE_FIELDS, f"poisoned run, step {s}")
+    assert np.isnan(gpu.field(_abi.FIELD_U)).sum() > 10
