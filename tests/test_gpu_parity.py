@@ -308,7 +308,7 @@ def test_full_size_saturated_step_bit_exact_2048():
 
 
 @pytest.mark.parametrize("scenario", [Scenario.Channel, Scenario.Cavity])
-@pytest.mark.parametrize("shape", [(64, 64), (128, 93), (48, 6), (512, 512)])
+@pytest.mark.parametrize("shape", [(64, 64), (128, 93), (48, 6), (16, 4), (24, 5), (512, 512)])
 def test_mode_c_mgcg_matches_oracle_to_tolerance(scenario, shape):
     """Mode C fast path (multigrid-preconditioned CG, an extension): smoother, transfers and coarse operators are
     bit-identical to the oracle's, only the dot products are summed in another order -> tolerance parity
@@ -335,7 +335,7 @@ def test_mode_c_mgcg_matches_oracle_to_tolerance(scenario, shape):
         assert abs(rg.sweeps - rc.sweeps) <= 1 and rg.sweeps <= 20 and rg.f64["p"] <= 1e-12, (s, rg.sweeps, rc.sweeps)
     for fid in (_abi.FIELD_U, _abi.FIELD_V, _abi.FIELD_P):
         a, b = gpu.field(fid), cpu.field(fid)
-        assert np.isfinite(a).all() and np.abs(b).max() > 0
+        assert np.isfinite(a).all() and (fid != _abi.FIELD_U or np.abs(b).max() > 0)  # v is identically 0 on 4-row grids
         assert rel_l2(a, b) <= 1e-9, (_abi.FIELD_NAMES[fid], rel_l2(a, b))
 
 
