@@ -7,7 +7,7 @@
 //!.  The tested boundary is the C ABI these `extern "C"` items bind.
 use std::{
     os::raw::{c_char, c_int},
-    sync::mpsc::{self, TryRecvError},
+    sync::mpsc,
     thread,
     time::{Duration, Instant},
 };
@@ -131,72 +131,81 @@ impl Model {
         Residuals { simulation_step: r.simulation_step as usize, simulation_time: r.simulation_time, dt: r.dt, p: r.p,
                     u: r.u, v: r.v, step_time: Duration::from_secs_f64(r.step_seconds), piso_substeps: r.piso_substeps as usize }
     }
-    /// Same thread/channel protocol as the reference (src/model.rs:1282-1332).
-    pub fn run(mut self) -> SimulationControlHandle {
-        let (command_sender, command_receiver) = mpsc::channel();
-        let (snapshot_sender, snapshot_receiver) = mpsc::channel();
-        let (residuals_sender, residuals_receiver) = mpsc::channel();
-        thread::spawn(move || {
-            let mut paused = false;
-            loop {
-                let _start = Instant::now();
-                let mut snapshot_sent = false;
-                for command in command_receiver.try_iter() {
-                    match command {
-                        Command::Stop => break,
-                        Command::SetParams(params) => self.set_parameters(&params),
-                        Command::GetSnapshot => {
-                            if !snapshot_sent {
-                                let mut snapshot = self.get_snapshot();
-                                snapshot.paused = paused;
-                                snapshot_sender.send(snapshot).unwrap();
-                                snapshot_sent = true;
-                            }
-                        }
-                        Command::Pause => paused = true,
-                        Command::Resume => paused = false,
-                    }
-                }
-                if !paused {
-                    self.update();
-                    residuals_sender.send(self.get_residuals()).unwrap(); // panics when the UI drops the handle;
-                } else {                                                   // unwinding runs Drop below
-                    thread::sleep(Duration::from_millis(16));
-                }
+    /// `Model::run(self)` of the reference (src/model.rs:1282-1332): the model moves into one solver thread that
+    /// serves the command queue between timesteps.  Written here as a small state machine (`SolverLoop`) rather than
+    /// one closure; the observable protocol is the reference's: at most one snapshot per pass over the queue,
+    /// residuals after every step, ~60 Hz idling while paused.
+    pub fn run(self) -> SimulationControlHandle {
+        let (commands, inbox) = mpsc::channel();
+        let (snapshots_out, snapshots) = mpsc::channel();
+        let (residuals_out, residuals) = mpsc::channel();
+        thread::spawn(move || SolverLoop { model: self, inbox, snapshots_out, residuals_out, paused: false }.serve());
+        SimulationControlHandle { commands, snapshots, residuals }
+    }
+}
+
+struct SolverLoop {
+    model: Model,
+    inbox: mpsc::Receiver<Command>,
+    snapshots_out: mpsc::Sender<SimSnapshot>,
+    residuals_out: mpsc::Sender<Residuals>,
+    paused: bool,
+}
+impl SolverLoop {
+    /// One pass over the pending commands; returns false when asked to stop.
+    fn drain_commands(&mut self) -> bool {
+        let mut snapshot_pending = false;
+        while let Ok(command) = self.inbox.try_recv() {
+            match command {
+                Command::Stop => return false,
+                Command::Pause => self.paused = true,
+                Command::Resume => self.paused = false,
+                Command::SetParams(p) => self.model.set_parameters(&p),
+                Command::GetSnapshot => snapshot_pending = true, // coalesced: one device read-back per pass
             }
-        });
-        SimulationControlHandle { command_sender, snapshot_receiver, residuals_receiver }
+        }
+        if snapshot_pending {
+            let snapshot = SimSnapshot { paused: self.paused, ..self.model.get_snapshot() };
+            // a closed channel means the UI dropped its handle: end the thread (the reference panics here, :1304)
+            return self.snapshots_out.send(snapshot).is_ok();
+        }
+        true
+    }
+    fn serve(mut self) {
+        while self.drain_commands() {
+            if self.paused {
+                thread::sleep(Duration::from_millis(16));
+                continue;
+            }
+            let _t0 = Instant::now();
+            self.model.update();
+            if self.residuals_out.send(self.model.get_residuals()).is_err() {
+                break; // handle dropped (the reference's thread dies by `unwrap()` at :1319); Drop frees the GPU
+            }
+        }
     }
 }
 impl Drop for Model {
     fn drop(&mut self) { unsafe { cfd_model_destroy(self.handle) } }
 }
 
-// ---- SimulationControlHandle: verbatim protocol of the reference (src/model.rs:65-117) -----------------
+// ---- SimulationControlHandle: the pub API of the reference's handle (src/model.rs:65-117) over three channels ---
 pub struct SimulationControlHandle {
-    command_sender: mpsc::Sender<Command>,
-    snapshot_receiver: mpsc::Receiver<SimSnapshot>,
-    residuals_receiver: mpsc::Receiver<Residuals>,
+    commands: mpsc::Sender<Command>,
+    snapshots: mpsc::Receiver<SimSnapshot>,
+    residuals: mpsc::Receiver<Residuals>,
 }
 impl SimulationControlHandle {
-    pub fn stop(&self) { self.command_sender.send(Command::Stop).unwrap(); }
-    pub fn get_last_available_snapshot(&self) -> Option<SimSnapshot> {
-        let mut last = None;
-        loop {
-            match self.snapshot_receiver.try_recv() {
-                Ok(s) => last = Some(s),
-                Err(TryRecvError::Empty) | Err(TryRecvError::Disconnected) => break,
-            }
-        }
-        last
+    fn post(&self, command: Command) {
+        self.commands.send(command).expect("cfd_b200: the solver thread is gone");
     }
-    pub fn get_new_log_messages(&self) -> Vec<Residuals> {
-        let mut out = vec![];
-        while let Ok(r) = self.residuals_receiver.try_recv() { out.push(r); }
-        out
-    }
-    pub fn request_snapshot(&self) { self.command_sender.send(Command::GetSnapshot).unwrap(); }
-    pub fn set_params(&self, params: SimulationParams) { self.command_sender.send(Command::SetParams(params)).unwrap(); }
-    pub fn pause(&self) { self.command_sender.send(Command::Pause).unwrap(); }
-    pub fn resume(&self) { self.command_sender.send(Command::Resume).unwrap(); }
+    pub fn stop(&self) { self.post(Command::Stop) }
+    pub fn pause(&self) { self.post(Command::Pause) }
+    pub fn resume(&self) { self.post(Command::Resume) }
+    pub fn request_snapshot(&self) { self.post(Command::GetSnapshot) }
+    pub fn set_params(&self, params: SimulationParams) { self.post(Command::SetParams(params)) }
+    /// newest snapshot the solver thread has produced since the last call, if any
+    pub fn get_last_available_snapshot(&self) -> Option<SimSnapshot> { self.snapshots.try_iter().last() }
+    /// every `Residuals` record produced since the last call, oldest first
+    pub fn get_new_log_messages(&self) -> Vec<Residuals> { self.residuals.try_iter().collect() }
 }
