@@ -1642,7 +1642,8 @@ int cfd_model_create_ex(const cfd_grid* grid, const cfd_params* params, const cf
   // the reference's 8-lane chunking panics unless nx % 8 is 0 (or 1); this build takes 0 only.
   if (grid->nx % 8 != 0 || grid->nx < 16 || grid->ny < 4)
     return fail(CFD_ERR_INVALID_ARGUMENT, "grid: need nx % 8 == 0, nx >= 16, ny >= 4 (the reference panics otherwise)");
-  if (grid->nx > (1u << 30) || grid->ny > (1u << 30)) return fail(CFD_ERR_INVALID_ARGUMENT, "grid too large");
+  if (grid->nx > (1u << 30) || grid->ny > (1u << 30) || (grid->nx + 1) * (grid->ny + 1) > 0x7fffffffull)
+    return fail(CFD_ERR_INVALID_ARGUMENT, "grid too large (at most 2^31 - 1 entries per field)");
   if (!(grid->dx > 0.0f) || !(grid->dy > 0.0f)) return fail(CFD_ERR_INVALID_ARGUMENT, "grid: dx, dy must be positive");
   if (o.precision != 64 && o.precision != 32) return fail(CFD_ERR_INVALID_ARGUMENT, "precision must be 64 or 32");
   if (o.world_size < 1 || o.rank < 0 || o.rank >= o.world_size) return fail(CFD_ERR_INVALID_ARGUMENT, "rank / world_size out of range");

@@ -62,6 +62,9 @@ def test_argument_validation_needs_no_gpu(lib):
     assert e.value.code == _abi.CFD_ERR_INVALID_ARGUMENT
     with pytest.raises(model.CfdError):
         model.Model(Grid.uniform(16, 2, 1.0, 1.0), SimulationParams())
+    with pytest.raises(model.CfdError) as e:
+        model.Model(Grid.uniform(65536, 65536, 1.0, 1.0), SimulationParams())  # 2^32 cells: 32-bit field indices
+    assert e.value.code == _abi.CFD_ERR_INVALID_ARGUMENT and "too large" in str(e.value)
 
 
 def test_no_cpu_fallback(lib):
