@@ -403,7 +403,8 @@ struct ModelImpl final : ModelBase {
     CFD_CUDA(cudaStreamSynchronize(stream));
     if ((rc = init_sweep_constants())) return rc;
     // Mode R strips: NCCL halo rows + allreduce after every sweep by default; CFD_FLAG_PEER_EXCHANGE opts into the fused
-    // peer-memory path (faster, but it hung at start-up in 2 of 8 two-GPU runs of tests/mgpu_strip_check.py)
+    // peer-memory path (faster; it hung at start-up in 2 of 8 two-GPU runs before its max records were double-buffered,
+    // and has passed only one run since)
     if (world > 1 && (opt.flags & CFD_FLAG_PEER_EXCHANGE) && !(opt.flags & CFD_FLAG_NCCL_EXCHANGE) && (rc = init_peer_memory())) return rc;
     ready = true;
     return CFD_OK;

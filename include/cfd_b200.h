@@ -119,7 +119,8 @@ typedef struct cfd_options {
 #define CFD_FLAG_NCCL_EXCHANGE 32u /* Mode R strips: NCCL send/recv + allreduce after every sweep (the default since the peer path became opt-in) */
 #define CFD_FLAG_PEER_EXCHANGE 512u /* Mode R strips: the sweep kernel stores its edge rows into the neighbours' halos and publishes its max over
                                       * NVLink peer memory (CUDA IPC), no NCCL in the sweep loop: 0.78 instead of 0.69 weak-scaling efficiency at 2 GPUs,
-                                      * but it hung at start-up in 2 of 8 two-GPU test runs, so it is opt-in until that is understood */
+                                      * but it hung at start-up in 2 of 8 two-GPU test runs (records reused across solves; fixed by double-buffering them,
+                                      * validated by a single run so far), so it stays opt-in until the fix has been repeated enough */
 #define CFD_FLAG_TEMPORAL 64u      /* two sweeps per HBM pass (k_jacobi_sweep_t2) instead of one per launch (A/B; slower, issue-bound) */
 #define CFD_FLAG_PERSISTENT_SWEEP 128u /* persistent warp-queue kernel (k_jacobi_sweep6) instead of one block per tile (A/B; slower) */
 #define CFD_FLAG_MG_NO_BOTTOM_KERNEL 256u /* MGCG: one launch per operation on every level instead of the single-block bottom kernel (A/B, cross-check) */
