@@ -267,3 +267,32 @@ def test_cpp_oracle_agrees_bit_for_bit_with_the_independent_numpy_restatement(pr
         for k, val in (("dt", b.dt), ("p", b.last_p), ("u", b.last_u), ("v", b.last_v), ("simulation_time", b.time)):
             assert r.f64[k] == float(val), (s, k, r.f64[k], float(val))
     assert saturated and np.abs(b.u).max() > 0
+
+
+def test_mgcg_start_vector_modes_converge_to_the_same_flow():
+    """mg_warm_start only changes where the first solve of a step STARTS (0 cold, 1 previous p', 2 linear and 3
+    quadratic extrapolation in time): every mode must reach the same velocities within the solver tolerance, and the
+    extrapolated starts must need fewer iterations than the cold start once the flow evolves smoothly."""
+    from cfd_demo_b200.types import PressureSolver
+    n = 96
+    g = Grid.uniform(n, n, 1.0, 1.0, None)
+    nu = 1e-3
+    prm = SimulationParams(dt=0.05 * (1.0 / n) ** 2 / nu, viscosity=nu, scenario=Scenario.Cavity,
+                           pressure_solver=PressureSolver.MGCG)
+    fields, iters = {}, {}
+    for mode in (0, 1, 2, 3):
+        c = default_consts()
+        c.ramp_up_steps = 5
+        c.mg_warm_start = mode
+        m = OracleModel(g, prm, precision=64, consts=c)
+        total = 0
+        for s in range(40):
+            m.update()
+            r = m.get_residuals()
+            assert r.jacobi_calls == 2 and r.f64["p"] <= 1e-8
+            if s >= 20:
+                total += r.sweeps
+        fields[mode], iters[mode] = m.field(_abi.FIELD_U), total
+    for mode in (1, 2, 3):
+        assert np.linalg.norm(fields[mode] - fields[0]) <= 1e-5 * np.linalg.norm(fields[0]), mode
+    assert iters[3] <= iters[2] <= iters[1] < iters[0], iters
