@@ -55,7 +55,7 @@ __device__ __forceinline__ MgPair<R> mg_pair(const MgFine<R>& c) {
 // boundary rules where the pair touches the ring (mirror; 0 at the channel outlet)
 template <class R>
 __device__ __forceinline__ R mg_lap(const MgFine<R>& c, R cc, R xe, R xw, R xn, R xs) {
-  return ((xe - cc) + (xw - cc)) / c.dx_sq + ((xn - cc) + (xs - cc)) / c.dy_sq;
+  return div_exact((xe - cc) + (xw - cc), c.ddx_sq) + div_exact((xn - cc) + (xs - cc), c.ddy_sq);
 }
 
 template <class R>
@@ -69,41 +69,105 @@ __device__ __forceinline__ R mg_fine_apply(const MgFine<R>& c, const R* __restri
   return mg_lap<R>(c, cc, xe, xw, xn, xs);
 }
 
-// x = guess (or 0), d = 0 on the whole grid, rho = rhs - L x on the unknowns (0 on the ring), rho.rho.
-// grid = (ceil(nx / 512), ceil(ny / kMgRows))
+// Start vector of a solve, derived on the fly from the p' the last first-solves ended with (the buffers rotate on the
+// host, nothing is copied): mode 3 = 3 a - 3 b + c (quadratic extrapolation in time), 2 = 2 a - b (linear, the JS
+// twin's "extrapolated initial guess", index.html:262-270), 1 = a (what the reference's Jacobi does by never resetting
+// p', src/model.rs:734-824), 0 = cold start.  Same expressions, same association as the oracle's mg_guess update.
+template <class R>
+struct MgStart {
+  const R *a, *b, *c;
+  int mode;
+};
+template <class R>
+__device__ __forceinline__ R mg_start_one(const MgStart<R>& g, size_t idx) {
+  if (g.mode == 3) return R(3) * g.a[idx] - R(3) * g.b[idx] + g.c[idx];
+  if (g.mode == 2) return R(2) * g.a[idx] - g.b[idx];
+  return g.a[idx];
+}
+template <class R>
+__device__ __forceinline__ typename Vec2<R>::type mg_start_pair(const MgStart<R>& g, size_t idx) {
+  using V = typename Vec2<R>::type;
+  const V a = *reinterpret_cast<const V*>(g.a + idx);
+  V o = a;
+  if (g.mode == 3) {
+    const V b = *reinterpret_cast<const V*>(g.b + idx), c = *reinterpret_cast<const V*>(g.c + idx);
+    o.x = R(3) * a.x - R(3) * b.x + c.x;
+    o.y = R(3) * a.y - R(3) * b.y + c.y;
+  } else if (g.mode == 2) {
+    const V b = *reinterpret_cast<const V*>(g.b + idx);
+    o.x = R(2) * a.x - b.x;
+    o.y = R(2) * a.y - b.y;
+  }
+  return o;
+}
+
+// x = start vector (or 0) on the whole grid, rho = rhs - L x on the unknowns (0 on the ring), rho.rho; the search
+// direction needs no initialisation (k_mg_dir_apply takes it as zero in a solve's first iteration).
+// grid = (ceil(nx / 512), ceil(ny / kMgRows)); a thread walks its column pair up the tile, the start vector's rows
+// j-1, j, j+1 rotate through registers.
 template <class R>
 __global__ void __launch_bounds__(kMgThreads) k_mg_init(MgFine<R> c, MgScalars* __restrict__ sc,
-                                                         const R* __restrict__ rhs, const R* __restrict__ guess,
-                                                         R* __restrict__ x, R* __restrict__ rho, R* __restrict__ d,
+                                                         const R* __restrict__ rhs, const MgStart<R> g,
+                                                         R* __restrict__ x, R* __restrict__ rho,
                                                          double* __restrict__ partials, unsigned* __restrict__ ticket) {
   using V = typename Vec2<R>::type;
+  const int nx = c.nx;
   const int c0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int j0 = c.init_lo + blockIdx.y * kMgRows, j1 = min(j0 + kMgRows, c.init_hi);
   double acc = 0.0;
-  if (c0 < c.nx) {
+  if (c0 < nx && j0 < j1) {
     V zero;
     zero.x = R(0); zero.y = R(0);
+    const bool warm = g.mode != 0;
+    const int cl = max(c0 - 1, 0), cr = min(c0 + 2, nx - 1);
+    // rows j0-1 and j0 of the start vector (row -1 does not exist: the stencil never reads below row 1's mirror)
+    V south = zero, cen = zero, north = zero;
+    if (warm) {
+      if (j0 >= 1) south = mg_start_pair<R>(g, (size_t)c0 + (size_t)(j0 - 1) * nx);
+      cen = mg_start_pair<R>(g, (size_t)c0 + (size_t)j0 * nx);
+    }
     for (int j = j0; j < j1; ++j) {
-      const size_t idx = (size_t)c0 + (size_t)j * c.nx;
+      const size_t idx = (size_t)c0 + (size_t)j * nx;
       const bool row_ok = j >= 1 && j <= c.ny - 2;
-      const bool ok0 = row_ok && c0 >= 1, ok1 = row_ok && c0 + 1 <= c.nx - 2;
+      const bool ok0 = row_ok && c0 >= 1, ok1 = row_ok && c0 + 1 <= nx - 2;
       V b = *reinterpret_cast<const V*>(rhs + idx);
-      V x0 = zero;
-      if (guess != nullptr) {
-        x0 = *reinterpret_cast<const V*>(guess + idx);
-        if (ok0) b.x = b.x - mg_fine_apply<R>(c, guess, c0, j);
-        if (ok1) b.y = b.y - mg_fine_apply<R>(c, guess, c0 + 1, j);
+      if (warm) {
+        if (j + 1 <= c.ny - 1) north = mg_start_pair<R>(g, idx + nx);
+        if (row_ok) {
+          const size_t row = (size_t)j * nx;
+          const R gl = mg_start_one<R>(g, row + cl), gr = mg_start_one<R>(g, row + cr);
+          if (ok0) {
+            const R xw = (c0 == 1) ? cen.x : gl;
+            const R xe = (c0 == nx - 2) ? (c.cavity ? cen.x : R(0)) : cen.y;
+            const R xn = (j == c.ny - 2) ? cen.x : north.x, xs = (j == 1) ? cen.x : south.x;
+            b.x = b.x - mg_lap<R>(c, cen.x, xe, xw, xn, xs);
+          }
+          if (ok1) {
+            const R xw = (c0 + 1 == 1) ? cen.y : cen.x;
+            const R xe = (c0 + 1 == nx - 2) ? (c.cavity ? cen.y : R(0)) : gr;
+            const R xn = (j == c.ny - 2) ? cen.y : north.y, xs = (j == 1) ? cen.y : south.y;
+            b.y = b.y - mg_lap<R>(c, cen.y, xe, xw, xn, xs);
+          }
+        }
       }
       if (!ok0) b.x = R(0);
       if (!ok1) b.y = R(0);
-      *reinterpret_cast<V*>(x + idx) = x0;
-      *reinterpret_cast<V*>(d + idx) = zero;
+      *reinterpret_cast<V*>(x + idx) = cen;
       *reinterpret_cast<V*>(rho + idx) = b;
       acc += (double)(b.x * b.x);
       acc += (double)(b.y * b.y);
+      south = cen;
+      cen = north;
     }
   }
   mg_finish_dot<R, kMgThreads>(c, sc, partials, ticket, acc, 0);
+}
+
+// the derived start vector, written out (state read-back: CFD_FIELD_MG_GUESS); whole owned rows, grid-stride
+template <class R>
+__global__ void __launch_bounds__(kMgThreads) k_mg_start_materialize(const MgStart<R> g, R* __restrict__ out, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) out[k] = mg_start_one<R>(g, k);
 }
 
 // The kernels below load every row of their tile before they compute (fully unrolled, rows past the tile's end
@@ -146,7 +210,11 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_dir_apply(MgFine<R> c, MgScal
                                                               R* __restrict__ d_new, R* __restrict__ w,
                                                               double* __restrict__ partials, unsigned* __restrict__ ticket) {
   using V = typename Vec2<R>::type;
+  if (sc->done) return;  // iterations are enqueued in batches; once the solve is over the rest are no-ops
   const R beta = (R)sc->beta;
+  // first iteration of a solve: d_old is identically zero by definition (and beta is 0) — it is neither initialised
+  // by k_mg_init nor read here; z + 0 * 0 keeps the oracle's arithmetic (mg_d = mg_z + 0 * mg_d over zeros)
+  const bool first = sc->iterations == 0;
   const int nx = c.nx;
   const int c0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int j0 = c.row_lo + blockIdx.y * kMgDirRows, j1 = min(j0 + kMgDirRows, c.row_hi);
@@ -160,7 +228,10 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_dir_apply(MgFine<R> c, MgScal
     for (int m = 0; m < kMgDirRows + 2; ++m) {
       const int j = min(j0 - 1 + m, c.row_hi);  // row_hi is the ring / halo row above the owned unknowns
       const size_t idx = (size_t)c0 + (size_t)j * nx;
-      const V zv = *reinterpret_cast<const V*>(z + idx), dv = *reinterpret_cast<const V*>(d_old + idx);
+      const V zv = *reinterpret_cast<const V*>(z + idx);
+      V dv;
+      dv.x = R(0); dv.y = R(0);
+      if (!first) dv = *reinterpret_cast<const V*>(d_old + idx);
       dn[m].x = zv.x + beta * dv.x;
       dn[m].y = zv.y + beta * dv.y;
     }
@@ -168,8 +239,8 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_dir_apply(MgFine<R> c, MgScal
     for (int r = 0; r < kMgDirRows; ++r) {
       const int j = min(j0 + r, c.row_hi - 1);
       const size_t row = (size_t)j * nx;
-      dl[r] = z[row + cl] + beta * d_old[row + cl];
-      dr[r] = z[row + cr] + beta * d_old[row + cr];
+      dl[r] = z[row + cl] + beta * (first ? R(0) : d_old[row + cl]);
+      dr[r] = z[row + cr] + beta * (first ? R(0) : d_old[row + cr]);
     }
 #pragma unroll
     for (int r = 0; r < kMgDirRows; ++r) {
@@ -208,6 +279,7 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_update(MgFine<R> c, MgScalars
                                                            R* __restrict__ x, R* __restrict__ rho,
                                                            double* __restrict__ partials, unsigned* __restrict__ ticket) {
   using V = typename Vec2<R>::type;
+  if (sc->done) return;
   const R alpha = (R)sc->alpha;
   const int c0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int j0 = c.row_lo + blockIdx.y * kMgUpdRows, j1 = min(j0 + kMgUpdRows, c.row_hi);
@@ -247,55 +319,22 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_update(MgFine<R> c, MgScalars
   mg_finish_dot<R, kMgThreads>(c, sc, partials, ticket, acc, 3);
 }
 
-// end of a step's first solve (mg_warm_start 3): next start vector = 3 x - 3 last + last2, last2 = last, last = x
-template <class R>
-__global__ void __launch_bounds__(kMgThreads) k_mg_extrapolate2(const R* __restrict__ x, R* __restrict__ last,
-                                                                 R* __restrict__ last2, R* __restrict__ guess, size_t n) {
-  using V = typename Vec2<R>::type;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n / 2; k += stride) {
-    const V xv = reinterpret_cast<const V*>(x)[k];
-    const V lv = reinterpret_cast<const V*>(last)[k];
-    const V mv = reinterpret_cast<const V*>(last2)[k];
-    V g;
-    g.x = R(3) * xv.x - R(3) * lv.x + mv.x;
-    g.y = R(3) * xv.y - R(3) * lv.y + mv.y;
-    reinterpret_cast<V*>(guess)[k] = g;
-    reinterpret_cast<V*>(last2)[k] = lv;
-    reinterpret_cast<V*>(last)[k] = xv;
-  }
-}
-
 // strips: advance the CG scalars from the sum-allreduced local_sum (the single-domain kernels do this themselves)
 template <class R>
 __global__ void k_mg_advance(MgFine<R> c, MgScalars* __restrict__ sc, int mode) {
+  if (mode != 0 && sc->done) return;
   if (threadIdx.x == 0 && blockIdx.x == 0) mg_advance<R>(c, sc, sc->local_sum, mode);
-}
-
-// end of a step's first solve (mg_warm_start 2): next start vector = 2 x - last, last = x; whole grid, grid-stride
-template <class R>
-__global__ void __launch_bounds__(kMgThreads) k_mg_extrapolate(const R* __restrict__ x, R* __restrict__ last,
-                                                                R* __restrict__ guess, size_t n) {
-  using V = typename Vec2<R>::type;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n / 2; k += stride) {
-    const V xv = reinterpret_cast<const V*>(x)[k];
-    const V lv = reinterpret_cast<const V*>(last)[k];
-    V g;
-    g.x = R(2) * xv.x - lv.x;
-    g.y = R(2) * xv.y - lv.y;
-    reinterpret_cast<V*>(guess)[k] = g;
-    reinterpret_cast<V*>(last)[k] = xv;
-  }
 }
 
 // First smoothing sweep of a V-cycle: the reference's Jacobi update (src/model.rs:788-793) applied to z = 0,
 //   z1 = omega * ((0 + 0 - rho) / denom) + (1 - omega) * 0,
 // and its boundary update (:807-815) — pointwise, so it needs neither the zero field nor the stencil.
 template <class R>
-__global__ void __launch_bounds__(kMgThreads) k_mg_first_sweep(MgFine<R> c, R omega, R one_minus_omega, R denom,
-                                                                const R* __restrict__ rho, R* __restrict__ z) {
+__global__ void __launch_bounds__(kMgThreads) k_mg_first_sweep(MgFine<R> c, R omega, R one_minus_omega, DivG<R> denom,
+                                                                const R* __restrict__ rho, R* __restrict__ z,
+                                                                const MgScalars* __restrict__ sc) {
   using V = typename Vec2<R>::type;
+  if (sc->done) return;
   const MgPair<R> p = mg_pair<R>(c);
   if (!p.any) return;
   const int nx = c.nx;
@@ -308,8 +347,8 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_first_sweep(MgFine<R> c, R om
     const int j = p.j0 + r;
     if (j < p.j1) {
       V o;
-      o.x = omega * (((R(0) + R(0)) - rv[r].x) / denom) + one_minus_omega * R(0);
-      o.y = omega * (((R(0) + R(0)) - rv[r].y) / denom) + one_minus_omega * R(0);
+      o.x = omega * div_exact((R(0) + R(0)) - rv[r].x, denom) + one_minus_omega * R(0);
+      o.y = omega * div_exact((R(0) + R(0)) - rv[r].y, denom) + one_minus_omega * R(0);
       if (p.c0 == 0) o.x = o.y;                             // p'[0,j] <- p'[1,j]
       if (p.c0 == nx - 2) o.y = c.cavity ? o.x : R(0);      // outlet 0 / cavity mirror
       *reinterpret_cast<V*>(z + p.c0 + (size_t)j * nx) = o;
@@ -325,9 +364,9 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_first_sweep(MgFine<R> c, R om
 template <class R>
 __global__ void __launch_bounds__(kMgThreads) k_mg_fine_restrict(MgFine<R> c, const R* __restrict__ z,
                                                                   const R* __restrict__ rho, int cmx, int c_lo,
-                                                                  R* __restrict__ crho) {
+                                                                  R* __restrict__ crho, const MgScalars* __restrict__ sc) {
   const int I = blockIdx.x * blockDim.x + threadIdx.x, J = c_lo + blockIdx.y;  // grid.y = owned rows of level 1
-  if (I >= cmx) return;
+  if (I >= cmx || sc->done) return;
   R acc = R(0);
 #pragma unroll
   for (int b = 0; b < 2; ++b)
@@ -343,10 +382,11 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_fine_restrict(MgFine<R> c, co
 // never read by a stencil on the unknowns and are left alone).  One thread per unknown.
 template <class R>
 __global__ void __launch_bounds__(kMgThreads) k_mg_fine_prolong(MgFine<R> c, R* __restrict__ z, int cmx,
-                                                                 const R* __restrict__ ce, int j_lo) {
+                                                                 const R* __restrict__ ce, int j_lo,
+                                                                 const MgScalars* __restrict__ sc) {
   // grid.y = rows handled: the owned unknown rows plus, on strips, the neighbours' edge rows (halo)
   const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = j_lo + blockIdx.y;
-  if (i > c.nx - 2) return;
+  if (i > c.nx - 2 || sc->done) return;
   const size_t idx = (size_t)i + (size_t)j * c.nx;
   const R v = z[idx] + ce[(size_t)((i - 1) / 2 + 1) + (size_t)((j - 1) / 2 + 1) * (cmx + 2)];
   z[idx] = v;
@@ -402,23 +442,26 @@ __device__ __forceinline__ void mgc_restrict_cell(const MgLevelDev<R>& L, const 
 
 template <class R>
 __global__ void __launch_bounds__(kMgThreads) k_mgc_sweep(MgLevelDev<R> L, const R* in, const R* rho, R* out, R omega,
-                                                           int zero_in, int row_lo) {
+                                                           int zero_in, int row_lo, const MgScalars* __restrict__ sc) {
   const int I = blockIdx.x * blockDim.x + threadIdx.x, J = row_lo + blockIdx.y;
+  if (sc->done) return;
   if (I < L.mx) mgc_sweep_cell<R>(L, in, rho, out, omega, zero_in != 0, I, J);
 }
 
 template <class R>
 __global__ void __launch_bounds__(kMgThreads) k_mgc_restrict(MgLevelDev<R> L, const R* e, const R* rho, int cmx,
-                                                              int c_lo, R* crho) {
+                                                              int c_lo, R* crho, const MgScalars* __restrict__ sc) {
   const int I = blockIdx.x * blockDim.x + threadIdx.x, J = c_lo + blockIdx.y;
+  if (sc->done) return;
   if (I < cmx) mgc_restrict_cell<R>(L, e, rho, cmx, crho, I, J);
 }
 
 // e_l += (correction of the parent); one thread per cell of level l
 template <class R>
-__global__ void __launch_bounds__(kMgThreads) k_mgc_prolong(int mx, R* e, int cmx, const R* ce, int row_lo) {
+__global__ void __launch_bounds__(kMgThreads) k_mgc_prolong(int mx, R* e, int cmx, const R* ce, int row_lo,
+                                                             const MgScalars* __restrict__ sc) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = row_lo + blockIdx.y;
-  if (i >= mx) return;
+  if (i >= mx || sc->done) return;
   const size_t idx = (size_t)(i + 1) + (size_t)(j + 1) * ((size_t)mx + 2);
   e[idx] += ce[(size_t)(i / 2 + 1) + (size_t)(j / 2 + 1) * ((size_t)cmx + 2)];
 }
@@ -441,7 +484,8 @@ struct MgBottom {
 };
 
 template <class R>
-__global__ void __launch_bounds__(kMgBottomThreads) k_mg_bottom(const MgBottom<R> B) {
+__global__ void __launch_bounds__(kMgBottomThreads) k_mg_bottom(const MgBottom<R> B, const MgScalars* __restrict__ sc) {
+  if (sc->done) return;
   R* cur[kMgBottomMax];
   R* oth[kMgBottomMax];
   const int tid = threadIdx.x;

@@ -214,9 +214,24 @@ struct ModelImpl final : ModelBase {
   std::vector<MgLevelHost> mg;
   Field<R> mg_rho, mg_b[3];  // mg_b: the search direction d and the two smoothing buffers of z, roles rotate
   int mg_id = 0;             // index of the buffer that holds d
-  Field<R> mg_guess;  // start vector of the next step's first solve (carried state)
-  Field<R> mg_last;   // p' the last first-solve ended with (carried state, mg_warm_start 2)
-  Field<R> mg_last2;  // the one before that (carried state, mg_warm_start 3)
+  // Start vector of a step's first solve (carried state).  mg_hist[0..2] = the p' the last three first-solves ended
+  // with, newest first; the start vector 3 h0 - 3 h1 + h2 (mg_warm_start 3; 2 h0 - h1; h0) is formed on the fly by
+  // k_mg_init, and the buffers ROTATE with the two p' buffers instead of being copied: after a first solve its
+  // result stays in pp[ipp] (mg_rotate_pending) until the next MGCG solve is about to overwrite p', which then takes
+  // the retired h2 buffer for p' and promotes the old p' buffer to h0.  Anything else that looks at these fields
+  // resolves the pending rotation by a copy first (resolve_mg_rotation).
+  Field<R> mg_hist[3];
+  CUtensorMap tmap_hist[3];
+  bool mg_rotate_pending = false;
+  Field<R> mg_guess;               // explicit start vector: only after cfd_model_set_field_f64(CFD_FIELD_MG_GUESS)
+  bool mg_guess_explicit = false;
+  // An outer round whose re-correction solve is converged before its first iteration has p' == 0: its corrector is the
+  // identity and is elided together with the solve's set-up pass.  Logical state while the flags are up:
+  bool pp_zero_pending = false;    // p' is identically zero although pp[ipp] still holds older data
+  bool star_alias = false;         // u_star / v_star equal the pre-BC current fields; only the entries the next
+                                   // predictor does not overwrite were actually copied (k_star_save_*)
+  int mg_pred[2] = {3, 0};         // iterations the previous step's first / re-correction solves took (batch size)
+  int solid_i0 = 0, solid_i1 = 0, solid_j0 = 0, solid_j1 = 0;  // bounding box of the solid cells (empty: no obstacle)
   CUtensorMap tmap_mg_b[3], tmap_mg_rho;
   cfdk::MgScalars* mg_scalars = nullptr;  // device
   cfdk::MgScalars* h_mg = nullptr;        // pinned host copy
@@ -235,6 +250,8 @@ struct ModelImpl final : ModelBase {
   CUtensorMap tmap_rhs_halo;         // rhs with the same halo box as p' (two-sweep kernel)
   int t2_rows_per_block = 20;        // tile height of the two-sweep kernel: rows + 4 halo rows = whole 4-row boxes
   cfdk::DivG<R> div_dx_sq, div_dy_sq, div_denom;  // divisors of the Jacobi update with hoisted reciprocals
+  cfdk::StepDivs<R>* d_divs = nullptr;            // device: dx, dy, dx^2, dy^2, dt (refreshed every step), denom
+  cfdk::StepDivs<R> h_divs;                       // host mirror (dt entry as of model creation)
   int sweep_rows_per_block = 32;
   int sweep6_resident_blocks = 148 * 4;  // one wave of the persistent sweep
   cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
@@ -283,10 +300,11 @@ struct ModelImpl final : ModelBase {
     for (auto& f : vbuf) cudaFree(f.base);
     cudaFree(p.base); cudaFree(rhs.base); cudaFree(pp[0].base); cudaFree(pp[1].base);
     cudaFree(mask_u.base); cudaFree(mask_v.base); cudaFree(solid.base);
-    cudaFree(err_slots); cudaFree(step_slots); cudaFree(staging); cudaFree(tickets);
+    cudaFree(err_slots); cudaFree(step_slots); cudaFree(staging); cudaFree(tickets); cudaFree(d_divs);
     cudaFree(cg_r.base); cudaFree(cg_d.base); cudaFree(cg_partials); cudaFree(cg_scalars);
     for (auto& L : mg) { cudaFree(L.weights); cudaFree(L.e); cudaFree(L.rho); cudaFree(L.tmp); }
-    cudaFree(mg_rho.base); cudaFree(mg_guess.base); cudaFree(mg_last.base); cudaFree(mg_last2.base);
+    cudaFree(mg_rho.base); cudaFree(mg_guess.base);
+    for (auto& f : mg_hist) cudaFree(f.base);
     for (auto& f : mg_b) cudaFree(f.base);
     cudaFree(mg_scalars); cudaFree(mg_partials); cudaFree(mg_err); cudaFree(mg_ticket);
     if (h_mg) cudaFreeHost(h_mg);
@@ -401,6 +419,14 @@ struct ModelImpl final : ModelBase {
     cfdk::k_build_masks<<<grd, blk, 0, stream>>>(g, solid.v, mask_u.v, mask_v.v, mj_lo, mj_hi);
     CFD_CUDA(cudaGetLastError());
     CFD_CUDA(cudaStreamSynchronize(stream));
+    if (grid.has_obstacle) {
+      // bounding box of the cells whose centre can lie inside the cylinder (two cells of margin around the f32 test)
+      const double x0 = ((double)grid.center_x - (double)grid.radius) / (double)grid.dx, x1 = ((double)grid.center_x + (double)grid.radius) / (double)grid.dx;
+      const double y0 = ((double)grid.center_y - (double)grid.radius) / (double)grid.dy, y1 = ((double)grid.center_y + (double)grid.radius) / (double)grid.dy;
+      auto clampi = [](double v, int lo, int hi) { return v < (double)lo ? lo : (v > (double)hi ? hi : (int)v); };
+      solid_i0 = clampi(std::floor(x0) - 2.0, 0, nx); solid_i1 = clampi(std::ceil(x1) + 3.0, 0, nx);
+      solid_j0 = clampi(std::floor(y0) - 2.0, 0, ny); solid_j1 = clampi(std::ceil(y1) + 3.0, 0, ny);
+    }
     if ((rc = init_sweep_constants())) return rc;
     // Mode R strips: NCCL halo rows + allreduce after every sweep by default; CFD_FLAG_PEER_EXCHANGE opts into the fused
     // peer-memory path (faster; it hung at start-up in 2 of 8 two-GPU runs before its max records were double-buffered,
@@ -514,38 +540,18 @@ struct ModelImpl final : ModelBase {
   // divisors of the Jacobi update (src/model.rs:740-746) and, for fp64, their reciprocals refined by the
   // same instruction sequence the compiler's division uses (cfdk::div_fast); launch geometry of the sweep
   int init_sweep_constants() {
-    div_dx_sq.y = dx * dx;                                      // :740
-    div_dy_sq.y = dy * dy;                                      // :742
-    div_denom.y = R(2.0) / (dx * dx) + R(2.0) / (dy * dy);      // :746
-    div_dx_sq.r = div_dy_sq.r = div_denom.r = R(0);
-    div_dx_sq.lo = div_dy_sq.lo = div_denom.lo = 0u;
-    div_dx_sq.span = div_dy_sq.span = div_denom.span = 0u;
-    if (sizeof(R) == 8) {
-      double hy[3] = {(double)div_dx_sq.y, (double)div_dy_sq.y, (double)div_denom.y}, hr[3];
-      double* d = nullptr;
-      CFD_CUDA(cudaMalloc((void**)&d, 6 * sizeof(double)));
-      CFD_CUDA(cudaMemcpyAsync(d, hy, sizeof hy, cudaMemcpyHostToDevice, stream));
-      cfdk::k_init_divc<<<1, 32, 0, stream>>>(d, d + 3, 3);
-      CFD_CUDA(cudaMemcpyAsync(hr, d + 3, sizeof hr, cudaMemcpyDeviceToHost, stream));
+    // every loop-invariant divisor with its hoisted reciprocal and dividend window, built on the device
+    // (cfdk::make_divg) and mirrored on the host for the kernels that take them by value
+    {
+      int rc0;
+      if (!d_divs && (rc0 = dalloc(&d_divs, (size_t)1))) return rc0;
+      const R denom = R(2.0) / (dx * dx) + R(2.0) / (dy * dy);  // :746
+      cfdk::k_step_divisors<R><<<1, 32, 0, stream>>>(d_divs, dx, dy, dt, denom);
+      CFD_CUDA(cudaMemcpyAsync(&h_divs, d_divs, sizeof h_divs, cudaMemcpyDeviceToHost, stream));
       CFD_CUDA(cudaStreamSynchronize(stream));
-      CFD_CUDA(cudaFree(d));
-      div_dx_sq.r = (R)hr[0]; div_dy_sq.r = (R)hr[1]; div_denom.r = (R)hr[2];
-      // dividend exponent window in which x / y is normal and finite for any significands, and
-      // x >= 2^-969 (the lower bound of the compiler's own fast path)
-      auto window = [](double y, unsigned* lo, unsigned* span) {
-        uint64_t bits;
-        memcpy(&bits, &y, sizeof bits);
-        const int ey = (int)((bits >> 52) & 0x7ff);
-        int lo_e = ey - 1018, hi_e = ey + 1020;
-        if (lo_e < 0x036) lo_e = 0x036;
-        if (hi_e > 0x7f8) hi_e = 0x7f8;
-        if (ey < 1 || ey > 0x7fd || hi_e <= lo_e) { *lo = 0u; *span = 0u; return; }
-        *lo = (unsigned)lo_e << 20;
-        *span = (unsigned)(hi_e - lo_e) << 20;
-      };
-      window(hy[0], &div_dx_sq.lo, &div_dx_sq.span);
-      window(hy[1], &div_dy_sq.lo, &div_dy_sq.span);
-      window(hy[2], &div_denom.lo, &div_denom.span);
+      div_dx_sq = h_divs.dx_sq;   // :740
+      div_dy_sq = h_divs.dy_sq;   // :742
+      div_denom = h_divs.denom;   // :746
     }
     {
       using Ring = cfdk::SweepChunkRing<R>;
@@ -626,6 +632,15 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
 
+  // the divergence divides by dt (:1436): its hoisted reciprocal comes from the device (make_divg) whenever dt changed
+  int refresh_dt_divisor(R dt_sub) {
+    if (memcmp(&dt_sub, &h_divs.dt.y, sizeof(R)) == 0) return CFD_OK;
+    cfdk::k_step_divisors<R><<<1, 32, 0, stream>>>(d_divs, dx, dy, dt_sub, R(2.0) / (dx * dx) + R(2.0) / (dy * dy));
+    CFD_CUDA(cudaMemcpyAsync(&h_divs, d_divs, sizeof h_divs, cudaMemcpyDeviceToHost, stream));
+    CFD_CUDA(cudaStreamSynchronize(stream));
+    return CFD_OK;
+  }
+
   // interior pressure rows this rank sweeps / owned row ranges of the staggered fields
   int sweep_row_begin() const { return ja > 1 ? ja : 1; }
   int sweep_row_end() const { return jb < ny - 1 ? jb : ny - 1; }
@@ -674,17 +689,34 @@ struct ModelImpl final : ModelBase {
   }
 
   // ---- one pressure solve: recompute_divergence (:1406-1440) + jacobi_pressure (:734-824) ----
-  int pressure_solve(R dt_sub, const Field<R>& us, const Field<R>& vs, int call_index, R* residual_out) {
+  // `elided` (may be null): set when the solve converged before its first iteration from p' = 0, i.e. the correction
+  // is identically zero and nothing was written to p' (pp_zero_pending) — the caller skips the corrector.
+  int pressure_solve(R dt_sub, const Field<R>& us, const Field<R>& vs, int call_index, R* residual_out, bool* elided = nullptr) {
     const int iters = opt.consts.jacobi_iterations;
     int rc;
+    if (elided) *elided = false;
     if ((rc = fetch_row_above(vs, ja, v_row_end()))) return rc;
+    const bool mgcg = pressure_solver == CFD_SOLVER_MGCG;
+    if (mgcg && (rc = mgcg_begin())) return rc;
+    // a cold-start MGCG solve that is expected to need no iteration: the divergence kernel sums rho.rho = rhs.rhs itself
+    const bool cold = mgcg && !(call_index == 0 && opt.consts.mg_warm_start != 0);
+    const bool decide_early = cold && elided != nullptr && mg_pred[call_index == 0 ? 0 : 1] == 0;
     {
-      dim3 blk(256), grd((nx + 255) / 256, jb - ja);
-      cfdk::k_divergence<R><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, rhs.v, ja, jb, err_slots, iters, tickets);
+      dim3 blk(256), grd((nx + 255) / 256, (jb - ja + cfdk::kDivRows - 1) / cfdk::kDivRows);
+      if (decide_early)
+        cfdk::k_divergence<R, true><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, rhs.v, ja, jb, err_slots, iters, tickets,
+                                                             h_divs.dx, h_divs.dy, h_divs.dt, mg_fine(dt_sub), mg_scalars,
+                                                             mg_partials, mg_ticket);
+      else
+        cfdk::k_divergence<R, false><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, rhs.v, ja, jb, err_slots, iters, tickets,
+                                                              h_divs.dx, h_divs.dy, h_divs.dt, cfdk::MgFine<R>{}, nullptr,
+                                                              nullptr, nullptr);
       ++launches;
     }
     if (pressure_solver == CFD_SOLVER_CG) return cg_solve(dt_sub, call_index, residual_out);
-    if (pressure_solver == CFD_SOLVER_MGCG) return mgcg_solve(dt_sub, call_index, residual_out);
+    if (mgcg) return mgcg_solve(dt_sub, call_index, residual_out, decide_early, elided);
+    if ((rc = materialize_pp_zero())) return rc;  // Jacobi warm-starts from p' (src/model.rs:734-824)
+    if ((rc = resolve_mg_rotation())) return rc;
     cfdk::JacobiConsts<R> c;
     c.dx_sq = dx * dx;                                   // :740
     c.dy_sq = dy * dy;                                   // :742
@@ -820,6 +852,8 @@ struct ModelImpl final : ModelBase {
 
   int cg_solve(R dt_sub, int call_index, R* residual_out) {
     int rc;
+    if ((rc = resolve_mg_rotation())) return rc;
+    pp_zero_pending = false;  // k_cg_init writes p' in full
     const int int_lo = sweep_row_begin(), int_hi = sweep_row_end();
     const dim3 blk(cfdk::kCgThreads);
     const dim3 g_all((nx + cfdk::kCgThreads - 1) / cfdk::kCgThreads, jb - ja);
@@ -926,10 +960,11 @@ struct ModelImpl final : ModelBase {
     if ((rc = falloc(&mg_rho, (size_t)nx))) return rc;
     for (auto& f : mg_b)
       if ((rc = falloc(&f, (size_t)nx))) return rc;
-    if ((rc = falloc(&mg_guess, (size_t)nx))) return rc;
-    if ((rc = falloc(&mg_last, (size_t)nx))) return rc;
-    if ((rc = falloc(&mg_last2, (size_t)nx))) return rc;
     using Ring = cfdk::SweepChunkRing<R>;
+    for (int k = 0; k < 3; ++k) {
+      if ((rc = falloc(&mg_hist[k], (size_t)nx))) return rc;
+      if ((rc = make_tensor_map(&tmap_hist[k], mg_hist[k].row(ja - kHalo), Ring::kPCols))) return rc;  // may become a p' buffer
+    }
     for (int k = 0; k < 3; ++k)
       if ((rc = make_tensor_map(&tmap_mg_b[k], mg_b[k].row(ja - kHalo), Ring::kPCols))) return rc;
     CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep5<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1033,19 +1068,19 @@ struct ModelImpl final : ModelBase {
     R *a = L.e, *b = L.tmp;
     int rc;
     if (l == mg_bottom_level && !(opt.flags & CFD_FLAG_MG_NO_BOTTOM_KERNEL) && !(L.mx == 1 && L.my == 1)) {
-      cfdk::k_mg_bottom<R><<<1, cfdk::kMgBottomThreads, 0, stream>>>(mg_bottom);
+      cfdk::k_mg_bottom<R><<<1, cfdk::kMgBottomThreads, 0, stream>>>(mg_bottom, mg_scalars);
       ++launches;
       L.cur = L.e;
       return CFD_OK;
     }
     if (L.mx == 1 && L.my == 1) {  // exact
-      cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, R(1), 1, 0);
+      cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, R(1), 1, 0, mg_scalars);
       ++launches;
       L.cur = b;
       return CFD_OK;
     }
     for (int s = 0; s < nu_s; ++s) {
-      cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, omega, s == 0 ? 1 : 0, lo);
+      cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, omega, s == 0 ? 1 : 0, lo, mg_scalars);
       ++launches;
       std::swap(a, b);
       if (dist && (rc = exchange_level(a, l))) return rc;
@@ -1053,7 +1088,7 @@ struct ModelImpl final : ModelBase {
     MgLevelHost& C = mg[(size_t)l + 1];
     const int c_lo = dist ? lvl_lo(l + 1, rank) : 0, c_hi = dist ? lvl_hi(l + 1, rank) : C.my;
     const dim3 grd_c((C.mx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, c_hi - c_lo);
-    cfdk::k_mgc_restrict<R><<<grd_c, blk, 0, stream>>>(L.dev, a, L.rho, C.mx, c_lo, C.rho);
+    cfdk::k_mgc_restrict<R><<<grd_c, blk, 0, stream>>>(L.dev, a, L.rho, C.mx, c_lo, C.rho, mg_scalars);
     ++launches;
     if (dist && !lvl_dist(l + 1) && (rc = gather_level(C.rho, l + 1))) return rc;
     if ((rc = mg_coarse_vcycle(l + 1))) return rc;
@@ -1061,11 +1096,11 @@ struct ModelImpl final : ModelBase {
       // strips: also correct the neighbours' edge rows (halo), from the parent's halo rows
       const int p_lo = dist ? (lo > 0 ? lo - 1 : 0) : 0, p_hi = dist ? (hi < L.my ? hi + 1 : L.my) : L.my;
       const dim3 grd_p((L.mx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, p_hi - p_lo);
-      cfdk::k_mgc_prolong<R><<<grd_p, blk, 0, stream>>>(L.mx, a, C.mx, C.cur, p_lo);
+      cfdk::k_mgc_prolong<R><<<grd_p, blk, 0, stream>>>(L.mx, a, C.mx, C.cur, p_lo, mg_scalars);
       ++launches;
     }
     for (int s = 0; s < nu_s; ++s) {
-      cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, omega, 0, lo);
+      cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, omega, 0, lo, mg_scalars);
       ++launches;
       std::swap(a, b);
       if (dist && (rc = exchange_level(a, l))) return rc;
@@ -1077,6 +1112,7 @@ struct ModelImpl final : ModelBase {
   cfdk::MgFine<R> mg_fine(R dt_sub) const {
     cfdk::MgFine<R> c;
     c.dx_sq = dx * dx; c.dy_sq = dy * dy; c.dt = dt_sub; c.tol = R(opt.consts.cg_tolerance);
+    c.ddx_sq = div_dx_sq; c.ddy_sq = div_dy_sq;
     c.n_unknowns = R((size_t)(nx - 2) * (size_t)(ny - 2));
     c.nx = nx; c.ny = ny; c.cavity = scenario == CFD_SCENARIO_CAVITY;
     c.row_lo = sweep_row_begin(); c.row_hi = sweep_row_end();
@@ -1120,20 +1156,24 @@ struct ModelImpl final : ModelBase {
                                                                            cfdk::SweepPeer<R>{}, dot);
       else
         cfdk::k_jacobi_sweep5<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_mg_b[zc], tmap_mg_rho, mg_b[zo].v, mg_err, 0,
-                                                                      cfdk::SweepPeer<R>{});
+                                                                      cfdk::SweepPeer<R>{}, dot);
       if (prof_smoother) {
         cudaEventRecord(ev_prof[ev_prof_used + 1], stream);
         ev_prof_used += 2;
       }
       ++launches;
+      if (with_dot) {  // rho.z from the sweep's per-block partials (-> beta)
+        cfdk::k_mg_reduce<R><<<1, 1024, 0, stream>>>(c, mg_scalars, mg_partials, (int)(grd2.x * grd2.y), 1);
+        ++launches;
+      }
       std::swap(zc, zo);
       return exchange_halo(mg_b[zc], ja, jb, 1);  // strips: the neighbours' new edge rows (no-op on one GPU)
     };
     {
       // first sweep from z = 0: pointwise (k_mg_first_sweep) instead of a stencil sweep over a zero field
       const dim3 g_vec((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads), (rows + cfdk::kMgRows - 1) / cfdk::kMgRows);
-      cfdk::k_mg_first_sweep<R><<<g_vec, cfdk::kMgThreads, 0, stream>>>(c, c2.omega, c2.one_minus_omega, div_denom.y,
-                                                                        mg_rho.v, mg_b[zc].v);
+      cfdk::k_mg_first_sweep<R><<<g_vec, cfdk::kMgThreads, 0, stream>>>(c, c2.omega, c2.one_minus_omega, div_denom,
+                                                                        mg_rho.v, mg_b[zc].v, mg_scalars);
       ++launches;
       if ((rc = exchange_halo(mg_b[zc], ja, jb, 1))) return rc;
     }
@@ -1143,7 +1183,7 @@ struct ModelImpl final : ModelBase {
       MgLevelHost& C = mg[1];
       const int c_lo = world > 1 ? lvl_lo(1, rank) : 0, c_hi = world > 1 ? lvl_hi(1, rank) : C.my;
       const dim3 blk(cfdk::kMgThreads), grd_c((C.mx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, c_hi - c_lo);
-      cfdk::k_mg_fine_restrict<R><<<grd_c, blk, 0, stream>>>(c, mg_b[zc].v, mg_rho.v, C.mx, c_lo, C.rho);
+      cfdk::k_mg_fine_restrict<R><<<grd_c, blk, 0, stream>>>(c, mg_b[zc].v, mg_rho.v, C.mx, c_lo, C.rho, mg_scalars);
       ++launches;
       if (world > 1 && !lvl_dist(1) && (rc = gather_level(C.rho, 1))) return rc;
       if ((rc = mg_coarse_vcycle(1))) return rc;
@@ -1151,7 +1191,7 @@ struct ModelImpl final : ModelBase {
       const int p_lo = world > 1 && c.row_lo > 1 ? c.row_lo - 1 : c.row_lo;
       const int p_hi = world > 1 && c.row_hi < ny - 1 ? c.row_hi + 1 : c.row_hi;
       const dim3 g_int((nx - 2 + cfdk::kMgThreads - 1) / cfdk::kMgThreads, p_hi - p_lo);
-      cfdk::k_mg_fine_prolong<R><<<g_int, blk, 0, stream>>>(c, mg_b[zc].v, C.mx, C.cur, p_lo);
+      cfdk::k_mg_fine_prolong<R><<<g_int, blk, 0, stream>>>(c, mg_b[zc].v, C.mx, C.cur, p_lo, mg_scalars);
       ++launches;
     }
     for (int s = 0; s < nu_s; ++s)
@@ -1162,9 +1202,71 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
 
-  int mgcg_solve(R dt_sub, int call_index, R* residual_out) {
+  // ---- carried start-vector state (see the members' comment) ----
+  cfdk::MgStart<R> mg_start(bool warm) const {
+    cfdk::MgStart<R> g;
+    g.a = g.b = g.c = nullptr;
+    g.mode = 0;
+    if (!warm) return g;
+    if (mg_guess_explicit) { g.a = mg_guess.v; g.mode = 1; return g; }
+    g.a = mg_hist[0].v; g.b = mg_hist[1].v; g.c = mg_hist[2].v;
+    g.mode = opt.consts.mg_warm_start;
+    return g;
+  }
+  void rotate_hist_names() {  // (h0, h1, h2) <- (h2's buffer, h0, h1)
+    std::swap(mg_hist[1], mg_hist[2]); std::swap(tmap_hist[1], tmap_hist[2]);
+    std::swap(mg_hist[0], mg_hist[1]); std::swap(tmap_hist[0], tmap_hist[1]);
+  }
+  // the hot path: p' is about to be overwritten by an MGCG solve -> the old p' buffer becomes h0, the retired h2 buffer p'
+  void rotate_mg_by_swap() {
+    if (!mg_rotate_pending) return;
+    std::swap(pp[ipp], mg_hist[2]);
+    std::swap(tmap_pp[ipp], tmap_hist[2]);
+    rotate_hist_names();
+    mg_rotate_pending = false;
+  }
+  // everything else (state read-back / overwrite, other solvers, peer-mapped p' buffers): same result by a copy
+  int resolve_mg_rotation() {
+    if (!mg_rotate_pending) return CFD_OK;
+    const size_t rl = (size_t)nx, rows = (size_t)(jb - ja) + 2;  // owned rows and one halo row each side
+    CFD_CUDA(cudaMemcpyAsync(mg_hist[2].row(ja - 1), pp[ipp].row(ja - 1), rows * rl * sizeof(R), cudaMemcpyDeviceToDevice, stream));
+    rotate_hist_names();
+    mg_rotate_pending = false;
+    return CFD_OK;
+  }
+  int materialize_pp_zero() {
+    if (!pp_zero_pending) return CFD_OK;
+    int rc;
+    if ((rc = resolve_mg_rotation())) return rc;  // pp[ipp] may still hold the last first-solve's result
+    CFD_CUDA(cudaMemsetAsync(pp[ipp].row(ja - 1), 0, ((size_t)(jb - ja) + 2) * (size_t)nx * sizeof(R), stream));
+    pp_zero_pending = false;
+    return CFD_OK;
+  }
+  // the complete star fields, should anyone ask for them while they alias the current ones
+  int materialize_star() {
+    if (!star_alias) return CFD_OK;
+    dim3 blk(256), grd((nx + 1 + 255) / 256, v_row_end() - ja);
+    cfdk::k_star_materialize<R><<<grd, blk, 0, stream>>>(nx, ny, solid.v, ubuf[iu].v, vbuf[iu].v, ubuf[ius].v, vbuf[ius].v, ja, jb,
+                                                         v_row_end());
+    CFD_CUDA(cudaGetLastError());
+    star_alias = false;
+    return CFD_OK;
+  }
+
+  // set-up shared by every MGCG solve, before the divergence kernel (which may already accumulate rho.rho)
+  int mgcg_begin() {
     int rc;
     if (mg.empty() && (rc = mg_setup())) return rc;
+    cfdk::MgScalars init;
+    memset(&init, 0, sizeof init);
+    init.max_iterations = opt.consts.cg_max_iterations;
+    *h_mg = init;
+    CFD_CUDA(cudaMemcpyAsync(mg_scalars, h_mg, sizeof init, cudaMemcpyHostToDevice, stream));
+    return CFD_OK;
+  }
+
+  int mgcg_solve(R dt_sub, int call_index, R* residual_out, bool decided_early, bool* elided) {
+    int rc;
     const cfdk::MgFine<R> c = mg_fine(dt_sub);
     const dim3 blk(cfdk::kMgThreads);
     const unsigned gx = (unsigned)((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads));
@@ -1172,57 +1274,76 @@ struct ModelImpl final : ModelBase {
     const dim3 g_all(gx, (jb - ja + cfdk::kMgRows - 1) / cfdk::kMgRows);            // every owned row (init)
     const dim3 g_dir(gx, (rows + cfdk::kMgDirRows - 1) / cfdk::kMgDirRows);         // owned rows of unknowns, 4-row tiles
     const dim3 g_upd(gx, (rows + cfdk::kMgUpdRows - 1) / cfdk::kMgUpdRows);
+    const bool first_solve = call_index == 0;
+    const bool warm = first_solve && opt.consts.mg_warm_start != 0;
+    int& pred = mg_pred[first_solve ? 0 : 1];
+    CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index], stream));
+    auto read_scalars = [&]() -> int {
+      CFD_CUDA(cudaMemcpyAsync(h_mg, mg_scalars, sizeof(cfdk::MgScalars), cudaMemcpyDeviceToHost, stream));
+      CFD_CUDA(cudaStreamSynchronize(stream));
+      return CFD_OK;
+    };
+    if (decided_early) {
+      // rho.rho came out of the divergence kernel (rho = rhs for a cold start)
+      if (world > 1 && (rc = mg_finish_strips(c, 0))) return rc;
+      if ((rc = read_scalars())) return rc;
+      if (h_mg->done) {  // converged with p' = 0: no set-up pass, no corrector
+        CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index + 1], stream));
+        pp_zero_pending = true;
+        pred = 0;
+        last_K += 1;
+        *residual_out = (R)h_mg->measure;
+        *elided = true;
+        return CFD_OK;
+      }
+    }
+    // p' is overwritten from here on: the last first-solve's result moves into the history by a buffer swap
+    // (peer-mapped p' buffers, Mode R's fused strips, must stay where they are: copy instead)
+    if (peer_ready) { if ((rc = resolve_mg_rotation())) return rc; }
+    else rotate_mg_by_swap();
+    pp_zero_pending = false;
     const Field<R>& xf = pp[ipp];
     R* x = xf.v;
     R* w = pp[ipp ^ 1].v;
-    cfdk::MgScalars init;
-    memset(&init, 0, sizeof init);
-    init.max_iterations = opt.consts.cg_max_iterations;
-    *h_mg = init;
-    CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index], stream));
-    CFD_CUDA(cudaMemcpyAsync(mg_scalars, h_mg, sizeof init, cudaMemcpyHostToDevice, stream));
-    // first solve of a step: start from mg_guess (mg_warm_start); its stencil needs the neighbours' edge rows
-    const bool first_solve = call_index == 0;
-    const bool warm = first_solve && opt.consts.mg_warm_start != 0;
-    if (warm && (rc = exchange_halo(mg_guess, ja, jb, 1))) return rc;
-    cfdk::k_mg_init<R><<<g_all, blk, 0, stream>>>(c, mg_scalars, rhs.v, warm ? mg_guess.v : nullptr, x, mg_rho.v,
-                                                  mg_b[mg_id].v, mg_partials, mg_ticket);
+    // first solve of a step: start from the extrapolated history (mg_warm_start); the stencil of the start vector needs
+    // the neighbours' edge rows, which every p' carries since the exchange at the end of its solve
+    if (warm && mg_guess_explicit && (rc = exchange_halo(mg_guess, ja, jb, 1))) return rc;
+    cfdk::k_mg_init<R><<<g_all, blk, 0, stream>>>(c, mg_scalars, rhs.v, mg_start(warm), x, mg_rho.v, mg_partials, mg_ticket);
     launches += 1;
+    if (warm) mg_guess_explicit = false;
     if ((rc = mg_finish_strips(c, 0))) return rc;
-    for (;;) {
-      CFD_CUDA(cudaMemcpyAsync(h_mg, mg_scalars, sizeof init, cudaMemcpyDeviceToHost, stream));
-      CFD_CUDA(cudaStreamSynchronize(stream));
-      if (h_mg->done) break;
-      int zi = 0;
-      if ((rc = mg_precondition(c, &zi))) return rc;
-      // rho.z (-> beta) came out of the V-cycle's last sweep; d_new goes to the smoothing buffer that is free now
-      const int dn = 3 - mg_id - zi;
-      cfdk::k_mg_dir_apply<R><<<g_dir, blk, 0, stream>>>(c, mg_scalars, mg_b[zi].v, mg_b[mg_id].v, mg_b[dn].v, w, mg_partials,
-                                                         mg_ticket);
-      mg_id = dn;
-      if ((rc = mg_finish_strips(c, 2))) return rc;
-      if ((rc = exchange_halo(mg_b[mg_id], ja, jb, 1))) return rc;  // strips: d's edge rows for the next L d
-      cfdk::k_mg_update<R><<<g_upd, blk, 0, stream>>>(c, mg_scalars, mg_b[mg_id].v, w, x, mg_rho.v, mg_partials, mg_ticket);
-      launches += 2;
-      if ((rc = mg_finish_strips(c, 3))) return rc;
-      CFD_CUDA(cudaGetLastError());
+    // CG iterations are enqueued in batches of the count this solve took last time; every kernel of an iteration is a
+    // no-op once the device-side `done` flag is up, so the host synchronises once per batch, not once per iteration
+    int batch = pred > 0 ? pred : 1;
+    if (!decided_early && pred == 0) {  // expected to converge at once: look before enqueuing a whole V-cycle
+      if ((rc = read_scalars())) return rc;
+      if (h_mg->done) batch = 0;
     }
+    while (batch > 0) {
+      for (int it = 0; it < batch; ++it) {
+        int zi = 0;
+        if ((rc = mg_precondition(c, &zi))) return rc;
+        // rho.z (-> beta) came out of the V-cycle's last sweep; d_new goes to the smoothing buffer that is free now
+        const int dn = 3 - mg_id - zi;
+        cfdk::k_mg_dir_apply<R><<<g_dir, blk, 0, stream>>>(c, mg_scalars, mg_b[zi].v, mg_b[mg_id].v, mg_b[dn].v, w, mg_partials,
+                                                           mg_ticket);
+        mg_id = dn;
+        if ((rc = mg_finish_strips(c, 2))) return rc;
+        if ((rc = exchange_halo(mg_b[mg_id], ja, jb, 1))) return rc;  // strips: d's edge rows for the next L d
+        cfdk::k_mg_update<R><<<g_upd, blk, 0, stream>>>(c, mg_scalars, mg_b[mg_id].v, w, x, mg_rho.v, mg_partials, mg_ticket);
+        launches += 2;
+        if ((rc = mg_finish_strips(c, 3))) return rc;
+      }
+      CFD_CUDA(cudaGetLastError());
+      if ((rc = read_scalars())) return rc;
+      batch = h_mg->done ? 0 : 1;
+    }
+    pred = h_mg->iterations;
     const int n_edge = (nx > ny ? nx : ny);
     cfdk::k_cg_fill_boundary<R><<<(n_edge + 255) / 256, 256, 0, stream>>>(nx, ny, c.cavity, x, ja, jb);
     ++launches;
     if ((rc = exchange_halo(xf, ja, jb, 1))) return rc;  // the corrector reads p'[j-1] (src/model.rs:1380)
-    if (first_solve) {
-      if (opt.consts.mg_warm_start == 3) {
-        cfdk::k_mg_extrapolate2<R><<<148 * 8, cfdk::kMgThreads, 0, stream>>>(xf.row(ja), mg_last.row(ja), mg_last2.row(ja),
-                                                                            mg_guess.row(ja), own_p());
-        ++launches;
-      } else if (opt.consts.mg_warm_start == 2) {
-        cfdk::k_mg_extrapolate<R><<<148 * 8, cfdk::kMgThreads, 0, stream>>>(xf.row(ja), mg_last.row(ja), mg_guess.row(ja), own_p());
-        ++launches;
-      } else {
-        CFD_CUDA(cudaMemcpyAsync(mg_guess.row(ja), xf.row(ja), own_p() * sizeof(R), cudaMemcpyDeviceToDevice, stream));
-      }
-    }
+    if (first_solve) mg_rotate_pending = true;           // this p' is the newest entry of the start-vector history
     CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index + 1], stream));
     CFD_CUDA(cudaGetLastError());
     last_S += (uint64_t)h_mg->iterations;
@@ -1235,7 +1356,7 @@ struct ModelImpl final : ModelBase {
                 const Field<R>& uo, const Field<R>& vo) {
     dim3 blk(256), grd((nx + 1 + 255) / 256, v_row_end() - ja);
     cfdk::k_corrector<R><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, uk.v, vk.v, pp[ipp].v, uo.v, vo.v, p.v,
-                                                  ja, jb, v_row_end());
+                                                  ja, jb, v_row_end(), h_divs.dx, h_divs.dy);
     ++launches;
     CFD_CUDA(cudaGetLastError());
     return CFD_OK;
@@ -1256,8 +1377,10 @@ struct ModelImpl final : ModelBase {
     } else {
       current_inlet_velocity = target_inlet_velocity;
     }
+    int rc0;
     const R dt_sub = dt / R(substep_count);  // :317
     last_piso_substeps = substep_count;
+    if ((rc0 = refresh_dt_divisor(dt_sub))) return rc0;
     last_K = 0;
     last_S = 0;
     int rc;
@@ -1269,17 +1392,24 @@ struct ModelImpl final : ModelBase {
       const auto s = scalars(dt_sub);
       const int ju_lo = ja > 1 ? ja : 1, ju_hi = jb < ny - 1 ? jb : ny - 1;      // u rows 1..ny-2
       const int jv_lo = ja > 1 ? ja : 1, jv_hi = v_row_end() < ny ? v_row_end() : ny;  // v rows 1..ny-1
-      dim3 blk(256);
-      dim3 gu((nx + 255) / 256, ju_hi - ju_lo), gv((nx - 1 + 255) / 256, jv_hi - jv_lo);
+      cfdk::PredDivs<R> pd;
+      pd.dx = h_divs.dx; pd.dy = h_divs.dy; pd.dx_sq = h_divs.dx_sq; pd.dy_sq = h_divs.dy_sq;
       if (velocity_scheme == CFD_SCHEME_SECOND_ORDER) {
-        cfdk::k_predict_u<R, true><<<gu, blk, 0, stream>>>(s, ubuf[X].v, vbuf[X].v, mask_u.v, ubuf[Y].v, ju_lo, ju_hi);
-        cfdk::k_predict_v<R, true><<<gv, blk, 0, stream>>>(s, ubuf[X].v, vbuf[X].v, mask_v.v, vbuf[Y].v, jv_lo, jv_hi);
+        dim3 blk(256);
+        dim3 gu((nx + 255) / 256, ju_hi - ju_lo), gv((nx - 1 + 255) / 256, jv_hi - jv_lo);
+        cfdk::k_predict_u<R, true><<<gu, blk, 0, stream>>>(s, pd, ubuf[X].v, vbuf[X].v, mask_u.v, ubuf[Y].v, ju_lo, ju_hi);
+        cfdk::k_predict_v<R, true><<<gv, blk, 0, stream>>>(s, pd, ubuf[X].v, vbuf[X].v, mask_v.v, vbuf[Y].v, jv_lo, jv_hi);
+        launches += 2;
       } else {
-        cfdk::k_predict_u<R, false><<<gu, blk, 0, stream>>>(s, ubuf[X].v, vbuf[X].v, mask_u.v, ubuf[Y].v, ju_lo, ju_hi);
-        cfdk::k_predict_v<R, false><<<gv, blk, 0, stream>>>(s, ubuf[X].v, vbuf[X].v, mask_v.v, vbuf[Y].v, jv_lo, jv_hi);
+        // first order: both equations in one pass over u and v
+        const int j_end = ju_hi > jv_hi ? ju_hi : jv_hi;
+        dim3 blk(128), grd((nx + 127) / 128, (j_end - ju_lo + cfdk::kPredRows - 1) / cfdk::kPredRows);
+        cfdk::k_predict_first<R><<<grd, blk, 0, stream>>>(s, pd, ubuf[X].v, vbuf[X].v, mask_u.v, mask_v.v, ubuf[Y].v, vbuf[Y].v,
+                                                          ju_lo, ju_hi, jv_hi);
+        launches += 1;
       }
-      launches += 2;
       CFD_CUDA(cudaGetLastError());
+      star_alias = false;  // interior written by the predictor, the carried entries were saved when the alias was made
     }
     // ---- first pressure solve + corrector (:676-693): new u, v go to the free buffer, keeping X as u_old
     R residual = 0;
@@ -1288,13 +1418,39 @@ struct ModelImpl final : ModelBase {
     if ((rc = corrector(dt_sub, ubuf[Y], vbuf[Y], ubuf[X], vbuf[X], ubuf[Z], vbuf[Z]))) return rc;
     int cur = Z, star = Y;
     // ---- outer re-correction loop (:696-724): `star <- current` is a role swap
+    bool alias = false;
     for (int it = 0; it < opt.consts.outer_rounds; ++it) {
-      const int t = star; star = cur; cur = t;  // star now aliases the latest u, v; `cur` is overwritten in full
-      if ((rc = pressure_solve(dt_sub, ubuf[star], vbuf[star], it + 1, &residual))) return rc;
+      { const int t = star; star = cur; cur = t; }  // star now aliases the latest u, v; `cur` is overwritten in full
+      bool elided = false;
+      if ((rc = pressure_solve(dt_sub, ubuf[star], vbuf[star], it + 1, &residual, &elided))) return rc;
       last_pressure_residual = residual;
-      if ((rc = corrector(dt_sub, ubuf[star], vbuf[star], ubuf[star], vbuf[star], ubuf[cur], vbuf[cur]))) return rc;
+      if (elided) {
+        // p' == 0: the corrector would copy star to cur unchanged (u* - dt * 0, p + 0).  Keep the roles instead: the
+        // latest fields stay current, the star fields logically equal them (star_alias)
+        { const int t = star; star = cur; cur = t; }
+        alias = true;
+      } else {
+        if ((rc = corrector(dt_sub, ubuf[star], vbuf[star], ubuf[star], vbuf[star], ubuf[cur], vbuf[cur]))) return rc;
+        alias = false;
+      }
       if (last_pressure_residual < R(opt.consts.outer_tolerance)) break;  // :721
     }
+    if (alias) {
+      // the entries of the star fields that stay observable or that the boundary conditions are about to
+      // change in the current fields: copy them now, before :728
+      const int n = (nx > ny ? nx : ny) + 2;
+      cfdk::k_star_save_edges<R><<<(n + 255) / 256, 256, 0, stream>>>(nx, ny, ubuf[cur].v, vbuf[cur].v, ubuf[star].v, vbuf[star].v,
+                                                                      ja, jb, v_row_end(), owns_bottom ? 1 : 0, owns_top ? 1 : 0);
+      ++launches;
+      const int sj0 = solid_j0 > ja ? solid_j0 : ja, sj1 = solid_j1 < jb ? solid_j1 : jb;
+      if (solid_i1 > solid_i0 && sj1 > sj0) {
+        dim3 blk(256), grd((solid_i1 - solid_i0 + 255) / 256, sj1 - sj0);
+        cfdk::k_star_save_solids<R><<<grd, blk, 0, stream>>>(nx, solid.v, ubuf[cur].v, vbuf[cur].v, ubuf[star].v, vbuf[star].v,
+                                                             solid_i0, solid_i1, sj0, sj1);
+        ++launches;
+      }
+    }
+    star_alias = alias;
     // ---- boundary conditions (:728 -> :827-875)
     {
       cfdk::BcScalars<R> b;
@@ -1304,9 +1460,13 @@ struct ModelImpl final : ModelBase {
       const int n = (nx > ny ? nx : ny) + 1;
       cfdk::k_bc_edges<R><<<(n + 255) / 256, 256, 0, stream>>>(b, ubuf[cur].v, vbuf[cur].v, ja, jb, owns_bottom ? 1 : 0,
                                                               owns_top ? 1 : 0);
-      dim3 blk(256), grd((nx + 255) / 256, jb - ja);
-      cfdk::k_bc_solids<R><<<grd, blk, 0, stream>>>(nx, solid.v, ubuf[cur].v, vbuf[cur].v, ja, jb);
-      launches += 2;
+      ++launches;
+      const int sj0 = solid_j0 > ja ? solid_j0 : ja, sj1 = solid_j1 < jb ? solid_j1 : jb;
+      if (solid_i1 > solid_i0 && sj1 > sj0) {  // :869-874 over the obstacle's bounding box
+        dim3 blk(256), grd((solid_i1 - solid_i0 + 255) / 256, sj1 - sj0);
+        cfdk::k_bc_solids<R><<<grd, blk, 0, stream>>>(nx, solid.v, ubuf[cur].v, vbuf[cur].v, solid_i0, solid_i1, sj0, sj1);
+        ++launches;
+      }
     }
     // ---- residuals and CFL maxima (:333-348, :878-881) over the owned rows, then over the ranks
     CFD_CUDA(cudaMemsetAsync(step_slots, 0, 4 * sizeof(unsigned long long), stream));
@@ -1515,7 +1675,19 @@ struct ModelImpl final : ModelBase {
   }
 
   // first owned entry and owned length of a real field
-  R* real_field(int field, size_t* n) {
+  R* real_field(int field, size_t* n, bool for_write = false) {
+    // logical state -> physical buffers first (all rare paths: parity harness / restart)
+    const bool star = field == CFD_FIELD_U_STAR || field == CFD_FIELD_V_STAR;
+    const bool current = field == CFD_FIELD_U || field == CFD_FIELD_V;
+    if ((star || (for_write && current)) && materialize_star() != CFD_OK) { *n = 0; return nullptr; }
+    if (field == CFD_FIELD_P_PRIME && materialize_pp_zero() != CFD_OK) { *n = 0; return nullptr; }
+    if (field == CFD_FIELD_P_PRIME && for_write && resolve_mg_rotation() != CFD_OK) { *n = 0; return nullptr; }
+    if (for_write && (field == CFD_FIELD_MG_LAST || field == CFD_FIELD_MG_LAST2) && !mg_guess_explicit) {
+      // the start vector is independent state in the oracle: pin its current value before the history changes
+      size_t ng;
+      if (!real_field(CFD_FIELD_MG_GUESS, &ng)) { *n = 0; return nullptr; }
+      mg_guess_explicit = true;
+    }
     switch (field) {
       case CFD_FIELD_P: *n = own_p(); return p.row(ja);
       case CFD_FIELD_U: *n = own_u(); return ubuf[iu].row(ja);
@@ -1529,10 +1701,25 @@ struct ModelImpl final : ModelBase {
       case CFD_FIELD_V_OLD: *n = own_v(); return vbuf[ifree].row(ja);
       case CFD_FIELD_MG_GUESS:
       case CFD_FIELD_MG_LAST:
-      case CFD_FIELD_MG_LAST2:
-        if (!mg_guess.base && mg_setup() != CFD_OK) { *n = 0; return nullptr; }
+      case CFD_FIELD_MG_LAST2: {
+        if (mg.empty() && mg_setup() != CFD_OK) { *n = 0; return nullptr; }
+        if (resolve_mg_rotation() != CFD_OK) { *n = 0; return nullptr; }
         *n = own_p();
-        return field == CFD_FIELD_MG_GUESS ? mg_guess.row(ja) : (field == CFD_FIELD_MG_LAST ? mg_last.row(ja) : mg_last2.row(ja));
+        if (field == CFD_FIELD_MG_LAST) return mg_hist[0].row(ja);
+        if (field == CFD_FIELD_MG_LAST2) return mg_hist[1].row(ja);
+        // the start vector is derived state: write it out (unless it was set explicitly)
+        if (!mg_guess.base && falloc(&mg_guess, (size_t)nx) != CFD_OK) { *n = 0; return nullptr; }
+        if (!mg_guess_explicit) {
+          cfdk::MgStart<R> g = mg_start(opt.consts.mg_warm_start != 0);
+          if (g.mode == 0) { g.a = mg_hist[0].v; g.mode = 1; }  // cold starts: the oracle still records the last p'
+          // from one halo row below to one above the owned rows (an explicit start vector needs its halo)
+          const size_t off = (size_t)((long)ja * (long)nx);
+          cfdk::MgStart<R> go = g;
+          go.a = g.a + off; go.b = g.b ? g.b + off : nullptr; go.c = g.c ? g.c + off : nullptr;
+          cfdk::k_mg_start_materialize<R><<<148 * 8, cfdk::kMgThreads, 0, stream>>>(go, mg_guess.row(ja), own_p());
+        }
+        return mg_guess.row(ja);
+      }
       default: *n = 0; return nullptr;
     }
   }
@@ -1572,7 +1759,7 @@ struct ModelImpl final : ModelBase {
   int set_field_f64(int field, const double* in, uint64_t len) override {
     CFD_CUDA(cudaSetDevice(device));
     size_t n;
-    R* dst = real_field(field, &n);
+    R* dst = real_field(field, &n, true);
     if (!dst) return fail(CFD_ERR_INVALID_ARGUMENT, "set_field_f64: field is not writable");
     if (len != n) return fail(CFD_ERR_INVALID_ARGUMENT, "set_field_f64: wrong length");
     int rc;
@@ -1582,8 +1769,11 @@ struct ModelImpl final : ModelBase {
     cfdk::k_from_f64<R><<<148 * 8, 256, 0, stream>>>((const double*)staging, dst, n);
     CFD_CUDA(cudaGetLastError());
     CFD_CUDA(cudaStreamSynchronize(stream));
-    // strips: p' halos are state too (they are refreshed only after a sweep)
+    // strips: p' halos are state too (they are refreshed only after a sweep); so are those of the start-vector history
     if (field == CFD_FIELD_P_PRIME && (rc = exchange_halo(pp[ipp], ja, jb, 1))) return rc;
+    if (field == CFD_FIELD_MG_LAST && (rc = exchange_halo(mg_hist[0], ja, jb, 1))) return rc;
+    if (field == CFD_FIELD_MG_LAST2 && (rc = exchange_halo(mg_hist[1], ja, jb, 1))) return rc;
+    if (field == CFD_FIELD_MG_GUESS) mg_guess_explicit = true;
     return CFD_OK;
   }
 

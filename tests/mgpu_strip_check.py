@@ -13,6 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cfd_demo_b200 import _abi  # noqa: E402
 from cfd_demo_b200.model import Model, nccl_unique_id  # noqa: E402
 from cfd_demo_b200.types import Cylinder, Grid, InletProfile, SimulationParams, VelocityScheme  # noqa: E402
+from oracle.cpu_oracle import OracleModel  # noqa: E402  (tests/ may use the oracle as the checker)
 
 
 def main():
@@ -42,7 +43,14 @@ def main():
          SimulationParams(velocity_scheme=VelocityScheme.SecondOrder, inlet_profile=InletProfile.Parabolic), 64, 14, 0),
         (Grid.uniform(264, 96, 30.0, 10.0, None), SimulationParams(velocity_scheme=VelocityScheme.SecondOrder), 32, 14, 0),
         (Grid.uniform(1040, 400, 30.0, 10.0, Cylinder(7.5, 5.0, 0.75)), SimulationParams(), 64, 12, 0),
+        # BASELINE configs[3]: channel past a masked cylinder, 8192 x 2048, reference defaults, into the saturated regime
+        # (K = 21, S = 1050 from about step 24 on), both velocity schemes
+        (Grid.uniform(8192, 2048, 40.0, 10.0, Cylinder(10.0, 5.0, 0.75)), SimulationParams(), 64, 28, 0),
+        (Grid.uniform(8192, 2048, 40.0, 10.0, Cylinder(10.0, 5.0, 0.75)),
+         SimulationParams(velocity_scheme=VelocityScheme.SecondOrder), 64, 26, 0),
     ]
+    if os.environ.get("CFD_STRIP_CHECK_SMALL") == "1":
+        cases = cases[:4]
     only_peer = os.environ.get("CFD_STRIP_CHECK_PEER") == "only"
     if only_peer:
         cases = []
@@ -62,6 +70,8 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         strip = Model.strip(grid, params, rank, world, uid[0], device=local, precision=precision, flags=flags)
         whole = Model(grid, params, precision=precision)
+        # small cases: the CPU oracle itself is the third party (strips == single domain == oracle, all bit for bit)
+        oracle = OracleModel(grid, params, precision=precision) if grid.nx * grid.ny <= 30000 else None
         ja, jb = strip.rows()
         nx, ny = grid.nx, grid.ny
         top = 1 if rank == world - 1 else 0
@@ -72,8 +82,14 @@ def main():
             assert (rs.jacobi_calls, rs.sweeps) == (rw.jacobi_calls, rw.sweeps), (ci, s, rs, rw)
             for k in ("dt", "p", "u", "v", "simulation_time"):
                 assert rs.f64[k] == rw.f64[k], (ci, s, k, rs.f64[k], rw.f64[k])
+            if oracle is not None:
+                oracle.update()
+                ro = oracle.get_residuals()
+                assert (rs.jacobi_calls, rs.sweeps, rs.f64["p"], rs.f64["u"]) == (ro.jacobi_calls, ro.sweeps, ro.f64["p"], ro.f64["u"]), (ci, s)
         for fid in fields:
-            a, b = strip.field(fid), whole.field(fid)
+            a, b = strip.field(fid), (oracle.field(fid) if oracle is not None else whole.field(fid))
+            if oracle is not None:
+                assert np.array_equal(whole.field(fid), b), (ci, rank, "single domain vs oracle", _abi.FIELD_NAMES[fid])
             if fid in (_abi.FIELD_U, _abi.FIELD_U_STAR, _abi.FIELD_U_OLD, _abi.FIELD_MASK_U):
                 ref = b.reshape(ny, nx + 1)[ja:jb].ravel()
             elif fid in (_abi.FIELD_V, _abi.FIELD_V_STAR, _abi.FIELD_V_OLD, _abi.FIELD_MASK_V):
@@ -85,6 +101,8 @@ def main():
         snap = strip.get_snapshot()
         assert np.array_equal(snap.u, strip.field(_abi.FIELD_U).astype(np.float32))
         assert rw.sweeps > 30
+        if grid.nx == 8192:
+            assert (rw.jacobi_calls, rw.sweeps) == (21, 1050), rw
         strip.close()
         whole.close()
         progress(f"mode R case {ci} ok")
@@ -138,6 +156,32 @@ def main():
             assert d <= 1e-9, (solver, scenario, _abi.FIELD_NAMES[fid], d)
         strip.close()
         whole.close()
+        dist.barrier()
+    # Mode C / MGCG at the SHIPPED stopping tolerance (cg_tolerance 1e-8), strips against the CPU ORACLE's fields directly
+    if not only_peer:
+        grid = Grid.uniform(520, 264, 520 / 256.0, 264 / 256.0, None)
+        params = SimulationParams(dt=2e-5, viscosity=0.01, scenario=Scenario.Cavity, pressure_solver=PressureSolver.MGCG)
+        uid = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        strip = Model.strip(grid, params, rank, world, uid[0], device=local)
+        oracle = OracleModel(grid, params, precision=64)
+        ja, jb = strip.rows()
+        nx, ny = grid.nx, grid.ny
+        top = 1 if rank == world - 1 else 0
+        differ = 0
+        for s in range(40):
+            strip.update()
+            oracle.update()
+            rs, ro = strip.get_residuals(), oracle.get_residuals()
+            assert rs.jacobi_calls == ro.jacobi_calls and abs(rs.sweeps - ro.sweeps) <= 1 and rs.f64["p"] <= 1e-8, (s, rs, ro)
+            differ += rs.sweeps != ro.sweeps
+        assert differ <= 3, differ
+        for fid, shape, hi in ((_abi.FIELD_P, (ny, nx), jb), (_abi.FIELD_U, (ny, nx + 1), jb), (_abi.FIELD_V, (ny + 1, nx), jb + top)):
+            a, b = strip.field(fid), oracle.field(fid).reshape(shape)[ja:hi].ravel()
+            d = np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+            progress(f"  shipped tolerance vs oracle: {_abi.FIELD_NAMES[fid]} rel l2 {d:.3e}")
+            assert d <= 1e-7, (_abi.FIELD_NAMES[fid], d)
+        strip.close()
         dist.barrier()
     if rank == 0:
         print(f"strips ok: {world} ranks bit-identical to the single-domain model on {len(cases)} cases")
