@@ -38,26 +38,37 @@ import numpy as np  # noqa: E402
 
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
+STOP_RULE_REL = ("||r||_2 <= 1e-8 * ||rhs||_2 of the step's first solve (cfd_solver_consts::cg_relative = 1, the relative L2 "
+                 "norm SURVEY 8d states for this config); re-correction solves measure against the same reference")
+
 WORKLOADS = {
     # BASELINE.json configs[2] / SURVEY 8(d) config 3: cavity Re = 1000 at 4096^2, dt below the explicit diffusion
-    # limit dx^2 / (4 nu) = 1.49e-5, pressure solve converged to 1e-8 (Mode C, MGCG).  Spin-up runs through the
-    # reference's 100-step ramp of the driving velocity (src/model.rs:311-316).
-    "cavity4096_modeC": dict(kind="modeC", nx=4096, ny=4096, lx=1.0, ly=1.0, cylinder=None, spinup=110,
+    # limit dx^2 / (4 nu) = 1.49e-5, pressure solve converged to a relative residual of 1e-8 (Mode C, MGCG).  Spin-up runs
+    # through the reference's 100-step ramp of the driving velocity (src/model.rs:311-316) and 40 steps beyond it, where
+    # every solve takes the same number of iterations (the count steps down 6 -> 3 in the 25 steps after the ramp).
+    "cavity4096_modeC": dict(kind="modeC", nx=4096, ny=4096, lx=1.0, ly=1.0, cylinder=None, spinup=140,
                              params=dict(dt=1.0e-5, viscosity=1.0e-3, target_inlet_velocity=1.0, scenario=1,
                                          pressure_solver=2),
-                             desc="lid-driven cavity Re=1000, 4096x4096, fp64, pressure solve converged to dt*rms(r) <= 1e-8 "
-                                  "every step (Mode C: CG preconditioned by a multigrid V(2,2)-cycle, the reference's "
-                                  "damped-Jacobi sweep kernel as fine-level smoother)"),
+                             consts=dict(cg_relative=1, cg_tolerance=1e-8), stop_rule=STOP_RULE_REL,
+                             desc="lid-driven cavity Re=1000, 4096x4096, fp64, pressure solve converged to a relative residual "
+                                  "of 1e-8 every step (Mode C: CG preconditioned by a multigrid V(2,2)-cycle, the reference's "
+                                  "damped-Jacobi sweep as fine-level smoother)"),
     # BASELINE.json configs[4]: the 16384^2 cavity; with --gpus N the SAME grid is cut into N strips (strong scaling)
-    "cavity16384_modeC": dict(kind="modeC", nx=16384, ny=16384, lx=1.0, ly=1.0, cylinder=None, spinup=110, strong=True,
+    "cavity16384_modeC": dict(kind="modeC", nx=16384, ny=16384, lx=1.0, ly=1.0, cylinder=None, spinup=140, strong=True,
                               params=dict(dt=0.6e-6, viscosity=1.0e-3, target_inlet_velocity=1.0, scenario=1,
                                           pressure_solver=2),
-                              desc="lid-driven cavity Re=1000, 16384x16384, fp64, Mode C (MGCG) converged to dt*rms(r) <= 1e-8, "
-                                   "strong scaling (the same grid on every GPU count)"),
-    "cavity1024_modeC": dict(kind="modeC", nx=1024, ny=1024, lx=1.0, ly=1.0, cylinder=None, spinup=110,
+                              consts=dict(cg_relative=1, cg_tolerance=1e-8), stop_rule=STOP_RULE_REL,
+                              desc="lid-driven cavity Re=1000, 16384x16384, fp64, Mode C (MGCG) converged to a relative residual of "
+                                   "1e-8, strong scaling (the same grid on every GPU count)"),
+    # BASELINE.json configs[1]
+    "cavity1024_modeC": dict(kind="modeC", nx=1024, ny=1024, lx=1.0, ly=1.0, cylinder=None, spinup=140,
                              params=dict(dt=2.0e-5, viscosity=1.0e-2, target_inlet_velocity=1.0, scenario=1,
                                          pressure_solver=2),
+                             consts=dict(cg_relative=1, cg_tolerance=1e-8), stop_rule=STOP_RULE_REL,
                              desc="lid-driven cavity Re=100, 1024x1024, fp64, Mode C (MGCG), L2-resident regime"),
+    "cavity1024_modeR": dict(kind="modeR", nx=1024, ny=1024, lx=1.0, ly=1.0, cylinder=None, spinup=32,
+                             params=dict(dt=2.0e-5, viscosity=1.0e-2, target_inlet_velocity=1.0, scenario=1),
+                             desc="lid-driven cavity Re=100, 1024x1024, fp64, Mode R (the reference's Jacobi + outer loop)"),
     # the reference's own algorithm; spin-up until the dense saturated regime where every step runs K=21, S=1050
     # (until p' is non-zero everywhere the sweeps still hit the slow zero-dividend path; ~21 steps at 4096x4096,
     # ~35 for the taller multi-GPU domains)
@@ -65,6 +76,13 @@ WORKLOADS = {
                               desc="channel 4096x4096 (reference scenario), fp64, Mode R = the reference's damped "
                                    "Jacobi (<=50 sweeps) + <=20 outer re-corrections, dense saturated regime "
                                    "(K=21 solves, S=1050 sweeps per step)"),
+    # BASELINE.json configs[3]: channel past a masked cylinder, 8192 x 2048, reference defaults; with --gpus N the SAME grid
+    # is cut into N strips (strong scaling; Mode R is bit-identical for any strip count)
+    "channel8192x2048_modeR": dict(kind="modeR", nx=8192, ny=2048, lx=40.0, ly=10.0, cylinder=(10.0, 5.0, 0.75), params={},
+                                   spinup=60, strong=True,
+                                   desc="channel past a masked cylinder, 8192x2048 (40 x 10, cylinder (10, 5, r 0.75), reference "
+                                        "defaults), fp64, Mode R, saturated regime (K=21, S=1050 per step), strong scaling over "
+                                        "row strips"),
     "default800_modeR": dict(kind="modeR", nx=800, ny=264, lx=30.0, ly=10.0, cylinder=(7.5, 5.0, 0.75), params={}, spinup=26,
                              desc="reference default_grid() 800x264 + cylinder, Mode R"),
 }
@@ -89,6 +107,30 @@ def make_grid(w):
 def make_params(w):
     from cfd_demo_b200.types import SimulationParams
     return SimulationParams(**w["params"])
+
+
+def make_consts(w):
+    """The workload's solver constants (cfd_solver_consts): the reference's literals plus the workload's overrides — the
+    same struct goes to the CUDA library and to the CPU oracle."""
+    from cfd_demo_b200 import _abi
+    from cfd_demo_b200.model import load_library
+    import ctypes as C
+    c = _abi.CfdSolverConsts()
+    load_library().cfd_solver_consts_default(C.byref(c))
+    for k, v in (w.get("consts") or {}).items():
+        setattr(c, k, v)
+    return c
+
+
+def workload_config(w, nx, ny):
+    """`config` of the JSON line: identical keys and values in both arms (ours / --impl reference) for the same workload."""
+    mode_c = w["kind"] == "modeC"
+    return {"workload": w["desc"], "nx": nx, "ny": ny,
+            "solver": "mgcg" if mode_c else "jacobi (reference)",
+            "stop_rule": w.get("stop_rule", "dt * rms(r) <= 1e-8" if mode_c else
+                               "reference: max|dp'| < 1e-4 or 50 sweeps; <= 20 re-corrections (src/model.rs:696-824)"),
+            "l2": "every field (134 MB at 4096^2) is larger than L2 (126 MB); no flush needed",
+            "timing": "ours: CUDA events on the model's stream around each update(), summed over K steps; reference: wall clock"}
 
 
 class ClockSampler:
@@ -204,10 +246,11 @@ def run_reference_mode_r(args, w):
     return {
         "impl": "reference", "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": s["step_seconds"] * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong" if w.get("strong") else "weak", "vs_baseline": None,
         "dtype": "f32" if precision == 32 else "f64", "data": "synthetic",
         "timesteps_per_s": 1.0 / s["step_seconds"],
-        "config": {"workload": w["desc"], "nx": w["nx"], "ny": w["ny"], "solves_per_step": 21, "sweeps_per_step": 1050},
+        "config": workload_config(w, w["nx"], w["ny"]),
+        "solves_per_step": 21, "sweeps_per_step": 1050,
         "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": "port", "sample": sample,
                          "host_cores": os.cpu_count(), "note": CPU_NOTE},
         "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -222,17 +265,19 @@ def run_reference_mode_c(args, w):
     cpu_oracle.build()
     precision = 32 if args.ref_precision == 32 else 64
     grid, params = make_grid(w), make_params(w)
-    m = OracleModel(grid, params, precision=precision)
+    m = OracleModel(grid, params, precision=precision, consts=make_consts(w))
     budget_s = float(os.environ.get("CFD_BENCH_REF_BUDGET_S", "150"))
     t_begin = time.perf_counter()
     for _ in range(max(args.warmup, 3)):
         m.update()
     times, iters = [], []
+    r = None
     for _ in range(max(1, args.steps)):
         t0 = time.perf_counter()
         m.update()
         times.append(time.perf_counter() - t0)
-        iters.append(m.get_residuals().sweeps)
+        r = m.get_residuals()
+        iters.append(r.sweeps)
         if time.perf_counter() - t_begin + times[-1] > budget_s:
             break
     step_s = sum(times) / len(times)
@@ -242,11 +287,15 @@ def run_reference_mode_c(args, w):
     return {
         "impl": "reference", "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong" if w.get("strong") else "weak", "vs_baseline": None,
         "dtype": "f32" if precision == 32 else "f64", "data": "synthetic",
         "timesteps_per_s": 1.0 / step_s, "steps_timed": len(times),
-        "config": {"workload": w["desc"], "nx": w["nx"], "ny": w["ny"], "solves_per_step": 2,
-                   "iterations_per_step": sum(iters) / len(iters)},
+        "config": workload_config(w, w["nx"], w["ny"]),
+        "solves_per_step": 2, "cg_iterations_per_step": sum(iters) / len(iters), "cg_iterations_list": iters,
+        "ms_per_cg_iteration": step_s * 1e3 / max(sum(iters) / len(iters), 1e-9),
+        "start_state": "from rest (the GPU arm starts from a state spun up on the device; same grid, parameters, solver "
+                       "constants and stopping rule)",
+        "stop": {"rel_residual": r.f64["p_rel"], "dt_rms_residual": r.f64["p"], "dt_rms_rhs": r.f64["rhs_rms"]},
         "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": "port", "sample": sample,
                          "host_cores": os.cpu_count(), "note": CPU_NOTE},
         "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -262,8 +311,8 @@ def run_reference(args, w):
     return 0
 
 
-def cpu_baseline_mode_r(w, nx, ny):
-    rounds = max(1, min(8, int(24.0 / (3.0 * w["nx"] * w["ny"] / (4096.0 * 4096.0) + 1e-9))))
+def cpu_baseline_mode_r(w, nx, ny, budget_s=24.0):
+    rounds = max(1, min(8, int(budget_s / (3.0 * w["nx"] * w["ny"] / (4096.0 * 4096.0) + 1e-9))))
     s = cpu_oracle_sample(w, 64, rounds)
     s32 = cpu_oracle_sample(w, 32, max(1, rounds // 2))
     return {"value": s["cells"] / s["step_seconds"], "unit": "cell-updates/s", "cores": 1, "kind": "port",
@@ -281,7 +330,7 @@ def cpu_baseline_mode_c(w, model):
     from cfd_demo_b200 import _abi
     from oracle.cpu_oracle import OracleModel
     grid, params = make_grid(w), make_params(w)
-    cpu = OracleModel(grid, params, precision=64)
+    cpu = OracleModel(grid, params, precision=64, consts=make_consts(w))
     r0 = model.get_residuals()
     for fid in (_abi.FIELD_P, _abi.FIELD_U, _abi.FIELD_V, _abi.FIELD_U_STAR, _abi.FIELD_V_STAR, _abi.FIELD_P_PRIME,
                 _abi.FIELD_MG_GUESS, _abi.FIELD_MG_LAST, _abi.FIELD_MG_LAST2):
@@ -298,80 +347,265 @@ def cpu_baseline_mode_c(w, model):
             "host_cores": os.cpu_count(),
             "sample": (f"oracle<double>: ONE timestep (step {rc.simulation_step}) from the GPU model's state, {dt_cpu:.2f} s, "
                        f"{rc.sweeps} MGCG iterations (GPU: {rg.sweeps}); relative L2 difference of u against the GPU's "
-                       f"same step: {du:.2e}")}
+                       f"same step: {du:.2e}; ||r||/||rhs|| oracle {rc.f64['p_rel']:.2e}, GPU {rg.f64['p_rel']:.2e}")}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU side
+# ---------------------------------------------------------------------------------------------------------
+class Ranks:
+    """torchrun environment of this process (one process per GPU)."""
+
+    def __init__(self):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.progress = time.time()
+
+    def tick(self):
+        self.progress = time.time()
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        self.tick()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor(values, dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+
+def build_model(w, rk, strips, flags=0):
+    """The workload's model on this rank: single domain, or this rank's strip of the (weak: N times taller) domain."""
+    import torch.distributed as dist
+    from cfd_demo_b200.model import Model, default_options, nccl_unique_id
+    from cfd_demo_b200.types import Cylinder, Grid
+    cyl = Cylinder(*w["cylinder"]) if w["cylinder"] else None
+    strong = bool(w.get("strong")) and strips
+    weak = strips and not strong
+    ny_job = w["ny"] * rk.world if weak else w["ny"]
+    grid = Grid.uniform(w["nx"], ny_job, w["lx"], w["ly"] * (rk.world if weak else 1), cyl)
+    params = make_params(w)
+    consts = make_consts(w)
+    if strips:
+        uid = [nccl_unique_id() if rk.rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        model = Model.strip(grid, params, rk.rank, rk.world, uid[0], device=rk.local, flags=flags, consts=consts)
+    else:
+        opts = default_options()
+        opts.device = rk.local
+        opts.flags = flags
+        opts.consts = consts
+        model = Model(grid, params, options=opts)
+    return model, grid, params, strong
+
+
+def step_bytes_mode_c(nx, ny, solves_full, solves_elided, iterations):
+    """Algorithmic bytes of one Mode C step (every operation reads its inputs and writes its outputs
+    once, s = 8 bytes): predictor 4 sN + 2 N, residual / CFL maxima 4 sN; a solve that runs = divergence 3 + set-up 4 +
+    corrector 7; a re-correction round that is converged before its first iteration = divergence 3 (its set-up pass and
+    its identity corrector are not executed and not counted); a CG iteration = 28.5 sN on level 0 (first sweep 2, sweep 3,
+    restriction 2.25, prolongation 2.25, two sweeps 6, rho.z 2, direction 3, L d 2, update 6) + 15.5 s N_l on the coarse
+    levels (sum N_l = N / 3)."""
+    n = nx * ny
+    return 8 * n * (8 + 14 * solves_full + 3 * solves_elided + (28.5 + 15.5 / 3.0) * iterations) + 2 * n
+
+
+def timed_steps(model, rk, steps, mode_c):
+    """K steps, state resident in HBM: device time from the model's own CUDA events, max over the ranks."""
+    rk.barrier()
+    t0 = time.perf_counter()
+    acc = dict(dev_ms=0.0, sweep_ms=0.0, sweeps=0, solves=0, launches=0, smooth_ms=0.0, smooth_n=0, first_its=0)
+    its, per_step_ms, last = [], [], None
+    for _ in range(steps):
+        model.update()
+        rk.tick()
+        s_ms, sw_ms, n_l = model.last_timing()
+        r = model.get_residuals()
+        acc["dev_ms"] += s_ms
+        acc["sweep_ms"] += sw_ms
+        acc["sweeps"] += r.sweeps
+        acc["solves"] += r.jacobi_calls
+        acc["launches"] += n_l
+        acc["first_its"] += r.f64["first_solve_iterations"]
+        its.append(int(r.sweeps))
+        per_step_ms.append(s_ms)
+        last = r
+        if mode_c:
+            a, b = model.last_smoother_timing()
+            acc["smooth_ms"] += a
+            acc["smooth_n"] += b
+    rk.barrier()
+    acc["wall_s"] = time.perf_counter() - t0
+    acc["its"], acc["per_step_ms"], acc["last"] = its, per_step_ms, last
+    return acc
+
+
+def parity_block(rk):
+    """N > 1, outside every timed region: the strip decomposition against a single-domain model of the same problem on
+    rank 0's GPU — Mode R (must be bit-identical, SURVEY N8: max-reductions only) and Mode C / MGCG at the shipped
+    stopping rule (dot products are summed in another order: relative L2).  1040 x 600 channel with a cylinder."""
+    import torch.distributed as dist
+    from cfd_demo_b200 import _abi
+    from cfd_demo_b200.model import Model, default_options, nccl_unique_id
+    from cfd_demo_b200.types import Cylinder, Grid, SimulationParams, PressureSolver
+    grid = Grid.uniform(1040, 600, 10.4, 6.0, Cylinder(2.6, 3.0, 0.45))
+    out = {"grid": "1040x600 channel + cylinder", "ranks": rk.world}
+    nx, ny = grid.nx, grid.ny
+    shapes = {_abi.FIELD_P: (ny, nx), _abi.FIELD_U: (ny, nx + 1), _abi.FIELD_V: (ny + 1, nx)}
+    for name, params, steps in (("mode_r", SimulationParams(), 14),
+                                ("mode_c_mgcg", SimulationParams(dt=1e-3, viscosity=0.01, pressure_solver=PressureSolver.MGCG), 8)):
+        uid = [nccl_unique_id() if rk.rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        consts = None
+        if name != "mode_r":
+            consts = make_consts({"consts": dict(cg_relative=1, cg_tolerance=1e-8)})
+        strip = Model.strip(grid, params, rk.rank, rk.world, uid[0], device=rk.local, consts=consts)
+        whole = None
+        if rk.rank == 0:
+            o = default_options()
+            o.device = rk.local
+            if consts is not None:
+                o.consts = consts
+            whole = Model(grid, params, options=o)
+        counters_equal, its_s, its_w = True, [], []
+        for _ in range(steps):
+            strip.update()
+            rk.tick()
+            rs = strip.get_residuals()
+            its_s.append(int(rs.sweeps))
+            if whole is not None:
+                whole.update()
+                rw = whole.get_residuals()
+                its_w.append(int(rw.sweeps))
+                if name == "mode_r":
+                    counters_equal &= (rs.jacobi_calls, rs.sweeps, rs.f64["p"], rs.f64["u"], rs.f64["v"], rs.f64["dt"]) == \
+                                      (rw.jacobi_calls, rw.sweeps, rw.f64["p"], rw.f64["u"], rw.f64["v"], rw.f64["dt"])
+        ja, jb = strip.rows()
+        top = 1 if rk.rank == rk.world - 1 else 0
+        res = {}
+        for fid, shape in shapes.items():
+            mine = strip.field(fid)
+            parts = [None] * rk.world if rk.rank == 0 else None
+            dist.gather_object((ja, jb + (top if fid == _abi.FIELD_V else 0), mine), parts, dst=0)
+            if rk.rank == 0:
+                ref = whole.field(fid).reshape(shape)
+                got = np.empty_like(ref)
+                for a, b, rows in parts:
+                    got[a:b] = rows.reshape(b - a, shape[1])
+                key = _abi.FIELD_NAMES[fid]
+                if name == "mode_r":
+                    res[key + "_entries_differing"] = int((got != ref).sum())
+                else:
+                    res[key + "_rel_l2"] = float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-300))
+        if rk.rank == 0:
+            if name == "mode_r":
+                res["residuals_and_counters_identical_every_step"] = bool(counters_equal)
+                res["sweeps_last_step"] = its_s[-1]
+            else:
+                res["iterations_per_step_strips"] = its_s
+                res["iterations_per_step_single_domain"] = its_w
+            res["steps"] = steps
+            out[name] = res
+            whole.close()
+        strip.close()
+        rk.barrier()
+    return out
+
+
+def run_extra(args, name, rk, steps=3):
+    """A secondary workload inside the default run (rank count of the run; no e2e, no CPU leg): ms/step, kernel share, roofline."""
+    w = WORKLOADS[name]
+    mode_c = w["kind"] == "modeC"
+    strips = rk.world > 1
+    model, grid, params, strong = build_model(w, rk, strips)
+    spinup = int(os.environ.get("CFD_BENCH_SPINUP", w["spinup"]))
+    for _ in range(spinup):
+        model.update()
+        rk.tick()
+    if mode_c:
+        model.profile_smoother(True)
+    for _ in range(2):
+        model.update()
+    acc = timed_steps(model, rk, steps, mode_c)
+    dev_s, = rk.max_over_ranks([acc["dev_ms"] * 1e-3])
+    nx, ny = grid.nx, grid.ny
+    peak, _ = peak_hbm()
+    k, s_ = acc["solves"] / steps, acc["sweeps"] / steps
+    rank_cells = nx * ny // rk.world if strips else nx * ny
+    if mode_c:
+        full = k - (k - 1 if acc["first_its"] == acc["sweeps"] else 0)  # re-correction rounds without an iteration are elided
+        bytes_step = step_bytes_mode_c(nx, ny, full, k - full, s_)
+        sweep_us = acc["smooth_ms"] * 1e3 / max(acc["smooth_n"], 1)
+    else:
+        bytes_step = 8 * nx * ny * (8 + 10 * k + 3 * s_) + 2 * nx * ny
+        sweep_us = acc["sweep_ms"] * 1e3 / max(acc["sweeps"], 1)
+    out = {"workload": w["desc"], "nx": nx, "ny": ny, "n_gpus": rk.world, "scaling": "strong" if strong else ("weak" if strips else "single GPU"),
+           "steps": steps, "ms_per_step": dev_s * 1e3 / steps, "cell_updates_per_s": nx * ny * steps / dev_s,
+           "solves_per_step": k, ("cg_iterations_per_step" if mode_c else "sweeps_per_step"): s_,
+           "step_frac_of_peak": bytes_step / (dev_s / steps) / 1e9 / (peak * rk.world),
+           "sweep_us": sweep_us, "sweep_frac_of_peak": 3 * 8 * rank_cells / (sweep_us * 1e-6) / 1e9 / peak if sweep_us > 0 else None}
+    if mode_c:
+        out["cg_iterations_list"] = acc["its"]
+        out["ms_per_cg_iteration"] = dev_s * 1e3 / max(acc["sweeps"], 1)
+    model.close()
+    rk.barrier()
+    return out
 
 
 def run_ours(args, w):
     import torch
     import torch.distributed as dist
-    from cfd_demo_b200.model import Model
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    rk = Ranks()
+    world, rank, local_rank = rk.world, rk.rank, rk.local
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("cpu:gloo,cuda:nccl")
     mode_c = w["kind"] == "modeC"
-    # N > 1: WEAK scaling over row strips — every GPU owns a w.nx x w.ny strip of one tall domain (nx x N*ny cells, same
-    # dx = dy).  Mode R: halo rows and max-reductions fused into the sweep kernel over NVLink peer memory.  Mode C
-    # (MGCG): level 0 and coarse levels 1-2 in strips (NCCL halo row after every sweep, sum-allreduce per dot
-    # product), level 3 gathered, the rest of the hierarchy replicated.
+    # N > 1: row strips.  Workloads marked `strong` cut the SAME grid into N strips; the others scale WEAKLY — every GPU
+    # owns a w.nx x w.ny strip of one tall domain (nx x N*ny cells, same dx = dy).  Mode R: NCCL halo rows + max-allreduce
+    # after every sweep (CFD_BENCH_FLAGS=512: the fused peer-memory sweep).  Mode C (MGCG): multigrid levels 0-3 in
+    # strips, level 4 gathered, the rest of the hierarchy replicated, dot products sum-allreduced (DESIGN.md section 7).
     # CFD_BENCH_REPLICAS=1: N independent replicas of the single-GPU workload instead (no data-path collective).
     strips = world > 1 and os.environ.get("CFD_BENCH_REPLICAS") != "1"
-    from cfd_demo_b200.types import Cylinder, Grid
-    cyl = Cylinder(*w["cylinder"]) if w["cylinder"] else None
-    strong = bool(w.get("strong")) and strips
-    weak = strips and not strong
-    ny_job = w["ny"] * world if weak else w["ny"]
-    grid = Grid.uniform(w["nx"], ny_job, w["lx"], w["ly"] * (world if weak else 1), cyl)
-    params = make_params(w)
+    flags = int(os.environ.get("CFD_BENCH_FLAGS", "0"))  # A/B hook
+    model, grid, params, strong = build_model(w, rk, strips, flags)
     nx, ny = grid.nx, grid.ny
     cells = nx * ny * (1 if (strips or world == 1) else world)  # whole job
-    from cfd_demo_b200.model import default_options, nccl_unique_id
-    if strips:
-        uid = [nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        model = Model.strip(grid, params, rank, world, uid[0], device=local_rank,
-                            flags=int(os.environ.get("CFD_BENCH_FLAGS", "0")))  # A/B hook (e.g. 512 = peer-memory exchange)
-    else:
-        opts = default_options()
-        opts.device = local_rank
-        opts.flags = int(os.environ.get("CFD_BENCH_FLAGS", "0"))
-        model = Model(grid, params, options=opts)
 
     # multi-rank runs: a rank that dies leaves the others waiting in a collective; abort instead of hanging the box
-    progress = {"t": time.time()}
     if world > 1:
         def watchdog():
             while True:
                 time.sleep(5.0)
-                if time.time() - progress["t"] > float(os.environ.get("CFD_BENCH_WATCHDOG_S", "240")):
+                if time.time() - rk.progress > float(os.environ.get("CFD_BENCH_WATCHDOG_S", "240")):
                     print(f"bench.py rank {rank}: no progress for too long, aborting", file=sys.stderr, flush=True)
                     os._exit(3)
         threading.Thread(target=watchdog, daemon=True).start()
 
-    def barrier():
-        progress["t"] = time.time()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
     # build the synthetic input on the device: spin the flow up (Mode R: to the dense regime where every step
-    # saturates at K=21, S=1050; Mode C: through the 100-step ramp of the lid velocity)
+    # saturates at K=21, S=1050; Mode C: through the 100-step ramp of the lid velocity and the transient after it)
     spinup = int(os.environ.get("CFD_BENCH_SPINUP", w["spinup"]))
     for i in range(spinup):
         model.update()
-        progress["t"] = time.time()
+        rk.tick()
         if os.environ.get("CFD_BENCH_VERBOSE") and rank == 0:
             r_, t_ = model.get_residuals(), model.last_timing()
-            print(f"spinup {i + 1}: K {r_.jacobi_calls} S {r_.sweeps} step_ms {t_[0]:.2f} per-sweep us {t_[1] * 1e3 / max(r_.sweeps, 1):.1f}",
-                  file=sys.stderr, flush=True)
+            print(f"spinup {i + 1}: K {r_.jacobi_calls} S {r_.sweeps} step_ms {t_[0]:.2f} per-sweep us {t_[1] * 1e3 / max(r_.sweeps, 1):.1f} "
+                  f"rel {r_.f64['p_rel']:.2e} abs {r_.f64['p']:.2e}", file=sys.stderr, flush=True)
     if mode_c:
-        model.profile_smoother(True)  # CUDA-event pairs around the smoother launches (48 records per step)
+        model.profile_smoother(True)  # CUDA-event pairs around the smoother launches
     for _ in range(args.warmup):
         model.update()
 
@@ -384,31 +618,13 @@ def run_ours(args, w):
         cudart = ctypes.CDLL("libcudart.so.12")
         cudart.cudaProfilerStart()
     # ---- timed region 1: K steps, state resident in HBM -------------------------------------------------
-    barrier()
-    t0 = time.perf_counter()
-    dev_ms, sweep_ms, sweeps, solves, launches, smooth_ms, smooth_n = 0.0, 0.0, 0, 0, 0, 0.0, 0
-    for _ in range(args.steps):
-        model.update()
-        progress["t"] = time.time()
-        s_ms, sw_ms, n_l = model.last_timing()
-        r = model.get_residuals()
-        dev_ms += s_ms
-        sweep_ms += sw_ms
-        sweeps += r.sweeps
-        solves += r.jacobi_calls
-        launches += n_l
-        if mode_c:
-            a, b = model.last_smoother_timing()
-            smooth_ms += a
-            smooth_n += b
-    barrier()
-    wall = time.perf_counter() - t0
+    acc = timed_steps(model, rk, args.steps, mode_c)
     if cudart is not None:
         cudart.cudaProfilerStop()
     # ---- timed region 2: the same K steps through the reference-facing calls with HOST buffers ------------
     model.profile_smoother(False)
     pinned = model.pinned_snapshot_buffers()
-    barrier()
+    rk.barrier()
     t1 = time.perf_counter()
     d2h = 0
     for _ in range(args.steps):
@@ -417,7 +633,7 @@ def run_ours(args, w):
         res = model.get_residuals()          # device -> host: the step's residual scalars
         snap = model.get_snapshot(out=pinned)  # device -> host: p, u, v narrowed to f32 (SimSnapshot, src/model.rs:36-42)
         d2h = (snap.p.nbytes + snap.u.nbytes + snap.v.nbytes + 8 * 8) * world
-    barrier()
+    rk.barrier()
     wall_e2e = time.perf_counter() - t1
     # the same with freshly allocated pageable buffers (what a caller holding plain Vec<f32>s gets)
     t2 = time.perf_counter()
@@ -443,27 +659,25 @@ def run_ours(args, w):
         wall_e2e_image = (time.perf_counter() - t3) / min(args.steps, 5)
     clocks = sampler.stop() if rank == 0 else None
 
-    # max over ranks
-    times = torch.tensor([dev_ms * 1e-3, wall, wall_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_s, wall_s, wall_e2e_s = [float(x) for x in times.tolist()]
+    dev_s, wall_s, wall_e2e_s = rk.max_over_ranks([acc["dev_ms"] * 1e-3, acc["wall_s"], wall_e2e])
     steps = args.steps
     value = cells * steps / dev_s
     e2e_value = cells * steps / wall_e2e_s
     peak, peak_src = peak_hbm()
     rank_cells = nx * ny // world if strips else nx * ny
     algo_bytes = 3 * 8 * rank_cells  # per launch (one rank's strip): read p', rhs; write p'new
+    sweeps, solves, launches = acc["sweeps"], acc["solves"], acc["launches"]
     if mode_c:
-        sweep_us = smooth_ms * 1e3 / max(smooth_n, 1)
-        roof_launches, roof_share = smooth_n, smooth_ms / max(dev_ms, 1e-9)
+        sweep_us = acc["smooth_ms"] * 1e3 / max(acc["smooth_n"], 1)
+        roof_launches, roof_share = acc["smooth_n"], acc["smooth_ms"] / max(acc["dev_ms"], 1e-9)
         kernel_name = ("cfdk::k_jacobi_sweep5<double> (the reference's damped-Jacobi sweep incl. boundary update, here the "
-                       "fine-level smoother of the V-cycle: 3 launches per CG iteration)")
+                       "fine-level smoother of the V-cycle; with the fused passes one plain launch per CG iteration, the one "
+                       "that also sums rho.z)")
     else:
-        sweep_us = sweep_ms * 1e3 / max(sweeps, 1)
-        roof_launches, roof_share = sweeps, sweep_ms / (dev_s * 1e3)
+        sweep_us = acc["sweep_ms"] * 1e3 / max(sweeps, 1)
+        roof_launches, roof_share = sweeps, acc["sweep_ms"] / (dev_s * 1e3)
         kernel_name = "cfdk::k_jacobi_sweep5<double> (one damped-Jacobi sweep incl. boundary update and max|dp'|)"
-    achieved = algo_bytes / (sweep_us * 1e-6) / 1e9
+    achieved = algo_bytes / (sweep_us * 1e-6) / 1e9 if sweep_us > 0 else 0.0
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_sweep_kernel.json")) as f:
@@ -473,49 +687,66 @@ def run_ours(args, w):
     except Exception:
         pass
     k_per_step, s_per_step = solves / steps, sweeps / steps
+    replicas = world if not strips else 1
     if mode_c:
-        # algorithmic bytes of a Mode C step: per CG iteration 28.5 s N on level 0 (first sweep
-        # 2, sweep 3, restriction 2.25, prolongation 2.25, 2 sweeps 6, rho.z 2, direction 3, L d 2, update 6) + 15.5 s N_l
-        # on every coarse level (sum N_l = N / 3); per solve 4 s N (init); per step 8 s N + 2 N + 10 s N per solve
-        step_bytes = (8 * nx * ny * (8 + 14 * k_per_step + (28.5 + 15.5 / 3.0) * s_per_step) + 2 * nx * ny) * \
-                     (world if not strips else 1)
+        # re-correction rounds that converge before their first iteration are elided (no set-up pass, no corrector)
+        elided = (solves - steps) / steps if acc["first_its"] == sweeps else 0.0
+        step_bytes = step_bytes_mode_c(nx, ny, k_per_step - elided, elided, s_per_step) * replicas
+        step_bytes_r1 = (8 * nx * ny * (8 + 14 * k_per_step + (28.5 + 15.5 / 3.0) * s_per_step) + 2 * nx * ny) * replicas
     else:
         step_bytes = 8 * cells * (8 + 10 * k_per_step + 3 * s_per_step) + 2 * cells  # whole job
+        step_bytes_r1 = step_bytes
     peak_job = peak * world
 
+    parity = None
+    if strips and os.environ.get("CFD_BENCH_NO_PARITY") != "1":
+        parity = parity_block(rk)
+    # CPU port timed on rank 0 at N = 1 only, from the state the timed regions ended in
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        from oracle import cpu_oracle
+        cpu_oracle.build()
+        cpu = cpu_baseline_mode_c(w, model) if mode_c else cpu_baseline_mode_r(w, nx, ny)
+    extras = {}
+    if args.workload == DEFAULT_WORKLOAD and os.environ.get("CFD_BENCH_NO_EXTRAS") != "1":
+        names = ["cavity16384_modeC"] + (["channel8192x2048_modeR"] if strips else
+                                          ["channel4096_modeR", "default800_modeR", "channel8192x2048_modeR"])
+        for name in names:
+            try:
+                extras[name] = run_extra(args, name, rk)
+            except Exception as e:  # an extra must never take the headline line down with it
+                extras[name] = {"error": repr(e)}
+                if world > 1:
+                    raise
+
     if rank == 0:
-        cpu = None
-        if not args.no_cpu_baseline and world == 1:  # CPU port timed on rank 0 at N = 1 only
-            from oracle import cpu_oracle
-            cpu_oracle.build()
-            cpu = cpu_baseline_mode_c(w, model) if mode_c else cpu_baseline_mode_r(w, nx, ny)
         if world == 1:
             multi = "single domain"
         elif strips and not mode_c:
-            peer = int(os.environ.get("CFD_BENCH_FLAGS", "0")) & 512
-            multi = (f"{world} row strips of {w['nx']}x{w['ny']} cells each, weak scaling, " +
+            multi = (f"{world} row strips, {'strong' if strong else 'weak'} scaling, " +
                      ("halo rows and max-reduction fused into the sweep kernel over NVLink peer memory (CFD_BENCH_FLAGS=512)"
-                      if peer else "NCCL halo rows + max-allreduce after every sweep (CFD_BENCH_FLAGS=512: fused peer-memory path)"))
+                      if flags & 512 else "NCCL halo rows + max-allreduce after every sweep (CFD_BENCH_FLAGS=512: fused peer-memory sweep)"))
         elif strips:
-            multi = (f"{world} row strips of one {nx}x{ny} cavity, {'strong' if strong else 'weak'} scaling: multigrid levels 0-2 in "
-                     f"strips with an NCCL halo row after every sweep, level 3 gathered and the rest replicated, dot products "
+            multi = (f"{world} row strips of one {nx}x{ny} cavity, {'strong' if strong else 'weak'} scaling: multigrid levels 0-3 in "
+                     f"strips with a halo row exchanged after every sweep, level 4 gathered and the rest replicated, dot products "
                      f"sum-allreduced")
         else:
             multi = f"{world} independent replicas of the workload, one per GPU (CFD_BENCH_REPLICAS=1)"
+        last = acc["last"]
         line = {
             "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
             "steps": steps, "warmup": args.warmup, "ms_per_step": dev_s * 1e3 / steps, "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "timesteps_per_s": steps / dev_s * (world if (world > 1 and not strips) else 1),
             "wall_ms_per_step": wall_s * 1e3 / steps,
-            "config": {"workload": w["desc"], "nx": nx, "ny": ny, "spinup_steps": spinup,
-                       "solves_per_step": k_per_step,
-                       ("cg_iterations_per_step" if mode_c else "sweeps_per_step"): s_per_step,
-                       "l2": "every field (134 MB at 4096^2) is larger than L2 (126 MB); no flush needed",
-                       "timing": "CUDA events on the model's stream around each update(), summed over K steps",
-                       "multi_gpu": multi},
+            "config": workload_config(w, w["nx"], w["ny"]),
+            "job": {"nx": nx, "ny": ny, "multi_gpu": multi, "spinup_steps": spinup,
+                    "start_state": "spun up on the device from rest (the reference arm starts from rest)"},
+            "solves_per_step": k_per_step,
+            ("cg_iterations_per_step" if mode_c else "sweeps_per_step"): s_per_step,
             "step_algorithmic_gbs": step_bytes / (dev_s / steps) / 1e9,
             "step_frac_of_peak": step_bytes / (dev_s / steps) / 1e9 / peak_job,
+            "step_frac_of_peak_counting_elided_passes": step_bytes_r1 / (dev_s / steps) / 1e9 / peak_job,
             "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": 28 * world, "d2h_bytes_per_step": d2h,
                     "ms_per_step": wall_e2e_s * 1e3 / steps,
                     "ms_per_step_pageable_destination": wall_e2e_pageable * 1e3,
@@ -533,6 +764,17 @@ def run_ours(args, w):
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
+        if mode_c:
+            line["cg_iterations_list"] = acc["its"]
+            line["ms_per_cg_iteration"] = dev_s * 1e3 / max(sweeps, 1)
+            line["ms_per_step_list"] = [round(x, 4) for x in acc["per_step_ms"]]
+            line["stop"] = {"rule": w.get("stop_rule", "dt * rms(r) <= cg_tolerance"),
+                            "rel_residual": last.f64["p_rel"], "dt_rms_residual": last.f64["p"],
+                            "dt_rms_rhs": last.f64["rhs_rms"], "of": "the last timed step (first solve / last solve / first solve)"}
+        if parity is not None:
+            line["parity"] = parity
+        if extras:
+            line["extra"] = extras
         print(json.dumps(line), flush=True)
     model.close()
     if world > 1:

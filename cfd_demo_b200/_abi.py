@@ -1,15 +1,16 @@
 """ctypes mirror of include/cfd_b200.h (PODs and constants only; no library is loaded here)."""
 import ctypes as C
 
-CFD_ABI_VERSION = 2
+CFD_ABI_VERSION = 3
 
 CFD_OK = 0
 CFD_ERR_INVALID_ARGUMENT = 1
 CFD_ERR_CUDA = 2
 CFD_ERR_UNSUPPORTED = 3
 CFD_ERR_NCCL = 4
+CFD_ERR_PEER_TIMEOUT = 5
 
-SCHEME_FIRST_ORDER, SCHEME_SECOND_ORDER = 0, 1
+SCHEME_FIRST_ORDER, SCHEME_SECOND_ORDER, SCHEME_QUICK = 0, 1, 2
 INLET_UNIFORM, INLET_PARABOLIC = 0, 1
 SOLVER_JACOBI, SOLVER_CG, SOLVER_MGCG = 0, 1, 2
 SCENARIO_CHANNEL, SCENARIO_CAVITY = 0, 1
@@ -32,6 +33,8 @@ FLAG_TEMPORAL = 64
 FLAG_PERSISTENT_SWEEP = 128
 FLAG_MG_NO_BOTTOM_KERNEL = 256
 FLAG_PEER_EXCHANGE = 512
+FLAG_MG_UNFUSED = 1024
+FLAG_PEER_STRIPS = 2048
 
 
 class CfdGrid(C.Structure):
@@ -52,7 +55,8 @@ class CfdSolverConsts(C.Structure):
                 ("outer_rounds", C.c_int32), ("cg_max_iterations", C.c_int32),
                 ("jacobi_omega", C.c_double), ("pressure_tolerance", C.c_double),
                 ("outer_tolerance", C.c_double), ("cfl", C.c_double), ("cg_tolerance", C.c_double),
-                ("mg_omega", C.c_double), ("mg_smoothing", C.c_int32), ("mg_warm_start", C.c_int32)]
+                ("mg_omega", C.c_double), ("mg_smoothing", C.c_int32), ("mg_warm_start", C.c_int32),
+                ("cg_relative", C.c_int32), ("adaptive_substeps", C.c_int32)]
 
 
 class CfdOptions(C.Structure):
@@ -68,7 +72,8 @@ class CfdResiduals(C.Structure):
                 ("step_seconds", C.c_double), ("piso_substeps", C.c_uint64),
                 ("jacobi_calls", C.c_uint64), ("sweeps", C.c_uint64),
                 ("simulation_time_f64", C.c_double), ("dt_f64", C.c_double), ("p_f64", C.c_double),
-                ("u_f64", C.c_double), ("v_f64", C.c_double)]
+                ("u_f64", C.c_double), ("v_f64", C.c_double),
+                ("p_rel_f64", C.c_double), ("rhs_rms_f64", C.c_double), ("first_solve_iterations", C.c_uint64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

@@ -53,20 +53,21 @@ __device__ __forceinline__ MgPair<R> mg_pair(const MgFine<R>& c) {
 
 // (L x) on the unknowns of one column pair; l / r = the columns left / right of the pair, already replaced by the
 // boundary rules where the pair touches the ring (mirror; 0 at the channel outlet)
-template <class R>
-__device__ __forceinline__ R mg_lap(const MgFine<R>& c, R cc, R xe, R xw, R xn, R xs) {
-  return div_exact((xe - cc) + (xw - cc), c.ddx_sq) + div_exact((xn - cc) + (xs - cc), c.ddy_sq);
+// Div = DivTry (hoisted reciprocals, one window flag per tile) or DivTrue (`/`): cfd_kernels.cuh
+template <class R, class Div>
+__device__ __forceinline__ R mg_lap(const MgFine<R>& c, Div& dv, R cc, R xe, R xw, R xn, R xs) {
+  return dv((xe - cc) + (xw - cc), c.ddx_sq) + dv((xn - cc) + (xs - cc), c.ddy_sq);
 }
 
-template <class R>
-__device__ __forceinline__ R mg_fine_apply(const MgFine<R>& c, const R* __restrict__ x, int i, int j) {
+template <class R, class Div>
+__device__ __forceinline__ R mg_fine_apply(const MgFine<R>& c, Div& dv, const R* __restrict__ x, int i, int j) {
   const size_t idx = (size_t)i + (size_t)j * c.nx;
   const R cc = x[idx];
   const R xe = (i == c.nx - 2) ? (c.cavity ? cc : R(0)) : x[idx + 1];
   const R xw = (i == 1) ? cc : x[idx - 1];
   const R xn = (j == c.ny - 2) ? cc : x[idx + c.nx];
   const R xs = (j == 1) ? cc : x[idx - c.nx];
-  return mg_lap<R>(c, cc, xe, xw, xn, xs);
+  return mg_lap<R>(c, dv, cc, xe, xw, xn, xs);
 }
 
 // Start vector of a solve, derived on the fly from the p' the last first-solves ended with (the buffers rotate on the
@@ -136,18 +137,21 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_init(MgFine<R> c, MgScalars* 
         if (row_ok) {
           const size_t row = (size_t)j * nx;
           const R gl = mg_start_one<R>(g, row + cl), gr = mg_start_one<R>(g, row + cr);
-          if (ok0) {
-            const R xw = (c0 == 1) ? cen.x : gl;
-            const R xe = (c0 == nx - 2) ? (c.cavity ? cen.x : R(0)) : cen.y;
-            const R xn = (j == c.ny - 2) ? cen.x : north.x, xs = (j == 1) ? cen.x : south.x;
-            b.x = b.x - mg_lap<R>(c, cen.x, xe, xw, xn, xs);
+          const R xw0 = (c0 == 1) ? cen.x : gl;
+          const R xe0 = (c0 == nx - 2) ? (c.cavity ? cen.x : R(0)) : cen.y;
+          const R xn0 = (j == c.ny - 2) ? cen.x : north.x, xs0 = (j == 1) ? cen.x : south.x;
+          const R xw1 = (c0 + 1 == 1) ? cen.y : cen.x;
+          const R xe1 = (c0 + 1 == nx - 2) ? (c.cavity ? cen.y : R(0)) : gr;
+          const R xn1 = (j == c.ny - 2) ? cen.y : north.y, xs1 = (j == 1) ? cen.y : south.y;
+          DivTry<R> dv;
+          R l0 = mg_lap<R>(c, dv, cen.x, xe0, xw0, xn0, xs0), l1 = mg_lap<R>(c, dv, cen.y, xe1, xw1, xn1, xs1);
+          if (__builtin_expect(!dv.ok, 0)) {
+            DivTrue<R> ex;
+            l0 = mg_lap<R>(c, ex, cen.x, xe0, xw0, xn0, xs0);
+            l1 = mg_lap<R>(c, ex, cen.y, xe1, xw1, xn1, xs1);
           }
-          if (ok1) {
-            const R xw = (c0 + 1 == 1) ? cen.y : cen.x;
-            const R xe = (c0 + 1 == nx - 2) ? (c.cavity ? cen.y : R(0)) : gr;
-            const R xn = (j == c.ny - 2) ? cen.y : north.y, xs = (j == 1) ? cen.y : south.y;
-            b.y = b.y - mg_lap<R>(c, cen.y, xe, xw, xn, xs);
-          }
+          if (ok0) b.x = b.x - l0;
+          if (ok1) b.y = b.y - l1;
         }
       }
       if (!ok0) b.x = R(0);
@@ -243,26 +247,38 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_dir_apply(MgFine<R> c, MgScal
       dr[r] = z[row + cr] + beta * (first ? R(0) : d_old[row + cr]);
     }
 #pragma unroll
+    V wv[kMgDirRows];
+    auto apply_tile = [&](auto& dv) {
+#pragma unroll
+      for (int r = 0; r < kMgDirRows; ++r) {
+        const int j = min(j0 + r, j1 - 1);
+        const V cen = dn[r + 1], south = dn[r], north = dn[r + 2];
+        const R xw0 = (c0 == 1) ? cen.x : dl[r];
+        const R xe0 = (c0 == nx - 2) ? (c.cavity ? cen.x : R(0)) : cen.y;
+        const R xn0 = (j == c.ny - 2) ? cen.x : north.x, xs0 = (j == 1) ? cen.x : south.x;
+        const R xw1 = (c0 + 1 == 1) ? cen.y : cen.x;
+        const R xe1 = (c0 + 1 == nx - 2) ? (c.cavity ? cen.y : R(0)) : dr[r];
+        const R xn1 = (j == c.ny - 2) ? cen.y : north.y, xs1 = (j == 1) ? cen.y : south.y;
+        wv[r].x = mg_lap<R>(c, dv, cen.x, xe0, xw0, xn0, xs0);
+        wv[r].y = mg_lap<R>(c, dv, cen.y, xe1, xw1, xn1, xs1);
+      }
+    };
+    DivTry<R> fast;
+    apply_tile(fast);
+    if (__builtin_expect(!fast.ok, 0)) {
+      DivTrue<R> exact;
+      apply_tile(exact);
+    }
+#pragma unroll
     for (int r = 0; r < kMgDirRows; ++r) {
       const int j = j0 + r;
       if (j < j1) {
-        const V cen = dn[r + 1], south = dn[r], north = dn[r + 2];
+        const V cen = dn[r + 1];
         V out;
-        out.x = R(0); out.y = R(0);
-        if (v0) {
-          const R xw = (c0 == 1) ? cen.x : dl[r];
-          const R xe = (c0 == nx - 2) ? (c.cavity ? cen.x : R(0)) : cen.y;
-          const R xn = (j == c.ny - 2) ? cen.x : north.x, xs = (j == 1) ? cen.x : south.x;
-          out.x = mg_lap<R>(c, cen.x, xe, xw, xn, xs);
-          acc += (double)(cen.x * out.x);
-        }
-        if (v1) {
-          const R xw = (c0 + 1 == 1) ? cen.y : cen.x;
-          const R xe = (c0 + 1 == nx - 2) ? (c.cavity ? cen.y : R(0)) : dr[r];
-          const R xn = (j == c.ny - 2) ? cen.y : north.y, xs = (j == 1) ? cen.y : south.y;
-          out.y = mg_lap<R>(c, cen.y, xe, xw, xn, xs);
-          acc += (double)(cen.y * out.y);
-        }
+        out.x = v0 ? wv[r].x : R(0);
+        out.y = v1 ? wv[r].y : R(0);
+        if (v0) acc += (double)(cen.x * out.x);
+        if (v1) acc += (double)(cen.y * out.y);
         *reinterpret_cast<V*>(d_new + c0 + (size_t)j * nx) = cen;
         *reinterpret_cast<V*>(w + c0 + (size_t)j * nx) = out;
       }
@@ -367,14 +383,23 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_fine_restrict(MgFine<R> c, co
                                                                   R* __restrict__ crho, const MgScalars* __restrict__ sc) {
   const int I = blockIdx.x * blockDim.x + threadIdx.x, J = c_lo + blockIdx.y;  // grid.y = owned rows of level 1
   if (I >= cmx || sc->done) return;
-  R acc = R(0);
+  auto children = [&](auto& dv) -> R {
+    R acc = R(0);
 #pragma unroll
-  for (int b = 0; b < 2; ++b)
+    for (int b = 0; b < 2; ++b)
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const int i = 1 + 2 * I + a, j = 1 + 2 * J + b;
-      if (i <= c.nx - 2 && j <= c.ny - 2) acc += rho[(size_t)i + (size_t)j * c.nx] - mg_fine_apply<R>(c, z, i, j);
-    }
+      for (int a = 0; a < 2; ++a) {
+        const int i = 1 + 2 * I + a, j = 1 + 2 * J + b;
+        if (i <= c.nx - 2 && j <= c.ny - 2) acc += rho[(size_t)i + (size_t)j * c.nx] - mg_fine_apply<R>(c, dv, z, i, j);
+      }
+    return acc;
+  };
+  DivTry<R> fast;
+  R acc = children(fast);
+  if (__builtin_expect(!fast.ok, 0)) {
+    DivTrue<R> exact;
+    acc = children(exact);
+  }
   crho[(size_t)(I + 1) + (size_t)(J + 1) * (cmx + 2)] = acc;
 }
 
@@ -394,6 +419,107 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_fine_prolong(MgFine<R> c, R* 
   if (i == c.nx - 2) z[idx + 1] = c.cavity ? v : R(0);
   if (j == 1) z[idx - c.nx] = v;
   if (j == c.ny - 2) z[idx + c.nx] = v;
+}
+
+// ---- fused smoothing passes of level 0 ---------------------------------------------------------------------------
+// One damped-Jacobi sweep (the reference's update, src/model.rs:788-793, via jacobi_cell — the very function the
+// tensor-TMA sweep kernel uses) whose INPUT field is formed on the fly instead of being read from memory:
+//   kMode 0: input = the first smoothing sweep applied to z = 0, i.e. k_mg_first_sweep(rho)  -> replaces the pair
+//            (k_mg_first_sweep, k_jacobi_sweep5) of a V(2,2) cycle by one pass that reads rho and writes z: 2 sN
+//            instead of 5 sN of traffic;
+//   kMode 1: input = z + (correction of the parent), i.e. k_mg_fine_prolong(z, ce)           -> replaces the pair
+//            (k_mg_fine_prolong, k_jacobi_sweep5): 3.25 sN instead of 5.25 sN.
+// The ring of the input follows the Jacobi boundary rules (:807-815: column 0 mirrors column 1, column nx-1 is zero at the
+// channel outlet / mirrors column nx-2 in the cavity, rows 0 and ny-1 mirror rows 1 and ny-2), exactly as the kernels
+// it replaces leave it; the output ring is written like the sweep kernel writes it.  Same per-cell arithmetic, same
+// association: bit-identical to the unfused sequence (CFD_FLAG_MG_UNFUSED keeps that one for the cross-check).
+// A thread owns the aligned column pair (2t, 2t+1) and kFsRows rows; grid = (ceil(nx / 512), ceil(rows / kFsRows)).
+constexpr int kFsRows = 4;
+template <class R, int kMode>
+__global__ void __launch_bounds__(kMgThreads) k_mg_fused_sweep(const MgFine<R> c, const JacobiConsts2<R> c2,
+                                                                const R* __restrict__ rho, const R* __restrict__ zin,
+                                                                int cmx, const R* __restrict__ ce, R* __restrict__ zout,
+                                                                const MgScalars* __restrict__ sc) {
+  using V = typename Vec2<R>::type;
+  if (sc->done) return;
+  const int nx = c.nx, ny = c.ny;
+  const int c0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int j0 = c.row_lo + blockIdx.y * kFsRows, j1 = min(j0 + kFsRows, c.row_hi);
+  if (c0 >= nx || j0 >= j1) return;
+  const bool ghost_l = c0 == 0, ghost_r = c0 == nx - 2;
+  const R* __restrict__ src = kMode == 0 ? rho : zin;
+  // every load of the tile first: the own pair on rows j0-1 .. j0+kFsRows (rows 0 and ny-1 mirror rows 1 and ny-2; rows
+  // past the tile are loaded clamped and never used), the columns left / right of the pair and rho on the tile's rows
+  V a[kFsRows + 2], ca[kFsRows + 2];
+  R al[kFsRows], ar[kFsRows], cl[kFsRows], cr[kFsRows];
+  V rh[kFsRows];
+#pragma unroll
+  for (int m = 0; m < kFsRows + 2; ++m) {
+    const int j = min(max(min(j0 - 1 + m, j1), 1), ny - 2);
+    a[m] = *reinterpret_cast<const V*>(src + c0 + (size_t)j * nx);
+    if (kMode == 1) {  // correction of the parent cells of (c0, j) and (c0 + 1, j); column 0 has none (value unused)
+      const size_t prow = (size_t)((j - 1) / 2 + 1) * (cmx + 2);
+      ca[m].x = ce[prow + (size_t)((c0 - 1) / 2 + 1)];
+      ca[m].y = ce[prow + (size_t)(c0 / 2 + 1)];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kFsRows; ++r) {
+    const int j = min(j0 + r, j1 - 1);
+    const size_t row = (size_t)j * nx;
+    al[r] = ghost_l ? R(0) : src[row + c0 - 1];   // unknown columns whenever they are used
+    ar[r] = ghost_r ? R(0) : src[row + c0 + 2];
+    if (kMode == 1) {
+      const size_t prow = (size_t)((j - 1) / 2 + 1) * (cmx + 2);
+      cl[r] = ghost_l ? R(0) : ce[prow + (size_t)((c0 - 2) / 2 + 1)];
+      cr[r] = ghost_r ? R(0) : ce[prow + (size_t)((c0 + 1) / 2 + 1)];
+    }
+    rh[r] = *reinterpret_cast<const V*>(rho + c0 + row);
+  }
+  // the input field, ring rules applied (mode 0 divides: DivTry for the tile, DivTrue if a quotient left its window)
+  V in[kFsRows + 2];
+  R inl[kFsRows], inr[kFsRows];
+  auto form = [&](auto& dv) {
+    auto raw1 = [&](R x, R corr) -> R {
+      if (kMode == 0) return c2.omega * dv((R(0) + R(0)) - x, c2.denom) + c2.one_minus_omega * R(0);
+      return x + corr;
+    };
+#pragma unroll
+    for (int m = 0; m < kFsRows + 2; ++m) {
+      V o;
+      o.x = raw1(a[m].x, ca[m].x);
+      o.y = raw1(a[m].y, ca[m].y);
+      if (ghost_l) o.x = o.y;                          // column 0 <- column 1
+      if (ghost_r) o.y = c.cavity ? o.x : R(0);        // outlet column 0 / cavity mirror
+      in[m] = o;
+    }
+#pragma unroll
+    for (int r = 0; r < kFsRows; ++r) {
+      inl[r] = raw1(al[r], cl[r]);
+      inr[r] = raw1(ar[r], cr[r]);
+    }
+  };
+  DivTry<R> fast;
+  form(fast);
+  if (kMode == 0 && __builtin_expect(!fast.ok, 0)) {
+    DivTrue<R> exact;
+    form(exact);
+  }
+#pragma unroll
+  for (int r = 0; r < kFsRows; ++r) {
+    const int j = j0 + r;
+    if (j >= j1) break;
+    const V cen = in[r + 1], south = in[r], north = in[r + 2];
+    R n0 = jacobi_cell<R>(c2, inl[r], cen.y, north.x, south.x, cen.x, rh[r].x);
+    R n1 = jacobi_cell<R>(c2, cen.x, inr[r], north.y, south.y, cen.y, rh[r].y);
+    if (ghost_l) n0 = n1;
+    if (ghost_r) n1 = c.cavity ? n0 : R(0);
+    V out;
+    out.x = n0; out.y = n1;
+    *reinterpret_cast<V*>(zout + c0 + (size_t)j * nx) = out;
+    if (j == 1) *reinterpret_cast<V*>(zout + c0) = out;                                   // bottom row <- row 1
+    if (j == ny - 2) *reinterpret_cast<V*>(zout + c0 + (size_t)(ny - 1) * nx) = out;      // top row <- row ny-2
+  }
 }
 
 // ---- coarse levels (l >= 1): fields (mx + 2) x (my + 2) with a ring of zeros ----

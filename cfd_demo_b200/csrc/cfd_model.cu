@@ -20,6 +20,7 @@
 #include "../../include/cfd_b200.h"
 #include "cfd_kernels.cuh"
 #include "cfd_mg.cuh"
+#include "cfd_peer.cuh"
 
 namespace {
 
@@ -109,6 +110,8 @@ void consts_default(cfd_solver_consts* c) {
   c->mg_omega = 0.8;             // extension (MGCG)
   c->mg_smoothing = 2;           // extension (MGCG)
   c->mg_warm_start = 3;          // extension (MGCG)
+  c->cg_relative = 0;            // extension (CG, MGCG)
+  c->adaptive_substeps = 0;      // extension (src/model.rs:352-363 is commented out in the reference)
 }
 
 constexpr int kMaxSweepSlots = 256;
@@ -255,7 +258,13 @@ struct ModelImpl final : ModelBase {
   int sweep_rows_per_block = 32;
   int sweep6_resident_blocks = 148 * 4;  // one wave of the persistent sweep
   cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
-  std::vector<cudaEvent_t> ev_sweep;  // pairs
+  std::vector<cudaEvent_t> ev_sweep;  // pairs, one per pressure solve of the step
+  size_t ev_sweep_used = 0;
+  Field<R> uold_buf, vold_buf;        // u_old / v_old of a step with several sub-steps (adaptive_substeps)
+  bool old_in_copy = false;
+  // Mode C bookkeeping of the last step's first solve (cfd_residuals::p_rel_f64, rhs_rms_f64, first_solve_iterations)
+  double step_bb = 0, last_p_rel = 0, last_rhs_rms = 0;
+  uint64_t last_first_solve_iterations = 0;
   // strips over peer memory (CUDA IPC): the neighbours' p' buffers and every rank's mailbox (cfd_kernels.cuh)
   cfdk::Mailbox* mailbox = nullptr;              // this rank's, device memory
   cfdk::Mailbox* peer_mailbox[cfdk::kMaxRanks] = {};
@@ -267,6 +276,20 @@ struct ModelImpl final : ModelBase {
   unsigned long long* peer_trace = nullptr;
   double dbg_work = 0, dbg_wait = 0, dbg_gap = 0, dbg_span = 0; unsigned long long dbg_n = 0, dbg_solves = 0;
   bool peer_ready = false;
+  // generic strips over peer memory (cfd_peer.cuh): every exchanged buffer is registered, its IPC handle all-gathered once,
+  // and exchange_rows / exchange_level / gather_level / the scalar all-reduces run as single small launches instead of NCCL
+  struct PeerBuf {
+    void* base = nullptr;
+    bool want_all = false;                   // mapped on every rank (gathered arrays), not only on the two neighbours
+    void* map[cfdk::kPeerMaxRanks] = {};     // [rank]: that rank's buffer mapped into this process (nullptr: not mapped)
+  };
+  std::vector<PeerBuf> peer_bufs;
+  size_t peer_synced = 0;
+  bool peer2_ready = false;
+  cfdk::PeerBox* box = nullptr;
+  cfdk::PeerBox* peer_box[cfdk::kPeerMaxRanks] = {};
+  unsigned int* peer_ticket = nullptr;
+  unsigned long long xseq = 0, rseq = 0, gseq = 0;
   bool ready = false;
 
   ModelImpl(const cfd_grid& g, const cfd_params& prm, const cfd_options& o) : grid(g), opt(o) {
@@ -298,6 +321,7 @@ struct ModelImpl final : ModelBase {
     if (comm) nccl_api().CommDestroy(comm);
     for (auto& f : ubuf) cudaFree(f.base);
     for (auto& f : vbuf) cudaFree(f.base);
+    cudaFree(uold_buf.base); cudaFree(vold_buf.base);
     cudaFree(p.base); cudaFree(rhs.base); cudaFree(pp[0].base); cudaFree(pp[1].base);
     cudaFree(mask_u.base); cudaFree(mask_v.base); cudaFree(solid.base);
     cudaFree(err_slots); cudaFree(step_slots); cudaFree(staging); cudaFree(tickets); cudaFree(d_divs);
@@ -339,6 +363,7 @@ struct ModelImpl final : ModelBase {
     }
     for (void* ptr : ipc_opened) cudaIpcCloseMemHandle(ptr);
     cudaFree(mailbox);
+    cudaFree(box); cudaFree(peer_ticket);
     if (ev_step0) cudaEventDestroy(ev_step0);
     if (ev_step1) cudaEventDestroy(ev_step1);
     for (auto e : ev_sweep) cudaEventDestroy(e);
@@ -402,7 +427,7 @@ struct ModelImpl final : ModelBase {
     // per-sweep tickets / stop flags / diagnostics (strips) and work counters (persistent sweep), cfd_kernels.cuh
     if ((rc = dalloc(&tickets, (size_t)1400))) return rc;
     CFD_CUDA(cudaHostAlloc((void**)&h_jres, sizeof(cfdk::JacobiResult), cudaHostAllocMapped));
-    CFD_CUDA(cudaHostAlloc((void**)&h_step, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    CFD_CUDA(cudaHostAlloc((void**)&h_step, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
     CFD_CUDA(cudaEventCreate(&ev_step0));
     CFD_CUDA(cudaEventCreate(&ev_step1));
     const int n_pairs = 2 * (opt.consts.outer_rounds + 1);
@@ -428,6 +453,9 @@ struct ModelImpl final : ModelBase {
       solid_j0 = clampi(std::floor(y0) - 2.0, 0, ny); solid_j1 = clampi(std::ceil(y1) + 3.0, 0, ny);
     }
     if ((rc = init_sweep_constants())) return rc;
+    for (int k = 0; k < 3; ++k) { peer_register(ubuf[k].base); peer_register(vbuf[k].base); }
+    peer_register(pp[0].base); peer_register(pp[1].base);
+    if ((rc = peer_sync())) return rc;
     // Mode R strips: NCCL halo rows + allreduce after every sweep by default; CFD_FLAG_PEER_EXCHANGE opts into the fused
     // peer-memory path (faster; it hung at start-up in 2 of 8 two-GPU runs before its max records were double-buffered,
     // and has passed only one run since)
@@ -490,6 +518,108 @@ struct ModelImpl final : ModelBase {
       peer_pp_up[1] = neighbour_origin(b1, rank + 1);
     }
     peer_ready = true;
+    return CFD_OK;
+  }
+
+  // ---- generic peer layer -----------------------------------------------------------------------------------------
+  bool want_peer2() const {
+    if (world <= 1 || world > cfdk::kPeerMaxRanks) return false;
+    if (opt.flags & CFD_FLAG_NCCL_EXCHANGE) return false;
+    if (const char* e = getenv("CFD_PEER_STRIPS")) return atoi(e) != 0;  // A/B hook
+    return (opt.flags & CFD_FLAG_PEER_STRIPS) != 0;
+  }
+  void peer_register(void* base, bool want_all = false) {
+    if (!want_peer2() || !base) return;
+    PeerBuf b;
+    b.base = base;
+    b.want_all = want_all;
+    peer_bufs.push_back(b);
+  }
+  const PeerBuf* peer_find(const void* base) const {
+    if (!peer2_ready) return nullptr;
+    for (size_t k = 0; k < peer_synced; ++k)
+      if (peer_bufs[k].base == base) return &peer_bufs[k];
+    return nullptr;
+  }
+  // collective: all-gathers the IPC handles of the buffers registered since the last call (every rank registers the same
+  // buffers in the same order) and maps the neighbours' (or everyone's) copies; the first call also sets up the mailboxes
+  int peer_sync() {
+    if (!want_peer2()) return CFD_OK;
+    int rc;
+    if (!box) {
+      if ((rc = dalloc(&box, (size_t)1))) return rc;
+      if ((rc = dalloc(&peer_ticket, (size_t)4))) return rc;
+      PeerBuf b;
+      b.base = box;
+      b.want_all = true;
+      peer_bufs.insert(peer_bufs.begin() + (long)peer_synced, b);
+    }
+    const size_t n_new = peer_bufs.size() - peer_synced;
+    if (n_new == 0) return CFD_OK;
+    CFD_CUDA(cudaStreamSynchronize(stream));
+    std::vector<cudaIpcMemHandle_t> mine(n_new), all(n_new * (size_t)world);
+    for (size_t k = 0; k < n_new; ++k) CFD_CUDA(cudaIpcGetMemHandle(&mine[k], peer_bufs[peer_synced + k].base));
+    unsigned char* d = nullptr;
+    const size_t bytes = n_new * sizeof(cudaIpcMemHandle_t);
+    CFD_CUDA(cudaMalloc((void**)&d, bytes * (size_t)(world + 1)));
+    CFD_CUDA(cudaMemcpyAsync(d, mine.data(), bytes, cudaMemcpyHostToDevice, stream));
+    CFD_NCCL(nccl_api().AllGather(d, d + bytes, bytes, ncclChar, comm, stream));
+    CFD_CUDA(cudaMemcpyAsync(all.data(), d + bytes, bytes * (size_t)world, cudaMemcpyDeviceToHost, stream));
+    CFD_CUDA(cudaStreamSynchronize(stream));
+    CFD_CUDA(cudaFree(d));
+    for (size_t k = 0; k < n_new; ++k) {
+      PeerBuf& b = peer_bufs[peer_synced + k];
+      for (int r = 0; r < world; ++r) {
+        if (r == rank) { b.map[r] = b.base; continue; }
+        if (!b.want_all && r != rank - 1 && r != rank + 1) continue;
+        void* ptr = nullptr;
+        CFD_CUDA(cudaIpcOpenMemHandle(&ptr, all[(size_t)r * n_new + k], cudaIpcMemLazyEnablePeerAccess));
+        ipc_opened.push_back(ptr);
+        b.map[r] = ptr;
+      }
+      if (b.base == box)
+        for (int r = 0; r < world; ++r) peer_box[r] = (cfdk::PeerBox*)b.map[r];
+    }
+    peer_synced = peer_bufs.size();
+    peer2_ready = true;
+    // nobody pushes into a mailbox or a buffer before every rank has mapped everything: one more collective as a barrier
+    CFD_NCCL(nccl_api().AllReduce(peer_ticket + 2, peer_ticket + 2, 1, ncclUint32, ncclMax, comm, stream));
+    CFD_CUDA(cudaStreamSynchronize(stream));
+    return CFD_OK;
+  }
+  cfdk::PeerAll peer_all() const {
+    cfdk::PeerAll a;
+    for (int r = 0; r < cfdk::kPeerMaxRanks; ++r) a.box[r] = r < world ? peer_box[r] : nullptr;
+    a.rank = rank; a.world = world;
+    return a;
+  }
+  // rows of a strip field or of a replicated coarse array to the two neighbours: src / dst as element offsets from the
+  // (virtual or real) origins, which the caller computed for its own copy and for the neighbours' copies
+  int peer_push(const void* src_down, void* dst_down, size_t bytes_down, const void* src_up, void* dst_up, size_t bytes_up) {
+    cfdk::PeerPush p;
+    memset(&p, 0, sizeof p);
+    p.mine = box; p.ticket = peer_ticket; p.seq = ++xseq;
+    if (rank > 0) {
+      p.flag[0] = &peer_box[rank - 1]->from_above;
+      p.src[0] = (const uint32_t*)src_down; p.dst[0] = (uint32_t*)dst_down; p.words[0] = bytes_down / 4;
+    }
+    if (rank < world - 1) {
+      p.flag[1] = &peer_box[rank + 1]->from_below;
+      p.src[1] = (const uint32_t*)src_up; p.dst[1] = (uint32_t*)dst_up; p.words[1] = bytes_up / 4;
+    }
+    const size_t most = p.words[0] > p.words[1] ? p.words[0] : p.words[1];
+    int grid = (int)((most + 1023) / 1024);
+    if (grid < 1) grid = 1;
+    if (grid > 64) grid = 64;
+    cfdk::k_peer_push<<<grid, 256, 0, stream>>>(p);
+    ++launches;
+    CFD_CUDA(cudaGetLastError());
+    return CFD_OK;
+  }
+  int peer_reduce(void* data, int n, int op) {
+    cfdk::k_peer_reduce<<<1, 32, 0, stream>>>(peer_all(), (unsigned long long*)data, n, op, ++rseq, nullptr);
+    ++launches;
+    CFD_CUDA(cudaGetLastError());
     return CFD_OK;
   }
 
@@ -660,8 +790,19 @@ struct ModelImpl final : ModelBase {
   int exchange_rows(const Field<R>& f, int a, int b, int down, int up, int send_down, int send_up,
                     cudaStream_t on = nullptr) {
     if (world == 1) return CFD_OK;
-    cudaStream_t stream = on ? on : this->stream;
     const size_t rl = f.rowlen;
+    if (const PeerBuf* pb = on ? nullptr : peer_find(f.base)) {
+      // the neighbours lay the field out exactly like this rank does (falloc): virtual origin = base + front -
+      // (first owned row - kHalo) * row length, rows in GLOBAL numbering; what this rank sends lands on the same row there
+      auto origin = [&](int r) -> R* {
+        return (R*)pb->map[r] + 256 / sizeof(R) - (long)(strip_row_start(ny, world, r) - kHalo) * (long)rl;
+      };
+      R* dst_down = rank > 0 ? origin(rank - 1) + (long)a * (long)rl : nullptr;
+      R* dst_up = rank < world - 1 ? origin(rank + 1) + (long)(b - send_up) * (long)rl : nullptr;
+      return peer_push(f.row(a), dst_down, (size_t)send_down * rl * sizeof(R), f.row(b - send_up), dst_up,
+                       (size_t)send_up * rl * sizeof(R));
+    }
+    cudaStream_t stream = on ? on : this->stream;
     CFD_NCCL(nccl_api().GroupStart());
     if (rank > 0) {
       if (send_down > 0) CFD_NCCL(nccl_api().Send(f.row(a), (size_t)send_down * rl, nccl_real(), rank - 1, comm, stream));
@@ -683,8 +824,21 @@ struct ModelImpl final : ModelBase {
 
   int allreduce_max_u64(unsigned long long* d, size_t n, cudaStream_t on = nullptr) {
     if (world == 1) return CFD_OK;
+    if (peer2_ready && !on && n <= 4) return peer_reduce(d, (int)n, 0);
     cudaStream_t stream = on ? on : this->stream;
     CFD_NCCL(nccl_api().AllReduce(d, d, n, ncclUint64, ncclMax, comm, stream));
+    return CFD_OK;
+  }
+
+  // CUDA-event pair of the next pressure solve of this step (begin = [k], end = [k + 1])
+  int next_solve_events(size_t* k) {
+    if (ev_sweep_used + 2 > ev_sweep.size()) {
+      const size_t old_n = ev_sweep.size();
+      ev_sweep.resize(ev_sweep_used + 16, nullptr);
+      for (size_t q = old_n; q < ev_sweep.size(); ++q) CFD_CUDA(cudaEventCreate(&ev_sweep[q]));
+    }
+    *k = ev_sweep_used;
+    ev_sweep_used += 2;
     return CFD_OK;
   }
 
@@ -695,26 +849,35 @@ struct ModelImpl final : ModelBase {
     const int iters = opt.consts.jacobi_iterations;
     int rc;
     if (elided) *elided = false;
+    size_t ev = 0;
+    if ((rc = next_solve_events(&ev))) return rc;
     if ((rc = fetch_row_above(vs, ja, v_row_end()))) return rc;
     const bool mgcg = pressure_solver == CFD_SOLVER_MGCG;
-    if (mgcg && (rc = mgcg_begin())) return rc;
+    const bool first_solve = call_index == 0;
+    if (mgcg && (rc = mgcg_begin(first_solve))) return rc;
     // a cold-start MGCG solve that is expected to need no iteration: the divergence kernel sums rho.rho = rhs.rhs itself
     const bool cold = mgcg && !(call_index == 0 && opt.consts.mg_warm_start != 0);
-    const bool decide_early = cold && elided != nullptr && mg_pred[call_index == 0 ? 0 : 1] == 0;
+    const bool decide_early = cold && elided != nullptr && mg_pred[first_solve ? 0 : 1] == 0;
     {
+      // MGCG: a step's first solve also needs ||rhs||^2 over the unknowns (reference of the relative stopping rule and of
+      // the reported ||r|| / ||rhs||): rr_mode 4, or 5 when that solve starts cold (then rho = rhs and the sum is rho.rho too)
+      const int rr_mode = mgcg && first_solve ? (cold ? 5 : 4) : 0;
       dim3 blk(256), grd((nx + 255) / 256, (jb - ja + cfdk::kDivRows - 1) / cfdk::kDivRows);
-      if (decide_early)
+      if (decide_early || rr_mode != 0) {
+        const cfdk::MgFine<R> c = mg_fine(dt_sub);
         cfdk::k_divergence<R, true><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, rhs.v, ja, jb, err_slots, iters, tickets,
-                                                             h_divs.dx, h_divs.dy, h_divs.dt, mg_fine(dt_sub), mg_scalars,
-                                                             mg_partials, mg_ticket);
-      else
+                                                             h_divs.dx, h_divs.dy, h_divs.dt, c, mg_scalars, mg_partials,
+                                                             mg_ticket, rr_mode);
+        if (rr_mode != 0 && (rc = mg_finish_strips(c, rr_mode))) return rc;  // strips: the ranks' sums -> bb
+      } else {
         cfdk::k_divergence<R, false><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, rhs.v, ja, jb, err_slots, iters, tickets,
                                                               h_divs.dx, h_divs.dy, h_divs.dt, cfdk::MgFine<R>{}, nullptr,
-                                                              nullptr, nullptr);
+                                                              nullptr, nullptr, 0);
+      }
       ++launches;
     }
-    if (pressure_solver == CFD_SOLVER_CG) return cg_solve(dt_sub, call_index, residual_out);
-    if (mgcg) return mgcg_solve(dt_sub, call_index, residual_out, decide_early, elided);
+    if (pressure_solver == CFD_SOLVER_CG) return cg_solve(dt_sub, call_index, residual_out, ev);
+    if (mgcg) return mgcg_solve(dt_sub, call_index, residual_out, decide_early, elided, ev);
     if ((rc = materialize_pp_zero())) return rc;  // Jacobi warm-starts from p' (src/model.rs:734-824)
     if ((rc = resolve_mg_rotation())) return rc;
     cfdk::JacobiConsts<R> c;
@@ -727,7 +890,7 @@ struct ModelImpl final : ModelBase {
     c.nx = nx; c.ny = ny; c.cavity = scenario == CFD_SCENARIO_CAVITY;
     c.row_begin = sweep_row_begin(); c.row_end = sweep_row_end();
     const int rows = c.row_end - c.row_begin;
-    CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index], stream));
+    CFD_CUDA(cudaEventRecord(ev_sweep[ev], stream));
     cfdk::JacobiConsts2<R> c2;
     c2.dx_sq = div_dx_sq; c2.dy_sq = div_dy_sq; c2.denom = div_denom;
     c2.omega = c.omega; c2.one_minus_omega = c.one_minus_omega; c2.tol = c.tol;
@@ -811,7 +974,7 @@ struct ModelImpl final : ModelBase {
       cfdk::k_jacobi_finalize<R><<<1, 32, 0, stream>>>(err_slots, iters, c.tol, h_jres);
       ++launches;
     }
-    CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index + 1], stream));
+    CFD_CUDA(cudaEventRecord(ev_sweep[ev + 1], stream));
     CFD_CUDA(cudaGetLastError());
     CFD_CUDA(cudaStreamSynchronize(stream));
     const int ran = h_jres->sweeps;
@@ -844,13 +1007,18 @@ struct ModelImpl final : ModelBase {
       return CFD_OK;
     }
     cfdk::k_cg_reduce<R><<<1, 1024, 0, stream>>>(c, cg_scalars, cg_partials, n, mode, 1);
-    CFD_NCCL(nccl_api().AllReduce(&cg_scalars->local_sum, &cg_scalars->local_sum, 1, ncclFloat64, ncclSum, comm, stream));
+    if (peer2_ready) {
+      int rc;
+      if ((rc = peer_reduce(&cg_scalars->local_sum, 1, 1))) return rc;
+    } else {
+      CFD_NCCL(nccl_api().AllReduce(&cg_scalars->local_sum, &cg_scalars->local_sum, 1, ncclFloat64, ncclSum, comm, stream));
+    }
     cfdk::k_cg_reduce<R><<<1, 32, 0, stream>>>(c, cg_scalars, cg_partials, n, mode, 2);
     launches += 2;
     return CFD_OK;
   }
 
-  int cg_solve(R dt_sub, int call_index, R* residual_out) {
+  int cg_solve(R dt_sub, int call_index, R* residual_out, size_t ev) {
     int rc;
     if ((rc = resolve_mg_rotation())) return rc;
     pp_zero_pending = false;  // k_cg_init writes p' in full
@@ -865,6 +1033,8 @@ struct ModelImpl final : ModelBase {
       if ((rc = dalloc(&cg_partials, (size_t)n_all))) return rc;
       if ((rc = dalloc(&cg_scalars, (size_t)1))) return rc;
       CFD_CUDA(cudaHostAlloc((void**)&h_cg, sizeof(cfdk::CgScalars), cudaHostAllocDefault));
+      peer_register(cg_d.base);
+      if ((rc = peer_sync())) return rc;
     }
     cfdk::CgConsts<R> c;
     c.dx_sq = dx * dx; c.dy_sq = dy * dy; c.dt = dt_sub; c.tol = R(opt.consts.cg_tolerance);
@@ -877,8 +1047,10 @@ struct ModelImpl final : ModelBase {
     cfdk::CgScalars init;
     memset(&init, 0, sizeof init);
     init.max_iterations = opt.consts.cg_max_iterations;
+    init.relative = opt.consts.cg_relative;
+    init.bb = call_index == 0 ? -1.0 : step_bb;  // first solve of the step: bb <- r.r of the cold start (k_cg_reduce)
     *h_cg = init;
-    CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index], stream));
+    CFD_CUDA(cudaEventRecord(ev_sweep[ev], stream));
     CFD_CUDA(cudaMemcpyAsync(cg_scalars, h_cg, sizeof init, cudaMemcpyHostToDevice, stream));
     cfdk::k_cg_init<R><<<g_all, blk, 0, stream>>>(c, rhs.v, x, cg_r.v, cg_d.v, cg_partials);
     ++launches;
@@ -903,8 +1075,9 @@ struct ModelImpl final : ModelBase {
     cfdk::k_cg_fill_boundary<R><<<(n_edge + 255) / 256, 256, 0, stream>>>(nx, ny, c.cavity, x, ja, jb);
     ++launches;
     if ((rc = exchange_halo(xf, ja, jb, 1))) return rc;  // the corrector reads p'[j-1] (src/model.rs:1380)
-    CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index + 1], stream));
+    CFD_CUDA(cudaEventRecord(ev_sweep[ev + 1], stream));
     CFD_CUDA(cudaGetLastError());
+    if (call_index == 0) note_first_solve(h_cg->bb, h_cg->rel, h_cg->iterations, dt_sub);
     last_S += (uint64_t)h_cg->iterations;
     last_K += 1;
     *residual_out = (R)h_cg->measure;
@@ -997,6 +1170,13 @@ struct ModelImpl final : ModelBase {
     }
     CFD_CUDA(cudaHostAlloc((void**)&h_mg, sizeof(cfdk::MgScalars), cudaHostAllocDefault));
     CFD_CUDA(cudaStreamSynchronize(stream));
+    // strips over peer memory: everything the V-cycle exchanges
+    peer_register(mg_rho.base);
+    for (auto& f : mg_b) peer_register(f.base);
+    for (auto& f : mg_hist) peer_register(f.base);
+    for (int l = 1; l <= mg_ld; ++l) { peer_register(mg[(size_t)l].e); peer_register(mg[(size_t)l].tmp); }
+    if (world > 1 && mg_ld + 1 < (int)mg.size()) peer_register(mg[(size_t)mg_ld + 1].rho, true);
+    if ((rc = peer_sync())) return rc;
     return CFD_OK;
   }
 
@@ -1023,6 +1203,13 @@ struct ModelImpl final : ModelBase {
   int exchange_level(R* f, int l) {
     const size_t pitch = (size_t)mg[(size_t)l].mx + 2;
     const int lo = lvl_lo(l, rank), hi = lvl_hi(l, rank);
+    if (const PeerBuf* pb = peer_find(f)) {
+      // coarse arrays are allocated in full on every rank: same offsets everywhere.  Down: my first owned row (lo + 1) is
+      // the lower rank's upper halo row; up: my last owned row (hi) is the upper rank's lower halo row
+      R* dst_down = rank > 0 ? (R*)pb->map[rank - 1] + (size_t)(lo + 1) * pitch : nullptr;
+      R* dst_up = rank < world - 1 ? (R*)pb->map[rank + 1] + (size_t)hi * pitch : nullptr;
+      return peer_push(f + (size_t)(lo + 1) * pitch, dst_down, pitch * sizeof(R), f + (size_t)hi * pitch, dst_up, pitch * sizeof(R));
+    }
     CFD_NCCL(nccl_api().GroupStart());
     if (rank > 0) {
       CFD_NCCL(nccl_api().Send(f + (size_t)(lo + 1) * pitch, pitch, nccl_real(), rank - 1, comm, stream));
@@ -1038,6 +1225,26 @@ struct ModelImpl final : ModelBase {
   // every rank receives every rank's rows of a level-l field (one in-place broadcast per owner, grouped)
   int gather_level(R* f, int l) {
     const size_t pitch = (size_t)mg[(size_t)l].mx + 2;
+    if (const PeerBuf* pb = peer_find(f)) {
+      if (!pb->want_all) return fail(CFD_ERR_UNSUPPORTED, "gather_level: buffer is not mapped on every rank");
+      const int lo = lvl_lo(l, rank), hi = lvl_hi(l, rank);
+      cfdk::PeerGather g;
+      memset(&g, 0, sizeof g);
+      const size_t off = (size_t)(lo + 1) * pitch;
+      g.src = (const uint32_t*)(f + off);
+      for (int r = 0; r < world; ++r) g.dst[r] = r == rank ? nullptr : (uint32_t*)((R*)pb->map[r] + off);
+      g.words = hi > lo ? (size_t)(hi - lo) * pitch * sizeof(R) / 4 : 0;
+      g.all = peer_all();
+      g.ticket = peer_ticket + 1;
+      g.seq = ++gseq;
+      int grid = (int)((g.words + 2047) / 2048);
+      if (grid < 1) grid = 1;
+      if (grid > 128) grid = 128;
+      cfdk::k_peer_gather<<<grid, 256, 0, stream>>>(g, nullptr);
+      ++launches;
+      CFD_CUDA(cudaGetLastError());
+      return CFD_OK;
+    }
     CFD_NCCL(nccl_api().GroupStart());
     for (int r = 0; r < world; ++r) {
       const int lo = lvl_lo(l, r), hi = lvl_hi(l, r);
@@ -1051,7 +1258,12 @@ struct ModelImpl final : ModelBase {
   // strips: finish a dot product whose rank-local sum sits in mg_scalars->local_sum
   int mg_finish_strips(const cfdk::MgFine<R>& c, int mode) {
     if (world == 1) return CFD_OK;
-    CFD_NCCL(nccl_api().AllReduce(&mg_scalars->local_sum, &mg_scalars->local_sum, 1, ncclFloat64, ncclSum, comm, stream));
+    if (peer2_ready) {
+      int rc;
+      if ((rc = peer_reduce(&mg_scalars->local_sum, 1, 1))) return rc;
+    } else {
+      CFD_NCCL(nccl_api().AllReduce(&mg_scalars->local_sum, &mg_scalars->local_sum, 1, ncclFloat64, ncclSum, comm, stream));
+    }
     cfdk::k_mg_advance<R><<<1, 32, 0, stream>>>(c, mg_scalars, mode);
     ++launches;
     return CFD_OK;
@@ -1169,7 +1381,18 @@ struct ModelImpl final : ModelBase {
       std::swap(zc, zo);
       return exchange_halo(mg_b[zc], ja, jb, 1);  // strips: the neighbours' new edge rows (no-op on one GPU)
     };
-    {
+    // V(nu, nu) with nu >= 2: the first two pre-smoothing sweeps are one pass over rho, and the prolongation is folded
+    // into the first post-smoothing sweep (k_mg_fused_sweep; bit-identical to the separate kernels, which
+    // CFD_FLAG_MG_UNFUSED keeps for the cross-check)
+    const bool fused = nu_s >= 2 && !(opt.flags & CFD_FLAG_MG_UNFUSED);
+    const dim3 g_fs((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads), (rows + cfdk::kFsRows - 1) / cfdk::kFsRows);
+    if (fused) {
+      if ((rc = exchange_halo(mg_rho, ja, jb, 1))) return rc;  // strips: the stencil of the second sweep reaches into rho's halo
+      cfdk::k_mg_fused_sweep<R, 0><<<g_fs, cfdk::kMgThreads, 0, stream>>>(c, c2, mg_rho.v, nullptr, 0, nullptr, mg_b[zo].v, mg_scalars);
+      ++launches;
+      std::swap(zc, zo);
+      if ((rc = exchange_halo(mg_b[zc], ja, jb, 1))) return rc;
+    } else {
       // first sweep from z = 0: pointwise (k_mg_first_sweep) instead of a stencil sweep over a zero field
       const dim3 g_vec((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads), (rows + cfdk::kMgRows - 1) / cfdk::kMgRows);
       cfdk::k_mg_first_sweep<R><<<g_vec, cfdk::kMgThreads, 0, stream>>>(c, c2.omega, c2.one_minus_omega, div_denom,
@@ -1177,8 +1400,9 @@ struct ModelImpl final : ModelBase {
       ++launches;
       if ((rc = exchange_halo(mg_b[zc], ja, jb, 1))) return rc;
     }
-    for (int s = 1; s < nu_s; ++s)
+    for (int s = fused ? 2 : 1; s < nu_s; ++s)
       if ((rc = smooth(false))) return rc;
+    bool prolong_fused = false;
     if (mg.size() > 1) {
       MgLevelHost& C = mg[1];
       const int c_lo = world > 1 ? lvl_lo(1, rank) : 0, c_hi = world > 1 ? lvl_hi(1, rank) : C.my;
@@ -1187,14 +1411,24 @@ struct ModelImpl final : ModelBase {
       ++launches;
       if (world > 1 && !lvl_dist(1) && (rc = gather_level(C.rho, 1))) return rc;
       if ((rc = mg_coarse_vcycle(1))) return rc;
-      // strips: also correct the neighbours' edge rows (halo) of z, from the parent's halo rows
-      const int p_lo = world > 1 && c.row_lo > 1 ? c.row_lo - 1 : c.row_lo;
-      const int p_hi = world > 1 && c.row_hi < ny - 1 ? c.row_hi + 1 : c.row_hi;
-      const dim3 g_int((nx - 2 + cfdk::kMgThreads - 1) / cfdk::kMgThreads, p_hi - p_lo);
-      cfdk::k_mg_fine_prolong<R><<<g_int, blk, 0, stream>>>(c, mg_b[zc].v, C.mx, C.cur, p_lo, mg_scalars);
-      ++launches;
+      if (fused) {
+        // z + correction is formed on the fly by the first post-smoothing sweep (halo rows: from the parent's halo rows)
+        cfdk::k_mg_fused_sweep<R, 1><<<g_fs, cfdk::kMgThreads, 0, stream>>>(c, c2, mg_rho.v, mg_b[zc].v, C.mx, C.cur, mg_b[zo].v,
+                                                                            mg_scalars);
+        ++launches;
+        std::swap(zc, zo);
+        if ((rc = exchange_halo(mg_b[zc], ja, jb, 1))) return rc;
+        prolong_fused = true;
+      } else {
+        // strips: also correct the neighbours' edge rows (halo) of z, from the parent's halo rows
+        const int p_lo = world > 1 && c.row_lo > 1 ? c.row_lo - 1 : c.row_lo;
+        const int p_hi = world > 1 && c.row_hi < ny - 1 ? c.row_hi + 1 : c.row_hi;
+        const dim3 g_int((nx - 2 + cfdk::kMgThreads - 1) / cfdk::kMgThreads, p_hi - p_lo);
+        cfdk::k_mg_fine_prolong<R><<<g_int, blk, 0, stream>>>(c, mg_b[zc].v, C.mx, C.cur, p_lo, mg_scalars);
+        ++launches;
+      }
     }
-    for (int s = 0; s < nu_s; ++s)
+    for (int s = prolong_fused ? 1 : 0; s < nu_s; ++s)
       if ((rc = smooth(s == nu_s - 1))) return rc;
     if ((rc = mg_finish_strips(c, 1))) return rc;
     CFD_CUDA(cudaGetLastError());
@@ -1254,18 +1488,28 @@ struct ModelImpl final : ModelBase {
   }
 
   // set-up shared by every MGCG solve, before the divergence kernel (which may already accumulate rho.rho)
-  int mgcg_begin() {
+  void note_first_solve(double bb, double rel, int iterations, R dt_sub) {
+    step_bb = bb;
+    last_p_rel = rel;
+    const R n_unknowns = R((size_t)(nx - 2) * (size_t)(ny - 2));
+    last_rhs_rms = (double)(dt_sub * (R)std::sqrt((double)((R)bb / n_unknowns)));
+    last_first_solve_iterations = (uint64_t)iterations;
+  }
+
+  int mgcg_begin(bool first_solve) {
     int rc;
     if (mg.empty() && (rc = mg_setup())) return rc;
     cfdk::MgScalars init;
     memset(&init, 0, sizeof init);
     init.max_iterations = opt.consts.cg_max_iterations;
+    init.relative = opt.consts.cg_relative;
+    init.bb = first_solve ? 0.0 : step_bb;  // a first solve's own ||rhs||^2 comes out of its divergence kernel
     *h_mg = init;
     CFD_CUDA(cudaMemcpyAsync(mg_scalars, h_mg, sizeof init, cudaMemcpyHostToDevice, stream));
     return CFD_OK;
   }
 
-  int mgcg_solve(R dt_sub, int call_index, R* residual_out, bool decided_early, bool* elided) {
+  int mgcg_solve(R dt_sub, int call_index, R* residual_out, bool decided_early, bool* elided, size_t ev) {
     int rc;
     const cfdk::MgFine<R> c = mg_fine(dt_sub);
     const dim3 blk(cfdk::kMgThreads);
@@ -1277,7 +1521,7 @@ struct ModelImpl final : ModelBase {
     const bool first_solve = call_index == 0;
     const bool warm = first_solve && opt.consts.mg_warm_start != 0;
     int& pred = mg_pred[first_solve ? 0 : 1];
-    CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index], stream));
+    CFD_CUDA(cudaEventRecord(ev_sweep[ev], stream));
     auto read_scalars = [&]() -> int {
       CFD_CUDA(cudaMemcpyAsync(h_mg, mg_scalars, sizeof(cfdk::MgScalars), cudaMemcpyDeviceToHost, stream));
       CFD_CUDA(cudaStreamSynchronize(stream));
@@ -1288,7 +1532,7 @@ struct ModelImpl final : ModelBase {
       if (world > 1 && (rc = mg_finish_strips(c, 0))) return rc;
       if ((rc = read_scalars())) return rc;
       if (h_mg->done) {  // converged with p' = 0: no set-up pass, no corrector
-        CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index + 1], stream));
+        CFD_CUDA(cudaEventRecord(ev_sweep[ev + 1], stream));
         pp_zero_pending = true;
         pred = 0;
         last_K += 1;
@@ -1344,7 +1588,8 @@ struct ModelImpl final : ModelBase {
     ++launches;
     if ((rc = exchange_halo(xf, ja, jb, 1))) return rc;  // the corrector reads p'[j-1] (src/model.rs:1380)
     if (first_solve) mg_rotate_pending = true;           // this p' is the newest entry of the start-vector history
-    CFD_CUDA(cudaEventRecord(ev_sweep[2 * call_index + 1], stream));
+    if (first_solve) note_first_solve(h_mg->bb, h_mg->rel, h_mg->iterations, dt_sub);
+    CFD_CUDA(cudaEventRecord(ev_sweep[ev + 1], stream));
     CFD_CUDA(cudaGetLastError());
     last_S += (uint64_t)h_mg->iterations;
     last_K += 1;
@@ -1370,8 +1615,6 @@ struct ModelImpl final : ModelBase {
     launches = 0;
     ev_prof_used = 0;
     CFD_CUDA(cudaEventRecord(ev_step0, stream));
-    // u_old <- u, v_old <- v (:307-308): the current buffers simply stay untouched until the step ends
-    const int X = iu, Y = ius, Z = ifree;
     if (simulation_step < (uint64_t)opt.consts.ramp_up_steps) {  // :311-316
       current_inlet_velocity = (R(simulation_step) / R(opt.consts.ramp_up_steps)) * target_inlet_velocity;
     } else {
@@ -1384,6 +1627,18 @@ struct ModelImpl final : ModelBase {
     last_K = 0;
     last_S = 0;
     int rc;
+    // u_old <- u, v_old <- v (:307-308): with one piso_step per update (the reference's substep_count, :267) the current
+    // buffers simply stay untouched until the step ends; several sub-steps (adaptive_substeps) need a real copy
+    const uint64_t n_sub = substep_count;
+    if (n_sub > 1) {
+      if (!uold_buf.base && ((rc = falloc(&uold_buf, (size_t)nx + 1)) || (rc = falloc(&vold_buf, (size_t)nx)))) return rc;
+      CFD_CUDA(cudaMemcpyAsync(uold_buf.row(ja), ubuf[iu].row(ja), own_u() * sizeof(R), cudaMemcpyDeviceToDevice, stream));
+      CFD_CUDA(cudaMemcpyAsync(vold_buf.row(ja), vbuf[iu].row(ja), own_v() * sizeof(R), cudaMemcpyDeviceToDevice, stream));
+    }
+    old_in_copy = n_sub > 1;
+    ev_sweep_used = 0;
+    for (uint64_t sub = 0; sub < n_sub; ++sub) {  // :322-329, piso_step (:529-730) inlined
+    const int X = iu, Y = ius, Z = ifree;
     // strips: the predictor stencils reach two rows into the neighbours (second order)
     if ((rc = exchange_halo(ubuf[X], ja, jb, kHalo))) return rc;
     if ((rc = exchange_halo(vbuf[X], ja, v_row_end(), kHalo))) return rc;
@@ -1394,11 +1649,16 @@ struct ModelImpl final : ModelBase {
       const int jv_lo = ja > 1 ? ja : 1, jv_hi = v_row_end() < ny ? v_row_end() : ny;  // v rows 1..ny-1
       cfdk::PredDivs<R> pd;
       pd.dx = h_divs.dx; pd.dy = h_divs.dy; pd.dx_sq = h_divs.dx_sq; pd.dy_sq = h_divs.dy_sq;
-      if (velocity_scheme == CFD_SCHEME_SECOND_ORDER) {
+      if (velocity_scheme != CFD_SCHEME_FIRST_ORDER) {
         dim3 blk(256);
         dim3 gu((nx + 255) / 256, ju_hi - ju_lo), gv((nx - 1 + 255) / 256, jv_hi - jv_lo);
-        cfdk::k_predict_u<R, true><<<gu, blk, 0, stream>>>(s, pd, ubuf[X].v, vbuf[X].v, mask_u.v, ubuf[Y].v, ju_lo, ju_hi);
-        cfdk::k_predict_v<R, true><<<gv, blk, 0, stream>>>(s, pd, ubuf[X].v, vbuf[X].v, mask_v.v, vbuf[Y].v, jv_lo, jv_hi);
+        if (velocity_scheme == CFD_SCHEME_QUICK) {  // extension: the JS twin's QUICK face values
+          cfdk::k_predict_u<R, 2><<<gu, blk, 0, stream>>>(s, pd, ubuf[X].v, vbuf[X].v, mask_u.v, ubuf[Y].v, ju_lo, ju_hi);
+          cfdk::k_predict_v<R, 2><<<gv, blk, 0, stream>>>(s, pd, ubuf[X].v, vbuf[X].v, mask_v.v, vbuf[Y].v, jv_lo, jv_hi);
+        } else {
+          cfdk::k_predict_u<R, 1><<<gu, blk, 0, stream>>>(s, pd, ubuf[X].v, vbuf[X].v, mask_u.v, ubuf[Y].v, ju_lo, ju_hi);
+          cfdk::k_predict_v<R, 1><<<gv, blk, 0, stream>>>(s, pd, ubuf[X].v, vbuf[X].v, mask_v.v, vbuf[Y].v, jv_lo, jv_hi);
+        }
         launches += 2;
       } else {
         // first order: both equations in one pass over u and v
@@ -1468,23 +1728,44 @@ struct ModelImpl final : ModelBase {
         ++launches;
       }
     }
+    iu = cur; ius = star; ifree = X;
+    }  // sub-steps
     // ---- residuals and CFL maxima (:333-348, :878-881) over the owned rows, then over the ranks
     CFD_CUDA(cudaMemsetAsync(step_slots, 0, 4 * sizeof(unsigned long long), stream));
     {
       const size_t nu_own = (size_t)(jb - ja) * (nx + 1), nv_own = (size_t)(v_row_end() - ja) * nx;
-      cfdk::k_step_maxima<R><<<148 * 8, 256, 0, stream>>>(ubuf[cur].row(ja), ubuf[X].row(ja), nu_own, vbuf[cur].row(ja),
-                                                         vbuf[X].row(ja), nv_own, step_slots);
+      const Field<R>& uo = old_in_copy ? uold_buf : ubuf[ifree];
+      const Field<R>& vo = old_in_copy ? vold_buf : vbuf[ifree];
+      cfdk::k_step_maxima<R><<<148 * 8, 256, 0, stream>>>(ubuf[iu].row(ja), uo.row(ja), nu_own, vbuf[iu].row(ja), vo.row(ja), nv_own,
+                                                         step_slots);
       ++launches;
     }
     if ((rc = allreduce_max_u64(step_slots, 4))) return rc;
     CFD_CUDA(cudaMemcpyAsync(h_step, step_slots, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    h_step[4] = 0ull;
+    if (peer2_ready) CFD_CUDA(cudaMemcpyAsync(h_step + 4, &box->error, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     CFD_CUDA(cudaEventRecord(ev_step1, stream));
     CFD_CUDA(cudaGetLastError());
     CFD_CUDA(cudaStreamSynchronize(stream));
-    iu = cur; ius = star; ifree = X;
+    if (h_step[4] != 0ull)
+      return fail(CFD_ERR_PEER_TIMEOUT, "strips over peer memory: a neighbour did not answer within 20 s (exchange / reduction " +
+                                            std::to_string((unsigned long long)h_step[4]) + "); the model's state is undefined");
     last_u_residual = (R)cfdk::bits_nonneg(h_step[0]);
     last_v_residual = (R)cfdk::bits_nonneg(h_step[1]);
     simulation_step += 1;    // :350
+    if (opt.consts.adaptive_substeps) {
+      // EXTENSION: the reference's sub-step adaptation, commented out at src/model.rs:352-363, made live
+      const R error_norm = last_pressure_residual;
+      const R tolerance = R(1e-3);
+      if (error_norm > tolerance) {
+        const R factor = error_norm / tolerance;
+        const R grown = std::ceil(R(substep_count) * factor);
+        substep_count = (uint64_t)(grown < R(20.0) ? grown : R(20.0));
+      } else if (error_norm < tolerance / R(2.0) && substep_count > 1) {
+        substep_count = (uint64_t)std::floor(R(substep_count) / R(2.0));
+        if (substep_count < 1) substep_count = 1;
+      }
+    }
     simulation_time += dt;   // :365
     // compute_automatic_time_step (:878-889) + the (dead) growth limiter (:368-377)
     {
@@ -1511,8 +1792,8 @@ struct ModelImpl final : ModelBase {
     CFD_CUDA(cudaEventElapsedTime(&ms, ev_step0, ev_step1));
     last_step_ms = ms;
     last_sweep_ms = 0;
-    for (uint64_t k = 0; k < last_K; ++k) {
-      CFD_CUDA(cudaEventElapsedTime(&ms, ev_sweep[2 * k], ev_sweep[2 * k + 1]));
+    for (size_t k = 0; k + 1 < ev_sweep_used; k += 2) {
+      CFD_CUDA(cudaEventElapsedTime(&ms, ev_sweep[k], ev_sweep[k + 1]));
       last_sweep_ms += ms;
     }
     last_launches = launches;
@@ -1528,8 +1809,12 @@ struct ModelImpl final : ModelBase {
 
   // Model::set_parameters, src/model.rs:1250-1257
   int set_params(const cfd_params& prm) override {
-    if (prm.pressure_solver < CFD_SOLVER_JACOBI || prm.pressure_solver > CFD_SOLVER_MGCG)
-      return fail(CFD_ERR_INVALID_ARGUMENT, "pressure_solver out of range");
+    // the same enum checks as cfd_model_create_ex (`scenario` is not a parameter of set_parameters and is ignored);
+    // dt and viscosity are taken as they are, like the reference's set_parameters (:1250-1257) — a NaN dt "just shows
+    // NaNs" there too
+    if (prm.pressure_solver < CFD_SOLVER_JACOBI || prm.pressure_solver > CFD_SOLVER_MGCG || prm.velocity_scheme < 0 ||
+        prm.velocity_scheme > CFD_SCHEME_QUICK || prm.inlet_profile < 0 || prm.inlet_profile > CFD_INLET_PARABOLIC)
+      return fail(CFD_ERR_INVALID_ARGUMENT, "set_parameters: enum value out of range");
     nu = R(prm.viscosity);
     dt = R(prm.dt);
     target_inlet_velocity = R(prm.target_inlet_velocity);
@@ -1671,6 +1956,10 @@ struct ModelImpl final : ModelBase {
     out->p_f64 = (double)last_pressure_residual;
     out->u_f64 = (double)last_u_residual;
     out->v_f64 = (double)last_v_residual;
+    const bool mode_c = pressure_solver != CFD_SOLVER_JACOBI;
+    out->p_rel_f64 = mode_c ? last_p_rel : 0.0;
+    out->rhs_rms_f64 = mode_c ? last_rhs_rms : 0.0;
+    out->first_solve_iterations = mode_c ? last_first_solve_iterations : 0;
     return CFD_OK;
   }
 
@@ -1697,8 +1986,8 @@ struct ModelImpl final : ModelBase {
       case CFD_FIELD_RHS: *n = own_p(); return rhs.row(ja);
       case CFD_FIELD_P_PRIME: *n = own_p(); return pp[ipp].row(ja);
       // after a step the free buffer still holds the fields the step started from (u_old, v_old)
-      case CFD_FIELD_U_OLD: *n = own_u(); return ubuf[ifree].row(ja);
-      case CFD_FIELD_V_OLD: *n = own_v(); return vbuf[ifree].row(ja);
+      case CFD_FIELD_U_OLD: *n = own_u(); return old_in_copy ? uold_buf.row(ja) : ubuf[ifree].row(ja);
+      case CFD_FIELD_V_OLD: *n = own_v(); return old_in_copy ? vold_buf.row(ja) : vbuf[ifree].row(ja);
       case CFD_FIELD_MG_GUESS:
       case CFD_FIELD_MG_LAST:
       case CFD_FIELD_MG_LAST2: {
@@ -1845,7 +2134,7 @@ int cfd_model_create_ex(const cfd_grid* grid, const cfd_params* params, const cf
   if (o.consts.outer_rounds < 0 || o.consts.outer_rounds > 1000) return fail(CFD_ERR_INVALID_ARGUMENT, "outer_rounds out of range");
   if (o.consts.mg_warm_start < 0 || o.consts.mg_warm_start > 3 || o.consts.mg_smoothing < 1 || o.consts.mg_smoothing > 16 || !(o.consts.mg_omega > 0.0) || !(o.consts.mg_omega <= 1.0))
     return fail(CFD_ERR_INVALID_ARGUMENT, "mg_smoothing must be in 1..16 and mg_omega in (0, 1]");
-  if (params->velocity_scheme < 0 || params->velocity_scheme > 1 || params->inlet_profile < 0 ||
+  if (params->velocity_scheme < 0 || params->velocity_scheme > CFD_SCHEME_QUICK || params->inlet_profile < 0 ||
       params->inlet_profile > 1 || params->scenario < 0 || params->scenario > 1 || params->pressure_solver < 0 ||
       params->pressure_solver > CFD_SOLVER_MGCG)
     return fail(CFD_ERR_INVALID_ARGUMENT, "params: enum value out of range");

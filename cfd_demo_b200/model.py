@@ -162,7 +162,7 @@ class Model:
 
     @classmethod
     def strip(cls, grid: Grid, params: SimulationParams, rank: int, world_size: int, unique_id: bytes,
-              device: int = -1, precision: int = 64, flags: int = 0) -> "Model":
+              device: int = -1, precision: int = 64, flags: int = 0, consts=None) -> "Model":
         """One rank of a row-strip decomposition over `world_size` GPUs (one process per GPU).  `unique_id` is
         the 128-byte id from `nccl_unique_id()` on rank 0, broadcast by the launcher.  Import torch BEFORE this
         module in such processes, so that the process shares one libnccl.so.2."""
@@ -170,6 +170,8 @@ class Model:
             raise CfdError(_abi.CFD_ERR_INVALID_ARGUMENT, "unique_id must be 128 bytes")
         opts = default_options()
         opts.precision, opts.device, opts.rank, opts.world_size, opts.flags = precision, device, rank, world_size, flags
+        if consts is not None:
+            opts.consts = consts
         buf = C.create_string_buffer(unique_id, 128)
         opts.nccl_unique_id = C.cast(buf, C.c_void_p)
         m = cls(grid, params, options=opts)

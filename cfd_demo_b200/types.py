@@ -22,6 +22,7 @@ f32 = np.float32
 class VelocityScheme(enum.IntEnum):
     FirstOrder = _abi.SCHEME_FIRST_ORDER
     SecondOrder = _abi.SCHEME_SECOND_ORDER
+    Quick = _abi.SCHEME_QUICK  # extension: the JS twin's QUICK face values (index.html:471-549, :643-723)
 
 
 class PressureSolver(enum.IntEnum):
@@ -130,7 +131,8 @@ class Residuals:
                          float(r.u), float(r.v), float(r.step_seconds), int(r.piso_substeps),
                          int(r.jacobi_calls), int(r.sweeps),
                          {"simulation_time": r.simulation_time_f64, "dt": r.dt_f64, "p": r.p_f64,
-                          "u": r.u_f64, "v": r.v_f64})
+                          "u": r.u_f64, "v": r.v_f64, "p_rel": r.p_rel_f64, "rhs_rms": r.rhs_rms_f64,
+                          "first_solve_iterations": int(r.first_solve_iterations)})
 
 
 @dataclass

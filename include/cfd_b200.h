@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define CFD_ABI_VERSION 2
+#define CFD_ABI_VERSION 3
 
 /* ---- status codes ---------------------------------------------------------------------------- */
 #define CFD_OK 0
@@ -29,11 +29,15 @@ extern "C" {
 #define CFD_ERR_CUDA 2
 #define CFD_ERR_UNSUPPORTED 3
 #define CFD_ERR_NCCL 4
+#define CFD_ERR_PEER_TIMEOUT 5 /* strips over peer memory: a neighbour did not answer within 20 s (it died or returned an error) */
 
 /* ---- enums (values are ABI) -------------------------------------------------------------------- */
 /* VelocityScheme, src/model.rs:142-146 */
 #define CFD_SCHEME_FIRST_ORDER 0
 #define CFD_SCHEME_SECOND_ORDER 1
+/* extension: the JS twin's QUICK face values (index.html:471-549 u, :643-723 v) inside the Rust
+ * model's predictor (same loops, flux velocities, Laplacian, masks as SecondOrder: src/model.rs:538-670) */
+#define CFD_SCHEME_QUICK 2
 /* InletProfile, src/model.rs:155-159 */
 #define CFD_INLET_UNIFORM 0
 #define CFD_INLET_PARABOLIC 1
@@ -100,6 +104,14 @@ typedef struct cfd_solver_consts {
                               * 2 p'_n - p'_(n-1) (the JS twin's "extrapolated initial guess", index.html:262-270);
                               * 3 (default) = quadratic, 3 p'_n - 3 p'_(n-1) + p'_(n-2);
                               * 0 and every re-correction solve = start from p' = 0 */
+  int32_t cg_relative;       /* extension (CG, MGCG) stopping rule: 0 (default) = dt * rms(r) <= cg_tolerance, the rms
+                              * divergence the correction leaves in the velocity; 1 = ||r||_2 <= cg_tolerance * ||rhs||_2 with
+                              * rhs the right-hand side of the step's FIRST solve (the relative L2 norm SURVEY 8d states for
+                              * the 4096^2 cavity; re-correction solves measure against the same reference) */
+  int32_t adaptive_substeps; /* extension: 0 (default) = substep_count stays 1 like the reference, whose
+                              * adaptation is commented out (src/model.rs:352-363); 1 = that commented-out rule is live:
+                              * after a step, error = last_pressure_residual; error > 1e-3 -> substeps = min(ceil(substeps *
+                              * error / 1e-3), 20); error < 1e-3 / 2 and substeps > 1 -> substeps = max(floor(substeps / 2), 1) */
 } cfd_solver_consts;
 
 typedef struct cfd_options {
@@ -124,6 +136,10 @@ typedef struct cfd_options {
 #define CFD_FLAG_TEMPORAL 64u      /* two sweeps per HBM pass (k_jacobi_sweep_t2) instead of one per launch (A/B; slower, issue-bound) */
 #define CFD_FLAG_PERSISTENT_SWEEP 128u /* persistent warp-queue kernel (k_jacobi_sweep6) instead of one block per tile (A/B; slower) */
 #define CFD_FLAG_MG_NO_BOTTOM_KERNEL 256u /* MGCG: one launch per operation on every level instead of the single-block bottom kernel (A/B, cross-check) */
+#define CFD_FLAG_MG_UNFUSED 1024u  /* MGCG: separate first-sweep / sweep and prolongation / sweep kernels instead of the fused passes (A/B, cross-check) */
+#define CFD_FLAG_PEER_STRIPS 2048u /* strips: halo rows, gathers and scalar reductions as single small kernels over NVLink peer memory
+                                    * (CUDA IPC; cfd_peer.cuh) instead of NCCL send/recv / broadcast / allreduce — every solver mode;
+                                    * waits are bounded (CFD_ERR_PEER_TIMEOUT).  Environment override: CFD_PEER_STRIPS=0/1 */
 #define CFD_FLAG_BULK_SWEEP 8u     /* row-by-row cp.async.bulk Jacobi kernel instead of the tensor-TMA one (A/B) */
 
 /* Residuals, src/model.rs:23-32.  f32 members mirror the reference; the trailing members are
@@ -136,6 +152,9 @@ typedef struct cfd_residuals {
   uint64_t jacobi_calls;      /* K: pressure solves in the last step (2..21) */
   uint64_t sweeps;            /* S: Jacobi sweeps (or CG iterations) in the last step */
   double simulation_time_f64, dt_f64, p_f64, u_f64, v_f64;
+  /* Mode C (CG, MGCG), last step: the first solve's final ||r||_2 / ||rhs||_2 and its dt * rms(rhs) (0 in Mode R) */
+  double p_rel_f64, rhs_rms_f64;
+  uint64_t first_solve_iterations; /* CG iterations of the step's first solve (the re-correction solves take the rest) */
 } cfd_residuals;
 
 typedef struct cfd_model cfd_model; /* opaque: owns device buffers, streams, graphs, (optional) NCCL comm */

@@ -26,6 +26,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <functional>
+#include <limits>
 #include <utility>
 #include <vector>
 
@@ -77,6 +78,11 @@ class Model {
   // ---- additions: constants as data, counters, strip support ----
   cfd_solver_consts consts;
   uint64_t last_jacobi_calls = 0, last_sweeps = 0;  // K and S of the last update()
+  int piso_solve_index = 0;                         // pressure solves so far in the current piso_step
+  // Mode C bookkeeping of the last step's first solve: ||rhs||^2 over the unknowns (the reference of the relative
+  // stopping rule, cg_relative), final ||r|| / ||rhs||, dt * rms(rhs), iterations
+  R mg_bb = 0, last_p_rel = 0, last_rhs_rms = 0;
+  uint64_t last_first_solve_iterations = 0;
   uint64_t total_sweeps = 0;
   size_t ja = 0, jb = 0;  // owned pressure rows [ja, jb); whole grid by default
   bool owns_top = true;   // owns v row ny
@@ -170,6 +176,8 @@ class Model {
     c->mg_omega = 0.8;
     c->mg_smoothing = 2;
     c->mg_warm_start = 3;
+    c->cg_relative = 0;
+    c->adaptive_substeps = 0;
   }
 
   // Model::set_parameters, src/model.rs:1250-1257
@@ -218,6 +226,20 @@ class Model {
     last_u_residual = max_residual_u;
     last_v_residual = max_residual_v;
     simulation_step += 1;   // :350
+    if (consts.adaptive_substeps) {
+      // EXTENSION: the reference's own sub-step adaptation, commented out at src/model.rs:352-363,
+      // made live.  f32 semantics of the Rust: `.ceil().min(20.0) as usize`, `(x / 2.0).floor() as usize`.
+      const R error_norm = last_pressure_residual;
+      const R tolerance = R(1e-3);
+      if (error_norm > tolerance) {
+        const R factor = error_norm / tolerance;
+        const R grown = std::ceil(R(substep_count) * factor);
+        substep_count = size_t(grown < R(20.0) ? grown : R(20.0));
+      } else if (error_norm < tolerance / R(2.0) && substep_count > 1) {
+        substep_count = size_t(std::floor(R(substep_count) / R(2.0)));
+        if (substep_count < 1) substep_count = 1;
+      }
+    }
     simulation_time += dt;  // :365
     const R previous_dt = dt;  // :368-377
     const R new_dt = compute_automatic_time_step();
@@ -231,6 +253,7 @@ class Model {
       hooks.exchange(u, nx + 1, ny, 2, 2);
       hooks.exchange(v, nx, ny + 1, 2, 2);
     }
+    piso_solve_index = 0;
     predictor_u(dt_sub);  // :538-580
     predictor_v(dt_sub);  // :586-670
     if (hooks.exchange) hooks.exchange(v_star, nx, ny + 1, 0, 1);
@@ -257,8 +280,10 @@ class Model {
 
   R pressure_solve(R dt_sub) {
     last_jacobi_calls += 1;
-    if (pressure_solver == CFD_SOLVER_CG) return cg_pressure(dt_sub);
-    if (pressure_solver == CFD_SOLVER_MGCG) return mgcg_pressure(dt_sub);
+    const bool first_solve = piso_solve_index == 0;
+    piso_solve_index += 1;
+    if (pressure_solver == CFD_SOLVER_CG) return cg_pressure(dt_sub, first_solve);
+    if (pressure_solver == CFD_SOLVER_MGCG) return mgcg_pressure(dt_sub, first_solve);
     return jacobi_pressure();
   }
 
@@ -268,7 +293,9 @@ class Model {
   void predictor_u(R dt_sub) {
     const size_t j_lo = std::max<size_t>(1, ja), j_hi = std::min(ny - 1, jb);
     const size_t W = nx + 1;
-    const bool second = velocity_scheme == CFD_SCHEME_SECOND_ORDER;
+    // EXTENSION: QUICK takes the SecondOrder code path (scalar face helpers per lane) with its own face values
+    const bool second = velocity_scheme != CFD_SCHEME_FIRST_ORDER;
+    const bool quick = velocity_scheme == CFD_SCHEME_QUICK;
     for (size_t j = j_lo; j < j_hi; ++j) {
       for (size_t i = 1; i < nx; i += LANES) {  // (1..nx).step_by(LANES)
         R v_n[LANES], v_s[LANES], u_n[LANES], u_s[LANES], u_e[LANES], u_w[LANES];
@@ -295,6 +322,11 @@ class Model {
               const R avg = (uw + uc) * R(0.5);
               u_w[k] = (avg >= R(0)) ? uw : uc;
             }
+          } else if (quick) {
+            u_n[k] = u_face_n_quick(c, j);
+            u_s[k] = u_face_s_quick(c, j);
+            u_e[k] = u_face_e_quick(c, j);
+            u_w[k] = u_face_w_quick(c, j);
           } else {
             u_n[k] = u_face_n_second_order(c, j);
             u_s[k] = u_face_s_second_order(c, j);
@@ -386,12 +418,98 @@ class Model {
   }
 
   // ------------------------------------------------------------------------------------------------
+  // EXTENSION (no Rust counterpart): the JS twin's QUICK face values, index.html:471-549 (u) and
+  // :643-723 (v), evaluated inside the Rust predictor exactly where the SecondOrder helpers are (same loops, same
+  // un-averaged flux velocities :1056-1069, same Laplacian and masks; the upwind side is picked like the Rust
+  // SecondOrder helpers pick it).  JS expressions, left to right: (-a + 6 b + 3 c) / 8, (3 a + 6 b - c) / 8,
+  // 1.5 a - 0.5 b.  Column nx of the u equation reads "next row" entries through the flat index like every other
+  // scheme; all reads stay inside the arrays.
+  // ------------------------------------------------------------------------------------------------
+  static R quick3(R a, R b, R c) { return (-a + R(6) * b + R(3) * c) / R(8); }   // upstream-weighted, flow towards c
+  static R quick3r(R a, R b, R c) { return (R(3) * a + R(6) * b - c) / R(8); }   // flow towards a
+  R u_face_e_quick(size_t i, size_t j) const {  // index.html:473-488
+    const size_t idx = i + j * (nx + 1);
+    if (CFDO_AT(u, idx) >= R(0)) {
+      if (i >= 2) return quick3(CFDO_AT(u, idx - 1), CFDO_AT(u, idx), CFDO_AT(u, idx + 1));
+      return R(1.5) * CFDO_AT(u, idx) - R(0.5) * CFDO_AT(u, idx - 1);
+    }
+    if (i + 2 <= nx) return quick3r(CFDO_AT(u, idx), CFDO_AT(u, idx + 1), CFDO_AT(u, idx + 2));
+    return CFDO_AT(u, idx + 1);
+  }
+  R u_face_w_quick(size_t i, size_t j) const {  // index.html:491-502
+    const size_t idx = i + j * (nx + 1);
+    if (CFDO_AT(u, idx - 1) >= R(0)) {
+      if (i >= 3) return quick3(CFDO_AT(u, idx - 2), CFDO_AT(u, idx - 1), CFDO_AT(u, idx));
+      return R(1.5) * CFDO_AT(u, idx - 1) - R(0.5) * CFDO_AT(u, idx);
+    }
+    return quick3r(CFDO_AT(u, idx - 1), CFDO_AT(u, idx), CFDO_AT(u, idx + 1));
+  }
+  R u_face_n_quick(size_t i, size_t j) const {  // index.html:505-523
+    const size_t W = nx + 1, idx = i + j * W;
+    const R u_north = CFDO_AT(u, idx + W);
+    if (get_v_north_scalar(i, j) >= R(0)) {
+      if (j >= 2) return quick3(CFDO_AT(u, idx - W), CFDO_AT(u, idx), u_north);
+      return R(1.5) * CFDO_AT(u, idx) - R(0.5) * CFDO_AT(u, idx - W);
+    }
+    if (j + 2 < ny) return quick3r(CFDO_AT(u, idx), u_north, CFDO_AT(u, idx + 2 * W));
+    return u_north;
+  }
+  R u_face_s_quick(size_t i, size_t j) const {  // index.html:526-544
+    const size_t W = nx + 1, idx = i + j * W;
+    const R u_south = CFDO_AT(u, idx - W);
+    if (get_v_south_scalar(i, j) >= R(0)) {
+      if (j >= 2) return quick3(CFDO_AT(u, idx - 2 * W), u_south, CFDO_AT(u, idx));
+      return R(1.5) * u_south - R(0.5) * CFDO_AT(u, idx);
+    }
+    if (j + 1 < ny) return quick3r(u_south, CFDO_AT(u, idx), CFDO_AT(u, idx + W));
+    return CFDO_AT(u, idx);
+  }
+  R v_face_e_quick(size_t i, size_t j) const {  // index.html:645-662
+    const size_t idx = i + j * nx;
+    if (CFDO_AT(u, (i + 1) + j * (nx + 1)) >= R(0)) {
+      if (i >= 2) return quick3(CFDO_AT(v, idx - 1), CFDO_AT(v, idx), CFDO_AT(v, idx + 1));
+      return R(1.5) * CFDO_AT(v, idx) - R(0.5) * CFDO_AT(v, idx - 1);
+    }
+    if (i + 2 < nx) return quick3r(CFDO_AT(v, idx), CFDO_AT(v, idx + 1), CFDO_AT(v, idx + 2));
+    return CFDO_AT(v, idx + 1);
+  }
+  R v_face_w_quick(size_t i, size_t j) const {  // index.html:665-678
+    const size_t idx = i + j * nx;
+    if (CFDO_AT(u, i + j * (nx + 1)) >= R(0)) {
+      if (i >= 3) return quick3(CFDO_AT(v, idx - 2), CFDO_AT(v, idx - 1), CFDO_AT(v, idx));
+      return R(1.5) * CFDO_AT(v, idx - 1) - R(0.5) * CFDO_AT(v, idx);
+    }
+    return quick3r(CFDO_AT(v, idx - 1), CFDO_AT(v, idx), CFDO_AT(v, idx + 1));
+  }
+  R v_face_n_quick(size_t i, size_t j) const {  // index.html:681-698
+    const size_t idx = i + j * nx, idx_n = idx + nx;
+    const R avg = R(0.5) * (CFDO_AT(v, idx) + CFDO_AT(v, idx_n));
+    if (avg >= R(0)) {
+      if (j >= 2) return quick3(CFDO_AT(v, idx - nx), CFDO_AT(v, idx), CFDO_AT(v, idx_n));
+      return R(1.5) * CFDO_AT(v, idx) - R(0.5) * CFDO_AT(v, idx - nx);
+    }
+    if (j + 1 < ny) return quick3r(CFDO_AT(v, idx), CFDO_AT(v, idx_n), CFDO_AT(v, idx + 2 * nx));
+    return CFDO_AT(v, idx_n);
+  }
+  R v_face_s_quick(size_t i, size_t j) const {  // index.html:701-718
+    const size_t idx = i + j * nx, idx_s = idx - nx;
+    const R avg = R(0.5) * (CFDO_AT(v, idx_s) + CFDO_AT(v, idx));
+    if (avg >= R(0)) {
+      if (j >= 2) return quick3(CFDO_AT(v, idx_s - nx), CFDO_AT(v, idx_s), CFDO_AT(v, idx));
+      return R(1.5) * CFDO_AT(v, idx_s) - R(0.5) * CFDO_AT(v, idx);
+    }
+    if (j + 1 < ny) return quick3r(CFDO_AT(v, idx_s), CFDO_AT(v, idx), CFDO_AT(v, idx + nx));
+    return CFDO_AT(v, idx);
+  }
+
+  // ------------------------------------------------------------------------------------------------
   // v predictor: loop src/model.rs:586-670, compute_vstar :439-521, face helpers :1073-1248
   // ------------------------------------------------------------------------------------------------
   void predictor_v(R dt_sub) {
     const size_t j_lo = std::max<size_t>(1, ja), j_hi = std::min(ny, owns_top ? jb + 1 : jb);
     const size_t W = nx + 1;
-    const bool second = velocity_scheme == CFD_SCHEME_SECOND_ORDER;
+    const bool second = velocity_scheme != CFD_SCHEME_FIRST_ORDER;
+    const bool quick = velocity_scheme == CFD_SCHEME_QUICK;
     for (size_t j = j_lo; j < j_hi; ++j) {
       for (size_t i = 1; i < nx - 1; i += LANES) {  // (1..(nx-1)).step_by(LANES)
         R a_ue[LANES] = {0}, a_uw[LANES] = {0}, a_vn[LANES] = {0}, a_vs[LANES] = {0}, a_ve[LANES] = {0},
@@ -420,6 +538,11 @@ class Model {
             a_ve[k] = (a_ue[k] >= R(0)) ? vc : CFDO_AT(v, idx + 1);
             // v_face_w_first_order(_scalar) :1116-1142
             a_vw[k] = (a_uw[k] >= R(0)) ? CFDO_AT(v, idx - 1) : vc;
+          } else if (quick) {
+            a_vn[k] = v_face_n_quick(c, j);
+            a_vs[k] = v_face_s_quick(c, j);
+            a_ve[k] = v_face_e_quick(c, j);
+            a_vw[k] = v_face_w_quick(c, j);
           } else {
             a_vn[k] = v_face_n_second_order(c, j);
             a_vs[k] = v_face_s_second_order(c, j);
@@ -647,7 +770,19 @@ class Model {
     return acc;
   }
 
-  R cg_pressure(R dt_sub) {
+  // Mode C stopping rule (cg_tolerance): dt * rms(r) <= tol, or with cg_relative ||r||_2 <= tol * ||rhs||_2 where
+  // rhs is the right-hand side of the piso_step's FIRST solve (bb = its sum of squares over the unknowns)
+  bool mode_c_converged(R rr, R dt_sub, R n_unknowns) const {
+    const R tol = R(consts.cg_tolerance);
+    if (consts.cg_relative) return mode_c_relative(rr) <= tol;
+    return dt_sub * std::sqrt(rr / n_unknowns) <= tol;
+  }
+  R mode_c_relative(R rr) const {
+    if (mg_bb > R(0)) return std::sqrt(rr / mg_bb);
+    return rr > R(0) ? std::numeric_limits<R>::infinity() : R(0);
+  }
+
+  R cg_pressure(R dt_sub, bool first_solve) {
     const size_t n = nx * ny;
     if (cg_r.size() != n) { cg_r.assign(n, R(0)); cg_d.assign(n, R(0)); cg_q.assign(n, R(0)); }
     const size_t j_lo = std::max<size_t>(1, ja), j_hi = std::min(ny - 1, jb);
@@ -668,10 +803,10 @@ class Model {
       rr += row;
     }
     rr = reduce(rr);
-    const R tol = R(consts.cg_tolerance);
     auto measure = [&](R rr_) { return dt_sub * std::sqrt(rr_ / n_unknowns); };
+    if (first_solve) { mg_bb = rr; last_rhs_rms = measure(rr); }  // cold start: r = -rhs
     int it = 0;
-    while (it < consts.cg_max_iterations && !(measure(rr) <= tol)) {
+    while (it < consts.cg_max_iterations && !mode_c_converged(rr, dt_sub, n_unknowns)) {
       cg_fill_boundary(cg_d);
       const R dq = reduce(cg_apply(cg_d, cg_q));
       const R alpha = rr / dq;
@@ -700,6 +835,7 @@ class Model {
       total_sweeps += 1;
     }
     cg_fill_boundary(p_prime);
+    if (first_solve) { last_p_rel = mode_c_relative(rr); last_first_solve_iterations = uint64_t(it); }
     const R res = measure(rr);
     last_pressure_residual = res;
     return res;
@@ -886,7 +1022,7 @@ class Model {
     for (int s = 0; s < nu_s; ++s) { mg_fine_sweep(mg_z, mg_rho, mg_z2); std::swap(mg_z, mg_z2); }
   }
 
-  R mgcg_pressure(R dt_sub) {
+  R mgcg_pressure(R dt_sub, bool first_solve) {
     assert((!hooks.exchange || hooks.gather_rows) && "MGCG on strips needs the gather hook");
     const size_t n = nx * ny;
     if (mg_levels.empty()) mg_build_levels();
@@ -895,8 +1031,8 @@ class Model {
     }
     const size_t j_lo = std::max<size_t>(1, ja), j_hi = std::min(ny - 1, jb);  // owned rows of unknowns
     const R n_unknowns = R((nx - 2) * (ny - 2));
-    const R tol = R(consts.cg_tolerance);
     auto measure = [&](R rr_) { return dt_sub * std::sqrt(rr_ / n_unknowns); };
+    auto converged = [&](R rr_) { return mode_c_converged(rr_, dt_sub, n_unknowns); };
     // dot products: row sums, then over the owned rows, then over the ranks (the CUDA path sums in another order
     // -> tolerance parity)
     auto dot = [&](const std::vector<R>& a, const std::vector<R>& b) {
@@ -908,8 +1044,8 @@ class Model {
       }
       return hooks.allreduce_sum ? hooks.allreduce_sum(acc) : acc;
     };
-    const bool first_solve = last_jacobi_calls == 1;  // pressure_solve() counted this call already
     const bool warm = consts.mg_warm_start != 0 && first_solve;
+    if (first_solve) { mg_bb = dot(rhs, rhs); last_rhs_rms = measure(mg_bb); }
     if (warm) p_prime = mg_guess; else std::fill(p_prime.begin(), p_prime.end(), R(0));
     if (warm && hooks.exchange) hooks.exchange(p_prime, nx, ny, 1, 1);
     std::fill(mg_rho.begin(), mg_rho.end(), R(0));
@@ -919,7 +1055,7 @@ class Model {
         mg_rho[i + j * nx] = warm ? rhs[i + j * nx] - mg_fine_apply(p_prime, i, j) : rhs[i + j * nx];
     R rr = dot(mg_rho, mg_rho);
     int it = 0;
-    if (!(measure(rr) <= tol) && consts.cg_max_iterations > 0) {
+    if (!converged(rr) && consts.cg_max_iterations > 0) {
       mg_precondition();
       R rz = dot(mg_rho, mg_z);
       for (size_t k = 0; k < n; ++k) mg_d[k] = mg_z[k] + R(0) * mg_d[k];
@@ -939,7 +1075,7 @@ class Model {
         ++it;
         last_sweeps += 1;
         total_sweeps += 1;
-        if (measure(rr) <= tol || it >= consts.cg_max_iterations) break;
+        if (converged(rr) || it >= consts.cg_max_iterations) break;
         mg_precondition();
         const R rz_new = dot(mg_rho, mg_z);
         const R beta = rz_new / rz;
@@ -965,6 +1101,7 @@ class Model {
         mg_guess = p_prime;
       }
     }
+    if (first_solve) { last_p_rel = mode_c_relative(rr); last_first_solve_iterations = uint64_t(it); }
     const R res = measure(rr);
     last_pressure_residual = res;
     return res;
@@ -1109,6 +1246,10 @@ class Model {
     out->p_f64 = double(last_pressure_residual);
     out->u_f64 = double(last_u_residual);
     out->v_f64 = double(last_v_residual);
+    const bool mode_c = pressure_solver != CFD_SOLVER_JACOBI;
+    out->p_rel_f64 = mode_c ? double(last_p_rel) : 0.0;
+    out->rhs_rms_f64 = mode_c ? double(last_rhs_rms) : 0.0;
+    out->first_solve_iterations = mode_c ? last_first_solve_iterations : 0;
   }
 };
 

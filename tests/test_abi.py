@@ -44,15 +44,16 @@ def test_struct_layouts_match_the_header(lib):
     # sizes follow from the header's member lists (natural alignment)
     assert C.sizeof(_abi.CfdGrid) == 48
     assert C.sizeof(_abi.CfdParams) == 28
-    assert C.sizeof(_abi.CfdSolverConsts) == 72
-    assert C.sizeof(_abi.CfdOptions) == 32 + 72
-    assert C.sizeof(_abi.CfdResiduals) == 8 + 5 * 4 + 4 + 8 + 3 * 8 + 5 * 8
+    assert C.sizeof(_abi.CfdSolverConsts) == 80  # ABI 3: + cg_relative, adaptive_substeps
+    assert C.sizeof(_abi.CfdOptions) == 32 + 80
+    assert C.sizeof(_abi.CfdResiduals) == 8 + 5 * 4 + 4 + 8 + 3 * 8 + 5 * 8 + 3 * 8  # ABI 3: + p_rel, rhs_rms, first_solve_iterations
     o = model.default_options()
     assert (o.precision, o.device, o.rank, o.world_size) == (64, -1, 0, 1)
     c = o.consts
     assert (c.ramp_up_steps, c.jacobi_iterations, c.outer_rounds) == (100, 50, 20)
     assert (c.jacobi_omega, c.pressure_tolerance, c.outer_tolerance, c.cfl) == (0.75, 1e-4, 1e-4, 0.2)
     assert (c.cg_tolerance, c.mg_omega, c.mg_smoothing, c.mg_warm_start) == (1e-8, 0.8, 2, 3)
+    assert (c.cg_relative, c.adaptive_substeps) == (0, 0)  # the reference's behaviour is the default
 
 
 def test_argument_validation_needs_no_gpu(lib):

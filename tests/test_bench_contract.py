@@ -26,7 +26,25 @@ def test_reference_arm_mode_c_line(oracle_built):
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == d["value"] and "MGCG iterations" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"].startswith("lid-driven cavity") and d["config"]["iterations_per_step"] > 0
+    assert d["config"]["workload"].startswith("lid-driven cavity") and d["cg_iterations_per_step"] > 0
+    assert d["stop"]["rel_residual"] <= 1e-8 and d["stop"]["dt_rms_rhs"] > 0  # the SURVEY norm, both norms printed
+    # both arms print the same `config` for the same workload (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import bench
+    w = bench.WORKLOADS["cavity1024_modeC"]
+    assert d["config"] == json.loads(json.dumps(bench.workload_config(w, w["nx"], w["ny"])))
+
+
+def test_every_baseline_config_has_a_workload():
+    sys.path.insert(0, ROOT)
+    import bench
+    W = bench.WORKLOADS
+    assert (W["default800_modeR"]["nx"], W["default800_modeR"]["ny"]) == (800, 264)                      # configs[0]
+    assert (W["cavity1024_modeC"]["nx"], W["cavity1024_modeR"]["nx"]) == (1024, 1024)                    # configs[1]: R and C
+    assert W["cavity4096_modeC"]["consts"]["cg_relative"] == 1                                           # configs[2]
+    c3 = W["channel8192x2048_modeR"]                                                                     # configs[3]
+    assert (c3["nx"], c3["ny"], c3["lx"], c3["ly"], c3["cylinder"], c3.get("strong")) == (8192, 2048, 40.0, 10.0, (10.0, 5.0, 0.75), True)
+    assert W["cavity16384_modeC"]["nx"] == 16384 and W["cavity16384_modeC"].get("strong") is True        # configs[4]
 
 
 def test_reference_arm_is_rank_zero_only(oracle_built):

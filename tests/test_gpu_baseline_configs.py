@@ -122,7 +122,7 @@ def test_config3_channel_8192x2048_saturated_step_bit_exact(scheme):
     mask = gpu.field(_abi.FIELD_MASK_U).reshape(2048, 8193)
     # (masked faces are not all zero in u: the corrector does not mask and the boundary conditions zero only the west /
     # south faces of solid cells, src/model.rs:869-874 — the oracle agrees bit for bit, above)
-    assert mask.sum() > 1000 and np.abs(u).max() > 1.0  # the flow accelerates around the cylinder
+    assert mask.sum() > 1000 and np.abs(u).max() > 0.2  # the inlet is still ramping up (step ~27 of 100, src/model.rs:311-316)
 
 
 # ---- state semantics of the elided work (Mode C fast path) ------------------------------------------------------------

@@ -1,0 +1,127 @@
+"""SURVEY 8f extensions on the GPU against the CPU oracle: QUICK face values, adaptive sub-stepping, the relative Mode C
+stopping rule, and the fused smoothing passes of the V-cycle against the separate kernels."""
+import numpy as np
+import pytest
+
+from cfd_demo_b200 import _abi
+from cfd_demo_b200.model import Model, default_options
+from cfd_demo_b200.types import (Grid, InletProfile, PressureSolver, Scenario, SimulationParams, VelocityScheme)
+from oracle.cpu_oracle import OracleModel, default_consts
+
+from helpers import STATE_FIELDS, assert_fields_identical, assert_residuals_identical, box_grid, channel_grid, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def pair(grid, params, precision=64, consts=None, flags=0):
+    o = default_options()
+    o.precision = precision
+    o.flags = flags
+    if consts is not None:
+        o.consts = consts
+    return Model(grid, params, options=o), OracleModel(grid, params, precision=precision, consts=consts)
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+@pytest.mark.parametrize("case", ["default", "ragged", "cavity"])
+def test_quick_scheme_bit_exact(precision, case):
+    """VelocityScheme::Quick (index.html:471-549, :643-723 inside the Rust predictor): Mode R, every state field,
+    residual and counter bit for bit, through the start-up transient into the saturated regime."""
+    if case == "default":
+        from cfd_demo_b200.types import default_grid
+        g, prm, steps = default_grid(), SimulationParams(velocity_scheme=VelocityScheme.Quick), 22
+    elif case == "ragged":
+        g = channel_grid(264, 41)
+        prm, steps = SimulationParams(velocity_scheme=VelocityScheme.Quick, inlet_profile=InletProfile.Parabolic,
+                                      target_inlet_velocity=2.0), 14
+    else:
+        g, prm, steps = box_grid(64), SimulationParams(dt=5e-4, viscosity=0.01, scenario=Scenario.Cavity,
+                                                       velocity_scheme=VelocityScheme.Quick), 15
+    gpu, cpu = pair(g, prm, precision)
+    for s in range(steps):
+        gpu.update()
+        cpu.update()
+        assert_residuals_identical(gpu.get_residuals(), cpu.get_residuals(), f"quick {case} step {s + 1}")
+    assert_fields_identical(gpu, cpu, STATE_FIELDS, f"quick {case}")
+    assert np.abs(gpu.field(_abi.FIELD_U)).max() > 0
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+def test_adaptive_substeps_bit_exact(precision):
+    """cfd_solver_consts::adaptive_substeps (the reference's commented-out rule, src/model.rs:352-363): the sub-step
+    count grows to its cap of 20 on this case; every step's residuals, counters and sub-step count, and the complete
+    state (u_old / v_old are the fields the STEP started from, not the last sub-step) must equal the oracle's."""
+    c = default_consts()
+    c.adaptive_substeps = 1
+    prm = SimulationParams(dt=0.02, target_inlet_velocity=3.0)
+    gpu, cpu = pair(channel_grid(96, 32), prm, precision, consts=c)
+    seen = set()
+    for s in range(27):
+        gpu.update()
+        cpu.update()
+        rg, rc = gpu.get_residuals(), cpu.get_residuals()
+        assert_residuals_identical(rg, rc, f"substeps step {s + 1}")
+        seen.add(rg.piso_substeps)
+        if s % 5 == 4:
+            assert_fields_identical(gpu, cpu, STATE_FIELDS, f"substeps step {s + 1}")
+    assert max(seen) > 4 and 1 in seen
+    assert_fields_identical(gpu, cpu, STATE_FIELDS, "substeps end")
+
+
+@pytest.mark.parametrize("solver", [PressureSolver.MGCG, PressureSolver.CG])
+def test_relative_stopping_rule_matches_oracle(solver):
+    """cg_relative = 1: ||r||_2 <= tol * ||rhs||_2 of the step's first solve (the norm SURVEY 8d states for the 4096^2
+    cavity).  Same iteration counts, the reported ||r|| / ||rhs|| and dt * rms(rhs) agree with the oracle's, u, v, p within 1e-9."""
+    c = default_consts()
+    c.cg_relative = 1
+    c.cg_tolerance = 1e-10
+    g = Grid.uniform(128, 96, 2.0, 1.5, None)
+    prm = SimulationParams(dt=1e-3, viscosity=0.01, scenario=Scenario.Cavity, pressure_solver=solver)
+    gpu, cpu = pair(g, prm, consts=c)
+    for s in range(10):
+        gpu.update()
+        cpu.update()
+        rg, rc = gpu.get_residuals(), cpu.get_residuals()
+        assert rg.jacobi_calls == rc.jacobi_calls
+        assert abs(rg.sweeps - rc.sweeps) <= (1 if solver == PressureSolver.MGCG else 4), (s, rg.sweeps, rc.sweeps)
+        if s >= 2:
+            assert 0 < rg.f64["p_rel"] <= 1e-10
+            assert abs(rg.f64["rhs_rms"] - rc.f64["rhs_rms"]) <= 1e-9 * rc.f64["rhs_rms"]
+            assert rg.f64["first_solve_iterations"] == rg.sweeps
+    for fid in (_abi.FIELD_U, _abi.FIELD_V, _abi.FIELD_P):
+        assert rel_l2(gpu.field(fid), cpu.field(fid)) <= 1e-9, _abi.FIELD_NAMES[fid]
+
+
+@pytest.mark.parametrize("scenario,shape", [(Scenario.Channel, (1040, 61)), (Scenario.Cavity, (264, 200)), (Scenario.Cavity, (16, 4))])
+def test_mgcg_fused_smoothing_passes_equal_the_separate_kernels(scenario, shape):
+    """k_mg_fused_sweep (first two pre-smoothing sweeps in one pass over rho; prolongation folded into the first
+    post-smoothing sweep) performs the same per-cell arithmetic as k_mg_first_sweep / k_jacobi_sweep5 / k_mg_fine_prolong
+    (CFD_FLAG_MG_UNFUSED): the complete state is bit-identical, on a width that is not a multiple of the block width too."""
+    nx, ny = shape
+    g = channel_grid(nx, ny, lx=nx / 16.0, ly=ny / 16.0, cylinder=ny >= 7) if scenario == Scenario.Channel else Grid.uniform(nx, ny, nx / 64.0, ny / 64.0, None)
+    prm = SimulationParams(dt=1e-3, viscosity=0.01, scenario=scenario, pressure_solver=PressureSolver.MGCG)
+    models = []
+    for flags in (0, _abi.FLAG_MG_UNFUSED):
+        o = default_options()
+        o.flags = flags
+        o.consts.cg_tolerance = 1e-12
+        m = Model(g, prm, options=o)
+        for _ in range(6):
+            m.update()
+        models.append(m)
+    assert models[0].get_residuals().sweeps == models[1].get_residuals().sweeps > 0
+    assert_fields_identical(models[0], models[1], STATE_FIELDS, "fused vs separate smoothing passes")
+    assert_fields_identical(models[0], models[1], [_abi.FIELD_MG_GUESS, _abi.FIELD_MG_LAST, _abi.FIELD_MG_LAST2], "start-vector history")
+
+
+def test_set_parameters_validates_enums():
+    from cfd_demo_b200.model import CfdError
+    m = Model(channel_grid(32, 8), SimulationParams())
+    bad = SimulationParams()
+    for field, value in (("velocity_scheme", 7), ("inlet_profile", -1), ("pressure_solver", 9)):
+        p = bad.to_c()
+        setattr(p, field, value)
+        import ctypes as C
+        assert m._lib.cfd_model_set_params(m._handle(), C.byref(p)) == _abi.CFD_ERR_INVALID_ARGUMENT, field
+    m.set_parameters(SimulationParams(velocity_scheme=VelocityScheme.Quick))
+    m.update()
