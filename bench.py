@@ -624,17 +624,34 @@ def run_ours(args, w):
     # ---- timed region 2: the same K steps through the reference-facing calls with HOST buffers ------------
     model.profile_smoother(False)
     pinned = model.pinned_snapshot_buffers()
+    pinned2 = model.pinned_snapshot_buffers()
+    # (a) the reference's own protocol: the snapshot of step n is requested after the step and picked up one step later
+    # (Command::GetSnapshot ... get_last_available_snapshot, src/model.rs:100-102, :1300-1306), so its device->host copy
+    # overlaps step n+1 — cfd_model_snapshot_begin / _end.  Every step's p, u, v arrive in host memory inside the region.
     rk.barrier()
     t1 = time.perf_counter()
     d2h = 0
-    for _ in range(args.steps):
+    for k in range(args.steps):
         model.set_parameters(params)         # host -> device: the 28-byte parameter block
         model.update()
         res = model.get_residuals()          # device -> host: the step's residual scalars
-        snap = model.get_snapshot(out=pinned)  # device -> host: p, u, v narrowed to f32 (SimSnapshot, src/model.rs:36-42)
-        d2h = (snap.p.nbytes + snap.u.nbytes + snap.v.nbytes + 8 * 8) * world
+        model.snapshot_begin(pinned if k % 2 == 0 else pinned2)  # device -> host: p, u, v narrowed to f32 (SimSnapshot, :36-42)
+        if k > 0:
+            snap = model.snapshot_end()      # the previous step's snapshot is complete in host memory
+    snap = model.snapshot_end()
+    d2h = (snap.p.nbytes + snap.u.nbytes + snap.v.nbytes + 8 * 8) * world
     rk.barrier()
     wall_e2e = time.perf_counter() - t1
+    # (b) the same with a blocking get_snapshot after every step (nothing overlaps)
+    rk.barrier()
+    t1b = time.perf_counter()
+    for _ in range(min(args.steps, 5)):
+        model.set_parameters(params)
+        model.update()
+        res = model.get_residuals()
+        snap = model.get_snapshot(out=pinned)
+    torch.cuda.synchronize()
+    wall_e2e_sync = (time.perf_counter() - t1b) / min(args.steps, 5)
     # the same with freshly allocated pageable buffers (what a caller holding plain Vec<f32>s gets)
     t2 = time.perf_counter()
     for _ in range(min(args.steps, 3)):
@@ -749,10 +766,12 @@ def run_ours(args, w):
             "step_frac_of_peak_counting_elided_passes": step_bytes_r1 / (dev_s / steps) / 1e9 / peak_job,
             "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": 28 * world, "d2h_bytes_per_step": d2h,
                     "ms_per_step": wall_e2e_s * 1e3 / steps,
+                    "ms_per_step_blocking_get_snapshot": wall_e2e_sync * 1e3,
                     "ms_per_step_pageable_destination": wall_e2e_pageable * 1e3,
                     "ms_per_step_rgba_image_instead": None if wall_e2e_image is None else wall_e2e_image * 1e3,
-                    "calls": "cfd_model_set_params + cfd_model_update + cfd_model_get_residuals + cfd_model_get_snapshot "
-                             "(into cfd_host_alloc'ed pinned buffers)"},
+                    "calls": "cfd_model_set_params + cfd_model_update + cfd_model_get_residuals + cfd_model_snapshot_begin / _end "
+                             "(every step's p, u, v as f32 into cfd_host_alloc'ed pinned buffers; the copy of step n overlaps step "
+                             "n+1, the reference's request-now / pick-up-later snapshot protocol)"},
             "gpu_launches": launches,
             "roofline": {"kernel": kernel_name,
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -143,9 +143,10 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_init(MgFine<R> c, MgScalars* 
           const R xw1 = (c0 + 1 == 1) ? cen.y : cen.x;
           const R xe1 = (c0 + 1 == nx - 2) ? (c.cavity ? cen.y : R(0)) : gr;
           const R xn1 = (j == c.ny - 2) ? cen.y : north.y, xs1 = (j == 1) ? cen.y : south.y;
-          DivTry<R> dv;
+          DivTry<R> dv(c.ddx_sq);
+          dv.also(c.ddy_sq);
           R l0 = mg_lap<R>(c, dv, cen.x, xe0, xw0, xn0, xs0), l1 = mg_lap<R>(c, dv, cen.y, xe1, xw1, xn1, xs1);
-          if (__builtin_expect(!dv.ok, 0)) {
+          if (__builtin_expect(!dv.ok(), 0)) {
             DivTrue<R> ex;
             l0 = mg_lap<R>(c, ex, cen.x, xe0, xw0, xn0, xs0);
             l1 = mg_lap<R>(c, ex, cen.y, xe1, xw1, xn1, xs1);
@@ -263,9 +264,10 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_dir_apply(MgFine<R> c, MgScal
         wv[r].y = mg_lap<R>(c, dv, cen.y, xe1, xw1, xn1, xs1);
       }
     };
-    DivTry<R> fast;
+    DivTry<R> fast(c.ddx_sq);
+    fast.also(c.ddy_sq);
     apply_tile(fast);
-    if (__builtin_expect(!fast.ok, 0)) {
+    if (__builtin_expect(!fast.ok(), 0)) {
       DivTrue<R> exact;
       apply_tile(exact);
     }
@@ -394,9 +396,10 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_fine_restrict(MgFine<R> c, co
       }
     return acc;
   };
-  DivTry<R> fast;
+  DivTry<R> fast(c.ddx_sq);
+  fast.also(c.ddy_sq);
   R acc = children(fast);
-  if (__builtin_expect(!fast.ok, 0)) {
+  if (__builtin_expect(!fast.ok(), 0)) {
     DivTrue<R> exact;
     acc = children(exact);
   }
@@ -499,9 +502,9 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_fused_sweep(const MgFine<R> c
       inr[r] = raw1(ar[r], cr[r]);
     }
   };
-  DivTry<R> fast;
+  DivTry<R> fast(c2.denom);
   form(fast);
-  if (kMode == 0 && __builtin_expect(!fast.ok, 0)) {
+  if (kMode == 0 && __builtin_expect(!fast.ok(), 0)) {
     DivTrue<R> exact;
     form(exact);
   }

@@ -21,6 +21,7 @@
 #include "cfd_kernels.cuh"
 #include "cfd_mg.cuh"
 #include "cfd_peer.cuh"
+#include "cfd_tracers.cuh"
 
 namespace {
 
@@ -123,6 +124,8 @@ struct ModelBase {
   virtual int update() = 0;
   virtual int set_params(const cfd_params& p) = 0;
   virtual int get_snapshot(float* p, float* u, float* v, float* dt) = 0;
+  virtual int snapshot_begin(float* p, float* u, float* v) = 0;
+  virtual int snapshot_end(float* dt) = 0;
   virtual int get_residuals(cfd_residuals* out) = 0;
   virtual int field_len(int field, uint64_t* len) = 0;
   virtual int get_field_f64(int field, double* out, uint64_t len) = 0;
@@ -130,6 +133,10 @@ struct ModelBase {
   virtual int rows(uint64_t* j0, uint64_t* j1) = 0;
   virtual int last_timing(double* step_ms, double* sweep_ms, uint64_t* launches) = 0;
   virtual int render(int mode, unsigned char* rgba, float* min_out, float* max_out) = 0;
+  virtual int tracers_inject() = 0;
+  virtual int tracers_update(double dt) = 0;
+  virtual int tracers_get(double* xy, uint64_t capacity, uint64_t* n) = 0;
+  virtual int tracers_clear() = 0;
   virtual int profile_smoother(int enable) = 0;
   virtual int last_smoother_timing(double* ms, uint64_t* launches) = 0;
 };
@@ -260,6 +267,21 @@ struct ModelImpl final : ModelBase {
   cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
   std::vector<cudaEvent_t> ev_sweep;  // pairs, one per pressure solve of the step
   size_t ev_sweep_used = 0;
+  // asynchronous snapshots: two device staging buffers, a copy stream, per-slot events
+  cudaStream_t copy_stream = nullptr;
+  float* snap_stage[2] = {nullptr, nullptr};
+  size_t snap_stage_floats = 0;
+  cudaEvent_t snap_ready[2] = {nullptr, nullptr}, snap_done[2] = {nullptr, nullptr};
+  float snap_dt[2] = {0.0f, 0.0f};
+  int snap_head = 0, snap_in_flight = 0;  // slots [head - in_flight, head) mod 2 are in flight
+  // tracer particles (cfd_tracers.cuh): positions in injection order, double-buffered for the stable compaction
+  double2* tr_pos[2] = {nullptr, nullptr};
+  unsigned char* tr_keep = nullptr;
+  unsigned* tr_count_dev = nullptr;
+  unsigned* h_tr_count = nullptr;  // pinned
+  size_t tr_capacity = 0;
+  unsigned tr_n = 0;
+  int tr_cur = 0;
   Field<R> uold_buf, vold_buf;        // u_old / v_old of a step with several sub-steps (adaptive_substeps)
   bool old_in_copy = false;
   // Mode C bookkeeping of the last step's first solve (cfd_residuals::p_rel_f64, rhs_rms_f64, first_solve_iterations)
@@ -322,6 +344,15 @@ struct ModelImpl final : ModelBase {
     for (auto& f : ubuf) cudaFree(f.base);
     for (auto& f : vbuf) cudaFree(f.base);
     cudaFree(uold_buf.base); cudaFree(vold_buf.base);
+    if (copy_stream) cudaStreamSynchronize(copy_stream);
+    for (int k = 0; k < 2; ++k) {
+      cudaFree(snap_stage[k]);
+      if (snap_ready[k]) cudaEventDestroy(snap_ready[k]);
+      if (snap_done[k]) cudaEventDestroy(snap_done[k]);
+    }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    cudaFree(tr_pos[0]); cudaFree(tr_pos[1]); cudaFree(tr_keep); cudaFree(tr_count_dev);
+    if (h_tr_count) cudaFreeHost(h_tr_count);
     cudaFree(p.base); cudaFree(rhs.base); cudaFree(pp[0].base); cudaFree(pp[1].base);
     cudaFree(mask_u.base); cudaFree(mask_v.base); cudaFree(solid.base);
     cudaFree(err_slots); cudaFree(step_slots); cudaFree(staging); cudaFree(tickets); cudaFree(d_divs);
@@ -595,10 +626,12 @@ struct ModelImpl final : ModelBase {
   }
   // rows of a strip field or of a replicated coarse array to the two neighbours: src / dst as element offsets from the
   // (virtual or real) origins, which the caller computed for its own copy and for the neighbours' copies
-  int peer_push(const void* src_down, void* dst_down, size_t bytes_down, const void* src_up, void* dst_up, size_t bytes_up) {
+  int peer_push(const void* src_down, void* dst_down, size_t bytes_down, const void* src_up, void* dst_up, size_t bytes_up,
+                unsigned long long* max_data = nullptr, int max_n = 0) {
     cfdk::PeerPush p;
     memset(&p, 0, sizeof p);
     p.mine = box; p.ticket = peer_ticket; p.seq = ++xseq;
+    if (max_data) { p.red = max_data; p.red_n = max_n; p.red_seq = ++rseq; p.all = peer_all(); }
     if (rank > 0) {
       p.flag[0] = &peer_box[rank - 1]->from_above;
       p.src[0] = (const uint32_t*)src_down; p.dst[0] = (uint32_t*)dst_down; p.words[0] = bytes_down / 4;
@@ -788,7 +821,7 @@ struct ModelImpl final : ModelBase {
   // refresh `down` halo rows below row `a` and `up` halo rows above row `b` of a field whose owned rows are
   // [a, b): the lower neighbour owns [.., a), the upper one [b, ..)
   int exchange_rows(const Field<R>& f, int a, int b, int down, int up, int send_down, int send_up,
-                    cudaStream_t on = nullptr) {
+                    cudaStream_t on = nullptr, unsigned long long* max_data = nullptr) {
     if (world == 1) return CFD_OK;
     const size_t rl = f.rowlen;
     if (const PeerBuf* pb = on ? nullptr : peer_find(f.base)) {
@@ -800,7 +833,7 @@ struct ModelImpl final : ModelBase {
       R* dst_down = rank > 0 ? origin(rank - 1) + (long)a * (long)rl : nullptr;
       R* dst_up = rank < world - 1 ? origin(rank + 1) + (long)(b - send_up) * (long)rl : nullptr;
       return peer_push(f.row(a), dst_down, (size_t)send_down * rl * sizeof(R), f.row(b - send_up), dst_up,
-                       (size_t)send_up * rl * sizeof(R));
+                       (size_t)send_up * rl * sizeof(R), max_data, max_data ? 1 : 0);
     }
     cudaStream_t stream = on ? on : this->stream;
     CFD_NCCL(nccl_api().GroupStart());
@@ -965,8 +998,12 @@ struct ModelImpl final : ModelBase {
           // strips, simple form: the next sweep needs the neighbours' new boundary rows and the GLOBAL max|dp'|
           // of this one.  A rank that skipped the sweep (converged) still takes part; what it exchanges is
           // never consumed.
-          if ((rc = exchange_halo(pp[out], ja, jb, 1))) return rc;
-          if ((rc = allreduce_max_u64(err_slots + s, 1))) return rc;
+          if (peer_find(pp[out].base)) {  // halo rows and the max in ONE launch over peer memory
+            if ((rc = exchange_rows(pp[out], ja, jb, 1, 1, 1, 1, nullptr, err_slots + s))) return rc;
+          } else {
+            if ((rc = exchange_halo(pp[out], ja, jb, 1))) return rc;
+            if ((rc = allreduce_max_u64(err_slots + s, 1))) return rc;
+          }
         }
       }
     }
@@ -1259,11 +1296,12 @@ struct ModelImpl final : ModelBase {
   int mg_finish_strips(const cfdk::MgFine<R>& c, int mode) {
     if (world == 1) return CFD_OK;
     if (peer2_ready) {
-      int rc;
-      if ((rc = peer_reduce(&mg_scalars->local_sum, 1, 1))) return rc;
-    } else {
-      CFD_NCCL(nccl_api().AllReduce(&mg_scalars->local_sum, &mg_scalars->local_sum, 1, ncclFloat64, ncclSum, comm, stream));
+      cfdk::k_mg_advance_peer<R><<<1, 32, 0, stream>>>(peer_all(), c, mg_scalars, mode, ++rseq);
+      ++launches;
+      CFD_CUDA(cudaGetLastError());
+      return CFD_OK;
     }
+    CFD_NCCL(nccl_api().AllReduce(&mg_scalars->local_sum, &mg_scalars->local_sum, 1, ncclFloat64, ncclSum, comm, stream));
     cfdk::k_mg_advance<R><<<1, 32, 0, stream>>>(c, mg_scalars, mode);
     ++launches;
     return CFD_OK;
@@ -1907,6 +1945,64 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
 
+  // get_snapshot in two halves (see the header): begin = narrow on the model's stream + copy on the copy stream
+  int snapshot_begin(float* hp, float* hu, float* hv) override {
+    CFD_CUDA(cudaSetDevice(device));
+    if (snap_in_flight >= 2) return fail(CFD_ERR_INVALID_ARGUMENT, "snapshot_begin: two snapshots are already in flight");
+    for (float* h : {hp, hu, hv}) {
+      if (!h) continue;
+      cudaPointerAttributes attr;
+      memset(&attr, 0, sizeof attr);
+      if (cudaPointerGetAttributes(&attr, h) != cudaSuccess || attr.type != cudaMemoryTypeHost) {
+        (void)cudaGetLastError();
+        return fail(CFD_ERR_INVALID_ARGUMENT, "snapshot_begin: destinations must be page-locked (cfd_host_alloc)");
+      }
+    }
+    const size_t np_ = own_p(), nu_ = own_u(), nv_ = own_v(), total = np_ + nu_ + nv_;
+    if (!copy_stream) {
+      CFD_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+      for (int k = 0; k < 2; ++k) {
+        CFD_CUDA(cudaEventCreateWithFlags(&snap_ready[k], cudaEventDisableTiming));
+        CFD_CUDA(cudaEventCreateWithFlags(&snap_done[k], cudaEventDisableTiming));
+      }
+    }
+    if (total > snap_stage_floats) {
+      if (snap_in_flight) return fail(CFD_ERR_INVALID_ARGUMENT, "snapshot_begin: staging buffers are busy");
+      for (int k = 0; k < 2; ++k) {
+        cudaFree(snap_stage[k]);
+        snap_stage[k] = nullptr;
+        CFD_CUDA(cudaMalloc((void**)&snap_stage[k], total * sizeof(float)));
+      }
+      snap_stage_floats = total;
+    }
+    const int slot = snap_head;
+    float* d = snap_stage[slot];
+    const int grid_sz = 148 * 8;
+    if (hp) cfdk::k_to_f32<R><<<grid_sz, 256, 0, stream>>>(p.row(ja), d, np_);
+    if (hu) cfdk::k_to_f32<R><<<grid_sz, 256, 0, stream>>>(ubuf[iu].row(ja), d + np_, nu_);
+    if (hv) cfdk::k_to_f32<R><<<grid_sz, 256, 0, stream>>>(vbuf[iu].row(ja), d + np_ + nu_, nv_);
+    CFD_CUDA(cudaGetLastError());
+    CFD_CUDA(cudaEventRecord(snap_ready[slot], stream));
+    CFD_CUDA(cudaStreamWaitEvent(copy_stream, snap_ready[slot], 0));
+    if (hp) CFD_CUDA(cudaMemcpyAsync(hp, d, np_ * sizeof(float), cudaMemcpyDeviceToHost, copy_stream));
+    if (hu) CFD_CUDA(cudaMemcpyAsync(hu, d + np_, nu_ * sizeof(float), cudaMemcpyDeviceToHost, copy_stream));
+    if (hv) CFD_CUDA(cudaMemcpyAsync(hv, d + np_ + nu_, nv_ * sizeof(float), cudaMemcpyDeviceToHost, copy_stream));
+    CFD_CUDA(cudaEventRecord(snap_done[slot], copy_stream));
+    snap_dt[slot] = (float)dt;
+    snap_head ^= 1;
+    snap_in_flight += 1;
+    return CFD_OK;
+  }
+  int snapshot_end(float* hdt) override {
+    if (snap_in_flight == 0) return fail(CFD_ERR_INVALID_ARGUMENT, "snapshot_end: no snapshot in flight");
+    CFD_CUDA(cudaSetDevice(device));
+    const int slot = (snap_head + 2 - snap_in_flight) & 1;  // the oldest one
+    CFD_CUDA(cudaEventSynchronize(snap_done[slot]));
+    if (hdt) *hdt = snap_dt[slot];
+    snap_in_flight -= 1;
+    return CFD_OK;
+  }
+
   // The UI's colour map (src/app.rs:235-404) on the device: nx x ny RGBA pixels into `rgba` (host memory)
   int render(int mode, unsigned char* rgba, float* min_out, float* max_out) override {
     if (world > 1) return fail(CFD_ERR_UNSUPPORTED, "render: single domain only in this version");
@@ -2072,6 +2168,71 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
 
+  // ---- tracer particles (index.html:1472-1543) ----
+  cfdk::TracerGeom tracer_geom() const {
+    cfdk::TracerGeom g;
+    g.nx = nx; g.ny = ny; g.dx = (double)dx; g.dy = (double)dy; g.lx = (double)lx; g.ly = (double)ly;
+    return g;
+  }
+  int tracers_reserve(size_t want) {
+    if (want <= tr_capacity) return CFD_OK;
+    size_t cap = tr_capacity ? tr_capacity : 1024;
+    while (cap < want) cap *= 2;
+    if (cap > 0x7fffffffull) return fail(CFD_ERR_INVALID_ARGUMENT, "too many tracers");
+    double2* fresh[2] = {nullptr, nullptr};
+    for (int k = 0; k < 2; ++k) CFD_CUDA(cudaMalloc((void**)&fresh[k], cap * sizeof(double2)));
+    if (tr_n) CFD_CUDA(cudaMemcpyAsync(fresh[0], tr_pos[tr_cur], (size_t)tr_n * sizeof(double2), cudaMemcpyDeviceToDevice, stream));
+    CFD_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(tr_pos[0]); cudaFree(tr_pos[1]); cudaFree(tr_keep);
+    tr_pos[0] = fresh[0]; tr_pos[1] = fresh[1]; tr_cur = 0;
+    tr_keep = nullptr;
+    CFD_CUDA(cudaMalloc((void**)&tr_keep, cap));
+    if (!tr_count_dev) {
+      CFD_CUDA(cudaMalloc((void**)&tr_count_dev, sizeof(unsigned)));
+      CFD_CUDA(cudaHostAlloc((void**)&h_tr_count, sizeof(unsigned), cudaHostAllocDefault));
+    }
+    tr_capacity = cap;
+    return CFD_OK;
+  }
+  int tracers_inject() override {
+    if (world > 1) return fail(CFD_ERR_UNSUPPORTED, "tracers: single domain only in this version");
+    CFD_CUDA(cudaSetDevice(device));
+    int rc;
+    if ((rc = tracers_reserve((size_t)tr_n + (size_t)ny))) return rc;
+    cfdk::k_tracers_inject<<<(ny + 255) / 256, 256, 0, stream>>>(tracer_geom(), tr_pos[tr_cur], tr_n);
+    CFD_CUDA(cudaGetLastError());
+    tr_n += (unsigned)ny;
+    return CFD_OK;
+  }
+  int tracers_update(double dt_tr) override {
+    if (world > 1) return fail(CFD_ERR_UNSUPPORTED, "tracers: single domain only in this version");
+    if (tr_n == 0) return CFD_OK;
+    CFD_CUDA(cudaSetDevice(device));
+    cfdk::k_tracers_advect<R><<<(tr_n + 255) / 256, 256, 0, stream>>>(tracer_geom(), ubuf[iu].v, vbuf[iu].v, dt_tr, tr_pos[tr_cur],
+                                                                     tr_keep, tr_n);
+    cfdk::k_tracers_compact<<<1, 1024, 0, stream>>>(tr_pos[tr_cur], tr_keep, tr_n, tr_pos[tr_cur ^ 1], tr_count_dev);
+    CFD_CUDA(cudaGetLastError());
+    CFD_CUDA(cudaMemcpyAsync(h_tr_count, tr_count_dev, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    CFD_CUDA(cudaStreamSynchronize(stream));
+    tr_n = *h_tr_count;
+    tr_cur ^= 1;
+    return CFD_OK;
+  }
+  int tracers_get(double* xy, uint64_t capacity, uint64_t* n) override {
+    if (n) *n = tr_n;
+    const uint64_t take = capacity < tr_n ? capacity : tr_n;
+    if (xy && take) {
+      CFD_CUDA(cudaSetDevice(device));
+      CFD_CUDA(cudaMemcpyAsync(xy, tr_pos[tr_cur], take * sizeof(double2), cudaMemcpyDeviceToHost, stream));
+      CFD_CUDA(cudaStreamSynchronize(stream));
+    }
+    return CFD_OK;
+  }
+  int tracers_clear() override {
+    tr_n = 0;
+    return CFD_OK;
+  }
+
   int profile_smoother(int enable) override {
     prof_smoother = enable != 0;
     return CFD_OK;
@@ -2181,6 +2342,16 @@ int cfd_model_get_snapshot(cfd_model* m, float* p, float* u, float* v, float* dt
   return m->impl->get_snapshot(p, u, v, dt);
 }
 
+int cfd_model_snapshot_begin(cfd_model* m, float* p, float* u, float* v) {
+  CFD_CHECK_MODEL(m);
+  return m->impl->snapshot_begin(p, u, v);
+}
+
+int cfd_model_snapshot_end(cfd_model* m, float* dt) {
+  CFD_CHECK_MODEL(m);
+  return m->impl->snapshot_end(dt);
+}
+
 int cfd_model_render_rgba(cfd_model* m, int32_t mode, uint8_t* rgba, float* min_out, float* max_out) {
   CFD_CHECK_MODEL(m);
   return m->impl->render(mode, rgba, min_out, max_out);
@@ -2227,6 +2398,33 @@ int cfd_strip_rows(uint64_t ny, int32_t world_size, int32_t rank, uint64_t* j0, 
 int cfd_model_last_timing(cfd_model* m, double* step_ms, double* sweep_ms, uint64_t* kernel_launches) {
   CFD_CHECK_MODEL(m);
   return m->impl->last_timing(step_ms, sweep_ms, kernel_launches);
+}
+
+int cfd_model_tracers_inject(cfd_model* m) {
+  CFD_CHECK_MODEL(m);
+  return m->impl->tracers_inject();
+}
+
+int cfd_model_tracers_update(cfd_model* m, double dt) {
+  CFD_CHECK_MODEL(m);
+  return m->impl->tracers_update(dt);
+}
+
+int cfd_model_tracers_count(cfd_model* m, uint64_t* n) {
+  CFD_CHECK_MODEL(m);
+  if (!n) return fail(CFD_ERR_INVALID_ARGUMENT, "null out");
+  return m->impl->tracers_get(nullptr, 0, n);
+}
+
+int cfd_model_tracers_get(cfd_model* m, double* xy, uint64_t capacity, uint64_t* n) {
+  CFD_CHECK_MODEL(m);
+  if (!xy && capacity) return fail(CFD_ERR_INVALID_ARGUMENT, "null out");
+  return m->impl->tracers_get(xy, capacity, n);
+}
+
+int cfd_model_tracers_clear(cfd_model* m) {
+  CFD_CHECK_MODEL(m);
+  return m->impl->tracers_clear();
 }
 
 int cfd_model_profile_smoother(cfd_model* m, int32_t enable) {

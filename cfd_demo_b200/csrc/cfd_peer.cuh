@@ -72,39 +72,6 @@ __device__ __forceinline__ bool peer_wait_geq(const unsigned long long* flag, un
   }
 }
 
-// ---- halo rows: push to the neighbours, then wait for theirs --------------------------------------------------------------
-struct PeerPush {
-  const uint32_t* src[2];        // [0] towards the rank below, [1] towards the rank above (4-byte words)
-  uint32_t* dst[2];              // the neighbours' halo rows (peer pointers)
-  unsigned long long words[2];   // may be 0 with a neighbour present: the flag is still raised (a pure synchronisation)
-  unsigned long long* flag[2];   // the neighbours' mailboxes: [0] the lower rank's from_above, [1] the upper rank's from_below;
-                                 // nullptr = no neighbour on that side
-  PeerBox* mine;
-  unsigned int* ticket;
-  unsigned long long seq;
-};
-
-__global__ void __launch_bounds__(256) k_peer_push(const PeerPush a) {
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-#pragma unroll
-  for (int k = 0; k < 2; ++k)
-    if (a.flag[k] != nullptr)
-      for (unsigned long long w = t; w < a.words[k]; w += stride) a.dst[k][w] = a.src[k][w];
-  __threadfence_system();  // every thread: its peer stores before the block's ticket
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  if (atomicAdd(a.ticket, 1u) != gridDim.x - 1) return;
-  *a.ticket = 0u;
-  __threadfence_system();
-  if (a.flag[0] != nullptr) peer_st_release(a.flag[0], a.seq);
-  if (a.flag[1] != nullptr) peer_st_release(a.flag[1], a.seq);
-  bool ok = true;
-  if (a.flag[0] != nullptr) ok &= peer_wait_geq(&a.mine->from_below, a.seq);
-  if (a.flag[1] != nullptr) ok &= peer_wait_geq(&a.mine->from_above, a.seq);
-  if (!ok) a.mine->error = a.seq;
-}
-
 // ---- scalar reductions over all ranks ------------------------------------------------------------------------------------
 struct PeerAll {
   PeerBox* box[kPeerMaxRanks];  // every rank's mailbox (box[rank] is the local one)
@@ -114,10 +81,8 @@ struct PeerAll {
 // data[0..n) (n <= 4) <- reduction over the ranks of data[0..n): op 0 = max of unsigned 64-bit patterns (non-negative doubles
 // order like their bit patterns), op 1 = sum of doubles in rank order.  One thread.  `skip` (may be null): a
 // device flag; when it is up the whole operation is a no-op ON EVERY RANK (the flag is itself a reduced quantity).
-__global__ void k_peer_reduce(const PeerAll p, unsigned long long* __restrict__ data, int n, int op, unsigned long long seq,
-                              const int* __restrict__ skip) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  if (skip != nullptr && *skip) return;
+__device__ __forceinline__ void peer_reduce_values(const PeerAll& p, unsigned long long* data, int n, int op,
+                                                   unsigned long long seq) {
   const int slot = (int)(seq % kPeerRedSlots);
   for (int r = 0; r < p.world; ++r) {
     PeerRed* rec = &p.box[r]->red[slot][p.rank];
@@ -141,6 +106,67 @@ __global__ void k_peer_reduce(const PeerAll p, unsigned long long* __restrict__ 
   if (!ok) mine->error = seq;
 }
 
+__global__ void k_peer_reduce(const PeerAll p, unsigned long long* __restrict__ data, int n, int op, unsigned long long seq,
+                              const int* __restrict__ skip) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (skip != nullptr && *skip) return;
+  peer_reduce_values(p, data, n, op, seq);
+}
+
+// MGCG on strips: the ranks' parts of a dot product (MgScalars::local_sum) summed over the ranks AND the CG scalars
+// advanced (mg_advance) in one single-thread launch — every rank ends up with identical scalars, hence the same `done`
+template <class R>
+__global__ void k_mg_advance_peer(const PeerAll p, const MgFine<R> c, MgScalars* __restrict__ sc, int mode, unsigned long long seq) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // (no early exit on sc->done: every rank must take part in every reduction it was enqueued for)
+  unsigned long long v = (unsigned long long)__double_as_longlong(sc->local_sum);
+  peer_reduce_values(p, &v, 1, 1, seq);
+  sc->local_sum = __longlong_as_double((long long)v);
+  if (mode != 0 && mode != 4 && mode != 5 && sc->done) return;
+  mg_advance<R>(c, sc, sc->local_sum, mode);
+}
+
+// ---- halo rows: push to the neighbours, then wait for theirs --------------------------------------------------------------
+struct PeerPush {
+  const uint32_t* src[2];        // [0] towards the rank below, [1] towards the rank above (4-byte words)
+  uint32_t* dst[2];              // the neighbours' halo rows (peer pointers)
+  unsigned long long words[2];   // may be 0 with a neighbour present: the flag is still raised (a pure synchronisation)
+  unsigned long long* flag[2];   // the neighbours' mailboxes: [0] the lower rank's from_above, [1] the upper rank's from_below;
+                                 // nullptr = no neighbour on that side
+  PeerBox* mine;
+  unsigned int* ticket;
+  unsigned long long seq;
+  // optional: a max-reduction over ALL ranks riding on the same launch (Mode R: the sweep's max|dp'| next to its halo rows)
+  unsigned long long* red;       // nullptr: none
+  int red_n;
+  unsigned long long red_seq;
+  PeerAll all;
+};
+
+__global__ void __launch_bounds__(256) k_peer_push(const PeerPush a) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    if (a.flag[k] != nullptr)
+      for (unsigned long long w = t; w < a.words[k]; w += stride) a.dst[k][w] = a.src[k][w];
+  // the block's peer stores happen-before thread 0's fence through the barrier (fences are cumulative), so one
+  // system-scope fence per block suffices; the last block's fence then covers every block through the ticket
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  __threadfence_system();
+  if (atomicAdd(a.ticket, 1u) != gridDim.x - 1) return;
+  *a.ticket = 0u;
+  __threadfence_system();
+  if (a.flag[0] != nullptr) peer_st_release(a.flag[0], a.seq);
+  if (a.flag[1] != nullptr) peer_st_release(a.flag[1], a.seq);
+  if (a.red != nullptr) peer_reduce_values(a.all, a.red, a.red_n, 0, a.red_seq);
+  bool ok = true;
+  if (a.flag[0] != nullptr) ok &= peer_wait_geq(&a.mine->from_below, a.seq);
+  if (a.flag[1] != nullptr) ok &= peer_wait_geq(&a.mine->from_above, a.seq);
+  if (!ok) a.mine->error = a.seq;
+}
+
 // ---- gather: every rank's rows of a replicated array to every rank ---------------------------------------------------------
 struct PeerGather {
   const uint32_t* src;             // this rank's rows (local array)
@@ -160,9 +186,9 @@ __global__ void __launch_bounds__(256) k_peer_gather(const PeerGather a, const i
     for (int r = 0; r < a.all.world; ++r)
       if (a.dst[r] != nullptr) a.dst[r][w] = v;
   }
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x != 0) return;
+  __threadfence_system();
   if (atomicAdd(a.ticket, 1u) != gridDim.x - 1) return;
   *a.ticket = 0u;
   __threadfence_system();

@@ -23,7 +23,7 @@
 
 namespace cfd {
 
-enum class VelocityScheme { FirstOrder = CFD_SCHEME_FIRST_ORDER, SecondOrder = CFD_SCHEME_SECOND_ORDER };
+enum class VelocityScheme { FirstOrder = CFD_SCHEME_FIRST_ORDER, SecondOrder = CFD_SCHEME_SECOND_ORDER, Quick = CFD_SCHEME_QUICK /* extension */ };
 enum class PressureSolver { Jacobi = CFD_SOLVER_JACOBI, CG = CFD_SOLVER_CG /* extension */, MGCG = CFD_SOLVER_MGCG /* extension */ };
 enum class InletProfile { Uniform = CFD_INLET_UNIFORM, Parabolic = CFD_INLET_PARABOLIC };
 enum class Scenario { Channel = CFD_SCENARIO_CHANNEL, Cavity = CFD_SCENARIO_CAVITY /* extension */ };
@@ -57,6 +57,7 @@ struct Residuals {
   std::chrono::duration<double> step_time;
   size_t piso_substeps;
   size_t jacobi_calls, sweeps;  // additions: K and S of the step
+  double p_rel, rhs_rms;        // additions (Mode C): ||r|| / ||rhs|| and dt * rms(rhs) of the step's first solve
 };
 
 struct SimSnapshot {
@@ -89,6 +90,19 @@ class Model {
     check(cfd_model_create(&g, &p, &m));
     h_.reset(m);
   }
+  // extension: with the solver constants spelled out (cfd_solver_consts, e.g. cg_relative for the converged solvers)
+  Model(const Grid& grid, const SimulationParams& params, const cfd_solver_consts& consts) : grid_(grid) {
+    cfd_grid g{grid.nx, grid.ny, grid.lx, grid.ly, grid.dx, grid.dy, grid.obstacle ? 1 : 0,
+               grid.obstacle ? grid.obstacle->center_x : 0.0f, grid.obstacle ? grid.obstacle->center_y : 0.0f,
+               grid.obstacle ? grid.obstacle->radius : 0.0f};
+    const cfd_params p = to_c(params);
+    cfd_options o;
+    cfd_options_default(&o);
+    o.consts = consts;
+    cfd_model* m = nullptr;
+    check(cfd_model_create_ex(&g, &p, &o, &m));
+    h_.reset(m);
+  }
   Model(Model&&) = default;
   Model& operator=(Model&&) = default;
 
@@ -111,7 +125,7 @@ class Model {
     check(cfd_model_get_residuals(h_.get(), &r));
     return Residuals{size_t(r.simulation_step), r.simulation_time, r.dt, r.p, r.u, r.v,
                      std::chrono::duration<double>(r.step_seconds), size_t(r.piso_substeps), size_t(r.jacobi_calls),
-                     size_t(r.sweeps)};
+                     size_t(r.sweeps), r.p_rel_f64, r.rhs_rms_f64};
   }
   std::unique_ptr<SimulationControlHandle> run() &&;                         // :1282 (consumes the model)
   const Grid& grid() const { return grid_; }

@@ -57,6 +57,8 @@ def load_library():
     lib.cfd_model_update_n.argtypes = [C.c_void_p, C.c_uint64]
     lib.cfd_model_set_params.argtypes = [C.c_void_p, P(_abi.CfdParams)]
     lib.cfd_model_get_snapshot.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, P(C.c_float)]
+    lib.cfd_model_snapshot_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cfd_model_snapshot_end.argtypes = [C.c_void_p, P(C.c_float)]
     lib.cfd_model_get_residuals.argtypes = [C.c_void_p, P(_abi.CfdResiduals)]
     lib.cfd_model_render_rgba.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, P(C.c_float), P(C.c_float)]
     lib.cfd_model_field_len.argtypes = [C.c_void_p, C.c_int32, P(C.c_uint64)]
@@ -68,6 +70,11 @@ def load_library():
     lib.cfd_nccl_unique_id.argtypes = [C.c_void_p]
     lib.cfd_model_profile_smoother.argtypes = [C.c_void_p, C.c_int32]
     lib.cfd_model_last_smoother_timing.argtypes = [C.c_void_p, P(C.c_double), P(C.c_uint64)]
+    lib.cfd_model_tracers_inject.argtypes = [C.c_void_p]
+    lib.cfd_model_tracers_update.argtypes = [C.c_void_p, C.c_double]
+    lib.cfd_model_tracers_count.argtypes = [C.c_void_p, P(C.c_uint64)]
+    lib.cfd_model_tracers_get.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, P(C.c_uint64)]
+    lib.cfd_model_tracers_clear.argtypes = [C.c_void_p]
     lib.cfd_host_alloc.argtypes = [C.c_uint64, P(C.c_void_p)]
     lib.cfd_host_free.argtypes = [C.c_void_p]
     lib.cfd_host_free.restype = None
@@ -90,8 +97,22 @@ def default_options() -> _abi.CfdOptions:
     return o
 
 
+def _checked_out(arr, count: int, dtype, what: str) -> np.ndarray:
+    """A caller-supplied destination must be exactly what the C side writes: `count` C-contiguous entries of `dtype`."""
+    a = arr.array if isinstance(arr, PinnedBuffer) else arr
+    if not isinstance(a, np.ndarray) or a.dtype != np.dtype(dtype) or not a.flags["C_CONTIGUOUS"] or a.size != int(count):
+        raise CfdError(_abi.CFD_ERR_INVALID_ARGUMENT,
+                       f"{what}: need a C-contiguous {np.dtype(dtype).name} array of {int(count)} entries, got "
+                       f"{getattr(a, 'dtype', type(a))} x {getattr(a, 'size', '?')}")
+    if not a.flags["WRITEABLE"]:
+        raise CfdError(_abi.CFD_ERR_INVALID_ARGUMENT, f"{what}: destination is read-only")
+    return a
+
+
 class PinnedBuffer:
-    """Page-locked host memory (cfd_host_alloc) viewed as a numpy array; snapshots into it skip the bounce copy."""
+    """Page-locked host memory (cfd_host_alloc) viewed as a numpy array; snapshots into it skip the bounce copy.
+    The buffer owns the memory: `close()` (or garbage collection of the buffer) frees it, after which `array` and every
+    view handed out from it (e.g. inside a `SimSnapshot`) must not be touched any more — copy what has to outlive it."""
 
     def __init__(self, count: int, dtype=np.float32):
         self._lib = load_library()
@@ -223,10 +244,10 @@ class Model:
     def get_snapshot(self, out=None) -> SimSnapshot:
         """`Model::get_snapshot` (src/model.rs:1259-1267): owned f32 copies of p, u, v in reference layout.
         `out` = three preallocated buffers (`pinned_snapshot_buffers()`) to fill instead of new arrays."""
+        sizes = self.snapshot_sizes()
         if out is not None:
-            p, u, v = (b.array if isinstance(b, PinnedBuffer) else b for b in out)
+            p, u, v = (_checked_out(b, n, np.float32, "get_snapshot") for b, n in zip(out, sizes))
         else:
-            sizes = self.snapshot_sizes()
             p = np.empty(sizes[0], dtype=np.float32)
             u = np.empty(sizes[1], dtype=np.float32)
             v = np.empty(sizes[2], dtype=np.float32)
@@ -235,12 +256,29 @@ class Model:
                                                            v.ctypes.data, C.byref(dt)))
         return SimSnapshot(p=p, u=u, v=v, dt=float(dt.value), paused=False)
 
+    def snapshot_begin(self, out):
+        """First half of `get_snapshot`: narrows the current fields on the device and starts their copy into the three
+        PINNED buffers `out` (`pinned_snapshot_buffers()`); returns at once, so the copy overlaps the next `update()`s.
+        The reference's UI works the same way: it posts `Command::GetSnapshot` and picks the snapshot up on a later frame
+        (src/model.rs:100-102, :1300-1306; src/app.rs:95-104).  At most two snapshots in flight."""
+        sizes = self.snapshot_sizes()
+        p, u, v = (_checked_out(b, n, np.float32, "snapshot_begin") for b, n in zip(out, sizes))
+        _check(self._lib, self._lib.cfd_model_snapshot_begin(self._handle(), p.ctypes.data, u.ctypes.data, v.ctypes.data))
+        self._snap_pending = getattr(self, "_snap_pending", []) + [(p, u, v, out)]
+
+    def snapshot_end(self) -> SimSnapshot:
+        """Second half: waits for the oldest snapshot in flight and returns it (views of the buffers given to `begin`)."""
+        dt = C.c_float()
+        _check(self._lib, self._lib.cfd_model_snapshot_end(self._handle(), C.byref(dt)))
+        p, u, v, _keep = self._snap_pending.pop(0)
+        return SimSnapshot(p=p, u=u, v=v, dt=float(dt.value), paused=False)
+
     def render_rgba(self, mode: int, out=None):
         """The UI's colour map (src/app.rs:235-404) computed on the device: (ny, nx, 4) uint8 RGBA, plus the (min, max)
         of the mapped quantity.  mode 0 pressure, 1 velocity magnitude, 2 vorticity."""
         if out is None:
             out = np.empty(self.nx * self.ny * 4, dtype=np.uint8)
-        arr = out.array if isinstance(out, PinnedBuffer) else out
+        arr = _checked_out(out, self.nx * self.ny * 4, np.uint8, "render_rgba")
         lo, hi = C.c_float(), C.c_float()
         _check(self._lib, self._lib.cfd_model_render_rgba(self._handle(), int(mode), arr.ctypes.data, C.byref(lo), C.byref(hi)))
         return arr.reshape(self.ny, self.nx, 4), float(lo.value), float(hi.value)
@@ -250,6 +288,26 @@ class Model:
         r = _abi.CfdResiduals()
         _check(self._lib, self._lib.cfd_model_get_residuals(self._handle(), C.byref(r)))
         return Residuals.from_c(r)
+
+    # -- tracer particles (the JS twin, index.html:1472-1543) ------------------------------
+    def tracers_inject(self):
+        """`initTracers` / `injectTracers`: one new tracer per cell row on the inlet."""
+        _check(self._lib, self._lib.cfd_model_tracers_inject(self._handle()))
+
+    def tracers_update(self, dt: float):
+        """`updateTracers(dt)`: advect with the current fields, drop the tracers that left the domain."""
+        _check(self._lib, self._lib.cfd_model_tracers_update(self._handle(), float(dt)))
+
+    def tracers(self) -> np.ndarray:
+        """(n, 2) float64 array of tracer positions, in injection order."""
+        n = C.c_uint64()
+        _check(self._lib, self._lib.cfd_model_tracers_count(self._handle(), C.byref(n)))
+        out = np.empty((int(n.value), 2), dtype=np.float64)
+        _check(self._lib, self._lib.cfd_model_tracers_get(self._handle(), out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def tracers_clear(self):
+        _check(self._lib, self._lib.cfd_model_tracers_clear(self._handle()))
 
     def run(self) -> "SimulationControlHandle":
         """`Model::run(self)` (src/model.rs:1282-1332): moves the model into one solver thread."""

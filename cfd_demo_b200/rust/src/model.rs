@@ -23,12 +23,28 @@ struct CfdResiduals {
     simulation_step: u64, simulation_time: f32, dt: f32, p: f32, u: f32, v: f32, step_seconds: f64,
     piso_substeps: u64, jacobi_calls: u64, sweeps: u64,
     simulation_time_f64: f64, dt_f64: f64, p_f64: f64, u_f64: f64, v_f64: f64,
+    p_rel_f64: f64, rhs_rms_f64: f64, first_solve_iterations: u64, // ABI 3
+}
+/// `cfd_solver_consts` (ABI 3): the reference's solver literals plus the extensions' knobs.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct SolverConsts {
+    pub ramp_up_steps: i32, pub jacobi_iterations: i32, pub outer_rounds: i32, pub cg_max_iterations: i32,
+    pub jacobi_omega: f64, pub pressure_tolerance: f64, pub outer_tolerance: f64, pub cfl: f64, pub cg_tolerance: f64,
+    pub mg_omega: f64, pub mg_smoothing: i32, pub mg_warm_start: i32, pub cg_relative: i32, pub adaptive_substeps: i32,
+}
+#[repr(C)]
+struct CfdOptions {
+    precision: i32, device: i32, rank: i32, world_size: i32, nccl_unique_id: *const std::ffi::c_void, flags: u32,
+    consts: SolverConsts,
 }
 #[repr(C)]
 struct CfdModel { _private: [u8; 0] }
 
 extern "C" {
     fn cfd_model_create(grid: *const CfdGrid, params: *const CfdParams, out: *mut *mut CfdModel) -> c_int;
+    fn cfd_options_default(out: *mut CfdOptions);
+    fn cfd_model_create_ex(grid: *const CfdGrid, params: *const CfdParams, opts: *const CfdOptions, out: *mut *mut CfdModel) -> c_int;
     fn cfd_model_destroy(m: *mut CfdModel);
     fn cfd_model_update(m: *mut CfdModel) -> c_int;
     fn cfd_model_set_params(m: *mut CfdModel, params: *const CfdParams) -> c_int;
@@ -55,6 +71,8 @@ pub struct SimulationParams {
     pub velocity_scheme: VelocityScheme,
     pub inlet_profile: InletProfile,
     pub pressure_solver: PressureSolver,
+    /// Extension (the reference hard-codes the channel, src/model.rs:807-815, :827-875); `Default` keeps it.
+    pub scenario: Scenario,
 }
 pub struct Residuals {
     pub simulation_step: usize, pub simulation_time: f32, pub dt: f32, pub p: f32, pub u: f32, pub v: f32,
@@ -65,7 +83,7 @@ pub struct SimSnapshot { pub p: Vec<f32>, pub u: Vec<f32>, pub v: Vec<f32>, pub 
 impl Default for SimulationParams {
     fn default() -> Self {
         Self { dt: 0.005, viscosity: 0.000001, target_inlet_velocity: 1.0, velocity_scheme: VelocityScheme::FirstOrder,
-               inlet_profile: InletProfile::Uniform, pressure_solver: PressureSolver::Jacobi }
+               inlet_profile: InletProfile::Uniform, pressure_solver: PressureSolver::Jacobi, scenario: Scenario::Channel }
     }
 }
 pub enum Command { Stop, GetSnapshot, SetParams(SimulationParams), Pause, Resume }
@@ -74,18 +92,39 @@ pub struct Grid { pub nx: usize, pub ny: usize, pub lx: f32, pub ly: f32, pub dx
 #[derive(Clone)]
 pub struct Cylinder { pub center_x: f32, pub center_y: f32, pub radius: f32 }
 #[derive(Debug, Clone, Copy, PartialEq, Eq)]
-pub enum VelocityScheme { FirstOrder, SecondOrder }
+pub enum VelocityScheme { FirstOrder, SecondOrder, /** extension: the JS twin's QUICK face values */ Quick }
+/// `Jacobi` is the reference's only variant (src/model.rs:149-152); `Cg` and `Mgcg` are the converged solvers the
+/// reference's doc comment asks for ("Jacobi, SOR or multigrid", :526) — app.rs's combo box lists whatever is here.
 #[derive(Debug, Clone, Copy, PartialEq, Eq)]
-pub enum PressureSolver { Jacobi }
+pub enum PressureSolver { Jacobi, Cg, Mgcg }
+#[derive(Debug, Clone, Copy, PartialEq, Eq)]
+pub enum Scenario { Channel, Cavity }
 #[derive(Debug, Clone, Copy, PartialEq, Eq)]
 pub enum InletProfile { Uniform, Parabolic }
 
 fn params_to_c(p: &SimulationParams) -> CfdParams {
     CfdParams {
         dt: p.dt, viscosity: p.viscosity, target_inlet_velocity: p.target_inlet_velocity,
-        velocity_scheme: match p.velocity_scheme { VelocityScheme::FirstOrder => 0, VelocityScheme::SecondOrder => 1 },
+        velocity_scheme: match p.velocity_scheme { VelocityScheme::FirstOrder => 0, VelocityScheme::SecondOrder => 1, VelocityScheme::Quick => 2 },
         inlet_profile: match p.inlet_profile { InletProfile::Uniform => 0, InletProfile::Parabolic => 1 },
-        pressure_solver: 0, scenario: 0,
+        pressure_solver: match p.pressure_solver { PressureSolver::Jacobi => 0, PressureSolver::Cg => 1, PressureSolver::Mgcg => 2 },
+        scenario: match p.scenario { Scenario::Channel => 0, Scenario::Cavity => 1 },
+    }
+}
+
+fn grid_to_c(grid: &Grid) -> CfdGrid {
+    CfdGrid {
+        nx: grid.nx as u64, ny: grid.ny as u64, lx: grid.lx, ly: grid.ly, dx: grid.dx, dy: grid.dy,
+        has_obstacle: grid.obstacle.is_some() as i32,
+        center_x: grid.obstacle.as_ref().map_or(0.0, |c| c.center_x),
+        center_y: grid.obstacle.as_ref().map_or(0.0, |c| c.center_y),
+        radius: grid.obstacle.as_ref().map_or(0.0, |c| c.radius),
+    }
+}
+impl Default for SolverConsts {
+    fn default() -> Self {
+        let mut o = std::mem::MaybeUninit::<CfdOptions>::uninit();
+        unsafe { cfd_options_default(o.as_mut_ptr()); o.assume_init().consts }
     }
 }
 
@@ -95,15 +134,23 @@ unsafe impl Send for Model {} // moved into exactly one solver thread, like the 
 
 impl Model {
     pub fn new(grid: Grid, params: &SimulationParams) -> Self {
-        let g = CfdGrid {
-            nx: grid.nx as u64, ny: grid.ny as u64, lx: grid.lx, ly: grid.ly, dx: grid.dx, dy: grid.dy,
-            has_obstacle: grid.obstacle.is_some() as i32,
-            center_x: grid.obstacle.as_ref().map_or(0.0, |c| c.center_x),
-            center_y: grid.obstacle.as_ref().map_or(0.0, |c| c.center_y),
-            radius: grid.obstacle.as_ref().map_or(0.0, |c| c.radius),
-        };
+        let g = grid_to_c(&grid);
         let mut handle = std::ptr::null_mut();
         check(unsafe { cfd_model_create(&g, &params_to_c(params), &mut handle) });
+        Self { grid, handle }
+    }
+    /// Extension: like `new`, with the solver constants spelled out (e.g. `cg_relative = 1` for the benchmarked
+    /// relative stopping rule of the converged solvers; `SolverConsts::default()` = the reference's literals).
+    pub fn with_consts(grid: Grid, params: &SimulationParams, consts: SolverConsts) -> Self {
+        let g = grid_to_c(&grid);
+        let mut o = std::mem::MaybeUninit::<CfdOptions>::uninit();
+        let mut handle = std::ptr::null_mut();
+        unsafe {
+            cfd_options_default(o.as_mut_ptr());
+            let mut o = o.assume_init();
+            o.consts = consts;
+            check(cfd_model_create_ex(&g, &params_to_c(params), &o, &mut handle));
+        }
         Self { grid, handle }
     }
     pub fn update(&mut self) { check(unsafe { cfd_model_update(self.handle) }) }

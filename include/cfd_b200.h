@@ -186,6 +186,15 @@ int cfd_model_set_params(cfd_model* m, const cfd_params* params);
  * Caller-allocated, reference layout: p nx*ny, u (nx+1)*ny, v nx*(ny+1); any pointer may be NULL.
  * With world_size > 1 each rank receives its own rows only (see cfd_model_rows). */
 int cfd_model_get_snapshot(cfd_model* m, float* p, float* u, float* v, float* dt);
+/* The same in two halves, so that the device->host copy of step n's snapshot overlaps the computation of step n+1 — the
+ * shape of the reference's own protocol, where the UI posts Command::GetSnapshot and picks the result up on a later frame
+ * while the solver thread keeps stepping (src/model.rs:100-102, :1300-1306; src/app.rs:95-104, :470).
+ * begin: narrows the CURRENT p, u, v to f32 into a device staging buffer (on the model's stream: the fields may change right
+ *        after) and starts the copy into p / u / v on a second stream; returns at once.  The destinations must be page-locked
+ *        (cfd_host_alloc) and stay valid until `end`; any of them may be NULL.  At most two snapshots may be in flight.
+ * end:   waits for the OLDEST snapshot in flight; *dt = the dt that was current at its `begin`. */
+int cfd_model_snapshot_begin(cfd_model* m, float* p, float* u, float* v);
+int cfd_model_snapshot_end(cfd_model* m, float* dt);
 /* Page-locked host memory for snapshot buffers (no reference counterpart: `SimSnapshot` owns plain Vec<f32>).
  * cfd_model_get_snapshot detects pinned destinations and lets the copy engine write them directly; pageable
  * destinations are served through pinned bounce buffers (chunked, PCIe transfer overlapped with the memcpy). */
@@ -213,6 +222,20 @@ int cfd_model_rows(cfd_model* m, uint64_t* j0, uint64_t* j1);
  * for a grid of ny rows.  Interior boundaries sit at 1 + (a multiple of 16), so that the unknown rows of a strip pair
  * up within the strip on the first four multigrid levels (MGCG on strips). */
 int cfd_strip_rows(uint64_t ny, int32_t world_size, int32_t rank, uint64_t* j0, uint64_t* j1);
+
+/* ---- tracer particles (the JS twin, index.html:1472-1543; no Rust counterpart) ------- */
+/* Tracers live on the device next to the fields, in injection order.  Single domain only (world_size 1).
+ * inject: initTracers / injectTracers (:1475-1483, :1537-1543) — appends one tracer per cell row on the inlet, at
+ *         (0, (j + 1/2) dy); the JS animation loop calls it at start and every 100 timesteps (:1233-1237).
+ * update: updateTracers(dt) (:1485-1497) — x += dt * u(x, y), y += dt * v(x, y) with the bilinearly interpolated
+ *         cell-centred velocity of the CURRENT fields (getVelocityAt, :1499-1526); tracers that leave [0, lx] x [0, ly] are
+ *         dropped, the others keep their order.  The JS passes the solver's dt after each timestep.
+ * get:    positions as (x, y) pairs of doubles, at most `capacity` tracers; *n = how many exist. */
+int cfd_model_tracers_inject(cfd_model* m);
+int cfd_model_tracers_update(cfd_model* m, double dt);
+int cfd_model_tracers_count(cfd_model* m, uint64_t* n);
+int cfd_model_tracers_get(cfd_model* m, double* xy, uint64_t capacity, uint64_t* n);
+int cfd_model_tracers_clear(cfd_model* m);
 
 /* ---- measurement hooks (bench.py / profiles; no reference counterpart) ------------------------------- */
 /* Device time in ms of the last cfd_model_update / update_n, and of the Jacobi sweeps inside it,

@@ -125,3 +125,101 @@ def test_set_parameters_validates_enums():
         assert m._lib.cfd_model_set_params(m._handle(), C.byref(p)) == _abi.CFD_ERR_INVALID_ARGUMENT, field
     m.set_parameters(SimulationParams(velocity_scheme=VelocityScheme.Quick))
     m.update()
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+def test_tracer_particles_match_the_js_restatement(precision):
+    """cfd_model_tracers_* (index.html:1472-1543) against oracle/tracers.py on the GPU model's own fields: after every
+    timestep the tracers are advected with the solver's dt (the JS loop, :1233-1237), every 10 steps a new row of tracers is
+    injected; positions and their order must agree bit for bit (double arithmetic, no contraction), tracers that leave
+    the domain disappear on both sides."""
+    from oracle import tracers as tr
+    g = channel_grid(96, 32, lx=6.0, ly=2.0)
+    prm = SimulationParams(dt=0.02, target_inlet_velocity=3.0, viscosity=1e-3)
+    o = default_options()
+    o.precision = precision
+    o.consts.ramp_up_steps = 4
+    gpu = Model(g, prm, options=o)
+    gpu.tracers_inject()
+    ref = tr.inject(np.zeros((0, 2)), g.ny, g.dy)
+    assert np.array_equal(gpu.tracers(), ref)
+    dropped = False
+    for s in range(60):
+        gpu.update()
+        dt = 25.0 * gpu.get_residuals().f64["dt"]  # the tracer step is the caller's choice; long enough to cross the domain
+        u, v = gpu.field(_abi.FIELD_U), gpu.field(_abi.FIELD_V)
+        gpu.tracers_update(dt)
+        n_before = ref.shape[0]
+        ref = tr.update(ref, u, v, g.nx, g.ny, g.dx, g.dy, g.lx, g.ly, dt)
+        dropped |= ref.shape[0] < n_before
+        if (s + 1) % 10 == 0:
+            gpu.tracers_inject()
+            ref = tr.inject(ref, g.ny, g.dy)
+        got = gpu.tracers()
+        assert got.shape == ref.shape, (s, got.shape, ref.shape)
+        assert np.array_equal(got, ref), (s, np.abs(got - ref).max())
+    assert ref.shape[0] > g.ny and dropped and ref[:, 0].max() > 1.0
+    gpu.tracers_clear()
+    assert gpu.tracers().shape == (0, 2)
+
+
+def test_asynchronous_snapshot_is_the_state_at_begin():
+    """cfd_model_snapshot_begin / _end: the snapshot is the state at `begin`, although two more timesteps run before `end`
+    (the fields are narrowed on the model's stream before they change; the copy overlaps the steps); two snapshots may be
+    in flight, a third `begin` is refused; pageable or mis-sized destinations are refused instead of being overrun."""
+    from cfd_demo_b200.model import CfdError
+    g = channel_grid(264, 96)
+    m = Model(g, SimulationParams())
+    for _ in range(6):
+        m.update()
+    a, b = m.pinned_snapshot_buffers(), m.pinned_snapshot_buffers()
+    want_a = [m.field(f).astype(np.float32) for f in (_abi.FIELD_P, _abi.FIELD_U, _abi.FIELD_V)]
+    dt_a = m.get_residuals().dt
+    m.snapshot_begin(a)
+    m.update()
+    want_b = [m.field(f).astype(np.float32) for f in (_abi.FIELD_P, _abi.FIELD_U, _abi.FIELD_V)]
+    m.snapshot_begin(b)
+    with pytest.raises(CfdError):
+        m.snapshot_begin(a)
+    m.update()
+    sa = m.snapshot_end()
+    sb = m.snapshot_end()
+    for got, want in zip((sa.p, sa.u, sa.v), want_a):
+        assert np.array_equal(got, want)
+    for got, want in zip((sb.p, sb.u, sb.v), want_b):
+        assert np.array_equal(got, want)
+    assert sa.dt == dt_a and not np.array_equal(sa.u, sb.u)
+    with pytest.raises(CfdError):
+        m.snapshot_end()
+    sizes = m.snapshot_sizes()
+    with pytest.raises(CfdError):  # pageable destinations cannot be written asynchronously
+        m.snapshot_begin([np.empty(n, dtype=np.float32) for n in sizes])
+    with pytest.raises(CfdError):  # wrong size / dtype: refused before anything is written (ADVICE r1)
+        m.get_snapshot(out=[np.empty(n - 1, dtype=np.float32) for n in sizes])
+    with pytest.raises(CfdError):
+        m.get_snapshot(out=[np.empty(n, dtype=np.float64) for n in sizes])
+    with pytest.raises(CfdError):
+        m.render_rgba(0, out=np.empty(10, dtype=np.uint8))
+
+
+def test_cpp_headless_driver_runs_the_headline_workload_family():
+    """The benchmarked path (lid-driven cavity, MGCG, relative stopping rule) through the C++ mirror of the reference API
+    (host/cfd_model.hpp -> the same C ABI the Rust shim binds): its per-step log must equal the Python mirror's run of the
+    same problem — iteration counts, the relative residual and dt * rms(rhs) to the printed precision."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cfd_demo_b200", "host", "cfd_headless")
+    n, steps, nu, dt = 512, 30, 1.0e-2, 8.0e-5
+    r = subprocess.run([exe, "cavity", str(n), str(steps), repr(nu), repr(dt)], capture_output=True, text=True, check=True)
+    c = default_consts()
+    c.cg_relative = 1
+    o = default_options()
+    o.consts = c
+    m = Model(box_grid(n), SimulationParams(dt=dt, viscosity=nu, scenario=Scenario.Cavity, pressure_solver=PressureSolver.MGCG), options=o)
+    for _ in range(steps):
+        m.update()
+    res = m.get_residuals()
+    line = [l for l in r.stdout.splitlines() if l.startswith(f"step {steps} ")][0]
+    assert f"K={res.jacobi_calls} iterations={res.sweeps} " in line, (line, res)
+    assert f"rel={res.f64['p_rel']:.3e}" in line and f"dt*rms(rhs)={res.f64['rhs_rms']:.3e}" in line, (line, res.f64)
+    assert res.sweeps > 0 and res.f64["p_rel"] <= 1e-8

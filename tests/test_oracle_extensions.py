@@ -99,3 +99,29 @@ def test_relative_stopping_rule(solver):
     for _ in range(8):
         a.update()
     assert rel_l2(m.field(_abi.FIELD_U), a.field(_abi.FIELD_U)) < 1e-5
+
+
+def test_tracers_restatement_known_answers():
+    """Facts read off index.html:1472-1543: tracers start on the inlet at row centres; in a uniform flow u = U, v = 0 a
+    tracer moves by U * dt per update (bilinear interpolation reproduces constants exactly) and is dropped once it is
+    past x = lx; in a linear shear u = y the interpolated velocity at a cell centre is that cell's value."""
+    from oracle import tracers as tr
+    nx, ny, lx, ly = 16, 8, 4.0, 2.0
+    dx, dy = lx / nx, ly / ny
+    t = tr.inject(np.zeros((0, 2)), ny, dy)
+    assert t.shape == (ny, 2) and not t[:, 0].any() and np.array_equal(t[:, 1], (np.arange(ny) + 0.5) * dy)
+    u = np.full((ny, nx + 1), 1.5)
+    v = np.zeros((ny + 1, nx))
+    for k in range(1, 4):
+        t = tr.update(t, u, v, nx, ny, dx, dy, lx, ly, 0.5)
+        assert t.shape[0] == ny and np.array_equal(t[:, 0], np.full(ny, 0.75 * k))
+    for _ in range(3):
+        t = tr.update(t, u, v, nx, ny, dx, dy, lx, ly, 0.5)
+    assert t.shape[0] == 0  # 6 * 0.75 = 4.5 > lx: all gone
+    ushear = np.tile(((np.arange(ny) + 0.5) * dy)[:, None], (1, nx + 1))
+    x = np.array([2.125]); y = np.array([(3 + 0.5) * dy])
+    ui, vi = tr.velocity_at(ushear, v, nx, ny, dx, dy, x, y)
+    # (x, y) = the centre of cell (8, 3) is the lower-left node of the interpolation square: rx = ry = 0.5 between cell centres
+    # (3, 4) ... the JS interpolates between the values of cells (i, j), (i+1, j), (i, j+1), (i+1, j+1) with weights from the
+    # position inside cell (i, j) — at its centre that is the mean of rows j and j+1
+    assert np.allclose(ui, 0.5 * ((3 + 0.5) * dy + (4 + 0.5) * dy)) and vi[0] == 0.0
