@@ -19,11 +19,19 @@
 
 namespace cfdk {
 
+constexpr int kMgClasses = 8;  // distinct (WE + WW, CYW) column / (WN + WS, CXH) row combinations a level's diagonal table holds
 template <class R>
 struct MgLevelDev {
   int mx, my;               // unknowns per direction; fields are (mx + 2) x (my + 2)
   const R *WE, *WW, *CYW;   // per column
   const R *WN, *WS, *CXH;   // per row
+  // The diagonal CXH[J] (WE[I] + WW[I]) + CYW[I] (WN[J] + WS[J]) takes only a handful of distinct values on a level (the
+  // grid is uniform except next to the boundary and where a trailing cell stayed single): they are tabulated per
+  // (row class, column class) together with their hoisted reciprocals (DivG), so that the sweep's division by the
+  // diagonal is the exact hoisted-reciprocal one instead of the compiler's 30-instruction sequence.  nullptr: no table
+  // (more than kMgClasses classes), the generic per-cell kernel is used.
+  const unsigned char *col_class, *row_class;
+  const DivG<R>* diag_table;  // [row class * kMgClasses + column class]
 };
 
 constexpr int kMgThreads = 256;
@@ -575,6 +583,71 @@ __global__ void __launch_bounds__(kMgThreads) k_mgc_sweep(MgLevelDev<R> L, const
   const int I = blockIdx.x * blockDim.x + threadIdx.x, J = row_lo + blockIdx.y;
   if (sc->done) return;
   if (I < L.mx) mgc_sweep_cell<R>(L, in, rho, out, omega, zero_in != 0, I, J);
+}
+
+// fills a level's diagonal table from the diagonal values (one thread per entry)
+template <class R>
+__global__ void k_mgc_diag_table(const R* __restrict__ diag, DivG<R>* __restrict__ table, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) table[k] = make_divg(diag[k]);
+}
+
+// k_mgc_sweep for a level with a diagonal table: same per-cell arithmetic (mgc_sweep_cell), a thread owns column I and
+// kMgcRows rows — the column's weights are loaded once, the centre column's rows rotate through registers, every load of
+// the tile is issued before the arithmetic, and the division by the diagonal is DivTry (DivTrue for the rare tile with a
+// dividend outside the window).  grid = (ceil(mx / 256), ceil(rows / kMgcRows)).
+constexpr int kMgcRows = 4;
+template <class R>
+__global__ void __launch_bounds__(kMgThreads) k_mgc_sweep_tab(MgLevelDev<R> L, const R* __restrict__ in,
+                                                               const R* __restrict__ rho, R* __restrict__ out, R omega,
+                                                               int zero_in, int row_lo, int row_hi,
+                                                               const MgScalars* __restrict__ sc) {
+  const int I = blockIdx.x * blockDim.x + threadIdx.x;
+  const int J0 = row_lo + blockIdx.y * kMgcRows, J1 = min(J0 + kMgcRows, row_hi);
+  if (sc->done || I >= L.mx || J0 >= J1) return;
+  const size_t W = (size_t)L.mx + 2;
+  const R we = L.WE[I], ww = L.WW[I], cyw = L.CYW[I];
+  const int cc_cls = L.col_class[I];
+  R ec[kMgcRows + 2], el[kMgcRows], er[kMgcRows], rh[kMgcRows];
+#pragma unroll
+  for (int m = 0; m < kMgcRows + 2; ++m) {
+    const int J = min(J0 - 1 + m, J1);  // array row J + 1; rows -1 and my are the ring of zeros
+    ec[m] = zero_in ? R(0) : in[(size_t)(I + 1) + (size_t)(J + 1) * W];
+  }
+#pragma unroll
+  for (int r = 0; r < kMgcRows; ++r) {
+    const int J = min(J0 + r, J1 - 1);
+    const size_t idx = (size_t)(I + 1) + (size_t)(J + 1) * W;
+    el[r] = zero_in ? R(0) : in[idx - 1];
+    er[r] = zero_in ? R(0) : in[idx + 1];
+    rh[r] = rho[idx];
+  }
+  R num[kMgcRows], res[kMgcRows];
+  DivG<R> dg[kMgcRows];
+#pragma unroll
+  for (int r = 0; r < kMgcRows; ++r) {
+    const int J = min(J0 + r, J1 - 1);
+    const R cxh = L.CXH[J], wn = L.WN[J], ws = L.WS[J];
+    const R cc = ec[r + 1];
+    // mg_coarse_apply, same association
+    const R le = cxh * (we * (er[r] - cc) + ww * (el[r] - cc)) + cyw * (wn * (ec[r + 2] - cc) + ws * (ec[r] - cc));
+    num[r] = le - rh[r];
+    dg[r] = L.diag_table[L.row_class[J] * kMgClasses + cc_cls];
+  }
+  DivTry<R> dv(dg[0]);
+#pragma unroll
+  for (int r = 1; r < kMgcRows; ++r) dv.also(dg[r]);
+#pragma unroll
+  for (int r = 0; r < kMgcRows; ++r) res[r] = dv(num[r], dg[r]);
+  if (__builtin_expect(!dv.ok(), 0)) {
+#pragma unroll
+    for (int r = 0; r < kMgcRows; ++r) res[r] = num[r] / dg[r].y;
+  }
+#pragma unroll
+  for (int r = 0; r < kMgcRows; ++r) {
+    const int J = J0 + r;
+    if (J < J1) out[(size_t)(I + 1) + (size_t)(J + 1) * W] = dg[r].y > R(0) ? ec[r + 1] + omega * res[r] : R(0);
+  }
 }
 
 template <class R>

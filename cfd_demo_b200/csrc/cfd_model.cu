@@ -219,6 +219,8 @@ struct ModelImpl final : ModelBase {
     R* weights = nullptr;                      // WE, WW, CYW (mx each), WN, WS, CXH (my each)
     R *e = nullptr, *rho = nullptr, *tmp = nullptr;  // (mx + 2) x (my + 2), ring of zeros; level 0 has none
     R* cur = nullptr;                          // whichever of e / tmp holds the level's correction
+    unsigned char* classes = nullptr;          // column + row classes of the level's diagonal table (MgLevelDev)
+    cfdk::DivG<R>* diag_table = nullptr;
     cfdk::MgLevelDev<R> dev;
   };
   std::vector<MgLevelHost> mg;
@@ -242,7 +244,7 @@ struct ModelImpl final : ModelBase {
                                    // predictor does not overwrite were actually copied (k_star_save_*)
   int mg_pred[2] = {3, 0};         // iterations the previous step's first / re-correction solves took (batch size)
   int solid_i0 = 0, solid_i1 = 0, solid_j0 = 0, solid_j1 = 0;  // bounding box of the solid cells (empty: no obstacle)
-  CUtensorMap tmap_mg_b[3], tmap_mg_rho;
+  CUtensorMap tmap_mg_b[3], tmap_mg_rho, tmap_mg_rho_halo;
   cfdk::MgScalars* mg_scalars = nullptr;  // device
   cfdk::MgScalars* h_mg = nullptr;        // pinned host copy
   double* mg_partials = nullptr;
@@ -307,6 +309,7 @@ struct ModelImpl final : ModelBase {
   };
   std::vector<PeerBuf> peer_bufs;
   size_t peer_synced = 0;
+  bool persist_ready = false;
   bool peer2_ready = false;
   cfdk::PeerBox* box = nullptr;
   cfdk::PeerBox* peer_box[cfdk::kPeerMaxRanks] = {};
@@ -357,7 +360,7 @@ struct ModelImpl final : ModelBase {
     cudaFree(mask_u.base); cudaFree(mask_v.base); cudaFree(solid.base);
     cudaFree(err_slots); cudaFree(step_slots); cudaFree(staging); cudaFree(tickets); cudaFree(d_divs);
     cudaFree(cg_r.base); cudaFree(cg_d.base); cudaFree(cg_partials); cudaFree(cg_scalars);
-    for (auto& L : mg) { cudaFree(L.weights); cudaFree(L.e); cudaFree(L.rho); cudaFree(L.tmp); }
+    for (auto& L : mg) { cudaFree(L.weights); cudaFree(L.e); cudaFree(L.rho); cudaFree(L.tmp); cudaFree(L.classes); cudaFree(L.diag_table); }
     cudaFree(mg_rho.base); cudaFree(mg_guess.base);
     for (auto& f : mg_hist) cudaFree(f.base);
     for (auto& f : mg_b) cudaFree(f.base);
@@ -458,7 +461,7 @@ struct ModelImpl final : ModelBase {
     // per-sweep tickets / stop flags / diagnostics (strips) and work counters (persistent sweep), cfd_kernels.cuh
     if ((rc = dalloc(&tickets, (size_t)1400))) return rc;
     CFD_CUDA(cudaHostAlloc((void**)&h_jres, sizeof(cfdk::JacobiResult), cudaHostAllocMapped));
-    CFD_CUDA(cudaHostAlloc((void**)&h_step, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+    CFD_CUDA(cudaHostAlloc((void**)&h_step, 8 * sizeof(unsigned long long), cudaHostAllocMapped));
     CFD_CUDA(cudaEventCreate(&ev_step0));
     CFD_CUDA(cudaEventCreate(&ev_step1));
     const int n_pairs = 2 * (opt.consts.outer_rounds + 1);
@@ -863,6 +866,11 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
 
+  // device scalars -> mapped pinned host memory by a one-warp kernel (not by the copy engine: see k_publish_words)
+  void publish(const void* dev, void* host_mapped, size_t bytes) {
+    cfdk::k_publish_words<<<1, 32, 0, stream>>>((const unsigned*)dev, (volatile unsigned*)host_mapped, (int)(bytes / 4));
+  }
+
   // CUDA-event pair of the next pressure solve of this step (begin = [k], end = [k + 1])
   int next_solve_events(size_t* k) {
     if (ev_sweep_used + 2 > ev_sweep.size()) {
@@ -943,7 +951,40 @@ struct ModelImpl final : ModelBase {
     if (grid6 < 1) grid6 = 1;
     const bool use_t2 = world == 1 && tuned_default && (opt.flags & CFD_FLAG_TEMPORAL) && (iters % 2 == 0) &&
                         rows >= 4;
-    if (use_t2) {
+    bool persisted = false;
+    if (world == 1 && tuned_default && !use6 && !(opt.flags & (CFD_FLAG_TEMPORAL | CFD_FLAG_NO_GRAPH))) {
+      // ---- small grids: the whole solve in ONE cooperative launch, p' / p'new / rhs of a block's rows in shared memory
+      int sms = 0, max_smem = 0, coop = 0;
+      CFD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+      CFD_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+      CFD_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+      // as many rows per block as shared memory holds (fewer blocks make the grid barrier cheaper; a block's 1024 threads
+      // update its rows in a few passes), but at least one block per ~8 rows so that small grids still use many SMs
+      int threads = 1024, target_rows = 8;
+      if (const char* e = getenv("CFD_PERSIST_THREADS")) threads = atoi(e);   // tuning hooks
+      if (const char* e = getenv("CFD_PERSIST_ROWS")) target_rows = atoi(e);
+      int blocks = (rows + target_rows - 1) / target_rows;
+      if (blocks > sms) blocks = sms;
+      if (blocks < 1) blocks = 1;
+      int rb = (rows + blocks - 1) / blocks;
+      while (rb > 1 && ((size_t)2 * (rb + 2) + rb) * (size_t)nx * sizeof(R) + 1024 > (size_t)max_smem && (rows + rb - 2) / (rb - 1) <= sms) --rb;
+      const size_t smem = ((size_t)2 * (rb + 2) + rb) * (size_t)nx * sizeof(R);
+      if (coop && rows >= 1 && smem + 1024 <= (size_t)max_smem) {
+        if (!persist_ready) {
+          CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_persist<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024));
+          persist_ready = true;
+        }
+        cfdk::PersistArgs<R> pa;
+        pa.c = c2; pa.pp0 = pp[0].v; pa.pp1 = pp[1].v; pa.rhs = rhs.v;
+        pa.ipp = ipp; pa.iters = iters; pa.rows_per_block = rb; pa.err_slots = err_slots; pa.out = h_jres;
+        void* args[] = {&pa};
+        CFD_CUDA(cudaLaunchCooperativeKernel((const void*)cfdk::k_jacobi_persist<R>, dim3((rows + rb - 1) / rb), dim3(threads), args, smem, stream));
+        ++launches;
+        persisted = true;
+      }
+    }
+    if (persisted) {
+    } else if (use_t2) {
       // ---- temporal blocking: two sweeps per pass over HBM (k_jacobi_sweep_t2), each pass followed by the
       // conditional fix-up that restores the reference's stopping point when the FIRST sweep of a pass converged
       cfdk::JacobiConsts2<R> ct = c2, cf = c2;
@@ -1007,7 +1048,7 @@ struct ModelImpl final : ModelBase {
         }
       }
     }
-    if (!(world > 1 && tuned_default && peer_ready)) {
+    if (!persisted && !(world > 1 && tuned_default && peer_ready)) {
       cfdk::k_jacobi_finalize<R><<<1, 32, 0, stream>>>(err_slots, iters, c.tol, h_jres);
       ++launches;
     }
@@ -1069,7 +1110,7 @@ struct ModelImpl final : ModelBase {
       if ((rc = falloc(&cg_d, (size_t)nx))) return rc;
       if ((rc = dalloc(&cg_partials, (size_t)n_all))) return rc;
       if ((rc = dalloc(&cg_scalars, (size_t)1))) return rc;
-      CFD_CUDA(cudaHostAlloc((void**)&h_cg, sizeof(cfdk::CgScalars), cudaHostAllocDefault));
+      CFD_CUDA(cudaHostAlloc((void**)&h_cg, sizeof(cfdk::CgScalars), cudaHostAllocMapped));
       peer_register(cg_d.base);
       if ((rc = peer_sync())) return rc;
     }
@@ -1094,7 +1135,7 @@ struct ModelImpl final : ModelBase {
     if ((rc = cg_reduce(c, n_all, 0))) return rc;
     const int batch = 32;
     for (;;) {
-      CFD_CUDA(cudaMemcpyAsync(h_cg, cg_scalars, sizeof init, cudaMemcpyDeviceToHost, stream));
+      publish(cg_scalars, h_cg, sizeof init);
       CFD_CUDA(cudaStreamSynchronize(stream));
       if (h_cg->done) break;
       for (int it = 0; it < batch; ++it) {
@@ -1151,6 +1192,46 @@ struct ModelImpl final : ModelBase {
       L.dev.mx = L.mx; L.dev.my = L.my;
       L.dev.WE = L.weights; L.dev.WW = L.weights + mx; L.dev.CYW = L.weights + 2 * mx;
       L.dev.WN = L.weights + 3 * mx; L.dev.WS = L.weights + 3 * mx + my; L.dev.CXH = L.weights + 3 * mx + 2 * my;
+      L.dev.col_class = nullptr; L.dev.row_class = nullptr; L.dev.diag_table = nullptr;
+      if (!mg.empty() && !(mx == 1 && my == 1)) {
+        // classes of columns by (WE + WW, CYW) and of rows by (WN + WS, CXH): the diagonal of a cell depends on them only
+        auto classify = [](const R* a, const R* b, size_t n, std::vector<unsigned char>& cls, std::vector<std::pair<R, R>>& keys) {
+          cls.resize(n);
+          for (size_t k = 0; k < n; ++k) {
+            const std::pair<R, R> key(a[k], b[k]);
+            size_t c = 0;
+            while (c < keys.size() && memcmp(&keys[c], &key, sizeof key) != 0) ++c;
+            if (c == keys.size()) keys.push_back(key);
+            if (keys.size() > (size_t)cfdk::kMgClasses) return false;
+            cls[k] = (unsigned char)c;
+          }
+          return true;
+        };
+        std::vector<R> a(mx), b(my);
+        for (size_t i = 0; i < mx; ++i) a[i] = WE[i] + WW[i];
+        for (size_t j = 0; j < my; ++j) b[j] = WN[j] + WS[j];
+        std::vector<unsigned char> ccls, rcls;
+        std::vector<std::pair<R, R>> ckeys, rkeys;
+        if (classify(a.data(), CYW, mx, ccls, ckeys) && classify(b.data(), CXH, my, rcls, rkeys)) {
+          std::vector<R> diag((size_t)cfdk::kMgClasses * cfdk::kMgClasses, R(0));
+          for (size_t r = 0; r < rkeys.size(); ++r)
+            for (size_t c = 0; c < ckeys.size(); ++c)  // CXH[J] * (WE[I] + WW[I]) + CYW[I] * (WN[J] + WS[J]), like mgc_sweep_cell
+              diag[r * cfdk::kMgClasses + c] = rkeys[r].second * ckeys[c].first + ckeys[c].second * rkeys[r].first;
+          unsigned char* d_cls = nullptr;
+          R* d_diag = nullptr;
+          if ((rc = dalloc(&d_cls, mx + my))) return rc;
+          if ((rc = dalloc(&d_diag, diag.size()))) return rc;
+          if ((rc = dalloc(&L.diag_table, diag.size()))) return rc;
+          CFD_CUDA(cudaMemcpyAsync(d_cls, ccls.data(), mx, cudaMemcpyHostToDevice, stream));
+          CFD_CUDA(cudaMemcpyAsync(d_cls + mx, rcls.data(), my, cudaMemcpyHostToDevice, stream));
+          CFD_CUDA(cudaMemcpyAsync(d_diag, diag.data(), diag.size() * sizeof(R), cudaMemcpyHostToDevice, stream));
+          cfdk::k_mgc_diag_table<R><<<1, 64, 0, stream>>>(d_diag, L.diag_table, (int)diag.size());
+          CFD_CUDA(cudaStreamSynchronize(stream));
+          CFD_CUDA(cudaFree(d_diag));
+          L.classes = d_cls;
+          L.dev.col_class = d_cls; L.dev.row_class = d_cls + mx; L.dev.diag_table = L.diag_table;
+        }
+      }
       if (!mg.empty()) {
         const size_t n = (mx + 2) * (my + 2);
         if ((rc = dalloc(&L.e, n))) return rc;
@@ -1180,6 +1261,8 @@ struct ModelImpl final : ModelBase {
     CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep5<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(Ring)));
     if ((rc = make_tensor_map(&tmap_mg_rho, mg_rho.row(ja - kHalo), cfdk::kStripCols))) return rc;
+    if ((rc = make_tensor_map(&tmap_mg_rho_halo, mg_rho.row(ja - kHalo), Ring::kPCols))) return rc;
+    CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep5<R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Ring)));
     if ((rc = dalloc(&mg_scalars, (size_t)1))) return rc;
     if ((rc = dalloc(&mg_err, (size_t)kMaxSweepSlots))) return rc;
     if ((rc = dalloc(&mg_ticket, (size_t)4))) return rc;
@@ -1205,7 +1288,7 @@ struct ModelImpl final : ModelBase {
       mg_bottom.lv[k].dev = L.dev;
       mg_bottom.lv[k].e = L.e; mg_bottom.lv[k].rho = L.rho; mg_bottom.lv[k].tmp = L.tmp;
     }
-    CFD_CUDA(cudaHostAlloc((void**)&h_mg, sizeof(cfdk::MgScalars), cudaHostAllocDefault));
+    CFD_CUDA(cudaHostAlloc((void**)&h_mg, sizeof(cfdk::MgScalars), cudaHostAllocMapped));
     CFD_CUDA(cudaStreamSynchronize(stream));
     // strips over peer memory: everything the V-cycle exchanges
     peer_register(mg_rho.base);
@@ -1329,8 +1412,12 @@ struct ModelImpl final : ModelBase {
       L.cur = b;
       return CFD_OK;
     }
+    // (the 4-row tiles leave the small levels with too few blocks: there the one-cell-per-thread kernel is faster)
+    const bool tab = L.dev.diag_table != nullptr && !(opt.flags & CFD_FLAG_MG_UNFUSED) && (long)L.mx * L.my >= 500000L;
+    const dim3 grd_t((L.mx + cfdk::kMgThreads - 1) / cfdk::kMgThreads, (hi - lo + cfdk::kMgcRows - 1) / cfdk::kMgcRows);
     for (int s = 0; s < nu_s; ++s) {
-      cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, omega, s == 0 ? 1 : 0, lo, mg_scalars);
+      if (tab) cfdk::k_mgc_sweep_tab<R><<<grd_t, blk, 0, stream>>>(L.dev, a, L.rho, b, omega, s == 0 ? 1 : 0, lo, hi, mg_scalars);
+      else cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, omega, s == 0 ? 1 : 0, lo, mg_scalars);
       ++launches;
       std::swap(a, b);
       if (dist && (rc = exchange_level(a, l))) return rc;
@@ -1350,7 +1437,8 @@ struct ModelImpl final : ModelBase {
       ++launches;
     }
     for (int s = 0; s < nu_s; ++s) {
-      cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, omega, 0, lo, mg_scalars);
+      if (tab) cfdk::k_mgc_sweep_tab<R><<<grd_t, blk, 0, stream>>>(L.dev, a, L.rho, b, omega, 0, lo, hi, mg_scalars);
+      else cfdk::k_mgc_sweep<R><<<grd, blk, 0, stream>>>(L.dev, a, L.rho, b, omega, 0, lo, mg_scalars);
       ++launches;
       std::swap(a, b);
       if (dist && (rc = exchange_level(a, l))) return rc;
@@ -1426,7 +1514,14 @@ struct ModelImpl final : ModelBase {
     const dim3 g_fs((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads), (rows + cfdk::kFsRows - 1) / cfdk::kFsRows);
     if (fused) {
       if ((rc = exchange_halo(mg_rho, ja, jb, 1))) return rc;  // strips: the stencil of the second sweep reaches into rho's halo
-      cfdk::k_mg_fused_sweep<R, 0><<<g_fs, cfdk::kMgThreads, 0, stream>>>(c, c2, mg_rho.v, nullptr, 0, nullptr, mg_b[zo].v, mg_scalars);
+      // the tensor-TMA sweep kernel in its kFirst form (input formed from the staged rho); CFD_FUSED0_SIMPLE=1: the
+      // register-tile kernel k_mg_fused_sweep<0> instead (A/B)
+      static const bool simple0 = getenv("CFD_FUSED0_SIMPLE") != nullptr;
+      if (simple0)
+        cfdk::k_mg_fused_sweep<R, 0><<<g_fs, cfdk::kMgThreads, 0, stream>>>(c, c2, mg_rho.v, nullptr, 0, nullptr, mg_b[zo].v, mg_scalars);
+      else
+        cfdk::k_jacobi_sweep5<R, false, true><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_mg_rho_halo, tmap_mg_rho, mg_b[zo].v, mg_err, 0,
+                                                                                 cfdk::SweepPeer<R>{}, dot);
       ++launches;
       std::swap(zc, zo);
       if ((rc = exchange_halo(mg_b[zc], ja, jb, 1))) return rc;
@@ -1561,7 +1656,7 @@ struct ModelImpl final : ModelBase {
     int& pred = mg_pred[first_solve ? 0 : 1];
     CFD_CUDA(cudaEventRecord(ev_sweep[ev], stream));
     auto read_scalars = [&]() -> int {
-      CFD_CUDA(cudaMemcpyAsync(h_mg, mg_scalars, sizeof(cfdk::MgScalars), cudaMemcpyDeviceToHost, stream));
+      publish(mg_scalars, h_mg, sizeof(cfdk::MgScalars));
       CFD_CUDA(cudaStreamSynchronize(stream));
       return CFD_OK;
     };
@@ -1779,9 +1874,9 @@ struct ModelImpl final : ModelBase {
       ++launches;
     }
     if ((rc = allreduce_max_u64(step_slots, 4))) return rc;
-    CFD_CUDA(cudaMemcpyAsync(h_step, step_slots, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     h_step[4] = 0ull;
-    if (peer2_ready) CFD_CUDA(cudaMemcpyAsync(h_step + 4, &box->error, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    publish(step_slots, h_step, 4 * sizeof(unsigned long long));
+    if (peer2_ready) publish(&box->error, h_step + 4, sizeof(unsigned long long));
     CFD_CUDA(cudaEventRecord(ev_step1, stream));
     CFD_CUDA(cudaGetLastError());
     CFD_CUDA(cudaStreamSynchronize(stream));

@@ -124,7 +124,8 @@ typedef struct cfd_options {
   cfd_solver_consts consts;
 } cfd_options;
 
-#define CFD_FLAG_NO_GRAPH 1u      /* reserved: no effect in this version (every kernel is launched directly) */
+#define CFD_FLAG_NO_GRAPH 1u      /* Mode R: one launch per Jacobi sweep also on small grids, instead of the single cooperative launch per
+                                   * solve (k_jacobi_persist) that grids whose rows fit into shared memory get by default (A/B, cross-check) */
 #define CFD_FLAG_BASELINE_SWEEP 2u /* simple one-column-per-thread Jacobi kernel, compiler divisions (cross-check) */
 #define CFD_FLAG_REGISTER_SWEEP 4u /* register-prefetch Jacobi kernel instead of the TMA-staged one (A/B) */
 #define CFD_FLAG_SWEEP4 16u        /* one-row-per-step tensor-TMA Jacobi kernel instead of the row-pair one (A/B) */

@@ -186,9 +186,11 @@ def test_division_by_constant_is_exact(mode):
 
 
 @pytest.mark.parametrize("precision", [64, 32])
-@pytest.mark.parametrize("other", [_abi.FLAG_BASELINE_SWEEP, _abi.FLAG_REGISTER_SWEEP, _abi.FLAG_BULK_SWEEP, _abi.FLAG_SWEEP4, _abi.FLAG_TEMPORAL, _abi.FLAG_PERSISTENT_SWEEP])
+@pytest.mark.parametrize("other", [_abi.FLAG_NO_GRAPH, _abi.FLAG_BASELINE_SWEEP, _abi.FLAG_REGISTER_SWEEP, _abi.FLAG_BULK_SWEEP, _abi.FLAG_SWEEP4, _abi.FLAG_TEMPORAL, _abi.FLAG_PERSISTENT_SWEEP])
 def test_tuned_sweep_equals_baseline_sweep(precision, other):
-    """The default sweep (TMA-staged rows, hoisted reciprocals) against the simple one-column kernel
+    """(On this grid the default is the single cooperative launch per solve, k_jacobi_persist; FLAG_NO_GRAPH is the
+    TMA-staged one-launch-per-sweep kernel that large grids get.)
+    The default sweep (TMA-staged rows, hoisted reciprocals) against the simple one-column kernel
     (CFD_FLAG_BASELINE_SWEEP) and the register-prefetch variant, on a grid wide enough to use several
     blocks per row and whose last 64-column strip is partial."""
     from cfd_demo_b200.model import default_options
