@@ -20,6 +20,9 @@
 #include "../../include/cfd_b200.h"
 #include "cfd_kernels.cuh"
 #include "cfd_mg.cuh"
+#ifdef CFD_WITH_AB_SWEEPS
+#include "cfd_sweeps_ab.cuh"  // A/B kernels: libcfd_b200_ab.so only
+#endif
 #include "cfd_peer.cuh"
 #include "cfd_tracers.cuh"
 
@@ -726,12 +729,13 @@ struct ModelImpl final : ModelBase {
       if ((rc2 = make_tensor_map(&tmap_pp[0], pp[0].row(ja - kHalo), Ring::kPCols))) return rc2;
       if ((rc2 = make_tensor_map(&tmap_pp[1], pp[1].row(ja - kHalo), Ring::kPCols))) return rc2;
       if ((rc2 = make_tensor_map(&tmap_rhs, rhs.row(ja - kHalo), cfdk::kStripCols))) return rc2;
+      CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep5<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(Ring)));
+#ifdef CFD_WITH_AB_SWEEPS
       if ((rc2 = make_tensor_map(&tmap_rhs_halo, rhs.row(ja - kHalo), Ring::kPCols))) return rc2;
       CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep_t2<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(cfdk::SweepT2Ring<R>)));
       CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep4<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)sizeof(Ring)));
-      CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep5<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(Ring)));
       CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_sweep6<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(Ring)));
@@ -740,6 +744,7 @@ struct ModelImpl final : ModelBase {
       cudaDeviceProp prop6;
       CFD_CUDA(cudaGetDeviceProperties(&prop6, device));
       sweep6_resident_blocks = prop6.multiProcessorCount * (per_sm6 < 1 ? 1 : per_sm6);
+#endif
     }
     // one thread per column pair, 128 threads per block; pick the rows per block so that the grid is a
     // whole number of waves of (SM count x resident blocks per SM)
@@ -749,6 +754,7 @@ struct ModelImpl final : ModelBase {
     const int kSweepThreads = cfdk::kSweepWarps * 32;
     const int bx = (nx / 2 + kSweepThreads - 1) / kSweepThreads;
     int per_sm = 4;
+#ifdef CFD_WITH_AB_SWEEPS
     if (opt.flags & CFD_FLAG_REGISTER_SWEEP)
       CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep2<R>, 128, 0));
     else if (opt.flags & CFD_FLAG_BULK_SWEEP)
@@ -757,6 +763,7 @@ struct ModelImpl final : ModelBase {
       CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep4<R>, kSweepThreads,
                                                              sizeof(cfdk::SweepChunkRing<R>)));
     else
+#endif
       CFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfdk::k_jacobi_sweep5<R>, kSweepThreads,
                                                              sizeof(cfdk::SweepChunkRing<R>)));
     if (per_sm < 1) per_sm = 1;
@@ -945,10 +952,12 @@ struct ModelImpl final : ModelBase {
     const size_t ring_bytes = sizeof(cfdk::SweepChunkRing<R>);
     const bool tuned_default = !(opt.flags & (CFD_FLAG_BASELINE_SWEEP | CFD_FLAG_REGISTER_SWEEP | CFD_FLAG_BULK_SWEEP | CFD_FLAG_SWEEP4));
     const bool use6 = tuned_default && (opt.flags & CFD_FLAG_PERSISTENT_SWEEP);  // persistent warp-queue kernel (A/B)
+#ifdef CFD_WITH_AB_SWEEPS
     const int n_units6 = ((nx + cfdk::kStripCols - 1) / cfdk::kStripCols) * ((rows + cfdk::kUnitRows - 1) / cfdk::kUnitRows);
     int grid6 = (n_units6 + cfdk::kSweepWarps - 1) / cfdk::kSweepWarps;
     if (grid6 > sweep6_resident_blocks) grid6 = sweep6_resident_blocks;
     if (grid6 < 1) grid6 = 1;
+#endif
     const bool use_t2 = world == 1 && tuned_default && (opt.flags & CFD_FLAG_TEMPORAL) && (iters % 2 == 0) &&
                         rows >= 4;
     bool persisted = false;
@@ -984,6 +993,7 @@ struct ModelImpl final : ModelBase {
       }
     }
     if (persisted) {
+#ifdef CFD_WITH_AB_SWEEPS
     } else if (use_t2) {
       // ---- temporal blocking: two sweeps per pass over HBM (k_jacobi_sweep_t2), each pass followed by the
       // conditional fix-up that restores the reference's stopping point when the FIRST sweep of a pass converged
@@ -999,6 +1009,7 @@ struct ModelImpl final : ModelBase {
                                                                       cfdk::SweepPeer<R>{});
         launches += 2;
       }
+#endif
     } else if (world > 1 && tuned_default && peer_ready) {
       // ---- strips over peer memory: the sweep stores its edge rows into the neighbours' halos and publishes its
       // max|dp'| to every rank's mailbox itself; convergence is checked two sweeps late (check_lag 2).
@@ -1006,10 +1017,12 @@ struct ModelImpl final : ModelBase {
       ++solve_counter;
       for (int s = 0; s < iters; ++s) {
         const int in = (ipp + s) & 1, out = in ^ 1;
+#ifdef CFD_WITH_AB_SWEEPS
         if (use6)
           cfdk::k_jacobi_sweep6<R><<<grid6, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s,
                                                                          sweep_peer(out), tickets + 1060 + s);
         else
+#endif
           cfdk::k_jacobi_sweep5<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s,
                                                                         sweep_peer(out));
         ++launches;
@@ -1021,6 +1034,7 @@ struct ModelImpl final : ModelBase {
         const int in = (ipp + s) & 1, out = in ^ 1;
         if (opt.flags & CFD_FLAG_BASELINE_SWEEP)
           cfdk::k_jacobi_sweep<R, kJacobiRows><<<grd1, blk1, 0, stream>>>(c, pp[in].v, rhs.v, pp[out].v, err_slots, s);
+#ifdef CFD_WITH_AB_SWEEPS
         else if (opt.flags & CFD_FLAG_REGISTER_SWEEP)
           cfdk::k_jacobi_sweep2<R><<<dim3((nx / 2 + 127) / 128, grd2.y), dim3(128), 0, stream>>>(c2, pp[in].v, rhs.v, pp[out].v,
                                                                                                err_slots, s);  // fixed 128-thread blocks
@@ -1031,6 +1045,7 @@ struct ModelImpl final : ModelBase {
         else if (use6)
           cfdk::k_jacobi_sweep6<R><<<grid6, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s,
                                                                          cfdk::SweepPeer<R>{}, tickets + 1060 + s);
+#endif
         else
           cfdk::k_jacobi_sweep5<R><<<grd2, blk2, ring_bytes, stream>>>(c2, tmap_pp[in], tmap_rhs, pp[out].v, err_slots, s,
                                                                         cfdk::SweepPeer<R>{});
@@ -2382,6 +2397,11 @@ int cfd_model_create_ex(const cfd_grid* grid, const cfd_params* params, const cf
     return fail(CFD_ERR_INVALID_ARGUMENT, "grid too large (at most 2^31 - 1 entries per field)");
   if (!(grid->dx > 0.0f) || !(grid->dy > 0.0f)) return fail(CFD_ERR_INVALID_ARGUMENT, "grid: dx, dy must be positive");
   if (o.precision != 64 && o.precision != 32) return fail(CFD_ERR_INVALID_ARGUMENT, "precision must be 64 or 32");
+#ifndef CFD_WITH_AB_SWEEPS
+  if (o.flags & (CFD_FLAG_REGISTER_SWEEP | CFD_FLAG_BULK_SWEEP | CFD_FLAG_SWEEP4 | CFD_FLAG_TEMPORAL | CFD_FLAG_PERSISTENT_SWEEP))
+    return fail(CFD_ERR_UNSUPPORTED, "the A/B sweep kernels (register prefetch, bulk copy, one-row, temporal, persistent queue) are "
+                                     "compiled into libcfd_b200_ab.so only (csrc/Makefile: make ab; load it with CFD_B200_LIB)");
+#endif
   if (o.world_size < 1 || o.rank < 0 || o.rank >= o.world_size) return fail(CFD_ERR_INVALID_ARGUMENT, "rank / world_size out of range");
   if (o.world_size > 1 && !o.nccl_unique_id) return fail(CFD_ERR_INVALID_ARGUMENT, "world_size > 1 needs nccl_unique_id");
   if (o.world_size > 1 && (grid->ny - 2) / (uint64_t)o.world_size < 17) return fail(CFD_ERR_INVALID_ARGUMENT, "strips need at least 17 unknown rows per rank");

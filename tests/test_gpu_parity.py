@@ -186,13 +186,12 @@ def test_division_by_constant_is_exact(mode):
 
 
 @pytest.mark.parametrize("precision", [64, 32])
-@pytest.mark.parametrize("other", [_abi.FLAG_NO_GRAPH, _abi.FLAG_BASELINE_SWEEP, _abi.FLAG_REGISTER_SWEEP, _abi.FLAG_BULK_SWEEP, _abi.FLAG_SWEEP4, _abi.FLAG_TEMPORAL, _abi.FLAG_PERSISTENT_SWEEP])
+@pytest.mark.parametrize("other", [_abi.FLAG_NO_GRAPH, _abi.FLAG_BASELINE_SWEEP])
 def test_tuned_sweep_equals_baseline_sweep(precision, other):
-    """(On this grid the default is the single cooperative launch per solve, k_jacobi_persist; FLAG_NO_GRAPH is the
-    TMA-staged one-launch-per-sweep kernel that large grids get.)
-    The default sweep (TMA-staged rows, hoisted reciprocals) against the simple one-column kernel
-    (CFD_FLAG_BASELINE_SWEEP) and the register-prefetch variant, on a grid wide enough to use several
-    blocks per row and whose last 64-column strip is partial."""
+    """On this grid the default is the single cooperative launch per solve (k_jacobi_persist); FLAG_NO_GRAPH is the
+    TMA-staged one-launch-per-sweep kernel that large grids get (k_jacobi_sweep5), FLAG_BASELINE_SWEEP the simple
+    one-column kernel with the compiler's divisions.  All three: complete state bit-identical, on a grid wide enough to
+    use several blocks per row and whose last 64-column strip is partial."""
     from cfd_demo_b200.model import default_options
     g = channel_grid(1040, 61)
     a = Model(g, SimulationParams(), precision=precision)
@@ -207,6 +206,27 @@ def test_tuned_sweep_equals_baseline_sweep(precision, other):
         assert np.array_equal(a.field(fid), b.field(fid)), _abi.FIELD_NAMES[fid]
     ra, rb = a.get_residuals(), b.get_residuals()
     assert (ra.jacobi_calls, ra.sweeps, ra.f64["p"]) == (rb.jacobi_calls, rb.sweeps, rb.f64["p"])
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+@pytest.mark.parametrize("flag", [_abi.FLAG_REGISTER_SWEEP, _abi.FLAG_BULK_SWEEP, _abi.FLAG_SWEEP4, _abi.FLAG_TEMPORAL, _abi.FLAG_PERSISTENT_SWEEP])
+def test_ab_sweep_kernels_live_in_their_own_library(precision, flag):
+    """The sweep kernels that lost their A/B (csrc/cfd_sweeps_ab.cuh) are not in the product library — it refuses their
+    flags — but in libcfd_b200_ab.so, where each still matches the shipped kernel bit for bit (tests/ab_sweep_check.py)."""
+    import os
+    import subprocess
+    import sys
+    from cfd_demo_b200.model import default_options
+    o = default_options()
+    o.flags = flag
+    with pytest.raises(CfdError) as e:
+        Model(channel_grid(64, 24), SimulationParams(), options=o)
+    assert e.value.code == _abi.CFD_ERR_UNSUPPORTED
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CFD_B200_LIB=os.path.join(root, "cfd_demo_b200", "libcfd_b200_ab.so"))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "ab_sweep_check.py"), str(flag), str(precision)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "ab sweep ok" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
 
 
 def test_cpp_headless_driver_matches_python_mirror():
