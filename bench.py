@@ -119,6 +119,10 @@ def make_consts(w):
     load_library().cfd_solver_consts_default(C.byref(c))
     for k, v in (w.get("consts") or {}).items():
         setattr(c, k, v)
+    # A/B hook: CFD_BENCH_CONSTS="mg_smoothing=4,mg_omega=0.8" overrides solver constants (both arms read it)
+    for item in filter(None, os.environ.get("CFD_BENCH_CONSTS", "").split(",")):
+        k, v = item.split("=")
+        setattr(c, k, type(getattr(c, k))(float(v)))
     return c
 
 

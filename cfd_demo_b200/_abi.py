@@ -17,10 +17,11 @@ SCENARIO_CHANNEL, SCENARIO_CAVITY = 0, 1
 
 FIELD_P, FIELD_U, FIELD_V, FIELD_U_STAR, FIELD_V_STAR, FIELD_RHS, FIELD_P_PRIME = range(7)
 FIELD_U_OLD, FIELD_V_OLD, FIELD_MASK_U, FIELD_MASK_V, FIELD_MG_GUESS, FIELD_MG_LAST, FIELD_MG_LAST2 = 7, 8, 9, 10, 11, 12, 13
+FIELD_MG_Z = 14  # read-only inspection: z of the last V-cycle
 FIELD_NAMES = {
     FIELD_P: "p", FIELD_U: "u", FIELD_V: "v", FIELD_U_STAR: "u_star", FIELD_V_STAR: "v_star",
     FIELD_RHS: "rhs", FIELD_P_PRIME: "p_prime", FIELD_U_OLD: "u_old", FIELD_V_OLD: "v_old",
-    FIELD_MASK_U: "mask_u", FIELD_MASK_V: "mask_v", FIELD_MG_GUESS: "mg_guess", FIELD_MG_LAST: "mg_last", FIELD_MG_LAST2: "mg_last2",
+    FIELD_MASK_U: "mask_u", FIELD_MASK_V: "mask_v", FIELD_MG_GUESS: "mg_guess", FIELD_MG_LAST: "mg_last", FIELD_MG_LAST2: "mg_last2", FIELD_MG_Z: "mg_z",
 }
 
 FLAG_NO_GRAPH = 1

@@ -586,10 +586,29 @@ __global__ void __launch_bounds__(kMgThreads) k_mgc_sweep(MgLevelDev<R> L, const
 }
 
 // fills a level's diagonal table from the diagonal values (one thread per entry)
+// table[n] = the intersection of the dividend windows of the positive entries (y, r unused): what a DivTry over
+// divisions by any of them tests against (cfd_mg_legs.cuh).  One block.
 template <class R>
 __global__ void k_mgc_diag_table(const R* __restrict__ diag, DivG<R>* __restrict__ table, int n) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n) table[k] = make_divg(diag[k]);
+  __syncthreads();
+  if (k == 0) {
+    unsigned lo = 0u, end = 0xffffffffu;
+    bool any = false;
+    for (int m = 0; m < n; ++m)
+      if (table[m].y > R(0)) {
+        const unsigned e = table[m].span == 0u ? table[m].lo : table[m].lo + table[m].span;
+        lo = table[m].lo > lo ? table[m].lo : lo;
+        end = e < end ? e : end;
+        any = true;
+      }
+    DivG<R> w;
+    w.y = R(1); w.r = R(1);
+    w.lo = lo;
+    w.span = any && end > lo ? end - lo : 0u;
+    table[n] = w;
+  }
 }
 
 // k_mgc_sweep for a level with a diagonal table: same per-cell arithmetic (mgc_sweep_cell), a thread owns column I and

@@ -20,6 +20,7 @@
 #include "../../include/cfd_b200.h"
 #include "cfd_kernels.cuh"
 #include "cfd_mg.cuh"
+#include "cfd_mg_legs.cuh"
 #ifdef CFD_WITH_AB_SWEEPS
 #include "cfd_sweeps_ab.cuh"  // A/B kernels: libcfd_b200_ab.so only
 #endif
@@ -169,7 +170,8 @@ inline int strip_row_start(int ny, int world, int r) {
   return (int)(1 + b);
 }
 
-constexpr int kHalo = 2;  // rows: the second-order predictor reaches j +- 2 (src/model.rs:999, 1044, 1195, 1239)
+constexpr int kPredHalo = 2;  // rows: the second-order predictor reaches j +- 2 (src/model.rs:999, 1044, 1195, 1239)
+constexpr int kHalo = 4;      // halo rows allocated: the V(4,4) legs of the multigrid cycle read 4 (cfd_mg_legs.cuh)
 
 template <class R>
 struct ModelImpl final : ModelBase {
@@ -260,6 +262,16 @@ struct ModelImpl final : ModelBase {
   double last_prof_ms = 0;
   uint64_t last_prof_launches = 0;
   int mg_bottom_level = 0;                // first level run by the single-block bottom kernel
+  int mg_last_z = -1;                     // mg_b index of the last V-cycle's result (CFD_FIELD_MG_Z)
+  bool mg_legs = false;                   // V-cycle legs as single launches (cfd_mg_legs.cuh)
+  // tiles of the leg kernels: large levels (by the number of smoothing sweeps NU: the staged region is the tile + NU) and
+  // small levels (more blocks)
+  template <int NU> struct LegTile { static constexpr int TX = NU >= 4 ? 64 : 128, TY = NU >= 4 ? 32 : 16; };
+  static constexpr int kLegSX = 64, kLegSY = 8;
+  int leg_tx() const { return mg_smoothing() >= 4 ? 64 : 128; }
+  int leg_ty() const { return mg_smoothing() >= 4 ? 32 : 16; }
+  // strips: halo rows of a coarse level's rho the legs need (x_nu is recomputed on nu rows beyond the owned ones)
+  int leg_rho_halo() const { return 2 * mg_smoothing() - 1; }
   cfdk::MgBottom<R> mg_bottom;
   CUtensorMap tmap_pp[2], tmap_rhs;  // 2-D tiled views of p' (ping, pong) and rhs for the tensor-TMA sweep
   CUtensorMap tmap_rhs_halo;         // rhs with the same halo box as p' (two-sweep kernel)
@@ -1236,7 +1248,7 @@ struct ModelImpl final : ModelBase {
           R* d_diag = nullptr;
           if ((rc = dalloc(&d_cls, mx + my))) return rc;
           if ((rc = dalloc(&d_diag, diag.size()))) return rc;
-          if ((rc = dalloc(&L.diag_table, diag.size()))) return rc;
+          if ((rc = dalloc(&L.diag_table, diag.size() + 1))) return rc;  // + the common dividend window (cfd_mg_legs.cuh)
           CFD_CUDA(cudaMemcpyAsync(d_cls, ccls.data(), mx, cudaMemcpyHostToDevice, stream));
           CFD_CUDA(cudaMemcpyAsync(d_cls + mx, rcls.data(), my, cudaMemcpyHostToDevice, stream));
           CFD_CUDA(cudaMemcpyAsync(d_diag, diag.data(), diag.size() * sizeof(R), cudaMemcpyHostToDevice, stream));
@@ -1286,7 +1298,10 @@ struct ModelImpl final : ModelBase {
       const size_t gx = (size_t)((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads));
       const size_t n_vec = gx * (size_t)((ny + 3) / 4 + 1);
       const size_t n_sweep = (size_t)((nx / 2 + cfdk::kSweepWarps * 32 - 1) / (cfdk::kSweepWarps * 32)) * (size_t)((ny - 2 + sweep_rows_per_block - 1) / sweep_rows_per_block);
-      if ((rc = dalloc(&mg_partials, n_vec > n_sweep ? n_vec : n_sweep))) return rc;
+      const size_t n_leg = (size_t)((nx - 2 + 63) / 64) * (size_t)((ny - 2 + 15) / 16);  // at least the leg kernels' grid
+      size_t n_max = n_vec > n_sweep ? n_vec : n_sweep;
+      if (n_leg > n_max) n_max = n_leg;
+      if ((rc = dalloc(&mg_partials, n_max))) return rc;
     }
     // the bottom of the V-cycle (every level from the first that fits 64 x 64) runs in one single-block launch
     mg_bottom_level = (int)mg.size() - 1;
@@ -1303,13 +1318,29 @@ struct ModelImpl final : ModelBase {
       mg_bottom.lv[k].dev = L.dev;
       mg_bottom.lv[k].e = L.e; mg_bottom.lv[k].rho = L.rho; mg_bottom.lv[k].tmp = L.tmp;
     }
+    // each level's descending / ascending leg as one launch (cfd_mg_legs.cuh): V(nu,nu) with nu = 2, 3, 4
+    static const bool no_legs = getenv("CFD_MG_NO_LEGS") != nullptr;
+    const int nu_legs = mg_smoothing();
+    mg_legs = nu_legs >= 2 && nu_legs <= 4 && !(opt.flags & CFD_FLAG_MG_UNFUSED) && mg.size() > 1 && !no_legs;
+    for (int l = 1; l <= mg_ld && mg_legs; ++l) {  // strips: the legs exchange leg_rho_halo() rows of a level's rho
+      if (!mg[(size_t)l].dev.diag_table) mg_legs = false;
+      for (int r = 0; r < world; ++r)
+        if (lvl_hi(l, r) - lvl_lo(l, r) < leg_rho_halo() + 1) mg_legs = false;
+    }
+    if (world > 1 && (nu_legs > kHalo || jb - ja < 2 * kHalo)) mg_legs = false;  // level 0: nu halo rows of rho and x_nu
+    if (mg_legs) {
+      if (nu_legs == 2) rc = leg_attributes<2>();
+      else if (nu_legs == 3) rc = leg_attributes<3>();
+      else rc = leg_attributes<4>();
+      if (rc) return rc;
+    }
     CFD_CUDA(cudaHostAlloc((void**)&h_mg, sizeof(cfdk::MgScalars), cudaHostAllocMapped));
     CFD_CUDA(cudaStreamSynchronize(stream));
     // strips over peer memory: everything the V-cycle exchanges
     peer_register(mg_rho.base);
     for (auto& f : mg_b) peer_register(f.base);
     for (auto& f : mg_hist) peer_register(f.base);
-    for (int l = 1; l <= mg_ld; ++l) { peer_register(mg[(size_t)l].e); peer_register(mg[(size_t)l].tmp); }
+    for (int l = 1; l <= mg_ld; ++l) { peer_register(mg[(size_t)l].e); peer_register(mg[(size_t)l].tmp); peer_register(mg[(size_t)l].rho); }
     if (world > 1 && mg_ld + 1 < (int)mg.size()) peer_register(mg[(size_t)mg_ld + 1].rho, true);
     if ((rc = peer_sync())) return rc;
     return CFD_OK;
@@ -1335,24 +1366,25 @@ struct ModelImpl final : ModelBase {
   bool lvl_dist(int l) const { return world > 1 && l <= mg_ld; }
 
   // one halo row each way of a coarse-level field (row pitch mx + 2; unknown row J is array row J + 1)
-  int exchange_level(R* f, int l) {
+  int exchange_level(R* f, int l, int d = 1) {
     const size_t pitch = (size_t)mg[(size_t)l].mx + 2;
     const int lo = lvl_lo(l, rank), hi = lvl_hi(l, rank);
+    const size_t n = (size_t)d * pitch;  // d rows each way (every strip owns at least d rows of the level: mg_setup checks)
     if (const PeerBuf* pb = peer_find(f)) {
-      // coarse arrays are allocated in full on every rank: same offsets everywhere.  Down: my first owned row (lo + 1) is
-      // the lower rank's upper halo row; up: my last owned row (hi) is the upper rank's lower halo row
+      // coarse arrays are allocated in full on every rank: same offsets everywhere.  Down: my first d owned rows (array rows
+      // lo + 1 ...) are the lower rank's upper halo rows; up: my last d owned rows (... hi) are the upper rank's lower halo rows
       R* dst_down = rank > 0 ? (R*)pb->map[rank - 1] + (size_t)(lo + 1) * pitch : nullptr;
-      R* dst_up = rank < world - 1 ? (R*)pb->map[rank + 1] + (size_t)hi * pitch : nullptr;
-      return peer_push(f + (size_t)(lo + 1) * pitch, dst_down, pitch * sizeof(R), f + (size_t)hi * pitch, dst_up, pitch * sizeof(R));
+      R* dst_up = rank < world - 1 ? (R*)pb->map[rank + 1] + (size_t)(hi - d + 1) * pitch : nullptr;
+      return peer_push(f + (size_t)(lo + 1) * pitch, dst_down, n * sizeof(R), f + (size_t)(hi - d + 1) * pitch, dst_up, n * sizeof(R));
     }
     CFD_NCCL(nccl_api().GroupStart());
     if (rank > 0) {
-      CFD_NCCL(nccl_api().Send(f + (size_t)(lo + 1) * pitch, pitch, nccl_real(), rank - 1, comm, stream));
-      CFD_NCCL(nccl_api().Recv(f + (size_t)lo * pitch, pitch, nccl_real(), rank - 1, comm, stream));
+      CFD_NCCL(nccl_api().Send(f + (size_t)(lo + 1) * pitch, n, nccl_real(), rank - 1, comm, stream));
+      CFD_NCCL(nccl_api().Recv(f + (size_t)(lo - d + 1) * pitch, n, nccl_real(), rank - 1, comm, stream));
     }
     if (rank < world - 1) {
-      CFD_NCCL(nccl_api().Send(f + (size_t)hi * pitch, pitch, nccl_real(), rank + 1, comm, stream));
-      CFD_NCCL(nccl_api().Recv(f + (size_t)(hi + 1) * pitch, pitch, nccl_real(), rank + 1, comm, stream));
+      CFD_NCCL(nccl_api().Send(f + (size_t)(hi - d + 1) * pitch, n, nccl_real(), rank + 1, comm, stream));
+      CFD_NCCL(nccl_api().Recv(f + (size_t)(hi + 1) * pitch, n, nccl_real(), rank + 1, comm, stream));
     }
     CFD_NCCL(nccl_api().GroupEnd());
     return CFD_OK;
@@ -1405,6 +1437,93 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
 
+  // ---- the V-cycle with one launch per leg (cfd_mg_legs.cuh) ----
+  template <int NU>
+  int leg_attributes() {
+    using T = LegTile<NU>;
+    CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mg0_down<R, T::TX, T::TY, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::LegSmem<R, T::TX, T::TY, NU>)));
+    CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mg0_up<R, T::TX, T::TY, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::LegSmem<R, T::TX, T::TY, NU>)));
+    CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mgc_down<R, T::TX, T::TY, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::LegSmemC<R, T::TX, T::TY, NU>)));
+    CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mgc_up<R, T::TX, T::TY, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::LegSmemC<R, T::TX, T::TY, NU>)));
+    CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mgc_down<R, kLegSX, kLegSY, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::LegSmemC<R, kLegSX, kLegSY, NU>)));
+    CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mgc_up<R, kLegSX, kLegSY, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::LegSmemC<R, kLegSX, kLegSY, NU>)));
+    return CFD_OK;
+  }
+
+  // level l >= 1 (a level with a diagonal table).  Strips: x_nu is also recomputed on NU rows beyond the owned ones (from
+  // the 2 NU - 1 halo rows of rho exchanged by the level above), so the ascending leg needs only the parents' halo row
+  template <int NU>
+  int leg_coarse_vcycle(int l) {
+    using T = LegTile<NU>;
+    MgLevelHost& L = mg[(size_t)l];
+    MgLevelHost& C = mg[(size_t)l + 1];
+    const R omega = R(opt.consts.mg_omega);
+    const bool dist = lvl_dist(l);
+    const int lo = dist ? lvl_lo(l, rank) : 0, hi = dist ? lvl_hi(l, rank) : L.my;
+    const bool big = (long)L.mx * L.my >= 500000L;
+    const int tx = big ? T::TX : kLegSX, ty = big ? T::TY : kLegSY;
+    const int x_lo = dist ? (lo >= NU ? lo - NU : 0) : 0, x_hi = dist ? (hi + NU <= L.my ? hi + NU : L.my) : L.my;
+    const int c_lo = dist ? lvl_lo(l + 1, rank) : 0, c_hi = dist ? lvl_hi(l + 1, rank) : C.my;
+    const dim3 g_dn((L.mx + tx - 1) / tx, (x_hi - x_lo + ty - 1) / ty), g_up((L.mx + tx - 1) / tx, (hi - lo + ty - 1) / ty);
+    int rc;
+    if (big) cfdk::k_mgc_down<R, T::TX, T::TY, NU><<<g_dn, cfdk::kLegThreads, sizeof(cfdk::LegSmemC<R, T::TX, T::TY, NU>), stream>>>(L.dev, L.rho, L.e, C.mx, C.rho, omega, x_lo, x_hi, c_lo, c_hi, mg_scalars);
+    else cfdk::k_mgc_down<R, kLegSX, kLegSY, NU><<<g_dn, cfdk::kLegThreads, sizeof(cfdk::LegSmemC<R, kLegSX, kLegSY, NU>), stream>>>(L.dev, L.rho, L.e, C.mx, C.rho, omega, x_lo, x_hi, c_lo, c_hi, mg_scalars);
+    ++launches;
+    if (dist) {
+      if (lvl_dist(l + 1)) { if ((rc = exchange_level(C.rho, l + 1, leg_rho_halo()))) return rc; }
+      else if ((rc = gather_level(C.rho, l + 1))) return rc;
+    }
+    if ((rc = mg_coarse_vcycle(l + 1))) return rc;
+    if (big) cfdk::k_mgc_up<R, T::TX, T::TY, NU><<<g_up, cfdk::kLegThreads, sizeof(cfdk::LegSmemC<R, T::TX, T::TY, NU>), stream>>>(L.dev, L.e, L.rho, C.mx, C.cur, L.tmp, omega, lo, hi, mg_scalars);
+    else cfdk::k_mgc_up<R, kLegSX, kLegSY, NU><<<g_up, cfdk::kLegThreads, sizeof(cfdk::LegSmemC<R, kLegSX, kLegSY, NU>), stream>>>(L.dev, L.e, L.rho, C.mx, C.cur, L.tmp, omega, lo, hi, mg_scalars);
+    ++launches;
+    L.cur = L.tmp;
+    if (dist && (rc = exchange_level(L.tmp, l))) return rc;  // the finer level's ascending leg reads one halo row of the correction
+    return CFD_OK;
+  }
+
+  // level 0: z <- V-cycle(rho); *zc / *zo = current / other smoothing buffer (mg_b indices), z ends up in *zc.  Strips: the
+  // descending leg recomputes x_k on the rows beyond the owned ones it still needs (NU halo rows of rho); the ascending leg
+  // reads NU halo rows of x_nu and one of the parents' correction
+  template <int NU>
+  int leg_fine_vcycle(const cfdk::MgFine<R>& c, const cfdk::JacobiConsts2<R>& c2, int* zc, int* zo) {
+    using T = LegTile<NU>;
+    MgLevelHost& C = mg[1];
+    const int rows = c.row_hi - c.row_lo;
+    const dim3 g_leg((nx - 2 + T::TX - 1) / T::TX, (rows + T::TY - 1) / T::TY);
+    const size_t leg_bytes = sizeof(cfdk::LegSmem<R, T::TX, T::TY, NU>);
+    int rc;
+    if ((rc = exchange_halo(mg_rho, ja, jb, NU))) return rc;
+    cfdk::k_mg0_down<R, T::TX, T::TY, NU><<<g_leg, cfdk::kLegThreads, leg_bytes, stream>>>(c, c2, mg_rho.v, mg_b[*zo].v, C.mx, C.rho, mg_scalars);
+    ++launches;
+    std::swap(*zc, *zo);
+    if (world > 1) {
+      if ((rc = exchange_halo(mg_b[*zc], ja, jb, NU))) return rc;
+      if (lvl_dist(1)) { if ((rc = exchange_level(C.rho, 1, leg_rho_halo()))) return rc; }
+      else if ((rc = gather_level(C.rho, 1))) return rc;
+    }
+    if ((rc = mg_coarse_vcycle(1))) return rc;
+    auto prof_mark = [&]() {  // CUDA-event pair around the ascending leg (bench.py's roofline kernel)
+      if (!prof_smoother) return;
+      if (ev_prof_used + 1 > ev_prof.size()) {
+        const size_t old_n = ev_prof.size();
+        ev_prof.resize(old_n + 64, nullptr);
+        for (size_t k = old_n; k < ev_prof.size(); ++k) cudaEventCreate(&ev_prof[k]);
+      }
+      cudaEventRecord(ev_prof[ev_prof_used++], stream);
+    };
+    prof_mark();
+    cfdk::k_mg0_up<R, T::TX, T::TY, NU><<<g_leg, cfdk::kLegThreads, leg_bytes, stream>>>(c, c2, mg_b[*zc].v, mg_rho.v, C.mx, C.cur, mg_b[*zo].v, mg_partials, mg_scalars);
+    prof_mark();
+    cfdk::k_mg_reduce<R><<<1, 1024, 0, stream>>>(c, mg_scalars, mg_partials, (int)(g_leg.x * g_leg.y), 1);
+    launches += 2;
+    std::swap(*zc, *zo);
+    if ((rc = exchange_halo(mg_b[*zc], ja, jb, 1))) return rc;  // strips: the neighbours' edge rows of z (no-op on one GPU)
+    if ((rc = mg_finish_strips(c, 1))) return rc;
+    CFD_CUDA(cudaGetLastError());
+    return CFD_OK;
+  }
+
   // correction of level l >= 1 from its rho (result in mg[l].cur)
   int mg_coarse_vcycle(int l) {
     MgLevelHost& L = mg[(size_t)l];
@@ -1426,6 +1545,11 @@ struct ModelImpl final : ModelBase {
       ++launches;
       L.cur = b;
       return CFD_OK;
+    }
+    if (mg_legs && L.dev.diag_table != nullptr) {
+      if (nu_s == 2) return leg_coarse_vcycle<2>(l);
+      if (nu_s == 3) return leg_coarse_vcycle<3>(l);
+      return leg_coarse_vcycle<4>(l);
     }
     // (the 4-row tiles leave the small levels with too few blocks: there the one-cell-per-thread kernel is faster)
     const bool tab = L.dev.diag_table != nullptr && !(opt.flags & CFD_FLAG_MG_UNFUSED) && (long)L.mx * L.my >= 500000L;
@@ -1525,6 +1649,14 @@ struct ModelImpl final : ModelBase {
     // V(nu, nu) with nu >= 2: the first two pre-smoothing sweeps are one pass over rho, and the prolongation is folded
     // into the first post-smoothing sweep (k_mg_fused_sweep; bit-identical to the separate kernels, which
     // CFD_FLAG_MG_UNFUSED keeps for the cross-check)
+    if (mg_legs) {
+      if (nu_s == 2) rc = leg_fine_vcycle<2>(c, c2, &zc, &zo);
+      else if (nu_s == 3) rc = leg_fine_vcycle<3>(c, c2, &zc, &zo);
+      else rc = leg_fine_vcycle<4>(c, c2, &zc, &zo);
+      if (rc) return rc;
+      *z_index = zc;
+      return CFD_OK;
+    }
     const bool fused = nu_s >= 2 && !(opt.flags & CFD_FLAG_MG_UNFUSED);
     const dim3 g_fs((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads), (rows + cfdk::kFsRows - 1) / cfdk::kFsRows);
     if (fused) {
@@ -1720,6 +1852,7 @@ struct ModelImpl final : ModelBase {
         cfdk::k_mg_dir_apply<R><<<g_dir, blk, 0, stream>>>(c, mg_scalars, mg_b[zi].v, mg_b[mg_id].v, mg_b[dn].v, w, mg_partials,
                                                            mg_ticket);
         mg_id = dn;
+        mg_last_z = zi;
         if ((rc = mg_finish_strips(c, 2))) return rc;
         if ((rc = exchange_halo(mg_b[mg_id], ja, jb, 1))) return rc;  // strips: d's edge rows for the next L d
         cfdk::k_mg_update<R><<<g_upd, blk, 0, stream>>>(c, mg_scalars, mg_b[mg_id].v, w, x, mg_rho.v, mg_partials, mg_ticket);
@@ -1788,8 +1921,8 @@ struct ModelImpl final : ModelBase {
     for (uint64_t sub = 0; sub < n_sub; ++sub) {  // :322-329, piso_step (:529-730) inlined
     const int X = iu, Y = ius, Z = ifree;
     // strips: the predictor stencils reach two rows into the neighbours (second order)
-    if ((rc = exchange_halo(ubuf[X], ja, jb, kHalo))) return rc;
-    if ((rc = exchange_halo(vbuf[X], ja, v_row_end(), kHalo))) return rc;
+    if ((rc = exchange_halo(ubuf[X], ja, jb, kPredHalo))) return rc;
+    if ((rc = exchange_halo(vbuf[X], ja, v_row_end(), kPredHalo))) return rc;
     // ---- predictor (:538-670): reads u, v; writes the interior of u_star, v_star (the rest is carried state)
     {
       const auto s = scalars(dt_sub);
@@ -2215,6 +2348,10 @@ struct ModelImpl final : ModelBase {
         }
         return mg_guess.row(ja);
       }
+      case CFD_FIELD_MG_Z:  // inspection only: z of the last V-cycle
+        if (mg.empty() || mg_last_z < 0) { *n = 0; return nullptr; }
+        *n = own_p();
+        return mg_b[mg_last_z].row(ja);
       default: *n = 0; return nullptr;
     }
   }

@@ -66,7 +66,8 @@ extern "C" {
 #define CFD_FIELD_MG_GUESS 11 /* MGCG extension: start vector of the next step's first solve (carried state) */
 #define CFD_FIELD_MG_LAST 12  /* MGCG extension: p' the last first-solve ended with (carried state, mg_warm_start 2) */
 #define CFD_FIELD_MG_LAST2 13 /* MGCG extension: the one before that (carried state, mg_warm_start 3) */
-#define CFD_FIELD_COUNT 14
+#define CFD_FIELD_MG_Z 14     /* MGCG extension, read-only inspection: the preconditioned residual z the solver's last V-cycle produced */
+#define CFD_FIELD_COUNT 15
 
 /* ---- PODs ---------------------------------------------------------------------------------------- */
 /* Grid + Option<Cylinder>, src/model.rs:121-139 */
