@@ -22,6 +22,17 @@ namespace cfdk {
 
 constexpr int kLegThreads = 256;
 
+// the legs' rare exact path: the compiler's own division, out of line (a call per division instead of ~35 inlined
+// instructions per division in every unrolled stage: the fall-back code would otherwise double the kernels' size)
+template <class R>
+struct DivSlow {
+  __device__ __forceinline__ R operator()(R x, const DivG<R>& d) const { return x / d.y; }
+};
+template <>
+struct DivSlow<double> {
+  __device__ __forceinline__ double operator()(double x, const DivG<double>& d) const { return div_true(x, d.y); }
+};
+
 template <int I, int N, class F>
 __device__ __forceinline__ void leg_static_for(F&& f) {
   if constexpr (I < N) {
@@ -109,7 +120,7 @@ __global__ void __launch_bounds__(kLegThreads) k_mg0_down(const MgFine<R> c, con
     DivTry<R> fast(c2.denom);
     stage1(fast);
     if (__builtin_expect(!fast.ok(), 0)) {
-      DivTrue<R> exact;
+      DivSlow<R> exact;
       stage1(exact);
     }
   }
@@ -164,7 +175,7 @@ __global__ void __launch_bounds__(kLegThreads) k_mg0_down(const MgFine<R> c, con
     fast.also(c.ddy_sq);
     stage3(fast);
     if (__builtin_expect(!fast.ok(), 0)) {
-      DivTrue<R> exact;
+      DivSlow<R> exact;
       stage3(exact);
     }
   }
@@ -219,15 +230,323 @@ __global__ void __launch_bounds__(kLegThreads) k_mg0_up(const MgFine<R> c, const
   if (tid == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = t;
 }
 
-// ---- coarse levels (l >= 1, fields (mx + 2) x (my + 2) with a ring of zeros; levels with a diagonal table) -------------
-template <class R, int TX, int TY, int NU>
-struct LegSmemC {
-  static constexpr int RX = TX + 2 * NU, RY = TY + 2 * NU;
-  LegSmem<R, TX, TY, NU> f;
-  R we[RX], ww[RX], cyw[RX], wn[RY], ws[RY], cxh[RY];
-  R dy[kMgClasses * kMgClasses], dr[kMgClasses * kMgClasses];  // the diagonal table: divisors and hoisted reciprocals
-  unsigned char ccls[RX], rcls[RY];
+// ---- level 0, column-strip form ------------------------------------------------------------------------------------------
+// Same legs, arranged for the instruction issue limit (the flat-indexed kernels above spend more than half of their
+// instructions on index arithmetic, clamps and per-cell division guards: profiles/r2_legs_ncu.md).  The staged region is
+// exactly 64 columns wide (tile = 64 - 2 NU columns x 32 rows, region rows = 32 + 2 NU); thread (tx, ty) owns column tx
+// of one of 4 row strips and walks it upwards with the vertical neighbours rotating through registers: per cell and
+// sweep 4 shared loads, 16 fp64 operations, one store, two integer instructions per division (DivTry; the thread redoes
+// its strip with DivTrue if a dividend left the window).  No clamps: a tile that touches the boundary of the array
+// rewrites the ring cells of each sweep's result from the unknowns they mirror (leg0_fix_ring) before the next sweep
+// reads them.
+template <class R, class Div>
+__device__ __forceinline__ R jacobi_cell_dv(const JacobiConsts2<R>& c, Div& dv, R left, R right, R top, R bot, R cen, R rhs) {
+  const R horizontal = dv(right + left, c.dx_sq), vertical = dv(top + bot, c.dy_sq);
+  const R p_update = dv(horizontal + vertical - rhs, c.denom);
+  return c.omega * p_update + c.one_minus_omega * cen;
+}
+
+template <int NU>
+struct Leg0 {
+  static constexpr int TX = 64 - 2 * NU, TY = 32, RX = 64, RY = TY + 2 * NU, kStrips = kLegThreads / 64;
 };
+template <class R, int NU>
+struct Leg0Smem {
+  R rho[Leg0<NU>::RY][64];
+  R a[Leg0<NU>::RY][64], b[Leg0<NU>::RY][64];
+};
+
+// what a block knows about its tile: region cell (x, y) <-> array cell (i0 - NU + x, j0 - NU + y); [xa, xb] x [ya, yb] =
+// the region cells that exist in the array (and, on strips, in this rank's rows + halo)
+struct Leg0Box {
+  int i0, j0, xa, xb, ya, yb;
+  int x_ring_l, x_ring_r, y_ring_b, y_ring_t;  // region index of array column 0 / nx-1, row 0 / ny-1 (or out of [0, 64) / [0, RY))
+  bool edge;
+};
+template <class R, int NU>
+__device__ __forceinline__ Leg0Box leg0_box(const MgFine<R>& c) {
+  using G = Leg0<NU>;
+  Leg0Box b;
+  b.i0 = 1 + (int)blockIdx.x * G::TX;
+  b.j0 = c.row_lo + (int)blockIdx.y * G::TY;
+  const int oi = b.i0 - NU, oj = b.j0 - NU;
+  const int j_first = c.row_lo - NU > 0 ? c.row_lo - NU : 0;
+  const int j_last = c.row_hi + NU - 1 < c.ny - 1 ? c.row_hi + NU - 1 : c.ny - 1;
+  b.xa = max(0, -oi); b.xb = min(63, c.nx - 1 - oi);
+  b.ya = max(0, j_first - oj); b.yb = min(G::RY - 1, j_last - oj);
+  b.x_ring_l = -oi; b.x_ring_r = c.nx - 1 - oi; b.y_ring_b = -oj; b.y_ring_t = c.ny - 1 - oj;
+  b.edge = b.x_ring_l >= 0 || b.x_ring_r < 64 || b.y_ring_b >= 0 || b.y_ring_t < G::RY;
+  return b;
+}
+
+// ring cells of a sweep's result (cells of the region at least M inside it) <- the unknowns they mirror; column nx-1 of the
+// channel is zero.  Call between two __syncthreads.
+template <class R, int NU, int M>
+__device__ __forceinline__ void leg0_fix_ring(const Leg0Box& b, int cavity, R (*f)[64], int tid) {
+  using G = Leg0<NU>;
+  constexpr int H = G::RY - 2 * M, W = 64 - 2 * M;
+  auto col_src = [&](int x) { return x == b.x_ring_l ? x + 1 : (x == b.x_ring_r ? x - 1 : x); };
+  // columns (rows that are not ring rows; the ring rows are written below, corners included)
+  for (int k = tid; k < 2 * H; k += kLegThreads) {
+    const int y = M + (k >> 1), x = (k & 1) ? b.x_ring_r : b.x_ring_l;
+    if (x >= M && x < 64 - M && y != b.y_ring_b && y != b.y_ring_t) f[y][x] = (!(k & 1) || cavity) ? f[y][col_src(x)] : R(0);
+  }
+  for (int k = tid; k < 2 * W; k += kLegThreads) {
+    const int x = M + (k >> 1), y = (k & 1) ? b.y_ring_t : b.y_ring_b;
+    if (y >= M && y < G::RY - M) {
+      const int ys = (k & 1) ? y - 1 : y + 1;
+      f[y][x] = (x == b.x_ring_r && !cavity) ? R(0) : f[ys][col_src(x)];
+    }
+  }
+}
+
+// one Jacobi sweep over the cells at least M inside the region: thread (tx, ty) walks column tx of row strip ty;
+// out(x, y, v) receives every value
+template <class R, int NU, int M, class Div, class F>
+__device__ __forceinline__ void leg0_sweep_strip(const JacobiConsts2<R>& c2, const Leg0Box& b, Div& dv, const R (*src)[64],
+                                                 const R (*rho)[64], int tx, int ty, F&& out) {
+  using G = Leg0<NU>;
+  constexpr int H = G::RY - 2 * M, HS = (H + G::kStrips - 1) / G::kStrips;
+  if (tx < max(M, b.xa) || tx > min(63 - M, b.xb)) return;
+  const int y0 = M + ty * HS, y_end = min(min(y0 + HS, G::RY - M), b.yb + 1);
+  R s_ = src[y0 - 1][tx], c_ = src[y0][tx];
+#pragma unroll
+  for (int r = 0; r < HS; ++r) {
+    const int y = y0 + r;
+    if (y < y_end) {
+      const R n_ = src[y + 1][tx];
+      if (y >= b.ya) out(tx, y, jacobi_cell_dv<R>(c2, dv, src[y][tx - 1], src[y][tx + 1], n_, s_, c_, rho[y][tx]));
+      s_ = c_;
+      c_ = n_;
+    }
+  }
+}
+
+template <class R, int NU>
+__global__ void __launch_bounds__(kLegThreads, 3) k_mg0_down2(const MgFine<R> c, const JacobiConsts2<R> c2,
+                                                               const R* __restrict__ rho, R* __restrict__ zout, int cmx,
+                                                               R* __restrict__ crho, const MgScalars* __restrict__ sc) {
+  using G = Leg0<NU>;
+  using S = Leg0Smem<R, NU>;
+  extern __shared__ __align__(16) unsigned char leg_smem_raw[];
+  S& s = *reinterpret_cast<S*>(leg_smem_raw);
+  if (sc->done) return;
+  const Leg0Box b = leg0_box<R, NU>(c);
+  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6, nx = c.nx;
+  const int oi = b.i0 - NU, oj = b.j0 - NU;
+  const int j_end = min(b.j0 + G::TY, c.row_hi);  // owned unknown rows of the tile: [j0, j_end)
+  // rho on the region and x_1 = the first smoothing sweep applied to z = 0 (k_mg_first_sweep's expression), pointwise
+  {
+    const bool col_ok = tx >= b.xa && tx <= b.xb;
+    const R* __restrict__ src = rho + (size_t)(oi + tx);
+    R v[(G::RY + G::kStrips - 1) / G::kStrips];
+#pragma unroll
+    for (int r = 0; r < (G::RY + G::kStrips - 1) / G::kStrips; ++r) {
+      const int y = ty + r * G::kStrips;
+      v[r] = (col_ok && y >= b.ya && y <= b.yb) ? src[(size_t)(oj + y) * nx] : R(0);
+    }
+    auto first = [&](auto& dv) {
+#pragma unroll
+      for (int r = 0; r < (G::RY + G::kStrips - 1) / G::kStrips; ++r) {
+        const int y = ty + r * G::kStrips;
+        if (y < G::RY) {
+          s.rho[y][tx] = v[r];
+          s.a[y][tx] = c2.omega * dv((R(0) + R(0)) - v[r], c2.denom) + c2.one_minus_omega * R(0);
+        }
+      }
+    };
+    DivTry<R> fast(c2.denom);
+    first(fast);
+    if (__builtin_expect(!fast.ok(), 0)) {
+      DivSlow<R> exact;
+      first(exact);
+    }
+  }
+  __syncthreads();
+  if (b.edge) {
+    leg0_fix_ring<R, NU, 0>(b, c.cavity, s.a, tid);
+    __syncthreads();
+  }
+  // x_k = sweep(x_{k-1}) on the cells at least k - 1 inside the region; the last one (the tile + 1) also goes to memory
+  leg_static_for<2, NU + 1>([&](auto kc) {
+    constexpr int K = decltype(kc)::value;
+    auto& src = (K % 2 == 0) ? s.a : s.b;
+    auto& dst = (K % 2 == 0) ? s.b : s.a;
+    auto stage = [&](auto& dv) {
+      leg0_sweep_strip<R, NU, K - 1>(c2, b, dv, src, s.rho, tx, ty, [&](int x, int y, R v) {
+        dst[y][x] = v;
+        if (K == NU) {
+          const int i = oi + x, j = oj + y;
+          if (x >= NU && x < 64 - NU && i <= nx - 2 && j >= b.j0 && j < j_end) zout[(size_t)i + (size_t)j * nx] = v;
+        }
+      });
+    };
+    DivTry<R> fast(c2.dx_sq);
+    fast.also(c2.dy_sq).also(c2.denom);
+    stage(fast);
+    if (__builtin_expect(!fast.ok(), 0)) {
+      DivSlow<R> exact;
+      stage(exact);
+    }
+    __syncthreads();
+    if (b.edge) {
+      leg0_fix_ring<R, NU, K - 1>(b, c.cavity, dst, tid);
+      __syncthreads();
+    }
+  });
+  auto& xn = (NU % 2 == 0) ? s.b : s.a;
+  auto& res = (NU % 2 == 0) ? s.a : s.b;  // free now: the residuals of the tile
+  if (b.edge) {
+    // the ring cells that mirror this tile's unknowns go to memory too (like every sweep kernel leaves them)
+    constexpr int W = 64 - 2 * (NU - 1), H = G::RY - 2 * (NU - 1);
+    for (int k = tid; k < W * H; k += kLegThreads) {
+      const int y = NU - 1 + k / W, x = NU - 1 + k % W;
+      const int i = oi + x, j = oj + y;
+      const bool ring = i == 0 || i == nx - 1 || j == 0 || j == c.ny - 1;
+      const int qi = min(max(i, 1), nx - 2), qj = min(max(j, 1), c.ny - 2);
+      if (ring && i <= nx - 1 && j <= c.ny - 1 && qi >= b.i0 && qi < b.i0 + G::TX && qj >= b.j0 && qj < j_end)
+        zout[(size_t)i + (size_t)j * nx] = xn[y][x];
+    }
+  }
+  // residuals rho - L x_nu on the tile (mg_lap's expressions), then rho_1 = their sums over the children of a coarse cell
+  // (k_mg_fine_restrict's order: row b outer, column a inner)
+  {
+    constexpr int HS = G::TY / G::kStrips;
+    auto stage = [&](auto& dv) {
+      if (tx >= NU && tx < 64 - NU && tx <= b.xb) {
+        const int y0 = NU + ty * HS;
+        R s_ = xn[y0 - 1][tx], c_ = xn[y0][tx];
+#pragma unroll
+        for (int r = 0; r < HS; ++r) {
+          const int y = y0 + r;
+          const R n_ = xn[y + 1][tx];
+          res[y][tx] = s.rho[y][tx] - mg_lap<R>(c, dv, c_, xn[y][tx + 1], xn[y][tx - 1], n_, s_);
+          s_ = c_;
+          c_ = n_;
+        }
+      }
+    };
+    DivTry<R> fast(c.ddx_sq);
+    fast.also(c.ddy_sq);
+    stage(fast);
+    if (__builtin_expect(!fast.ok(), 0)) {
+      DivSlow<R> exact;
+      stage(exact);
+    }
+  }
+  __syncthreads();
+  constexpr int CX = G::TX / 2, CY = G::TY / 2;
+  for (int k = tid; k < CX * CY; k += kLegThreads) {
+    const int cy = k / CX, cx = k - cy * CX;
+    const int I = (int)blockIdx.x * CX + cx, J = (b.j0 - 1) / 2 + cy;
+    if (1 + 2 * I <= nx - 2 && 1 + 2 * J < j_end) {
+      R acc = R(0);
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+        for (int aa = 0; aa < 2; ++aa) {
+          const int i = 1 + 2 * I + aa, j = 1 + 2 * J + bb;
+          if (i <= nx - 2 && j <= c.ny - 2) acc += res[j - oj][i - oi];
+        }
+      crho[(size_t)(I + 1) + (size_t)(J + 1) * (cmx + 2)] = acc;
+    }
+  }
+}
+
+// ascending leg of level 0, column-strip form: z = NU sweeps of (x_nu + correction of the parents); rho.z -> one partial per block
+template <class R, int NU>
+__global__ void __launch_bounds__(kLegThreads, 3) k_mg0_up2(const MgFine<R> c, const JacobiConsts2<R> c2,
+                                                             const R* __restrict__ zin, const R* __restrict__ rho, int cmx,
+                                                             const R* __restrict__ ce, R* __restrict__ zout,
+                                                             double* __restrict__ partials, const MgScalars* __restrict__ sc) {
+  using G = Leg0<NU>;
+  using S = Leg0Smem<R, NU>;
+  extern __shared__ __align__(16) unsigned char leg_smem_raw[];
+  S& s = *reinterpret_cast<S*>(leg_smem_raw);
+  __shared__ double s_red[kLegThreads / 32];
+  if (sc->done) return;
+  const Leg0Box b = leg0_box<R, NU>(c);
+  const int tid = threadIdx.x, tx = tid & 63, ty = tid >> 6, nx = c.nx;
+  const int oi = b.i0 - NU, oj = b.j0 - NU;
+  const int j_end = min(b.j0 + G::TY, c.row_hi);
+  {
+    const bool col_ok = tx >= b.xa && tx <= b.xb;
+    const int i = oi + tx;
+    const int qi = min(max(i, 1), nx - 2);
+    const size_t pcol = (size_t)((qi - 1) / 2 + 1);
+#pragma unroll
+    for (int r = 0; r < (G::RY + G::kStrips - 1) / G::kStrips; ++r) {
+      const int y = ty + r * G::kStrips;
+      if (y < G::RY) {
+        R v = R(0), q = R(0);
+        if (col_ok && y >= b.ya && y <= b.yb) {
+          const int j = oj + y;
+          const int qj = min(max(j, 1), c.ny - 2);
+          const size_t idx = (size_t)i + (size_t)j * nx;
+          v = zin[idx] + ce[pcol + (size_t)((qj - 1) / 2 + 1) * (cmx + 2)];
+          q = rho[idx];
+        }
+        s.a[y][tx] = v;
+        s.rho[y][tx] = q;
+      }
+    }
+  }
+  __syncthreads();
+  if (b.edge) {
+    leg0_fix_ring<R, NU, 0>(b, c.cavity, s.a, tid);
+    __syncthreads();
+  }
+  double acc = 0.0;
+  leg_static_for<1, NU + 1>([&](auto kc) {
+    constexpr int K = decltype(kc)::value;
+    auto& src = (K % 2 == 1) ? s.a : s.b;
+    auto& dst = (K % 2 == 1) ? s.b : s.a;
+    auto stage = [&](auto& dv) {
+      if (K == NU) acc = 0.0;
+      auto out = [&](int x, int y, R v) {
+        if (K == NU) {  // the tile's unknowns: straight to memory, rho.z; (edge tiles: everything also to dst for the ring cells)
+          const int i = oi + x, j = oj + y;
+          if (b.edge) dst[y][x] = v;
+          if (x >= NU && x < 64 - NU && i <= nx - 2 && j >= b.j0 && j < j_end) {
+            acc += (double)(s.rho[y][x] * v);
+            zout[(size_t)i + (size_t)j * nx] = v;
+          }
+        } else {
+          dst[y][x] = v;
+        }
+      };
+      // the last sweep: the tile; on an edge tile the tile + 1, whose ring cells go to memory as well
+      if (K == NU && !b.edge) leg0_sweep_strip<R, NU, NU>(c2, b, dv, src, s.rho, tx, ty, out);
+      else leg0_sweep_strip<R, NU, (K == NU ? NU - 1 : K)>(c2, b, dv, src, s.rho, tx, ty, out);
+    };
+    DivTry<R> fast(c2.dx_sq);
+    fast.also(c2.dy_sq).also(c2.denom);
+    stage(fast);
+    if (__builtin_expect(!fast.ok(), 0)) {
+      DivSlow<R> exact;
+      stage(exact);
+    }
+    if (K != NU || b.edge) __syncthreads();
+    if (b.edge) {
+      leg0_fix_ring<R, NU, (K == NU ? NU - 1 : K)>(b, c.cavity, dst, tid);
+      __syncthreads();
+    }
+  });
+  if (b.edge) {
+    auto& zn = (NU % 2 == 1) ? s.b : s.a;
+    constexpr int W = 64 - 2 * (NU - 1), H = G::RY - 2 * (NU - 1);
+    for (int k = tid; k < W * H; k += kLegThreads) {
+      const int y = NU - 1 + k / W, x = NU - 1 + k % W;
+      const int i = oi + x, j = oj + y;
+      const bool ring = i == 0 || i == nx - 1 || j == 0 || j == c.ny - 1;
+      const int qi = min(max(i, 1), nx - 2), qj = min(max(j, 1), c.ny - 2);
+      if (ring && i <= nx - 1 && j <= c.ny - 1 && qi >= b.i0 && qi < b.i0 + G::TX && qj >= b.j0 && qj < j_end)
+        zout[(size_t)i + (size_t)j * nx] = zn[y][x];
+    }
+  }
+  const double t = block_sum<kLegThreads / 32>(acc, s_red);
+  if (tid == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = t;
+}
 
 // one cell of a damped-Jacobi sweep on a coarse level: mgc_sweep_cell's arithmetic (k_mgc_sweep_tab's form)
 template <class R, class Div>
@@ -237,6 +556,537 @@ __device__ __forceinline__ R mgc_cell(R we, R ww, R cyw, R wn, R ws, R cxh, R cc
   const R res = dv(le - rho, dg);
   return dg.y > R(0) ? cc + omega * res : R(0);
 }
+
+// ---- register-tiled form (level 0 and coarse levels) ------------------------------------------------------------------
+// The shipped legs.  The staged region is 64 columns x 36 rows (tile = (64 - 2 NU) x (36 - 2 NU)); thread (tx, ty) owns
+// column tx of the FIXED row strip [9 ty, 9 ty + 9) through every sweep: its 9 cells and their right-hand sides live in
+// registers, shared memory only carries each sweep's result to the neighbouring threads (per cell and sweep: 2 shared
+// loads for the horizontal neighbours, 16 fp64 operations, 1 shared store, 2 integer instructions per division).  Every
+// thread computes all of its cells in every sweep, without predicates: the cells a sweep does not need (closer than k to
+// the region's edge) are computed from clamped neighbours and never read by a cell that matters.  Tiles that touch the
+// boundary of the array rewrite the ring cells of each sweep's result from the unknowns they mirror (leg0_fix_ring) and
+// reload their registers; cells outside the array start from rho = 1 (any harmless non-zero value).
+template <int NU>
+struct Leg3 {
+  static constexpr int TX = 64 - 2 * NU, TY = 36 - 2 * NU, RY = 36, HS = 9;
+};
+template <class R>
+struct Leg3Smem {
+  R a[36][64], b[36][64];
+};
+
+template <class R, int NU>
+__device__ __forceinline__ Leg0Box leg3_box(const MgFine<R>& c) {
+  using G = Leg3<NU>;
+  Leg0Box b;
+  b.i0 = 1 + (int)blockIdx.x * G::TX;
+  b.j0 = c.row_lo + (int)blockIdx.y * G::TY;
+  const int oi = b.i0 - NU, oj = b.j0 - NU;
+  const int j_first = c.row_lo - NU > 0 ? c.row_lo - NU : 0;
+  const int j_last = c.row_hi + NU - 1 < c.ny - 1 ? c.row_hi + NU - 1 : c.ny - 1;
+  b.xa = max(0, -oi); b.xb = min(63, c.nx - 1 - oi);
+  b.ya = max(0, j_first - oj); b.yb = min(G::RY - 1, j_last - oj);
+  b.x_ring_l = -oi; b.x_ring_r = c.nx - 1 - oi; b.y_ring_b = -oj; b.y_ring_t = c.ny - 1 - oj;
+  b.edge = b.x_ring_l >= 0 || b.x_ring_r < 64 || b.y_ring_b >= 0 || b.y_ring_t < G::RY;
+  return b;
+}
+
+// ring cells of a 64 x 36 staged field <- the unknowns they mirror (every ring cell inside the region; column nx-1 of the
+// channel: zero).  Call between two __syncthreads.
+template <class R>
+__device__ __forceinline__ void leg3_fix_ring(const Leg0Box& b, int cavity, R (*f)[64], int tid) {
+  auto col_src = [&](int x) { return x == b.x_ring_l ? x + 1 : (x == b.x_ring_r ? x - 1 : x); };
+  for (int k = tid; k < 2 * 36; k += kLegThreads) {
+    const int y = k >> 1, x = (k & 1) ? b.x_ring_r : b.x_ring_l;
+    if (x >= 0 && x < 64 && y != b.y_ring_b && y != b.y_ring_t) f[y][x] = (!(k & 1) || cavity) ? f[y][col_src(x)] : R(0);
+  }
+  for (int k = tid; k < 2 * 64; k += kLegThreads) {
+    const int x = k >> 1, y = (k & 1) ? b.y_ring_t : b.y_ring_b;
+    if (y >= 0 && y < 36) {
+      const int ys = (k & 1) ? y - 1 : y + 1;
+      f[y][x] = (x == b.x_ring_r && !cavity) ? R(0) : f[ys][col_src(x)];
+    }
+  }
+}
+
+// what a thread of the register-tiled legs knows about its strip
+struct Leg3Thread {
+  int tx, y0, txl, txr, y_below, y_above;
+  __device__ __forceinline__ explicit Leg3Thread(int tid) {
+    tx = tid & 63; y0 = (tid >> 6) * 9;
+    txl = max(tx - 1, 0); txr = min(tx + 1, 63);
+    y_below = max(y0 - 1, 0); y_above = min(y0 + 9, 35);
+  }
+};
+
+// one Jacobi sweep of the thread's 9 cells, in place in `cur` (the vertical neighbours inside the strip are the thread's own
+// registers); the result goes to dst for the neighbours.  Redone with true divisions if a dividend left the window.
+template <class R>
+__device__ __forceinline__ void leg3_sweep0(const JacobiConsts2<R>& c2, const Leg3Thread& t, const R (*src)[64], R (*dst)[64],
+                                            R (&cur)[9], const R (&q)[9]) {
+  auto pass = [&](auto& dv) {
+    R s_ = src[t.y_below][t.tx];
+    const R above = src[t.y_above][t.tx];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const R c_ = cur[r], n_ = r < 8 ? cur[r + 1] : above;
+      cur[r] = jacobi_cell_dv<R>(c2, dv, src[t.y0 + r][t.txl], src[t.y0 + r][t.txr], n_, s_, c_, q[r]);
+      s_ = c_;
+    }
+  };
+  DivTry<R> fast(c2.dx_sq);
+  fast.also(c2.dy_sq).also(c2.denom);
+  pass(fast);
+  if (__builtin_expect(!fast.ok(), 0)) {
+#pragma unroll
+    for (int r = 0; r < 9; ++r) cur[r] = src[t.y0 + r][t.tx];
+    DivSlow<R> exact;
+    pass(exact);
+  }
+#pragma unroll
+  for (int r = 0; r < 9; ++r) dst[t.y0 + r][t.tx] = cur[r];
+}
+
+template <class R>
+__device__ __forceinline__ void leg3_reload(const Leg3Thread& t, const R (*f)[64], R (&cur)[9]) {
+#pragma unroll
+  for (int r = 0; r < 9; ++r) cur[r] = f[t.y0 + r][t.tx];
+}
+
+// the ring cells that mirror this tile's unknowns go to memory too (like every sweep kernel leaves them)
+template <class R, int NU>
+__device__ __forceinline__ void leg3_store_ring(const Leg0Box& b, const MgFine<R>& c, const R (*f)[64], R* __restrict__ zout,
+                                                int j_end, int tid) {
+  using G = Leg3<NU>;
+  constexpr int W = G::TX + 2, H = G::TY + 2;
+  const int oi = b.i0 - NU, oj = b.j0 - NU;
+  for (int k = tid; k < W * H; k += kLegThreads) {
+    const int y = NU - 1 + k / W, x = NU - 1 + k % W;
+    const int i = oi + x, j = oj + y;
+    const bool ring = i == 0 || i == c.nx - 1 || j == 0 || j == c.ny - 1;
+    const int qi = min(max(i, 1), c.nx - 2), qj = min(max(j, 1), c.ny - 2);
+    if (ring && i <= c.nx - 1 && j <= c.ny - 1 && qi >= b.i0 && qi < b.i0 + G::TX && qj >= b.j0 && qj < j_end)
+      zout[(size_t)i + (size_t)j * c.nx] = f[y][x];
+  }
+}
+
+template <class R, int NU>
+__global__ void __launch_bounds__(kLegThreads, 3) k_mg0_down3(const MgFine<R> c, const JacobiConsts2<R> c2,
+                                                               const R* __restrict__ rho, R* __restrict__ zout, int cmx,
+                                                               R* __restrict__ crho, const MgScalars* __restrict__ sc) {
+  using G = Leg3<NU>;
+  extern __shared__ __align__(16) unsigned char leg_smem_raw[];
+  Leg3Smem<R>& s = *reinterpret_cast<Leg3Smem<R>*>(leg_smem_raw);
+  if (sc->done) return;
+  const Leg0Box b = leg3_box<R, NU>(c);
+  const int tid = threadIdx.x, nx = c.nx;
+  const Leg3Thread t(tid);
+  const int oi = b.i0 - NU, oj = b.j0 - NU;
+  const int j_end = min(b.j0 + G::TY, c.row_hi);  // owned unknown rows of the tile: [j0, j_end)
+  R q[9], cur[9];
+  // rho of the thread's cells, x_1 = the first smoothing sweep applied to z = 0 (k_mg_first_sweep's expression)
+  {
+    const bool col_ok = t.tx >= b.xa && t.tx <= b.xb;
+    const R* __restrict__ src = rho + (long)(oi + t.tx);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int y = t.y0 + r;
+      q[r] = (col_ok && y >= b.ya && y <= b.yb) ? src[(long)(oj + y) * nx] : R(1);
+    }
+    auto first = [&](auto& dv) {
+#pragma unroll
+      for (int r = 0; r < 9; ++r) cur[r] = c2.omega * dv((R(0) + R(0)) - q[r], c2.denom) + c2.one_minus_omega * R(0);
+    };
+    DivTry<R> fast(c2.denom);
+    first(fast);
+    if (__builtin_expect(!fast.ok(), 0)) {
+      DivSlow<R> exact;
+      first(exact);
+    }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) s.a[t.y0 + r][t.tx] = cur[r];
+  }
+  __syncthreads();
+  if (b.edge) {
+    leg3_fix_ring<R>(b, c.cavity, s.a, tid);
+    __syncthreads();
+    leg3_reload<R>(t, s.a, cur);
+  }
+  leg_static_for<2, NU + 1>([&](auto kc) {
+    constexpr int K = decltype(kc)::value;
+    auto& src = (K % 2 == 0) ? s.a : s.b;
+    auto& dst = (K % 2 == 0) ? s.b : s.a;
+    leg3_sweep0<R>(c2, t, src, dst, cur, q);
+    __syncthreads();
+    if (b.edge) {
+      leg3_fix_ring<R>(b, c.cavity, dst, tid);
+      __syncthreads();
+      leg3_reload<R>(t, dst, cur);
+    }
+  });
+  auto& xn = (NU % 2 == 0) ? s.b : s.a;
+  auto& res = (NU % 2 == 0) ? s.a : s.b;  // free now: the residuals of the tile
+  // x_nu of the tile's unknowns
+  if (t.tx >= NU && t.tx < 64 - NU && oi + t.tx <= nx - 2) {
+    R* __restrict__ out = zout + (long)(oi + t.tx);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int y = t.y0 + r, j = oj + y;
+      if (y >= NU && y < NU + G::TY && j < j_end) out[(long)j * nx] = cur[r];
+    }
+  }
+  if (b.edge) leg3_store_ring<R, NU>(b, c, xn, zout, j_end, tid);
+  // residuals rho - L x_nu (mg_lap's expressions), then rho_1 = their sums over the children of a coarse cell
+  // (k_mg_fine_restrict's order: row b outer, column a inner)
+  {
+    R rs[9];
+    auto pass = [&](auto& dv) {
+      R s_ = xn[t.y_below][t.tx];
+      const R above = xn[t.y_above][t.tx];
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        const R n_ = r < 8 ? cur[r + 1] : above;
+        rs[r] = q[r] - mg_lap<R>(c, dv, cur[r], xn[t.y0 + r][t.txr], xn[t.y0 + r][t.txl], n_, s_);
+        s_ = cur[r];
+      }
+    };
+    DivTry<R> fast(c.ddx_sq);
+    fast.also(c.ddy_sq);
+    pass(fast);
+    if (__builtin_expect(!fast.ok(), 0)) {
+      DivSlow<R> exact;
+      pass(exact);
+    }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) res[t.y0 + r][t.tx] = rs[r];
+  }
+  __syncthreads();
+  constexpr int CX = G::TX / 2, CY = G::TY / 2;
+  for (int k = tid; k < CX * CY; k += kLegThreads) {
+    const int cy = k / CX, cx = k - cy * CX;
+    const int I = (int)blockIdx.x * CX + cx, J = (b.j0 - 1) / 2 + cy;
+    if (1 + 2 * I <= nx - 2 && 1 + 2 * J < j_end) {
+      R acc = R(0);
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+        for (int aa = 0; aa < 2; ++aa) {
+          const int i = 1 + 2 * I + aa, j = 1 + 2 * J + bb;
+          if (i <= nx - 2 && j <= c.ny - 2) acc += res[j - oj][i - oi];
+        }
+      crho[(size_t)(I + 1) + (size_t)(J + 1) * (cmx + 2)] = acc;
+    }
+  }
+}
+
+// ascending leg of level 0, register-tiled: z = NU sweeps of (x_nu + correction of the parents); rho.z -> one partial per block
+template <class R, int NU>
+__global__ void __launch_bounds__(kLegThreads, 3) k_mg0_up3(const MgFine<R> c, const JacobiConsts2<R> c2,
+                                                             const R* __restrict__ zin, const R* __restrict__ rho, int cmx,
+                                                             const R* __restrict__ ce, R* __restrict__ zout,
+                                                             double* __restrict__ partials, const MgScalars* __restrict__ sc) {
+  using G = Leg3<NU>;
+  extern __shared__ __align__(16) unsigned char leg_smem_raw[];
+  Leg3Smem<R>& s = *reinterpret_cast<Leg3Smem<R>*>(leg_smem_raw);
+  __shared__ double s_red[kLegThreads / 32];
+  if (sc->done) return;
+  const Leg0Box b = leg3_box<R, NU>(c);
+  const int tid = threadIdx.x, nx = c.nx;
+  const Leg3Thread t(tid);
+  const int oi = b.i0 - NU, oj = b.j0 - NU;
+  const int j_end = min(b.j0 + G::TY, c.row_hi);
+  R q[9], cur[9];
+  {
+    const bool col_ok = t.tx >= b.xa && t.tx <= b.xb;
+    const int i = oi + t.tx;
+    const int qi = min(max(i, 1), nx - 2);
+    const R* __restrict__ pc = ce + (long)((qi - 1) / 2 + 1);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int y = t.y0 + r;
+      R v = R(1), w = R(1);
+      if (col_ok && y >= b.ya && y <= b.yb) {
+        const int j = oj + y;
+        const int qj = min(max(j, 1), c.ny - 2);
+        const long idx = (long)i + (long)j * nx;
+        v = zin[idx] + pc[(long)((qj - 1) / 2 + 1) * (cmx + 2)];
+        w = rho[idx];
+      }
+      cur[r] = v;
+      q[r] = w;
+      s.a[y][t.tx] = v;
+    }
+  }
+  __syncthreads();
+  if (b.edge) {
+    leg3_fix_ring<R>(b, c.cavity, s.a, tid);
+    __syncthreads();
+    leg3_reload<R>(t, s.a, cur);
+  }
+  leg_static_for<1, NU + 1>([&](auto kc) {
+    constexpr int K = decltype(kc)::value;
+    auto& src = (K % 2 == 1) ? s.a : s.b;
+    auto& dst = (K % 2 == 1) ? s.b : s.a;
+    leg3_sweep0<R>(c2, t, src, dst, cur, q);
+    if (K != NU || b.edge) __syncthreads();
+    if (b.edge) {
+      leg3_fix_ring<R>(b, c.cavity, dst, tid);
+      __syncthreads();
+      if (K != NU) leg3_reload<R>(t, dst, cur);
+    }
+  });
+  // the tile's unknowns to memory, rho.z
+  double acc = 0.0;
+  if (t.tx >= NU && t.tx < 64 - NU && oi + t.tx <= nx - 2) {
+    R* __restrict__ out = zout + (long)(oi + t.tx);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int y = t.y0 + r, j = oj + y;
+      if (y >= NU && y < NU + G::TY && j < j_end) {
+        acc += (double)(q[r] * cur[r]);
+        out[(long)j * nx] = cur[r];
+      }
+    }
+  }
+  if (b.edge) leg3_store_ring<R, NU>(b, c, (NU % 2 == 1) ? s.b : s.a, zout, j_end, tid);
+  const double tot = block_sum<kLegThreads / 32>(acc, s_red);
+  if (tid == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = tot;
+}
+
+// ---- coarse levels, register-tiled ----
+// Cells outside the level are the ring of zeros (and beyond): they get the null class of the diagonal table (divisor 0 ->
+// mgc_cell returns 0), zero weights and rho = 1, so they stay zero through every sweep without a predicate.
+template <class R>
+struct Leg3SmemC {
+  Leg3Smem<R> f;
+  R wn[36], ws[36], cxh[36];
+  R dy[kMgClasses * kMgClasses + 1], dr[kMgClasses * kMgClasses + 1];  // + the null class
+  int rcls8[36];  // row class * kMgClasses; rows outside the level: >= the null class
+};
+constexpr int kLegNullClass = kMgClasses * kMgClasses;
+
+struct Leg3Col {  // a thread's column of a coarse level
+  int cls;        // column class; outside the level: the null class
+  bool in;
+};
+
+template <class R, int NU>
+__device__ __forceinline__ void leg3_load_level(Leg3SmemC<R>& s, const MgLevelDev<R>& L, int J0, int tid) {
+  for (int k = tid; k < 36; k += kLegThreads) {
+    const int J = J0 - NU + k;
+    const bool in = J >= 0 && J < L.my;
+    s.wn[k] = in ? L.WN[J] : R(0);
+    s.ws[k] = in ? L.WS[J] : R(0);
+    s.cxh[k] = in ? L.CXH[J] : R(0);
+    s.rcls8[k] = in ? (int)L.row_class[J] * kMgClasses : kLegNullClass;
+  }
+  for (int k = tid; k <= kLegNullClass; k += kLegThreads) {
+    s.dy[k] = k < kLegNullClass ? L.diag_table[k].y : R(0);
+    s.dr[k] = k < kLegNullClass ? L.diag_table[k].r : R(0);
+  }
+}
+
+// one sweep of the thread's 9 cells of a coarse level, in place in `cur` (mgc_cell = mgc_sweep_cell's arithmetic)
+template <class R>
+__device__ __forceinline__ void leg3_sweep_c(const Leg3SmemC<R>& s, const DivG<R>& win, const Leg3Thread& t, const Leg3Col& col,
+                                             R we, R ww, R cyw, R omega, const R (*src)[64], R (*dst)[64], R (&cur)[9],
+                                             const R (&q)[9]) {
+  auto pass = [&](auto& dv) {
+    R s_ = src[t.y_below][t.tx];
+    const R above = src[t.y_above][t.tx];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int y = t.y0 + r;
+      const R c_ = cur[r], n_ = r < 8 ? cur[r + 1] : above;
+      DivG<R> dg;
+      const int cls = min(s.rcls8[y] + col.cls, kLegNullClass);
+      dg.y = s.dy[cls]; dg.r = s.dr[cls]; dg.lo = 0u; dg.span = 0u;
+      cur[r] = mgc_cell<R>(we, ww, cyw, s.wn[y], s.ws[y], s.cxh[y], c_, src[y][t.txr], src[y][t.txl], n_, s_, q[r], dg, omega, dv);
+      s_ = c_;
+    }
+  };
+  DivTry<R> fast(win);
+  pass(fast);
+  if (__builtin_expect(!fast.ok(), 0)) {
+#pragma unroll
+    for (int r = 0; r < 9; ++r) cur[r] = src[t.y0 + r][t.tx];
+    DivSlow<R> exact;
+    pass(exact);
+  }
+#pragma unroll
+  for (int r = 0; r < 9; ++r) dst[t.y0 + r][t.tx] = cur[r];
+}
+
+// descending leg of level l >= 1, register-tiled (arguments as k_mgc_down)
+template <class R, int NU>
+__global__ void __launch_bounds__(kLegThreads, 2) k_mgc_down3(const MgLevelDev<R> L, const R* __restrict__ rho,
+                                                               R* __restrict__ xout, int cmx, R* __restrict__ crho, R omega,
+                                                               int row_lo, int row_hi, int c_lo, int c_hi,
+                                                               const MgScalars* __restrict__ sc) {
+  using G = Leg3<NU>;
+  extern __shared__ __align__(16) unsigned char leg_smem_raw[];
+  Leg3SmemC<R>& s = *reinterpret_cast<Leg3SmemC<R>*>(leg_smem_raw);
+  if (sc->done) return;
+  const int tid = threadIdx.x, mx = L.mx, my = L.my;
+  const Leg3Thread t(tid);
+  const int I0 = (int)blockIdx.x * G::TX, J0 = row_lo + (int)blockIdx.y * G::TY;
+  const int J_end = min(J0 + G::TY, row_hi);
+  const long W = (long)mx + 2;
+  const int I = I0 - NU + t.tx;
+  Leg3Col col;
+  col.in = I >= 0 && I < mx;
+  col.cls = col.in ? (int)L.col_class[I] : kLegNullClass;
+  const R we = col.in ? L.WE[I] : R(0), ww = col.in ? L.WW[I] : R(0), cyw = col.in ? L.CYW[I] : R(0);
+  leg3_load_level<R, NU>(s, L, J0, tid);
+  R q[9], cur[9];
+  {
+    const R* __restrict__ src = rho + (long)(I + 1);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int J = J0 - NU + t.y0 + r;
+      q[r] = (col.in && J >= 0 && J < my) ? src[(long)(J + 1) * W] : R(1);
+    }
+  }
+  __syncthreads();
+  const DivG<R> win = L.diag_table[kMgClasses * kMgClasses];  // intersection of the table's dividend windows
+  // x_1 = sweep of the zero field: cc + omega * ((L 0 - rho) / diag) with cc = 0, L 0 = +0
+  {
+    auto first = [&](auto& dv) {
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        DivG<R> dg;
+        const int cls = min(s.rcls8[t.y0 + r] + col.cls, kLegNullClass);
+        dg.y = s.dy[cls]; dg.r = s.dr[cls]; dg.lo = 0u; dg.span = 0u;
+        const R res = dv(R(0) - q[r], dg);
+        cur[r] = dg.y > R(0) ? R(0) + omega * res : R(0);
+      }
+    };
+    DivTry<R> fast(win);
+    first(fast);
+    if (__builtin_expect(!fast.ok(), 0)) {
+      DivSlow<R> exact;
+      first(exact);
+    }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) s.f.a[t.y0 + r][t.tx] = cur[r];
+  }
+  __syncthreads();
+  leg_static_for<2, NU + 1>([&](auto kc) {
+    constexpr int K = decltype(kc)::value;
+    auto& src = (K % 2 == 0) ? s.f.a : s.f.b;
+    auto& dst = (K % 2 == 0) ? s.f.b : s.f.a;
+    leg3_sweep_c<R>(s, win, t, col, we, ww, cyw, omega, src, dst, cur, q);
+    __syncthreads();
+  });
+  auto& xn = (NU % 2 == 0) ? s.f.b : s.f.a;
+  auto& res = (NU % 2 == 0) ? s.f.a : s.f.b;
+  if (t.tx >= NU && t.tx < 64 - NU && col.in) {
+    R* __restrict__ out = xout + (long)(I + 1);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int y = t.y0 + r, J = J0 - NU + y;
+      if (y >= NU && y < NU + G::TY && J < J_end && J < my) out[(long)(J + 1) * W] = cur[r];
+    }
+  }
+  // residuals rho_l - L_l x_nu (mg_coarse_apply's expression), then rho_{l+1} = their sums over the children
+  // (mgc_restrict_cell's order)
+  {
+    R s_ = xn[t.y_below][t.tx];
+    const R above = xn[t.y_above][t.tx];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int y = t.y0 + r;
+      const R cc = cur[r], n_ = r < 8 ? cur[r + 1] : above;
+      const R le = s.cxh[y] * (we * (xn[y][t.txr] - cc) + ww * (xn[y][t.txl] - cc)) + cyw * (s.wn[y] * (n_ - cc) + s.ws[y] * (s_ - cc));
+      res[y][t.tx] = q[r] - le;
+      s_ = cc;
+    }
+  }
+  __syncthreads();
+  constexpr int CX = G::TX / 2, CY = G::TY / 2;
+  for (int k = tid; k < CX * CY; k += kLegThreads) {
+    const int cy = k / CX, cx = k - cy * CX;
+    const int Ic = I0 / 2 + cx, Jc = J0 / 2 + cy;
+    if (2 * Ic < mx && 2 * Jc < my && 2 * Jc < J_end && Jc >= c_lo && Jc < c_hi) {
+      R acc = R(0);
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+        for (int aa = 0; aa < 2; ++aa) {
+          const int i = 2 * Ic + aa, j = 2 * Jc + bb;
+          if (i < mx && j < my) acc += res[j - (J0 - NU)][i - (I0 - NU)];
+        }
+      crho[(size_t)(Ic + 1) + (size_t)(Jc + 1) * ((size_t)cmx + 2)] = acc;
+    }
+  }
+}
+
+// ascending leg of level l >= 1, register-tiled (arguments as k_mgc_up)
+template <class R, int NU>
+__global__ void __launch_bounds__(kLegThreads, 2) k_mgc_up3(const MgLevelDev<R> L, const R* __restrict__ xin,
+                                                             const R* __restrict__ rho, int cmx, const R* __restrict__ ce,
+                                                             R* __restrict__ xout, R omega, int row_lo, int row_hi,
+                                                             const MgScalars* __restrict__ sc) {
+  using G = Leg3<NU>;
+  extern __shared__ __align__(16) unsigned char leg_smem_raw[];
+  Leg3SmemC<R>& s = *reinterpret_cast<Leg3SmemC<R>*>(leg_smem_raw);
+  if (sc->done) return;
+  const int tid = threadIdx.x, mx = L.mx, my = L.my;
+  const Leg3Thread t(tid);
+  const int I0 = (int)blockIdx.x * G::TX, J0 = row_lo + (int)blockIdx.y * G::TY;
+  const int J_end = min(J0 + G::TY, row_hi);
+  const long W = (long)mx + 2;
+  const int I = I0 - NU + t.tx;
+  Leg3Col col;
+  col.in = I >= 0 && I < mx;
+  col.cls = col.in ? (int)L.col_class[I] : kLegNullClass;
+  const R we = col.in ? L.WE[I] : R(0), ww = col.in ? L.WW[I] : R(0), cyw = col.in ? L.CYW[I] : R(0);
+  leg3_load_level<R, NU>(s, L, J0, tid);
+  R q[9], cur[9];
+  {
+    const R* __restrict__ pc = ce + (long)(I / 2 + 1);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int y = t.y0 + r, J = J0 - NU + y;
+      R v = R(0), w = R(1);
+      if (col.in && J >= 0 && J < my) {
+        const long idx = (long)(I + 1) + (long)(J + 1) * W;
+        v = xin[idx] + pc[(long)(J / 2 + 1) * ((long)cmx + 2)];
+        w = rho[idx];
+      }
+      cur[r] = v;
+      q[r] = w;
+      s.f.a[y][t.tx] = v;
+    }
+  }
+  __syncthreads();
+  const DivG<R> win = L.diag_table[kMgClasses * kMgClasses];
+  leg_static_for<1, NU + 1>([&](auto kc) {
+    constexpr int K = decltype(kc)::value;
+    auto& src = (K % 2 == 1) ? s.f.a : s.f.b;
+    auto& dst = (K % 2 == 1) ? s.f.b : s.f.a;
+    leg3_sweep_c<R>(s, win, t, col, we, ww, cyw, omega, src, dst, cur, q);
+    if (K != NU) __syncthreads();
+  });
+  if (t.tx >= NU && t.tx < 64 - NU && col.in) {
+    R* __restrict__ out = xout + (long)(I + 1);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int y = t.y0 + r, J = J0 - NU + y;
+      if (y >= NU && y < NU + G::TY && J < J_end && J < my) out[(long)(J + 1) * W] = cur[r];
+    }
+  }
+}
+
+// ---- coarse levels (l >= 1, fields (mx + 2) x (my + 2) with a ring of zeros; levels with a diagonal table) -------------
+template <class R, int TX, int TY, int NU>
+struct LegSmemC {
+  static constexpr int RX = TX + 2 * NU, RY = TY + 2 * NU;
+  LegSmem<R, TX, TY, NU> f;
+  R we[RX], ww[RX], cyw[RX], wn[RY], ws[RY], cxh[RY];
+  R dy[kMgClasses * kMgClasses], dr[kMgClasses * kMgClasses];  // the diagonal table: divisors and hoisted reciprocals
+  unsigned char ccls[RX], rcls[RY];
+};
 
 template <class R, int TX, int TY, int NU>
 __device__ __forceinline__ void leg_load_level(LegSmemC<R, TX, TY, NU>& s, const MgLevelDev<R>& L, int I0, int J0, int tid) {
@@ -321,7 +1171,7 @@ __global__ void __launch_bounds__(kLegThreads, 2) k_mgc_down(const MgLevelDev<R>
     DivTry<R> fast(win);
     stage1(fast);
     if (__builtin_expect(!fast.ok(), 0)) {
-      DivTrue<R> exact;
+      DivSlow<R> exact;
       stage1(exact);
     }
   }
@@ -345,7 +1195,7 @@ __global__ void __launch_bounds__(kLegThreads, 2) k_mgc_down(const MgLevelDev<R>
     DivTry<R> fast(win);
     stage(fast);
     if (__builtin_expect(!fast.ok(), 0)) {
-      DivTrue<R> exact;
+      DivSlow<R> exact;
       stage(exact);
     }
     __syncthreads();
@@ -433,7 +1283,7 @@ __global__ void __launch_bounds__(kLegThreads, 2) k_mgc_up(const MgLevelDev<R> L
     DivTry<R> fast(win);
     stage(fast);
     if (__builtin_expect(!fast.ok(), 0)) {
-      DivTrue<R> exact;
+      DivSlow<R> exact;
       stage(exact);
     }
     if (K != NU) __syncthreads();

@@ -268,6 +268,11 @@ struct ModelImpl final : ModelBase {
   // small levels (more blocks)
   template <int NU> struct LegTile { static constexpr int TX = NU >= 4 ? 64 : 128, TY = NU >= 4 ? 32 : 16; };
   static constexpr int kLegSX = 64, kLegSY = 8;
+  // form of the leg kernels: 3 register-tiled (shipped), 2 column strips, 1 flat-indexed (A/B and cross-checks: CFD_MG_LEGS=1|2|3)
+  static int leg_form() {
+    static const int form = [] { const char* e = getenv("CFD_MG_LEGS"); return e ? atoi(e) : 3; }();
+    return form;
+  }
   int leg_tx() const { return mg_smoothing() >= 4 ? 64 : 128; }
   int leg_ty() const { return mg_smoothing() >= 4 ? 32 : 16; }
   // strips: halo rows of a coarse level's rho the legs need (x_nu is recomputed on nu rows beyond the owned ones)
@@ -1298,7 +1303,7 @@ struct ModelImpl final : ModelBase {
       const size_t gx = (size_t)((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads));
       const size_t n_vec = gx * (size_t)((ny + 3) / 4 + 1);
       const size_t n_sweep = (size_t)((nx / 2 + cfdk::kSweepWarps * 32 - 1) / (cfdk::kSweepWarps * 32)) * (size_t)((ny - 2 + sweep_rows_per_block - 1) / sweep_rows_per_block);
-      const size_t n_leg = (size_t)((nx - 2 + 63) / 64) * (size_t)((ny - 2 + 15) / 16);  // at least the leg kernels' grid
+      const size_t n_leg = (size_t)((nx - 2 + 55) / 56) * (size_t)((ny - 2 + 15) / 16 + 1);  // at least the leg kernels' grids
       size_t n_max = n_vec > n_sweep ? n_vec : n_sweep;
       if (n_leg > n_max) n_max = n_leg;
       if ((rc = dalloc(&mg_partials, n_max))) return rc;
@@ -1441,6 +1446,12 @@ struct ModelImpl final : ModelBase {
   template <int NU>
   int leg_attributes() {
     using T = LegTile<NU>;
+    CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mg0_down3<R, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::Leg3Smem<R>)));
+    CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mg0_up3<R, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::Leg3Smem<R>)));
+    CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mgc_down3<R, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::Leg3SmemC<R>)));
+    CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mgc_up3<R, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::Leg3SmemC<R>)));
+    CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mg0_down2<R, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::Leg0Smem<R, NU>)));
+    CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mg0_up2<R, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::Leg0Smem<R, NU>)));
     CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mg0_down<R, T::TX, T::TY, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::LegSmem<R, T::TX, T::TY, NU>)));
     CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mg0_up<R, T::TX, T::TY, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::LegSmem<R, T::TX, T::TY, NU>)));
     CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mgc_down<R, T::TX, T::TY, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::LegSmemC<R, T::TX, T::TY, NU>)));
@@ -1462,11 +1473,16 @@ struct ModelImpl final : ModelBase {
     const int lo = dist ? lvl_lo(l, rank) : 0, hi = dist ? lvl_hi(l, rank) : L.my;
     const bool big = (long)L.mx * L.my >= 500000L;
     const int tx = big ? T::TX : kLegSX, ty = big ? T::TY : kLegSY;
-    const int x_lo = dist ? (lo >= NU ? lo - NU : 0) : 0, x_hi = dist ? (hi + NU <= L.my ? hi + NU : L.my) : L.my;
+    // (the tiles pair rows 2 J, 2 J + 1 for the restriction: the first row of the launch must be even)
+    const int x_lo = dist ? (lo >= NU ? (lo - NU) & ~1 : 0) : 0, x_hi = dist ? (hi + NU <= L.my ? hi + NU : L.my) : L.my;
     const int c_lo = dist ? lvl_lo(l + 1, rank) : 0, c_hi = dist ? lvl_hi(l + 1, rank) : C.my;
     const dim3 g_dn((L.mx + tx - 1) / tx, (x_hi - x_lo + ty - 1) / ty), g_up((L.mx + tx - 1) / tx, (hi - lo + ty - 1) / ty);
     int rc;
-    if (big) cfdk::k_mgc_down<R, T::TX, T::TY, NU><<<g_dn, cfdk::kLegThreads, sizeof(cfdk::LegSmemC<R, T::TX, T::TY, NU>), stream>>>(L.dev, L.rho, L.e, C.mx, C.rho, omega, x_lo, x_hi, c_lo, c_hi, mg_scalars);
+    const bool tiled = leg_form() == 3;
+    using G3 = cfdk::Leg3<NU>;
+    const dim3 g_dn3((L.mx + G3::TX - 1) / G3::TX, (x_hi - x_lo + G3::TY - 1) / G3::TY), g_up3((L.mx + G3::TX - 1) / G3::TX, (hi - lo + G3::TY - 1) / G3::TY);
+    if (tiled) cfdk::k_mgc_down3<R, NU><<<g_dn3, cfdk::kLegThreads, sizeof(cfdk::Leg3SmemC<R>), stream>>>(L.dev, L.rho, L.e, C.mx, C.rho, omega, x_lo, x_hi, c_lo, c_hi, mg_scalars);
+    else if (big) cfdk::k_mgc_down<R, T::TX, T::TY, NU><<<g_dn, cfdk::kLegThreads, sizeof(cfdk::LegSmemC<R, T::TX, T::TY, NU>), stream>>>(L.dev, L.rho, L.e, C.mx, C.rho, omega, x_lo, x_hi, c_lo, c_hi, mg_scalars);
     else cfdk::k_mgc_down<R, kLegSX, kLegSY, NU><<<g_dn, cfdk::kLegThreads, sizeof(cfdk::LegSmemC<R, kLegSX, kLegSY, NU>), stream>>>(L.dev, L.rho, L.e, C.mx, C.rho, omega, x_lo, x_hi, c_lo, c_hi, mg_scalars);
     ++launches;
     if (dist) {
@@ -1474,11 +1490,13 @@ struct ModelImpl final : ModelBase {
       else if ((rc = gather_level(C.rho, l + 1))) return rc;
     }
     if ((rc = mg_coarse_vcycle(l + 1))) return rc;
-    if (big) cfdk::k_mgc_up<R, T::TX, T::TY, NU><<<g_up, cfdk::kLegThreads, sizeof(cfdk::LegSmemC<R, T::TX, T::TY, NU>), stream>>>(L.dev, L.e, L.rho, C.mx, C.cur, L.tmp, omega, lo, hi, mg_scalars);
+    if (tiled) cfdk::k_mgc_up3<R, NU><<<g_up3, cfdk::kLegThreads, sizeof(cfdk::Leg3SmemC<R>), stream>>>(L.dev, L.e, L.rho, C.mx, C.cur, L.tmp, omega, lo, hi, mg_scalars);
+    else if (big) cfdk::k_mgc_up<R, T::TX, T::TY, NU><<<g_up, cfdk::kLegThreads, sizeof(cfdk::LegSmemC<R, T::TX, T::TY, NU>), stream>>>(L.dev, L.e, L.rho, C.mx, C.cur, L.tmp, omega, lo, hi, mg_scalars);
     else cfdk::k_mgc_up<R, kLegSX, kLegSY, NU><<<g_up, cfdk::kLegThreads, sizeof(cfdk::LegSmemC<R, kLegSX, kLegSY, NU>), stream>>>(L.dev, L.e, L.rho, C.mx, C.cur, L.tmp, omega, lo, hi, mg_scalars);
     ++launches;
     L.cur = L.tmp;
-    if (dist && (rc = exchange_level(L.tmp, l))) return rc;  // the finer level's ascending leg reads one halo row of the correction
+    // the finer level's ascending leg reads the parents of its NU halo rows: (NU + 1) / 2 halo rows of this correction
+    if (dist && (rc = exchange_level(L.tmp, l, (NU + 1) / 2))) return rc;
     return CFD_OK;
   }
 
@@ -1493,8 +1511,18 @@ struct ModelImpl final : ModelBase {
     const dim3 g_leg((nx - 2 + T::TX - 1) / T::TX, (rows + T::TY - 1) / T::TY);
     const size_t leg_bytes = sizeof(cfdk::LegSmem<R, T::TX, T::TY, NU>);
     int rc;
+    // register-tiled kernels (k_mg0_down3 / _up3); CFD_MG_LEGS=2: column strips, 1: flat-indexed (A/B, cross-check)
+    const int form = leg_form();
+    using G = cfdk::Leg0<NU>;
+    using G3 = cfdk::Leg3<NU>;
+    const dim3 g_leg2((nx - 2 + G::TX - 1) / G::TX, (rows + G::TY - 1) / G::TY);
+    const dim3 g_leg3((nx - 2 + G3::TX - 1) / G3::TX, (rows + G3::TY - 1) / G3::TY);
+    const size_t leg2_bytes = sizeof(cfdk::Leg0Smem<R, NU>), leg3_bytes = sizeof(cfdk::Leg3Smem<R>);
+    const int n_partials = form == 1 ? (int)(g_leg.x * g_leg.y) : form == 2 ? (int)(g_leg2.x * g_leg2.y) : (int)(g_leg3.x * g_leg3.y);
     if ((rc = exchange_halo(mg_rho, ja, jb, NU))) return rc;
-    cfdk::k_mg0_down<R, T::TX, T::TY, NU><<<g_leg, cfdk::kLegThreads, leg_bytes, stream>>>(c, c2, mg_rho.v, mg_b[*zo].v, C.mx, C.rho, mg_scalars);
+    if (form == 1) cfdk::k_mg0_down<R, T::TX, T::TY, NU><<<g_leg, cfdk::kLegThreads, leg_bytes, stream>>>(c, c2, mg_rho.v, mg_b[*zo].v, C.mx, C.rho, mg_scalars);
+    else if (form == 2) cfdk::k_mg0_down2<R, NU><<<g_leg2, cfdk::kLegThreads, leg2_bytes, stream>>>(c, c2, mg_rho.v, mg_b[*zo].v, C.mx, C.rho, mg_scalars);
+    else cfdk::k_mg0_down3<R, NU><<<g_leg3, cfdk::kLegThreads, leg3_bytes, stream>>>(c, c2, mg_rho.v, mg_b[*zo].v, C.mx, C.rho, mg_scalars);
     ++launches;
     std::swap(*zc, *zo);
     if (world > 1) {
@@ -1513,9 +1541,11 @@ struct ModelImpl final : ModelBase {
       cudaEventRecord(ev_prof[ev_prof_used++], stream);
     };
     prof_mark();
-    cfdk::k_mg0_up<R, T::TX, T::TY, NU><<<g_leg, cfdk::kLegThreads, leg_bytes, stream>>>(c, c2, mg_b[*zc].v, mg_rho.v, C.mx, C.cur, mg_b[*zo].v, mg_partials, mg_scalars);
+    if (form == 1) cfdk::k_mg0_up<R, T::TX, T::TY, NU><<<g_leg, cfdk::kLegThreads, leg_bytes, stream>>>(c, c2, mg_b[*zc].v, mg_rho.v, C.mx, C.cur, mg_b[*zo].v, mg_partials, mg_scalars);
+    else if (form == 2) cfdk::k_mg0_up2<R, NU><<<g_leg2, cfdk::kLegThreads, leg2_bytes, stream>>>(c, c2, mg_b[*zc].v, mg_rho.v, C.mx, C.cur, mg_b[*zo].v, mg_partials, mg_scalars);
+    else cfdk::k_mg0_up3<R, NU><<<g_leg3, cfdk::kLegThreads, leg3_bytes, stream>>>(c, c2, mg_b[*zc].v, mg_rho.v, C.mx, C.cur, mg_b[*zo].v, mg_partials, mg_scalars);
     prof_mark();
-    cfdk::k_mg_reduce<R><<<1, 1024, 0, stream>>>(c, mg_scalars, mg_partials, (int)(g_leg.x * g_leg.y), 1);
+    cfdk::k_mg_reduce<R><<<1, 1024, 0, stream>>>(c, mg_scalars, mg_partials, n_partials, 1);
     launches += 2;
     std::swap(*zc, *zo);
     if ((rc = exchange_halo(mg_b[*zc], ja, jb, 1))) return rc;  // strips: the neighbours' edge rows of z (no-op on one GPU)

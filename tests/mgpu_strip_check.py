@@ -123,18 +123,21 @@ def main():
         (PressureSolver.MGCG, Scenario.Channel, Grid.uniform(1040, 600, 10.4, 6.0, Cylinder(2.6, 3.0, 0.45)), 8),
         (PressureSolver.MGCG, Scenario.Cavity, Grid.uniform(2056, 1100, 2056 / 1024.0, 1100 / 1024.0, None), 5),
     ]
+    nu_s = int(os.environ.get("CFD_STRIP_CHECK_NU", "3"))  # smoothing sweeps of the V-cycle (bench.py ships V(3,3))
     for solver, scenario, grid, n_steps in mode_c:
         params = SimulationParams(dt=1e-3, viscosity=0.01, scenario=scenario, pressure_solver=solver)
         uid = [nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         opts = default_options()
         opts.consts.cg_tolerance = 1e-13
+        opts.consts.mg_smoothing = nu_s
         opts.device, opts.rank, opts.world_size = local, rank, world
         buf = C.create_string_buffer(uid[0], 128)
         opts.nccl_unique_id = C.cast(buf, C.c_void_p)
         strip = Model(grid, params, options=opts)
         o1 = default_options()
         o1.consts.cg_tolerance = 1e-13
+        o1.consts.mg_smoothing = nu_s
         o1.device = local
         whole = Model(grid, params, options=o1)
         ja, jb = strip.rows()
@@ -163,8 +166,11 @@ def main():
         params = SimulationParams(dt=2e-5, viscosity=0.01, scenario=Scenario.Cavity, pressure_solver=PressureSolver.MGCG)
         uid = [nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
-        strip = Model.strip(grid, params, rank, world, uid[0], device=local)
-        oracle = OracleModel(grid, params, precision=64)
+        from oracle.cpu_oracle import default_consts
+        shipped = default_consts()
+        shipped.mg_smoothing = nu_s
+        strip = Model.strip(grid, params, rank, world, uid[0], device=local, consts=shipped)
+        oracle = OracleModel(grid, params, precision=64, consts=shipped)
         ja, jb = strip.rows()
         nx, ny = grid.nx, grid.ny
         top = 1 if rank == world - 1 else 0

@@ -103,14 +103,15 @@ def _leg_grid(scenario, shape):
     return Grid.uniform(nx, ny, nx / 64.0, ny / 64.0, None)
 
 
+@pytest.mark.parametrize("nu", [2, 3, 4])
 @pytest.mark.parametrize("precision", [64, 32])
 @pytest.mark.parametrize("scenario,shape", LEG_SHAPES)
-def test_mgcg_vcycle_legs_are_bit_identical_to_the_separate_kernels(scenario, shape, precision):
+def test_mgcg_vcycle_legs_are_bit_identical_to_the_separate_kernels(scenario, shape, precision, nu):
     """cfd_mg_legs.cuh (each level's descending / ascending leg of the V(2,2)-cycle as one launch) performs the same
     per-cell arithmetic as the one-operation-per-launch kernels (CFD_FLAG_MG_UNFUSED): with one CG iteration per solve
     the V-cycle's result z (CFD_FIELD_MG_Z) must be bit-identical, ring included, on widths / heights that are not
     multiples of the tile, odd level sizes, channel (zero outlet column) and cavity (mirror) boundary rules, fp64 and
-    fp32.  Tolerance: 0."""
+    fp32, V(2,2), V(3,3) and V(4,4).  Tolerance: 0."""
     from oracle.cpu_oracle import default_consts
     g = _leg_grid(scenario, shape)
     prm = SimulationParams(dt=1e-3, viscosity=0.01, scenario=scenario, pressure_solver=PressureSolver.MGCG)
@@ -122,6 +123,7 @@ def test_mgcg_vcycle_legs_are_bit_identical_to_the_separate_kernels(scenario, sh
         o.consts.cg_max_iterations = 1
         o.consts.outer_rounds = 0
         o.consts.mg_warm_start = 0
+        o.consts.mg_smoothing = nu
         o.precision = precision
         m = Model(g, prm, options=o)
         # the first V-cycle of the run's first non-trivial solve (the driving velocity ramps up from 0: the first steps have
