@@ -412,15 +412,27 @@ def build_model(w, rk, strips, flags=0):
     return model, grid, params, strong
 
 
-def step_bytes_mode_c(nx, ny, solves_full, solves_elided, iterations):
-    """Algorithmic bytes of one Mode C step (every operation reads its inputs and writes its outputs
-    once, s = 8 bytes): predictor 4 sN + 2 N, residual / CFL maxima 4 sN; a solve that runs = divergence 3 + set-up 4 +
-    corrector 7; a re-correction round that is converged before its first iteration = divergence 3 (its set-up pass and
-    its identity corrector are not executed and not counted); a CG iteration = 28.5 sN on level 0 (first sweep 2, sweep 3,
-    restriction 2.25, prolongation 2.25, two sweeps 6, rho.z 2, direction 3, L d 2, update 6) + 15.5 s N_l on the coarse
-    levels (sum N_l = N / 3)."""
+def step_bytes_mode_c(nx, ny, solves_full, solves_elided, iterations, nu=2, fused=False):
+    """Algorithmic bytes of one Mode C step (SURVEY 8d's rule: every stage reads each of its inputs
+    and writes each of its outputs once, s = 8 bytes): predictor 4 sN + 2 N, residual / CFL maxima 4 sN; a solve that runs
+    = divergence 3 + set-up 4 + corrector 7; a re-correction round that is converged before its first iteration =
+    divergence 3 (its set-up pass and its identity corrector are not executed and not counted).  A CG iteration with a
+    V(nu,nu) cycle, stage by stage (fused=False): level 0 = first sweep 2 + (nu - 1) sweeps 3 + restriction 2.25 +
+    prolongation 2.25 + nu sweeps 3 + rho.z 2 + direction 3 + L d 2 + update 6 = 19.5 + 3 (2 nu - 1) sN (28.5 at nu = 2);
+    a coarse level = 6.5 + 3 (2 nu - 1) s N_l (sum N_l = N / 3).  fused=True: the compulsory traffic of the kernels as they
+    run (each leg of the cycle is one pass: level 0 descending 2.25 + ascending 3.25 + direction / L d 5 + update 6 = 16.5,
+    a coarse level 5.5) -- the conservative figure beside the stage-by-stage one."""
     n = nx * ny
-    return 8 * n * (8 + 14 * solves_full + 3 * solves_elided + (28.5 + 15.5 / 3.0) * iterations) + 2 * n
+    if fused:
+        per_it = 16.5 + 5.5 / 3.0
+    else:
+        per_it = 19.5 + 3 * (2 * nu - 1) + (6.5 + 3 * (2 * nu - 1)) / 3.0
+    return 8 * n * (8 + 14 * solves_full + 3 * solves_elided + per_it * iterations) + 2 * n
+
+
+def legs_active(consts, flags):
+    """Whether the library runs the V-cycle with one launch per leg (cfd_mg_legs.cuh; same rule as mg_setup)."""
+    return 2 <= consts.mg_smoothing <= 4 and not (flags & 1024) and os.environ.get("CFD_MG_NO_LEGS") is None
 
 
 def timed_steps(model, rk, steps, mode_c):
@@ -547,7 +559,7 @@ def run_extra(args, name, rk, steps=3):
     rank_cells = nx * ny // rk.world if strips else nx * ny
     if mode_c:
         full = k - (k - 1 if acc["first_its"] == acc["sweeps"] else 0)  # re-correction rounds without an iteration are elided
-        bytes_step = step_bytes_mode_c(nx, ny, full, k - full, s_)
+        bytes_step = step_bytes_mode_c(nx, ny, full, k - full, s_, nu=make_consts(w).mg_smoothing)
         sweep_us = acc["smooth_ms"] * 1e3 / max(acc["smooth_n"], 1)
     else:
         bytes_step = 8 * nx * ny * (8 + 10 * k + 3 * s_) + 2 * nx * ny
@@ -557,6 +569,14 @@ def run_extra(args, name, rk, steps=3):
            "solves_per_step": k, ("cg_iterations_per_step" if mode_c else "sweeps_per_step"): s_,
            "step_frac_of_peak": bytes_step / (dev_s / steps) / 1e9 / (peak * rk.world),
            "sweep_us": sweep_us, "sweep_frac_of_peak": 3 * 8 * rank_cells / (sweep_us * 1e-6) / 1e9 / peak if sweep_us > 0 else None}
+    if mode_c and legs_active(make_consts(w), 0):
+        # the timed launch is the ascending leg of level 0 (nu sweeps + prolongation + rho.z in one pass), not a single sweep
+        nu = make_consts(w).mg_smoothing
+        out["sweep_us"] = None
+        out["sweep_frac_of_peak"] = None
+        out["ascending_leg_us"] = sweep_us
+        out["ascending_leg_frac_of_peak_stage_bytes"] = (3 * nu + 4.25) * 8 * rank_cells / (sweep_us * 1e-6) / 1e9 / peak if sweep_us > 0 else None
+        out["step_frac_of_peak_fused_traffic"] = step_bytes_mode_c(nx, ny, full, k - full, s_, nu=nu, fused=True) / (dev_s / steps) / 1e9 / (peak * rk.world)
     if mode_c:
         out["cg_iterations_list"] = acc["its"]
         out["ms_per_cg_iteration"] = dev_s * 1e3 / max(acc["sweeps"], 1)
@@ -688,7 +708,26 @@ def run_ours(args, w):
     rank_cells = nx * ny // world if strips else nx * ny
     algo_bytes = 3 * 8 * rank_cells  # per launch (one rank's strip): read p', rhs; write p'new
     sweeps, solves, launches = acc["sweeps"], acc["solves"], acc["launches"]
-    if mode_c:
+    consts = make_consts(w)
+    legs = mode_c and legs_active(consts, flags)
+    nu = int(consts.mg_smoothing)
+    traffic_file = "ncu_sweep_kernel.json"
+    roof_note = None
+    if legs:
+        # the dominant kernel: the ascending leg of the V-cycle on level 0 -- nu damped-Jacobi sweeps (the reference's update,
+        # src/model.rs:788-793), the prolongation and rho.z in ONE pass (cfd_mg_legs.cuh).  Algorithmic bytes by SURVEY 8d's
+        # rule, stage by stage: nu sweeps x 3 sN + prolongation 2.25 sN + rho.z 2 sN; the kernel itself moves 3.25 sN
+        # (temporal blocking: `frac` may exceed 1, `traffic` / `frac_of_peak_by_traffic` say what went through HBM)
+        sweep_us = acc["smooth_ms"] * 1e3 / max(acc["smooth_n"], 1)
+        roof_launches, roof_share = acc["smooth_n"], acc["smooth_ms"] / max(acc["dev_ms"], 1e-9)
+        algo_bytes = int((3 * nu + 4.25) * 8 * rank_cells)
+        kernel_name = (f"cfdk::k_mg0_up3<double, {nu}> (ascending leg of the V({nu},{nu})-cycle on level 0: the prolongation, {nu} sweeps "
+                       f"of the reference's damped-Jacobi update incl. its boundary rules and rho.z in one pass over HBM)")
+        traffic_file = "ncu_leg_kernel.json"
+        roof_note = (f"algorithmic bytes = the stages' compulsory traffic (SURVEY 8d): {nu} sweeps x 3 sN + prolongation 2.25 sN + rho.z "
+                     f"2 sN = {3 * nu + 4.25} sN; the fused kernel's own compulsory traffic is 3.25 sN (temporal blocking), it is bound "
+                     f"by fp64 issue, not by HBM: see profiles/r2_legs_ncu.md")
+    elif mode_c:
         sweep_us = acc["smooth_ms"] * 1e3 / max(acc["smooth_n"], 1)
         roof_launches, roof_share = acc["smooth_n"], acc["smooth_ms"] / max(acc["dev_ms"], 1e-9)
         kernel_name = ("cfdk::k_jacobi_sweep5<double> (the reference's damped-Jacobi sweep incl. boundary update, here the "
@@ -701,9 +740,9 @@ def run_ours(args, w):
     achieved = algo_bytes / (sweep_us * 1e-6) / 1e9 if sweep_us > 0 else 0.0
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "ncu_sweep_kernel.json")) as f:
+        with open(os.path.join(ROOT, "profiles", traffic_file)) as f:
             t = json.load(f)
-            if t.get("nx") == nx and t.get("ny") == rank_cells // nx:
+            if t.get("nx") == nx and t.get("ny") == rank_cells // nx and (not legs or t.get("nu") == nu):
                 traffic = t.get("dram_bytes_per_launch")
     except Exception:
         pass
@@ -712,11 +751,13 @@ def run_ours(args, w):
     if mode_c:
         # re-correction rounds that converge before their first iteration are elided (no set-up pass, no corrector)
         elided = (solves - steps) / steps if acc["first_its"] == sweeps else 0.0
-        step_bytes = step_bytes_mode_c(nx, ny, k_per_step - elided, elided, s_per_step) * replicas
-        step_bytes_r1 = (8 * nx * ny * (8 + 14 * k_per_step + (28.5 + 15.5 / 3.0) * s_per_step) + 2 * nx * ny) * replicas
+        step_bytes = step_bytes_mode_c(nx, ny, k_per_step - elided, elided, s_per_step, nu=nu) * replicas
+        step_bytes_r1 = step_bytes_mode_c(nx, ny, k_per_step, 0.0, s_per_step, nu=nu) * replicas
+        step_bytes_fused = step_bytes_mode_c(nx, ny, k_per_step - elided, elided, s_per_step, nu=nu, fused=legs) * replicas
     else:
         step_bytes = 8 * cells * (8 + 10 * k_per_step + 3 * s_per_step) + 2 * cells  # whole job
         step_bytes_r1 = step_bytes
+        step_bytes_fused = step_bytes
     peak_job = peak * world
 
     parity = None
@@ -749,8 +790,9 @@ def run_ours(args, w):
                       if flags & 512 else "NCCL halo rows + max-allreduce after every sweep (CFD_BENCH_FLAGS=512: fused peer-memory sweep)"))
         elif strips:
             multi = (f"{world} row strips of one {nx}x{ny} cavity, {'strong' if strong else 'weak'} scaling: multigrid levels 0-3 in "
-                     f"strips with a halo row exchanged after every sweep, level 4 gathered and the rest replicated, dot products "
-                     f"sum-allreduced")
+                     f"strips (one launch per leg of the V-cycle; per level the halo rows of rho before the descending leg and of the "
+                     f"correction after the ascending one are exchanged), level 4 gathered and the rest replicated, dot products "
+                     f"sum-allreduced; transport: {'NVLink peer memory (CFD_PEER_STRIPS=1)' if os.environ.get('CFD_PEER_STRIPS') == '1' else 'NCCL'}")
         else:
             multi = f"{world} independent replicas of the workload, one per GPU (CFD_BENCH_REPLICAS=1)"
         last = acc["last"]
@@ -768,6 +810,11 @@ def run_ours(args, w):
             "step_algorithmic_gbs": step_bytes / (dev_s / steps) / 1e9,
             "step_frac_of_peak": step_bytes / (dev_s / steps) / 1e9 / peak_job,
             "step_frac_of_peak_counting_elided_passes": step_bytes_r1 / (dev_s / steps) / 1e9 / peak_job,
+            "step_frac_of_peak_fused_traffic": step_bytes_fused / (dev_s / steps) / 1e9 / peak_job,
+            "step_bytes_accounting": ("step_frac_of_peak: SURVEY 8d's rule, every executed stage reads its inputs and writes its outputs "
+                                      "once (a V(nu,nu) iteration = 19.5 + 3 (2 nu - 1) sN on level 0, 6.5 + 3 (2 nu - 1) s N_l on a "
+                                      "coarse level); _fused_traffic: the compulsory traffic of the kernels as they run (each leg of the "
+                                      "cycle is one pass over HBM: 16.5 sN + 5.5 s N_l per iteration) -- the conservative figure"),
             "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": 28 * world, "d2h_bytes_per_step": d2h,
                     "ms_per_step": wall_e2e_s * 1e3 / steps,
                     "ms_per_step_blocking_get_snapshot": wall_e2e_sync * 1e3,
@@ -783,7 +830,9 @@ def run_ours(args, w):
                          "peak_source": peak_src, "traffic": traffic,
                          "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_us": sweep_us,
                          "launches_timed": roof_launches,
-                         "share_of_step": roof_share},
+                         "share_of_step": roof_share,
+                         "frac_of_peak_by_traffic": (traffic / (sweep_us * 1e-6) / 1e9 / peak) if (traffic and sweep_us > 0) else None,
+                         "note": roof_note},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

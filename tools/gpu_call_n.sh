@@ -1,0 +1,19 @@
+#!/bin/bash
+# Round-2 GPU call N (1 GPU): register-tiled legs — parity tests, bench (form 3 vs 2), launch list.
+out=gpurun_out/r2n; mkdir -p $out
+timeout 900 python -m pytest tests -m gpu -q --maxfail=12 --durations=5 -k "mgcg or mode_c or legs or relative" > $out/pytest.txt 2>&1; echo "pytest rc=$?" >> $out/pytest.txt
+tail -12 $out/pytest.txt
+export CFD_BENCH_NO_EXTRAS=1
+for form in 3 2; do
+CFD_MG_LEGS=$form timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $out/bench_form$form.json 2> $out/bench_form$form.err; echo "bench form=$form rc=$?"
+python - "$out/bench_form$form.json" <<'PY'
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+print(sys.argv[1], {k:d.get(k) for k in ('ms_per_step','cg_iterations_per_step','ms_per_cg_iteration','step_frac_of_peak')}, 'e2e', d['e2e']['ms_per_step'], 'roof', d['roofline']['avg_launch_us'], d['stop']['rel_residual'])
+PY
+done
+timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/bench_short.json 2>&1 &&
+CFD_BENCH_PROFILE=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 2000 --csv \
+  --log-file $out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/ncu.log 2>&1
+echo "ncu rc=$?"
+python tools/launch_list.py $out/launches.csv "r2 call N, V(3,3), register-tiled legs" > $out/launch_list.txt 2>&1; head -32 $out/launch_list.txt
