@@ -687,11 +687,13 @@ __global__ void __launch_bounds__(kLegThreads, 3) k_mg0_down3(const MgFine<R> c,
   // rho of the thread's cells, x_1 = the first smoothing sweep applied to z = 0 (k_mg_first_sweep's expression)
   {
     const bool col_ok = t.tx >= b.xa && t.tx <= b.xb;
-    const R* __restrict__ src = rho + (long)(oi + t.tx);
+    const R* __restrict__ src = rho + min(max(oi + t.tx, 0), nx - 1);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) q[r] = src[(long)(oj + min(max(t.y0 + r, b.ya), b.yb)) * nx];  // clamped, branch-free
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
       const int y = t.y0 + r;
-      q[r] = (col_ok && y >= b.ya && y <= b.yb) ? src[(long)(oj + y) * nx] : R(1);
+      if (!(col_ok && y >= b.ya && y <= b.yb)) q[r] = R(1);
     }
     auto first = [&](auto& dv) {
 #pragma unroll
@@ -797,24 +799,30 @@ __global__ void __launch_bounds__(kLegThreads, 3) k_mg0_up3(const MgFine<R> c, c
   const int j_end = min(b.j0 + G::TY, c.row_hi);
   R q[9], cur[9];
   {
+    // every load of the strip first, from clamped (always valid) addresses and without branches: a load whose consumer sits
+    // in the same conditional block costs one DRAM round trip per row (profiles/r2_legs_ncu.md)
     const bool col_ok = t.tx >= b.xa && t.tx <= b.xb;
-    const int i = oi + t.tx;
+    const int i = min(max(oi + t.tx, 0), nx - 1);
     const int qi = min(max(i, 1), nx - 2);
     const R* __restrict__ pc = ce + (long)((qi - 1) / 2 + 1);
+    const R* __restrict__ pz = zin + i;
+    const R* __restrict__ pr = rho + i;
+    R zv[9], cv[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int j = oj + min(max(t.y0 + r, b.ya), b.yb);
+      const int qj = min(max(j, 1), c.ny - 2);
+      zv[r] = pz[(long)j * nx];
+      cv[r] = pc[(long)((qj - 1) / 2 + 1) * (cmx + 2)];
+      q[r] = pr[(long)j * nx];
+    }
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
       const int y = t.y0 + r;
-      R v = R(1), w = R(1);
-      if (col_ok && y >= b.ya && y <= b.yb) {
-        const int j = oj + y;
-        const int qj = min(max(j, 1), c.ny - 2);
-        const long idx = (long)i + (long)j * nx;
-        v = zin[idx] + pc[(long)((qj - 1) / 2 + 1) * (cmx + 2)];
-        w = rho[idx];
-      }
-      cur[r] = v;
-      q[r] = w;
-      s.a[y][t.tx] = v;
+      const bool ok = col_ok && y >= b.ya && y <= b.yb;
+      cur[r] = ok ? zv[r] + cv[r] : R(1);
+      if (!ok) q[r] = R(1);
+      s.a[y][t.tx] = cur[r];
     }
   }
   __syncthreads();
@@ -862,13 +870,10 @@ struct Leg3SmemC {
   R wn[36], ws[36], cxh[36];
   R dy[kMgClasses * kMgClasses + 1], dr[kMgClasses * kMgClasses + 1];  // + the null class
   int rcls8[36];  // row class * kMgClasses; rows outside the level: >= the null class
+  R c0[3];        // column 0's weights and class: what leg3_tile_uniform compares every column with
+  int c0_cls;
 };
 constexpr int kLegNullClass = kMgClasses * kMgClasses;
-
-struct Leg3Col {  // a thread's column of a coarse level
-  int cls;        // column class; outside the level: the null class
-  bool in;
-};
 
 template <class R, int NU>
 __device__ __forceinline__ void leg3_load_level(Leg3SmemC<R>& s, const MgLevelDev<R>& L, int J0, int tid) {
@@ -886,11 +891,38 @@ __device__ __forceinline__ void leg3_load_level(Leg3SmemC<R>& s, const MgLevelDe
   }
 }
 
-// one sweep of the thread's 9 cells of a coarse level, in place in `cur` (mgc_cell = mgc_sweep_cell's arithmetic)
+// Row data of a coarse level as the sweeps see it: the general form looks every row up in shared memory (weights, class ->
+// diagonal table); on a tile whose 36 rows and 64 columns all carry the same weights (every tile away from the level's
+// boundary and from a trailing unpaired cell) the row weights and the one diagonal are block constants in registers — the
+// same numbers through the same expressions, 2 instead of 8 shared loads per cell and sweep.
 template <class R>
-__device__ __forceinline__ void leg3_sweep_c(const Leg3SmemC<R>& s, const DivG<R>& win, const Leg3Thread& t, const Leg3Col& col,
-                                             R we, R ww, R cyw, R omega, const R (*src)[64], R (*dst)[64], R (&cur)[9],
-                                             const R (&q)[9]) {
+struct Leg3RowsSmem {
+  const Leg3SmemC<R>& s;
+  int col_cls;
+  __device__ __forceinline__ R wn(int y) const { return s.wn[y]; }
+  __device__ __forceinline__ R ws(int y) const { return s.ws[y]; }
+  __device__ __forceinline__ R cxh(int y) const { return s.cxh[y]; }
+  __device__ __forceinline__ DivG<R> dg(int y) const {
+    DivG<R> d;
+    const int cls = min(s.rcls8[y] + col_cls, kLegNullClass);
+    d.y = s.dy[cls]; d.r = s.dr[cls]; d.lo = 0u; d.span = 0u;
+    return d;
+  }
+};
+template <class R>
+struct Leg3RowsUniform {
+  R wn_, ws_, cxh_;
+  DivG<R> dg_;
+  __device__ __forceinline__ R wn(int) const { return wn_; }
+  __device__ __forceinline__ R ws(int) const { return ws_; }
+  __device__ __forceinline__ R cxh(int) const { return cxh_; }
+  __device__ __forceinline__ DivG<R> dg(int) const { return dg_; }
+};
+
+// one sweep of the thread's 9 cells of a coarse level, in place in `cur` (mgc_cell = mgc_sweep_cell's arithmetic)
+template <class R, class Rows>
+__device__ __forceinline__ void leg3_sweep_c(const Rows& rw, const DivG<R>& win, const Leg3Thread& t, R we, R ww, R cyw, R omega,
+                                             const R (*src)[64], R (*dst)[64], R (&cur)[9], const R (&q)[9]) {
   auto pass = [&](auto& dv) {
     R s_ = src[t.y_below][t.tx];
     const R above = src[t.y_above][t.tx];
@@ -898,10 +930,7 @@ __device__ __forceinline__ void leg3_sweep_c(const Leg3SmemC<R>& s, const DivG<R
     for (int r = 0; r < 9; ++r) {
       const int y = t.y0 + r;
       const R c_ = cur[r], n_ = r < 8 ? cur[r + 1] : above;
-      DivG<R> dg;
-      const int cls = min(s.rcls8[y] + col.cls, kLegNullClass);
-      dg.y = s.dy[cls]; dg.r = s.dr[cls]; dg.lo = 0u; dg.span = 0u;
-      cur[r] = mgc_cell<R>(we, ww, cyw, s.wn[y], s.ws[y], s.cxh[y], c_, src[y][t.txr], src[y][t.txl], n_, s_, q[r], dg, omega, dv);
+      cur[r] = mgc_cell<R>(we, ww, cyw, rw.wn(y), rw.ws(y), rw.cxh(y), c_, src[y][t.txr], src[y][t.txl], n_, s_, q[r], rw.dg(y), omega, dv);
       s_ = c_;
     }
   };
@@ -917,46 +946,61 @@ __device__ __forceinline__ void leg3_sweep_c(const Leg3SmemC<R>& s, const DivG<R
   for (int r = 0; r < 9; ++r) dst[t.y0 + r][t.tx] = cur[r];
 }
 
-// descending leg of level l >= 1, register-tiled (arguments as k_mgc_down)
+// what a thread of the coarse legs knows about its column, and whether the whole tile is uniform
+template <class R>
+struct Leg3ColW {
+  R we, ww, cyw;
+  int cls;  // column class; outside the level: the null class
+  bool in;
+};
 template <class R, int NU>
-__global__ void __launch_bounds__(kLegThreads, 2) k_mgc_down3(const MgLevelDev<R> L, const R* __restrict__ rho,
-                                                               R* __restrict__ xout, int cmx, R* __restrict__ crho, R omega,
-                                                               int row_lo, int row_hi, int c_lo, int c_hi,
-                                                               const MgScalars* __restrict__ sc) {
+__device__ __forceinline__ Leg3ColW<R> leg3_column(const MgLevelDev<R>& L, int I) {
+  Leg3ColW<R> c;
+  c.in = I >= 0 && I < L.mx;
+  c.cls = c.in ? (int)L.col_class[I] : kLegNullClass;
+  c.we = c.in ? L.WE[I] : R(0);
+  c.ww = c.in ? L.WW[I] : R(0);
+  c.cyw = c.in ? L.CYW[I] : R(0);
+  return c;
+}
+// call after leg3_load_level + __syncthreads (contains a barrier): do all 64 columns and all 36 rows carry the same numbers?
+template <class R>
+__device__ __forceinline__ bool leg3_tile_uniform(Leg3SmemC<R>& s, const Leg3ColW<R>& col, int tid) {
+  if (tid == 0) { s.c0[0] = col.we; s.c0[1] = col.ww; s.c0[2] = col.cyw; s.c0_cls = col.cls; }
+  __syncthreads();
+  bool same = col.we == s.c0[0] && col.ww == s.c0[1] && col.cyw == s.c0[2] && col.cls == s.c0_cls && col.cls < kLegNullClass;
+  if (tid < 36) same = same && s.wn[tid] == s.wn[0] && s.ws[tid] == s.ws[0] && s.cxh[tid] == s.cxh[0] && s.rcls8[tid] == s.rcls8[0] &&
+                       s.rcls8[tid] < kLegNullClass;
+  return __syncthreads_and(same) != 0;
+}
+
+template <class R, int NU, class Rows>
+__device__ __forceinline__ void leg3_down_body(Leg3SmemC<R>& s, const Rows& rw, const MgLevelDev<R>& L, const Leg3ColW<R>& col,
+                                               const Leg3Thread& t, const R* __restrict__ rho, R* __restrict__ xout, int cmx,
+                                               R* __restrict__ crho, R omega, int I0, int J0, int J_end, int c_lo, int c_hi, int tid) {
   using G = Leg3<NU>;
-  extern __shared__ __align__(16) unsigned char leg_smem_raw[];
-  Leg3SmemC<R>& s = *reinterpret_cast<Leg3SmemC<R>*>(leg_smem_raw);
-  if (sc->done) return;
-  const int tid = threadIdx.x, mx = L.mx, my = L.my;
-  const Leg3Thread t(tid);
-  const int I0 = (int)blockIdx.x * G::TX, J0 = row_lo + (int)blockIdx.y * G::TY;
-  const int J_end = min(J0 + G::TY, row_hi);
+  const int mx = L.mx, my = L.my;
   const long W = (long)mx + 2;
   const int I = I0 - NU + t.tx;
-  Leg3Col col;
-  col.in = I >= 0 && I < mx;
-  col.cls = col.in ? (int)L.col_class[I] : kLegNullClass;
-  const R we = col.in ? L.WE[I] : R(0), ww = col.in ? L.WW[I] : R(0), cyw = col.in ? L.CYW[I] : R(0);
-  leg3_load_level<R, NU>(s, L, J0, tid);
+  const R we = col.we, ww = col.ww, cyw = col.cyw;
   R q[9], cur[9];
   {
-    const R* __restrict__ src = rho + (long)(I + 1);
+    const R* __restrict__ src = rho + (long)(min(max(I, 0), mx - 1) + 1);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) q[r] = src[(long)(min(max(J0 - NU + t.y0 + r, 0), my - 1) + 1) * W];  // clamped, branch-free
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
       const int J = J0 - NU + t.y0 + r;
-      q[r] = (col.in && J >= 0 && J < my) ? src[(long)(J + 1) * W] : R(1);
+      if (!(col.in && J >= 0 && J < my)) q[r] = R(1);
     }
   }
-  __syncthreads();
   const DivG<R> win = L.diag_table[kMgClasses * kMgClasses];  // intersection of the table's dividend windows
   // x_1 = sweep of the zero field: cc + omega * ((L 0 - rho) / diag) with cc = 0, L 0 = +0
   {
     auto first = [&](auto& dv) {
 #pragma unroll
       for (int r = 0; r < 9; ++r) {
-        DivG<R> dg;
-        const int cls = min(s.rcls8[t.y0 + r] + col.cls, kLegNullClass);
-        dg.y = s.dy[cls]; dg.r = s.dr[cls]; dg.lo = 0u; dg.span = 0u;
+        const DivG<R> dg = rw.dg(t.y0 + r);
         const R res = dv(R(0) - q[r], dg);
         cur[r] = dg.y > R(0) ? R(0) + omega * res : R(0);
       }
@@ -975,7 +1019,7 @@ __global__ void __launch_bounds__(kLegThreads, 2) k_mgc_down3(const MgLevelDev<R
     constexpr int K = decltype(kc)::value;
     auto& src = (K % 2 == 0) ? s.f.a : s.f.b;
     auto& dst = (K % 2 == 0) ? s.f.b : s.f.a;
-    leg3_sweep_c<R>(s, win, t, col, we, ww, cyw, omega, src, dst, cur, q);
+    leg3_sweep_c<R>(rw, win, t, we, ww, cyw, omega, src, dst, cur, q);
     __syncthreads();
   });
   auto& xn = (NU % 2 == 0) ? s.f.b : s.f.a;
@@ -997,7 +1041,7 @@ __global__ void __launch_bounds__(kLegThreads, 2) k_mgc_down3(const MgLevelDev<R
     for (int r = 0; r < 9; ++r) {
       const int y = t.y0 + r;
       const R cc = cur[r], n_ = r < 8 ? cur[r + 1] : above;
-      const R le = s.cxh[y] * (we * (xn[y][t.txr] - cc) + ww * (xn[y][t.txl] - cc)) + cyw * (s.wn[y] * (n_ - cc) + s.ws[y] * (s_ - cc));
+      const R le = rw.cxh(y) * (we * (xn[y][t.txr] - cc) + ww * (xn[y][t.txl] - cc)) + cyw * (rw.wn(y) * (n_ - cc) + rw.ws(y) * (s_ - cc));
       res[y][t.tx] = q[r] - le;
       s_ = cc;
     }
@@ -1021,6 +1065,86 @@ __global__ void __launch_bounds__(kLegThreads, 2) k_mgc_down3(const MgLevelDev<R
   }
 }
 
+// descending leg of level l >= 1, register-tiled (arguments as k_mgc_down)
+template <class R, int NU>
+__global__ void __launch_bounds__(kLegThreads, 2) k_mgc_down3(const MgLevelDev<R> L, const R* __restrict__ rho,
+                                                               R* __restrict__ xout, int cmx, R* __restrict__ crho, R omega,
+                                                               int row_lo, int row_hi, int c_lo, int c_hi,
+                                                               const MgScalars* __restrict__ sc) {
+  using G = Leg3<NU>;
+  extern __shared__ __align__(16) unsigned char leg_smem_raw[];
+  Leg3SmemC<R>& s = *reinterpret_cast<Leg3SmemC<R>*>(leg_smem_raw);
+  if (sc->done) return;
+  const int tid = threadIdx.x;
+  const Leg3Thread t(tid);
+  const int I0 = (int)blockIdx.x * G::TX, J0 = row_lo + (int)blockIdx.y * G::TY;
+  const int J_end = min(J0 + G::TY, row_hi);
+  const Leg3ColW<R> col = leg3_column<R, NU>(L, I0 - NU + t.tx);
+  leg3_load_level<R, NU>(s, L, J0, tid);
+  __syncthreads();
+  if (leg3_tile_uniform<R>(s, col, tid)) {
+    Leg3RowsUniform<R> rw;
+    rw.wn_ = s.wn[0]; rw.ws_ = s.ws[0]; rw.cxh_ = s.cxh[0];
+    const int cls = s.rcls8[0] + col.cls;
+    rw.dg_.y = s.dy[cls]; rw.dg_.r = s.dr[cls]; rw.dg_.lo = 0u; rw.dg_.span = 0u;
+    leg3_down_body<R, NU>(s, rw, L, col, t, rho, xout, cmx, crho, omega, I0, J0, J_end, c_lo, c_hi, tid);
+  } else {
+    const Leg3RowsSmem<R> rw{s, col.cls};
+    leg3_down_body<R, NU>(s, rw, L, col, t, rho, xout, cmx, crho, omega, I0, J0, J_end, c_lo, c_hi, tid);
+  }
+}
+
+template <class R, int NU, class Rows>
+__device__ __forceinline__ void leg3_up_body(Leg3SmemC<R>& s, const Rows& rw, const MgLevelDev<R>& L, const Leg3ColW<R>& col,
+                                             const Leg3Thread& t, const R* __restrict__ xin, const R* __restrict__ rho, int cmx,
+                                             const R* __restrict__ ce, R* __restrict__ xout, R omega, int I0, int J0, int J_end) {
+  using G = Leg3<NU>;
+  const int mx = L.mx, my = L.my;
+  const long W = (long)mx + 2;
+  const int I = I0 - NU + t.tx;
+  R q[9], cur[9];
+  {
+    // every load first, from clamped addresses and without branches (see k_mg0_up3)
+    const int Ic = min(max(I, 0), mx - 1);
+    const R* __restrict__ pc = ce + (long)(Ic / 2 + 1);
+    const R* __restrict__ px = xin + (long)(Ic + 1);
+    const R* __restrict__ pr = rho + (long)(Ic + 1);
+    R xv[9], cv[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int Jc = min(max(J0 - NU + t.y0 + r, 0), my - 1);
+      xv[r] = px[(long)(Jc + 1) * W];
+      cv[r] = pc[(long)(Jc / 2 + 1) * ((long)cmx + 2)];
+      q[r] = pr[(long)(Jc + 1) * W];
+    }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int y = t.y0 + r, J = J0 - NU + y;
+      const bool ok = col.in && J >= 0 && J < my;
+      cur[r] = ok ? xv[r] + cv[r] : R(0);
+      if (!ok) q[r] = R(1);
+      s.f.a[y][t.tx] = cur[r];
+    }
+  }
+  __syncthreads();
+  const DivG<R> win = L.diag_table[kMgClasses * kMgClasses];
+  leg_static_for<1, NU + 1>([&](auto kc) {
+    constexpr int K = decltype(kc)::value;
+    auto& src = (K % 2 == 1) ? s.f.a : s.f.b;
+    auto& dst = (K % 2 == 1) ? s.f.b : s.f.a;
+    leg3_sweep_c<R>(rw, win, t, col.we, col.ww, col.cyw, omega, src, dst, cur, q);
+    if (K != NU) __syncthreads();
+  });
+  if (t.tx >= NU && t.tx < 64 - NU && col.in) {
+    R* __restrict__ out = xout + (long)(I + 1);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int y = t.y0 + r, J = J0 - NU + y;
+      if (y >= NU && y < NU + G::TY && J < J_end && J < my) out[(long)(J + 1) * W] = cur[r];
+    }
+  }
+}
+
 // ascending leg of level l >= 1, register-tiled (arguments as k_mgc_up)
 template <class R, int NU>
 __global__ void __launch_bounds__(kLegThreads, 2) k_mgc_up3(const MgLevelDev<R> L, const R* __restrict__ xin,
@@ -1031,50 +1155,22 @@ __global__ void __launch_bounds__(kLegThreads, 2) k_mgc_up3(const MgLevelDev<R> 
   extern __shared__ __align__(16) unsigned char leg_smem_raw[];
   Leg3SmemC<R>& s = *reinterpret_cast<Leg3SmemC<R>*>(leg_smem_raw);
   if (sc->done) return;
-  const int tid = threadIdx.x, mx = L.mx, my = L.my;
+  const int tid = threadIdx.x;
   const Leg3Thread t(tid);
   const int I0 = (int)blockIdx.x * G::TX, J0 = row_lo + (int)blockIdx.y * G::TY;
   const int J_end = min(J0 + G::TY, row_hi);
-  const long W = (long)mx + 2;
-  const int I = I0 - NU + t.tx;
-  Leg3Col col;
-  col.in = I >= 0 && I < mx;
-  col.cls = col.in ? (int)L.col_class[I] : kLegNullClass;
-  const R we = col.in ? L.WE[I] : R(0), ww = col.in ? L.WW[I] : R(0), cyw = col.in ? L.CYW[I] : R(0);
+  const Leg3ColW<R> col = leg3_column<R, NU>(L, I0 - NU + t.tx);
   leg3_load_level<R, NU>(s, L, J0, tid);
-  R q[9], cur[9];
-  {
-    const R* __restrict__ pc = ce + (long)(I / 2 + 1);
-#pragma unroll
-    for (int r = 0; r < 9; ++r) {
-      const int y = t.y0 + r, J = J0 - NU + y;
-      R v = R(0), w = R(1);
-      if (col.in && J >= 0 && J < my) {
-        const long idx = (long)(I + 1) + (long)(J + 1) * W;
-        v = xin[idx] + pc[(long)(J / 2 + 1) * ((long)cmx + 2)];
-        w = rho[idx];
-      }
-      cur[r] = v;
-      q[r] = w;
-      s.f.a[y][t.tx] = v;
-    }
-  }
   __syncthreads();
-  const DivG<R> win = L.diag_table[kMgClasses * kMgClasses];
-  leg_static_for<1, NU + 1>([&](auto kc) {
-    constexpr int K = decltype(kc)::value;
-    auto& src = (K % 2 == 1) ? s.f.a : s.f.b;
-    auto& dst = (K % 2 == 1) ? s.f.b : s.f.a;
-    leg3_sweep_c<R>(s, win, t, col, we, ww, cyw, omega, src, dst, cur, q);
-    if (K != NU) __syncthreads();
-  });
-  if (t.tx >= NU && t.tx < 64 - NU && col.in) {
-    R* __restrict__ out = xout + (long)(I + 1);
-#pragma unroll
-    for (int r = 0; r < 9; ++r) {
-      const int y = t.y0 + r, J = J0 - NU + y;
-      if (y >= NU && y < NU + G::TY && J < J_end && J < my) out[(long)(J + 1) * W] = cur[r];
-    }
+  if (leg3_tile_uniform<R>(s, col, tid)) {
+    Leg3RowsUniform<R> rw;
+    rw.wn_ = s.wn[0]; rw.ws_ = s.ws[0]; rw.cxh_ = s.cxh[0];
+    const int cls = s.rcls8[0] + col.cls;
+    rw.dg_.y = s.dy[cls]; rw.dg_.r = s.dr[cls]; rw.dg_.lo = 0u; rw.dg_.span = 0u;
+    leg3_up_body<R, NU>(s, rw, L, col, t, xin, rho, cmx, ce, xout, omega, I0, J0, J_end);
+  } else {
+    const Leg3RowsSmem<R> rw{s, col.cls};
+    leg3_up_body<R, NU>(s, rw, L, col, t, xin, rho, cmx, ce, xout, omega, I0, J0, J_end);
   }
 }
 

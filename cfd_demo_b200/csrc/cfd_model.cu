@@ -1450,6 +1450,12 @@ struct ModelImpl final : ModelBase {
     CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mg0_up3<R, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::Leg3Smem<R>)));
     CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mgc_down3<R, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::Leg3SmemC<R>)));
     CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mgc_up3<R, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::Leg3SmemC<R>)));
+    // (the default carve-out left room for 3 blocks of 37 KB per SM: ask for the largest shared-memory partition, the legs
+    // do not use L1 for anything that matters)
+    CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mg0_down3<R, NU>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mg0_up3<R, NU>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mgc_down3<R, NU>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mgc_up3<R, NU>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mg0_down2<R, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::Leg0Smem<R, NU>)));
     CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mg0_up2<R, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::Leg0Smem<R, NU>)));
     CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mg0_down<R, T::TX, T::TY, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(cfdk::LegSmem<R, T::TX, T::TY, NU>)));
