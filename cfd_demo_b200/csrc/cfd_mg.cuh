@@ -704,31 +704,55 @@ struct MgBottom {
   MgBottomLevel<R> lv[kMgBottomMax];
 };
 
-template <class R>
+// kSmem: every field of every bottom level lives in dynamic shared memory (3 x (mx + 2) x (my + 2) values per level,
+// ~145 KB for a 64 x 64 first level): a phase then costs a barrier and shared-memory latency instead of an L2 round trip
+// (~1.2 us per phase, 7 levels x (2 nu + 2) phases).  Same per-cell functions on other pointers: bit-identical.
+template <class R, bool kSmem>
 __global__ void __launch_bounds__(kMgBottomThreads) k_mg_bottom(const MgBottom<R> B, const MgScalars* __restrict__ sc) {
+  extern __shared__ __align__(16) unsigned char mg_bottom_raw[];
   if (sc->done) return;
   R* cur[kMgBottomMax];
   R* oth[kMgBottomMax];
+  R *fe[kMgBottomMax], *frho[kMgBottomMax], *ftmp[kMgBottomMax];  // the fields the phases work on
   const int tid = threadIdx.x;
+  if (kSmem) {
+    R* p = reinterpret_cast<R*>(mg_bottom_raw);
+    size_t total = 0;
+    for (int l = 0; l < B.n; ++l) {
+      const size_t n = (size_t)(B.lv[l].dev.mx + 2) * (size_t)(B.lv[l].dev.my + 2);
+      fe[l] = p + total; frho[l] = p + total + n; ftmp[l] = p + total + 2 * n;
+      total += 3 * n;
+    }
+    for (size_t k = tid; k < total; k += kMgBottomThreads) p[k] = R(0);  // the rings of zeros (and everything else)
+    __syncthreads();
+    const int mx = B.lv[0].dev.mx, my = B.lv[0].dev.my;
+    for (int k = tid; k < mx * my; k += kMgBottomThreads) {
+      const size_t idx = (size_t)(k % mx + 1) + (size_t)(k / mx + 1) * ((size_t)mx + 2);
+      frho[0][idx] = B.lv[0].rho[idx];
+    }
+    __syncthreads();
+  } else {
+    for (int l = 0; l < B.n; ++l) { fe[l] = B.lv[l].e; frho[l] = B.lv[l].rho; ftmp[l] = B.lv[l].tmp; }
+  }
   for (int l = 0; l < B.n; ++l) {
     const MgBottomLevel<R>& L = B.lv[l];
     const int mx = L.dev.mx, my = L.dev.my, cells = mx * my;
-    R *a = L.e, *b = L.tmp;
+    R *a = fe[l], *b = ftmp[l];
     if (mx == 1 && my == 1) {  // exact
-      if (tid == 0) mgc_sweep_cell<R>(L.dev, a, L.rho, b, R(1), true, 0, 0);
+      if (tid == 0) mgc_sweep_cell<R>(L.dev, a, frho[l], b, R(1), true, 0, 0);
       cur[l] = b; oth[l] = a;
       __syncthreads();
       break;
     }
     for (int s = 0; s < B.nu; ++s) {
-      for (int k = tid; k < cells; k += kMgBottomThreads) mgc_sweep_cell<R>(L.dev, a, L.rho, b, B.omega, s == 0, k % mx, k / mx);
+      for (int k = tid; k < cells; k += kMgBottomThreads) mgc_sweep_cell<R>(L.dev, a, frho[l], b, B.omega, s == 0, k % mx, k / mx);
       __syncthreads();
       R* t = a; a = b; b = t;
     }
     cur[l] = a; oth[l] = b;
     const MgBottomLevel<R>& C = B.lv[l + 1];
     const int cmx = C.dev.mx, ccells = cmx * C.dev.my;
-    for (int k = tid; k < ccells; k += kMgBottomThreads) mgc_restrict_cell<R>(L.dev, a, L.rho, cmx, C.rho, k % cmx, k / cmx);
+    for (int k = tid; k < ccells; k += kMgBottomThreads) mgc_restrict_cell<R>(L.dev, a, frho[l], cmx, frho[l + 1], k % cmx, k / cmx);
     __syncthreads();
   }
   for (int l = B.n - 2; l >= 0; --l) {
@@ -743,13 +767,20 @@ __global__ void __launch_bounds__(kMgBottomThreads) k_mg_bottom(const MgBottom<R
     }
     __syncthreads();
     for (int s = 0; s < B.nu; ++s) {
-      for (int k = tid; k < cells; k += kMgBottomThreads) mgc_sweep_cell<R>(L.dev, a, L.rho, b, B.omega, false, k % mx, k / mx);
+      for (int k = tid; k < cells; k += kMgBottomThreads) mgc_sweep_cell<R>(L.dev, a, frho[l], b, B.omega, false, k % mx, k / mx);
       __syncthreads();
       R* t = a; a = b; b = t;
     }
     cur[l] = a; oth[l] = b;
   }
   // after nu + nu swaps the correction of a (non-trivial) level is back in its `e` buffer, where the caller expects it
+  if (kSmem) {
+    const int mx = B.lv[0].dev.mx, my = B.lv[0].dev.my;
+    for (int k = tid; k < mx * my; k += kMgBottomThreads) {
+      const size_t idx = (size_t)(k % mx + 1) + (size_t)(k / mx + 1) * ((size_t)mx + 2);
+      B.lv[0].e[idx] = cur[0][idx];
+    }
+  }
 }
 
 }  // namespace cfdk

@@ -102,6 +102,24 @@ NcclApi& nccl_api() {
                                     ":" + std::to_string(__LINE__) + ")");                          \
   } while (0)
 
+// A grouped NCCL section that is always closed: CFD_NCCL returns on the first failing call, and a group left open would
+// swallow every later NCCL call of the thread (including ncclCommDestroy) instead of reporting the one error.
+struct NcclGroupGuard {
+  bool open = false;
+  ncclResult_t begin() {
+    const ncclResult_t r = nccl_api().GroupStart();
+    open = r == ncclSuccess;
+    return r;
+  }
+  ncclResult_t end() {
+    open = false;
+    return nccl_api().GroupEnd();
+  }
+  ~NcclGroupGuard() {
+    if (open) nccl_api().GroupEnd();
+  }
+};
+
 void consts_default(cfd_solver_consts* c) {
   c->ramp_up_steps = 100;        // src/model.rs:269
   c->jacobi_iterations = 50;     // :737
@@ -262,6 +280,7 @@ struct ModelImpl final : ModelBase {
   double last_prof_ms = 0;
   uint64_t last_prof_launches = 0;
   int mg_bottom_level = 0;                // first level run by the single-block bottom kernel
+  size_t mg_bottom_smem = 0;              // > 0: the bottom kernel keeps its levels in this much shared memory
   int mg_last_z = -1;                     // mg_b index of the last V-cycle's result (CFD_FIELD_MG_Z)
   bool mg_legs = false;                   // V-cycle legs as single launches (cfd_mg_legs.cuh)
   // tiles of the leg kernels: large levels (by the number of smoothing sweeps NU: the staged region is the tile + NU) and
@@ -863,7 +882,8 @@ struct ModelImpl final : ModelBase {
                        (size_t)send_up * rl * sizeof(R), max_data, max_data ? 1 : 0);
     }
     cudaStream_t stream = on ? on : this->stream;
-    CFD_NCCL(nccl_api().GroupStart());
+    NcclGroupGuard group;
+    CFD_NCCL(group.begin());
     if (rank > 0) {
       if (send_down > 0) CFD_NCCL(nccl_api().Send(f.row(a), (size_t)send_down * rl, nccl_real(), rank - 1, comm, stream));
       if (down > 0) CFD_NCCL(nccl_api().Recv(f.row(a - down), (size_t)down * rl, nccl_real(), rank - 1, comm, stream));
@@ -872,7 +892,7 @@ struct ModelImpl final : ModelBase {
       if (send_up > 0) CFD_NCCL(nccl_api().Send(f.row(b - send_up), (size_t)send_up * rl, nccl_real(), rank + 1, comm, stream));
       if (up > 0) CFD_NCCL(nccl_api().Recv(f.row(b), (size_t)up * rl, nccl_real(), rank + 1, comm, stream));
     }
-    CFD_NCCL(nccl_api().GroupEnd());
+    CFD_NCCL(group.end());
     return CFD_OK;
   }
   // symmetric halo of depth d on a field with owned rows [a, b)
@@ -1318,10 +1338,21 @@ struct ModelImpl final : ModelBase {
     mg_bottom.n = (int)mg.size() - mg_bottom_level;
     mg_bottom.nu = mg_smoothing();
     mg_bottom.omega = R(opt.consts.mg_omega);
+    size_t bottom_bytes = 0;
     for (int k = 0; k < mg_bottom.n; ++k) {
       const MgLevelHost& L = mg[(size_t)(mg_bottom_level + k)];
       mg_bottom.lv[k].dev = L.dev;
       mg_bottom.lv[k].e = L.e; mg_bottom.lv[k].rho = L.rho; mg_bottom.lv[k].tmp = L.tmp;
+      bottom_bytes += 3 * (size_t)(L.mx + 2) * (size_t)(L.my + 2) * sizeof(R);
+    }
+    // CFD_MG_BOTTOM_SMEM=1 (A/B): the bottom levels' fields in shared memory when they fit (k_mg_bottom<kSmem>).  Measured
+    // (r2v): 64.0 us against 66.0 us per launch — the single block is bound by instruction issue (1024 threads x ~300
+    // instructions per phase on ONE SM), not by the L2 round trips, so the default stays the global-memory form.
+    static const bool bottom_smem = getenv("CFD_MG_BOTTOM_SMEM") != nullptr;
+    mg_bottom_smem = 0;
+    if (mg_bottom_level >= 1 && bottom_bytes <= (size_t)200 * 1024 && bottom_smem) {
+      mg_bottom_smem = bottom_bytes;
+      CFD_CUDA(cudaFuncSetAttribute(cfdk::k_mg_bottom<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bottom_bytes));
     }
     // each level's descending / ascending leg as one launch (cfd_mg_legs.cuh): V(nu,nu) with nu = 2, 3, 4
     static const bool no_legs = getenv("CFD_MG_NO_LEGS") != nullptr;
@@ -1382,7 +1413,8 @@ struct ModelImpl final : ModelBase {
       R* dst_up = rank < world - 1 ? (R*)pb->map[rank + 1] + (size_t)(hi - d + 1) * pitch : nullptr;
       return peer_push(f + (size_t)(lo + 1) * pitch, dst_down, n * sizeof(R), f + (size_t)(hi - d + 1) * pitch, dst_up, n * sizeof(R));
     }
-    CFD_NCCL(nccl_api().GroupStart());
+    NcclGroupGuard group;
+    CFD_NCCL(group.begin());
     if (rank > 0) {
       CFD_NCCL(nccl_api().Send(f + (size_t)(lo + 1) * pitch, n, nccl_real(), rank - 1, comm, stream));
       CFD_NCCL(nccl_api().Recv(f + (size_t)(lo - d + 1) * pitch, n, nccl_real(), rank - 1, comm, stream));
@@ -1391,7 +1423,7 @@ struct ModelImpl final : ModelBase {
       CFD_NCCL(nccl_api().Send(f + (size_t)(hi - d + 1) * pitch, n, nccl_real(), rank + 1, comm, stream));
       CFD_NCCL(nccl_api().Recv(f + (size_t)(hi + 1) * pitch, n, nccl_real(), rank + 1, comm, stream));
     }
-    CFD_NCCL(nccl_api().GroupEnd());
+    CFD_NCCL(group.end());
     return CFD_OK;
   }
   // every rank receives every rank's rows of a level-l field (one in-place broadcast per owner, grouped)
@@ -1417,30 +1449,51 @@ struct ModelImpl final : ModelBase {
       CFD_CUDA(cudaGetLastError());
       return CFD_OK;
     }
-    CFD_NCCL(nccl_api().GroupStart());
+    NcclGroupGuard group;
+    CFD_NCCL(group.begin());
     for (int r = 0; r < world; ++r) {
       const int lo = lvl_lo(l, r), hi = lvl_hi(l, r);
       if (hi <= lo) continue;
       R* rows = f + (size_t)(lo + 1) * pitch;
       CFD_NCCL(nccl_api().Broadcast(rows, rows, (size_t)(hi - lo) * pitch, nccl_real(), r, comm, stream));
     }
-    CFD_NCCL(nccl_api().GroupEnd());
+    CFD_NCCL(group.end());
     return CFD_OK;
   }
   // strips: finish a dot product whose rank-local sum sits in mg_scalars->local_sum
   int mg_finish_strips(const cfdk::MgFine<R>& c, int mode) {
-    if (world == 1) return CFD_OK;
-    if (peer2_ready) {
-      cfdk::k_mg_advance_peer<R><<<1, 32, 0, stream>>>(peer_all(), c, mg_scalars, mode, ++rseq);
-      ++launches;
-      CFD_CUDA(cudaGetLastError());
-      return CFD_OK;
-    }
+    int rc;
+    if ((rc = mg_reduce_strips())) return rc;
+    return mg_advance_strips(c, mode);
+  }
+  // the two halves of mg_finish_strips: the sum over the ranks (NCCL transport: an 8-byte allreduce, which may sit in one
+  // grouped launch with a halo exchange, see nccl_batch) and the advance of the CG scalars (peer transport: one kernel does both)
+  int mg_reduce_strips() {
+    if (world == 1 || peer2_ready) return CFD_OK;
     CFD_NCCL(nccl_api().AllReduce(&mg_scalars->local_sum, &mg_scalars->local_sum, 1, ncclFloat64, ncclSum, comm, stream));
-    cfdk::k_mg_advance<R><<<1, 32, 0, stream>>>(c, mg_scalars, mode);
-    ++launches;
     return CFD_OK;
   }
+  int mg_advance_strips(const cfdk::MgFine<R>& c, int mode) {
+    if (world == 1) return CFD_OK;
+    if (peer2_ready) cfdk::k_mg_advance_peer<R><<<1, 32, 0, stream>>>(peer_all(), c, mg_scalars, mode, ++rseq);
+    else cfdk::k_mg_advance<R><<<1, 32, 0, stream>>>(c, mg_scalars, mode);
+    ++launches;
+    CFD_CUDA(cudaGetLastError());
+    return CFD_OK;
+  }
+  // NCCL transport: the exchanges enqueued while the returned guard is open form ONE grouped launch (halo rows of two fields,
+  // or halo rows together with the allreduce of a dot product): one latency on the critical path instead of two.  Peer
+  // transport: nothing to batch (every exchange is its own small kernel; the guard stays closed).
+  int nccl_batch(NcclGroupGuard* g) {
+    if (world > 1 && !peer2_ready && !peer_ready) CFD_NCCL(g->begin());
+    return CFD_OK;
+  }
+  int nccl_batch_end(NcclGroupGuard* g) {
+    if (g->open) CFD_NCCL(g->end());
+    return CFD_OK;
+  }
+  // strips with the leg kernels: the descending leg of level 0 reads nu halo rows of rho
+  int exchange_rho_for_legs() { return mg_legs ? exchange_halo(mg_rho, ja, jb, mg_smoothing()) : CFD_OK; }
 
   // ---- the V-cycle with one launch per leg (cfd_mg_legs.cuh) ----
   template <int NU>
@@ -1525,16 +1578,19 @@ struct ModelImpl final : ModelBase {
     const dim3 g_leg3((nx - 2 + G3::TX - 1) / G3::TX, (rows + G3::TY - 1) / G3::TY);
     const size_t leg2_bytes = sizeof(cfdk::Leg0Smem<R, NU>), leg3_bytes = sizeof(cfdk::Leg3Smem<R>);
     const int n_partials = form == 1 ? (int)(g_leg.x * g_leg.y) : form == 2 ? (int)(g_leg2.x * g_leg2.y) : (int)(g_leg3.x * g_leg3.y);
-    if ((rc = exchange_halo(mg_rho, ja, jb, NU))) return rc;
+    // (strips: the NU halo rows of rho were exchanged together with the reduction that followed the kernel that wrote rho)
     if (form == 1) cfdk::k_mg0_down<R, T::TX, T::TY, NU><<<g_leg, cfdk::kLegThreads, leg_bytes, stream>>>(c, c2, mg_rho.v, mg_b[*zo].v, C.mx, C.rho, mg_scalars);
     else if (form == 2) cfdk::k_mg0_down2<R, NU><<<g_leg2, cfdk::kLegThreads, leg2_bytes, stream>>>(c, c2, mg_rho.v, mg_b[*zo].v, C.mx, C.rho, mg_scalars);
     else cfdk::k_mg0_down3<R, NU><<<g_leg3, cfdk::kLegThreads, leg3_bytes, stream>>>(c, c2, mg_rho.v, mg_b[*zo].v, C.mx, C.rho, mg_scalars);
     ++launches;
     std::swap(*zc, *zo);
     if (world > 1) {
+      NcclGroupGuard batch;  // x_nu's halo rows and the level-1 rho in one grouped launch
+      if ((rc = nccl_batch(&batch))) return rc;
       if ((rc = exchange_halo(mg_b[*zc], ja, jb, NU))) return rc;
       if (lvl_dist(1)) { if ((rc = exchange_level(C.rho, 1, leg_rho_halo()))) return rc; }
       else if ((rc = gather_level(C.rho, 1))) return rc;
+      if ((rc = nccl_batch_end(&batch))) return rc;
     }
     if ((rc = mg_coarse_vcycle(1))) return rc;
     auto prof_mark = [&]() {  // CUDA-event pair around the ascending leg (bench.py's roofline kernel)
@@ -1554,8 +1610,14 @@ struct ModelImpl final : ModelBase {
     cfdk::k_mg_reduce<R><<<1, 1024, 0, stream>>>(c, mg_scalars, mg_partials, n_partials, 1);
     launches += 2;
     std::swap(*zc, *zo);
-    if ((rc = exchange_halo(mg_b[*zc], ja, jb, 1))) return rc;  // strips: the neighbours' edge rows of z (no-op on one GPU)
-    if ((rc = mg_finish_strips(c, 1))) return rc;
+    {
+      NcclGroupGuard batch;  // strips: the neighbours' edge rows of z and the sum of rho.z in one grouped launch
+      if ((rc = nccl_batch(&batch))) return rc;
+      if ((rc = exchange_halo(mg_b[*zc], ja, jb, 1))) return rc;
+      if ((rc = mg_reduce_strips())) return rc;
+      if ((rc = nccl_batch_end(&batch))) return rc;
+    }
+    if ((rc = mg_advance_strips(c, 1))) return rc;
     CFD_CUDA(cudaGetLastError());
     return CFD_OK;
   }
@@ -1571,7 +1633,8 @@ struct ModelImpl final : ModelBase {
     R *a = L.e, *b = L.tmp;
     int rc;
     if (l == mg_bottom_level && !(opt.flags & CFD_FLAG_MG_NO_BOTTOM_KERNEL) && !(L.mx == 1 && L.my == 1)) {
-      cfdk::k_mg_bottom<R><<<1, cfdk::kMgBottomThreads, 0, stream>>>(mg_bottom, mg_scalars);
+      if (mg_bottom_smem > 0) cfdk::k_mg_bottom<R, true><<<1, cfdk::kMgBottomThreads, mg_bottom_smem, stream>>>(mg_bottom, mg_scalars);
+      else cfdk::k_mg_bottom<R, false><<<1, cfdk::kMgBottomThreads, 0, stream>>>(mg_bottom, mg_scalars);
       ++launches;
       L.cur = L.e;
       return CFD_OK;
@@ -1871,7 +1934,14 @@ struct ModelImpl final : ModelBase {
     cfdk::k_mg_init<R><<<g_all, blk, 0, stream>>>(c, mg_scalars, rhs.v, mg_start(warm), x, mg_rho.v, mg_partials, mg_ticket);
     launches += 1;
     if (warm) mg_guess_explicit = false;
-    if ((rc = mg_finish_strips(c, 0))) return rc;
+    {
+      NcclGroupGuard nb;  // strips: rho.rho and (legs) the halo rows of rho the first descending leg reads
+      if ((rc = nccl_batch(&nb))) return rc;
+      if ((rc = mg_reduce_strips())) return rc;
+      if ((rc = exchange_rho_for_legs())) return rc;
+      if ((rc = nccl_batch_end(&nb))) return rc;
+    }
+    if ((rc = mg_advance_strips(c, 0))) return rc;
     // CG iterations are enqueued in batches of the count this solve took last time; every kernel of an iteration is a
     // no-op once the device-side `done` flag is up, so the host synchronises once per batch, not once per iteration
     int batch = pred > 0 ? pred : 1;
@@ -1889,11 +1959,24 @@ struct ModelImpl final : ModelBase {
                                                            mg_ticket);
         mg_id = dn;
         mg_last_z = zi;
-        if ((rc = mg_finish_strips(c, 2))) return rc;
-        if ((rc = exchange_halo(mg_b[mg_id], ja, jb, 1))) return rc;  // strips: d's edge rows for the next L d
+        {
+          NcclGroupGuard nb;  // strips: d.w and d's edge rows for the next L d
+          if ((rc = nccl_batch(&nb))) return rc;
+          if ((rc = mg_reduce_strips())) return rc;
+          if ((rc = exchange_halo(mg_b[mg_id], ja, jb, 1))) return rc;
+          if ((rc = nccl_batch_end(&nb))) return rc;
+        }
+        if ((rc = mg_advance_strips(c, 2))) return rc;
         cfdk::k_mg_update<R><<<g_upd, blk, 0, stream>>>(c, mg_scalars, mg_b[mg_id].v, w, x, mg_rho.v, mg_partials, mg_ticket);
         launches += 2;
-        if ((rc = mg_finish_strips(c, 3))) return rc;
+        {
+          NcclGroupGuard nb;  // strips: rho.rho and (legs) the new rho's halo rows for the next descending leg
+          if ((rc = nccl_batch(&nb))) return rc;
+          if ((rc = mg_reduce_strips())) return rc;
+          if ((rc = exchange_rho_for_legs())) return rc;
+          if ((rc = nccl_batch_end(&nb))) return rc;
+        }
+        if ((rc = mg_advance_strips(c, 3))) return rc;
       }
       CFD_CUDA(cudaGetLastError());
       if ((rc = read_scalars())) return rc;
