@@ -98,7 +98,7 @@ typedef struct cfd_solver_consts {
   double cfl;
   double cg_tolerance;       /* extension (CG, MGCG): stop when dt * rms(Poisson residual) <= this */
   double mg_omega;           /* extension (MGCG): damping of the Jacobi smoother, default 0.8 */
-  int32_t mg_smoothing;      /* extension (MGCG): pre- and post-smoothing sweeps per level, default 2 */
+  int32_t mg_smoothing;      /* extension (MGCG): pre- and post-smoothing sweeps per level, default 2 (bench.py: 3; 2..4 run with one launch per leg of the V-cycle) */
   int32_t mg_warm_start;     /* extension (MGCG), start vector of the FIRST solve of a step: 1 = the p' the first solve
                               * of the previous step ended with — like the reference's Jacobi, which never resets p'
                               * (src/model.rs:734-824); 2 = linear extrapolation in time from the last two,
