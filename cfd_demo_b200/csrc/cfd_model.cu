@@ -280,6 +280,9 @@ struct ModelImpl final : ModelBase {
   double last_prof_ms = 0;
   uint64_t last_prof_launches = 0;
   int mg_bottom_level = 0;                // first level run by the single-block bottom kernel
+  unsigned* persist_barrier = nullptr;    // two alternating arrival counters of k_jacobi_persist2
+  unsigned long long persist_launches = 0;
+  bool persist2_ready = false;
   size_t mg_bottom_smem = 0;              // > 0: the bottom kernel keeps its levels in this much shared memory
   int mg_last_z = -1;                     // mg_b index of the last V-cycle's result (CFD_FIELD_MG_Z)
   bool mg_legs = false;                   // V-cycle legs as single launches (cfd_mg_legs.cuh)
@@ -1006,9 +1009,12 @@ struct ModelImpl final : ModelBase {
       CFD_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
       // as many rows per block as shared memory holds (fewer blocks make the grid barrier cheaper; a block's 1024 threads
       // update its rows in a few passes), but at least one block per ~8 rows so that small grids still use many SMs
-      int threads = 1024, target_rows = 8;
+      // (r2y, 800 x 264, k_jacobi_persist2: 2 rows per block 5.2 us per sweep, 4: 6.0, 8: 8.1, 16: 9.1 — a block's rows cost
+      // more than its share of the barrier: use every SM)
+      int threads = 1024, target_rows = 2;
       if (const char* e = getenv("CFD_PERSIST_THREADS")) threads = atoi(e);   // tuning hooks
       if (const char* e = getenv("CFD_PERSIST_ROWS")) target_rows = atoi(e);
+      if (const char* e = getenv("CFD_PERSIST_FORM")) { if (atoi(e) == 1 && !getenv("CFD_PERSIST_ROWS")) target_rows = 8; }
       int blocks = (rows + target_rows - 1) / target_rows;
       if (blocks > sms) blocks = sms;
       if (blocks < 1) blocks = 1;
@@ -1023,8 +1029,30 @@ struct ModelImpl final : ModelBase {
         cfdk::PersistArgs<R> pa;
         pa.c = c2; pa.pp0 = pp[0].v; pa.pp1 = pp[1].v; pa.rhs = rhs.v;
         pa.ipp = ipp; pa.iters = iters; pa.rows_per_block = rb; pa.err_slots = err_slots; pa.out = h_jres;
-        void* args[] = {&pa};
-        CFD_CUDA(cudaLaunchCooperativeKernel((const void*)cfdk::k_jacobi_persist<R>, dim3((rows + rb - 1) / rb), dim3(threads), args, smem, stream));
+        // CFD_PERSIST_FORM=1: the first form (grid.sync once per sweep, A/B); default: barrier off the critical path
+        static const bool form1 = getenv("CFD_PERSIST_FORM") != nullptr && atoi(getenv("CFD_PERSIST_FORM")) == 1;
+        if (form1) {
+          void* args[] = {&pa};
+          CFD_CUDA(cudaLaunchCooperativeKernel((const void*)cfdk::k_jacobi_persist<R>, dim3((rows + rb - 1) / rb), dim3(threads), args, smem, stream));
+        } else {
+          if (!persist_barrier && (rc = dalloc(&persist_barrier, (size_t)2))) return rc;
+          if (!persist2_ready) {
+            CFD_CUDA(cudaFuncSetAttribute(cfdk::k_jacobi_persist2<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024));
+            persist2_ready = true;
+          }
+          cfdk::PersistArgs2<R> p2;
+          p2.a = pa;
+          p2.barrier = persist_barrier + (persist_launches & 1);
+          p2.barrier_next = persist_barrier + ((persist_launches + 1) & 1);
+          ++persist_launches;
+          const int pairs = nx / 2;
+          p2.tc = pairs < threads ? pairs : threads;
+          p2.groups = threads / p2.tc;
+          if (p2.groups > rb) p2.groups = rb;
+          if (p2.groups < 1) p2.groups = 1;
+          void* args[] = {&p2};
+          CFD_CUDA(cudaLaunchCooperativeKernel((const void*)cfdk::k_jacobi_persist2<R>, dim3((rows + rb - 1) / rb), dim3(p2.tc * p2.groups), args, smem, stream));
+        }
         ++launches;
         persisted = true;
       }
