@@ -13,7 +13,12 @@
 // SAME per-cell expressions as the one-operation-per-launch kernels (jacobi_cell / mg_lap on level 0, mgc_cell =
 // mgc_sweep_cell's arithmetic on the coarse levels; no FMA, same association), so each leg is bit-identical to the
 // sequence it replaces (CFD_FLAG_MG_UNFUSED keeps that one for the cross-check); only rho.z is summed in another
-// order.  Divisions: DivTry per thread, recomputed with DivTrue by the thread whose window test failed.
+// order.  Divisions: DivTry per thread, recomputed with the compiler's division (DivSlow) by the thread whose window test failed.
+//
+// Three forms live in this file: the flat-indexed kernels right below (k_mg0_down/_up, k_mgc_down/_up: the plain statement of
+// the idea, CFD_MG_LEGS=1), column strips (k_mg0_down2/_up2, CFD_MG_LEGS=2) and the register-tiled kernels that ship
+// (k_mg0_down3/_up3, k_mgc_down3/_up3: section "register-tiled form"); the first two are kept for A/B and as cross-checks.
+// What ncu says about each: profiles/r2_legs_ncu.md.
 #pragma once
 
 #include <type_traits>
