@@ -63,3 +63,19 @@ def test_default_workload_is_the_baseline_config():
     assert (w["nx"], w["ny"], w["kind"]) == (4096, 4096, "modeC") and w["params"]["scenario"] == 1
     assert abs(1.0 * 1.0 / w["params"]["viscosity"] - 1000.0) < 1e-6          # Re = U L / nu
     assert w["params"]["dt"] < (1.0 / 4096) ** 2 / (4 * w["params"]["viscosity"])  # explicit diffusion limit
+
+
+def test_mode_c_byte_accounting_matches_design():
+    """stage-by-stage bytes of a V(nu,nu) iteration are 19.5 + 3 (2 nu - 1) sN on level 0 and 6.5 + 3 (2 nu - 1)
+    s N_l on a coarse level (28.5 / 15.5 at nu = 2, round 1's figures); as the fused legs run, 16.5 and 5.5."""
+    import bench
+    n = 64 * 64
+    base = bench.step_bytes_mode_c(64, 64, 1, 1, 0, nu=2)
+    assert base == 8 * n * (8 + 14 + 3) + 2 * n
+    per_it2 = bench.step_bytes_mode_c(64, 64, 1, 1, 1, nu=2) - base
+    per_it3 = bench.step_bytes_mode_c(64, 64, 1, 1, 1, nu=3) - base
+    fused = bench.step_bytes_mode_c(64, 64, 1, 1, 1, nu=3, fused=True) - base
+    assert abs(per_it2 - 8 * n * (28.5 + 15.5 / 3)) < 1e-6
+    assert abs(per_it3 - 8 * n * (34.5 + 21.5 / 3)) < 1e-6
+    assert abs(fused - 8 * n * (16.5 + 5.5 / 3)) < 1e-6
+    assert fused < per_it2 < per_it3
