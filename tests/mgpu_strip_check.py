@@ -51,6 +51,7 @@ def main():
     ]
     if os.environ.get("CFD_STRIP_CHECK_SMALL") == "1":
         cases = cases[:4]
+    fits = lambda g: (g.ny - 2) // world >= 17  # the library's minimum strip height (cfd_model_create_ex)
     only_peer = os.environ.get("CFD_STRIP_CHECK_PEER") == "only"
     if only_peer:
         cases = []
@@ -64,6 +65,7 @@ def main():
         ]
     fields = [_abi.FIELD_P, _abi.FIELD_U, _abi.FIELD_V, _abi.FIELD_U_STAR, _abi.FIELD_V_STAR, _abi.FIELD_RHS,
               _abi.FIELD_P_PRIME, _abi.FIELD_U_OLD, _abi.FIELD_V_OLD, _abi.FIELD_MASK_U, _abi.FIELD_MASK_V]
+    cases = [c for c in cases if fits(c[0])]
     for ci, (grid, params, precision, steps, flags) in enumerate(cases):
         # a fresh communicator per case
         uid = [nccl_unique_id() if rank == 0 else None]
@@ -124,6 +126,7 @@ def main():
         (PressureSolver.MGCG, Scenario.Cavity, Grid.uniform(2056, 1100, 2056 / 1024.0, 1100 / 1024.0, None), 5),
     ]
     nu_s = int(os.environ.get("CFD_STRIP_CHECK_NU", "3"))  # smoothing sweeps of the V-cycle (bench.py ships V(3,3))
+    mode_c = [c for c in mode_c if fits(c[2])]
     for solver, scenario, grid, n_steps in mode_c:
         params = SimulationParams(dt=1e-3, viscosity=0.01, scenario=scenario, pressure_solver=solver)
         uid = [nccl_unique_id() if rank == 0 else None]
