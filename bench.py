@@ -299,6 +299,12 @@ def run_reference_mode_c(args, w):
         "ms_per_cg_iteration": step_s * 1e3 / max(sum(iters) / len(iters), 1e-9),
         "start_state": "from rest (the GPU arm starts from a state spun up on the device; same grid, parameters, solver "
                        "constants and stopping rule)",
+        "like_for_like_note": ("the work of a step is proportional to its CG iterations: this arm's steps, taken from rest inside the "
+                               "100-step ramp of the lid speed, need the iteration counts listed in cg_iterations_list, the GPU "
+                               "arm's spun-up steps need 2; the CPU port cannot reach the spun-up state within the time budget "
+                               "(140 steps of ~5 s).  The same-state comparison is the GPU arm's own cpu_baseline (the GPU model's "
+                               "state loaded into this port, which then computes the same next step with the same iteration "
+                               "count); ms_per_cg_iteration here is the figure that carries over."),
         "stop": {"rel_residual": r.f64["p_rel"], "dt_rms_residual": r.f64["p"], "dt_rms_rhs": r.f64["rhs_rms"]},
         "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": "port", "sample": sample,
                          "host_cores": os.cpu_count(), "note": CPU_NOTE},
