@@ -61,6 +61,8 @@ def main():
     cyl = Cylinder(7.5, 5.0, 0.75)
     cg = default_consts()
     cg.cg_tolerance = 1e-13
+    cg3 = default_consts()  # the cycle bench.py ships: V(3,3), relative stopping rule
+    cg3.cg_tolerance, cg3.cg_relative, cg3.mg_smoothing = 1e-12, 1, 3
     cases = [
         ("modeR first order", Grid.uniform(64, 24, 30.0, 10.0, cyl), SimulationParams(), 64, None, 14, True),
         ("modeR second order f32", Grid.uniform(72, 26, 30.0, 10.0, cyl),
@@ -75,6 +77,8 @@ def main():
          SimulationParams(dt=1e-3, viscosity=0.01, scenario=Scenario.Cavity, pressure_solver=PressureSolver.MGCG), 64, cg, 8, False),
         ("modeC mgcg channel", Grid.uniform(96, 103, 9.6, 10.3, Cylinder(2.4, 5.0, 0.9)),
          SimulationParams(dt=1e-3, viscosity=0.01, pressure_solver=PressureSolver.MGCG), 64, cg, 8, False),
+        ("modeC mgcg V(3,3) relative rule", Grid.uniform(64, 120, 64 / 64.0, 120 / 64.0, None),
+         SimulationParams(dt=1e-3, viscosity=0.01, scenario=Scenario.Cavity, pressure_solver=PressureSolver.MGCG), 64, cg3, 8, False),
     ]
     for name, grid, params, precision, consts, steps, exact in cases:
         nx, ny = grid.nx, grid.ny
