@@ -124,3 +124,23 @@ def test_strip_partition_is_contiguous_and_pairs_up_on_four_multigrid_levels(lib
         pairs = cur[:n - n % 2].reshape(-1, 2)
         assert (pairs[:, 0] == pairs[:, 1]).all()
         cur = np.concatenate([pairs[:, 0], cur[n - n % 2:]])
+
+
+def test_python_constants_match_the_header():
+    """Field ids, flags and enum values of cfd_demo_b200/_abi.py are the header's #defines (the ctypes mirror is written
+    by hand: a drifted constant would read the wrong field without any error)."""
+    import re
+    from cfd_demo_b200 import _abi
+    text = open(os.path.join(ROOT, "include", "cfd_b200.h")).read()
+    defines = {m.group(1): int(m.group(2).rstrip("u"), 0) for m in re.finditer(r"#define\s+(CFD_\w+)\s+(\d+u?)\b", text)}
+    checked = 0
+    for name, value in vars(_abi).items():
+        if not name.isupper() or not isinstance(value, int):
+            continue
+        for key in ("CFD_" + name, "CFD_" + name.replace("SOLVER_", "SOLVER_").replace("SCENARIO_", "SCENARIO_")):
+            if key in defines:
+                assert defines[key] == value, (name, value, defines[key])
+                checked += 1
+                break
+    assert checked >= 20, checked
+    assert defines["CFD_FIELD_COUNT"] == max(v for k, v in vars(_abi).items() if k.startswith("FIELD_") and isinstance(v, int)) + 1
