@@ -956,6 +956,8 @@ struct ModelImpl final : ModelBase {
         cfdk::k_divergence<R, true><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, rhs.v, ja, jb, err_slots, iters, tickets,
                                                              h_divs.dx, h_divs.dy, h_divs.dt, c, mg_scalars, mg_partials,
                                                              mg_ticket, rr_mode);
+        cfdk::k_mg_reduce<R><<<1, 1024, 0, stream>>>(c, mg_scalars, mg_partials, (int)(grd.x * grd.y), rr_mode);
+        ++launches;
         if (rr_mode != 0 && (rc = mg_finish_strips(c, rr_mode))) return rc;  // strips: the ranks' sums -> bb
       } else {
         cfdk::k_divergence<R, false><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, rhs.v, ja, jb, err_slots, iters, tickets,
