@@ -273,6 +273,10 @@ struct ModelImpl final : ModelBase {
   double* mg_partials = nullptr;
   unsigned long long* mg_err = nullptr;   // scratch max|dz| slot of the smoothing sweeps
   unsigned* mg_ticket = nullptr;          // last-block ticket of the fused dot-product reductions
+  bool mg_finish_launch = true;           // dot products of k_mg_init / k_mg_dir_apply / k_mg_update: per-block partials + k_mg_reduce
+  bool fuse_corr_div = true;              // k_corrector_div (CFD_FUSED_CORRECTOR=0: the separate kernels)
+  int corr_rows = cfdk::kCorrRows;        // its tile height (CFD_CORR_ROWS=8: the A/B form)
+  bool corr_div_ready = false;            // rhs and the rhs^2 partials of the fields the last corrector wrote are in place
   // measurement hook: CUDA-event pairs around every k_jacobi_sweep5 launch of the MGCG smoother (bench.py roofline)
   bool prof_smoother = false;
   std::vector<cudaEvent_t> ev_prof;
@@ -828,6 +832,9 @@ struct ModelImpl final : ModelBase {
       if (want < 6) want = 6;
       rpb = (int)(((want - 2) / 4) * 4 + 2);  // rows + 2 halo rows = whole number of 4-row boxes
     }
+    if (const char* e = getenv("CFD_FUSED_CORRECTOR")) fuse_corr_div = atoi(e) != 0;  // A/B hooks
+    if (const char* e = getenv("CFD_CORR_ROWS")) corr_rows = atoi(e) == 8 ? 8 : cfdk::kCorrRows;
+    if (const char* e = getenv("CFD_MG_FINISH_LAUNCH")) mg_finish_launch = atoi(e) != 0;
     if (const char* e = getenv("CFD_SWEEP_ROWS")) {  // tuning hook (tools/tune_sweep.py)
       const int v = atoi(e);
       if (v >= 2) rpb = v;
@@ -946,7 +953,14 @@ struct ModelImpl final : ModelBase {
     // a cold-start MGCG solve that is expected to need no iteration: the divergence kernel sums rho.rho = rhs.rhs itself
     const bool cold = mgcg && !(call_index == 0 && opt.consts.mg_warm_start != 0);
     const bool decide_early = cold && elided != nullptr && mg_pred[first_solve ? 0 : 1] == 0;
-    {
+    const bool have_rhs = corr_div_ready;  // the corrector that produced us / vs also left their divergence and its rhs^2 partials
+    corr_div_ready = false;
+    if (have_rhs) {
+      if (!decide_early) return fail(CFD_ERR_UNSUPPORTED, "fused corrector + divergence without an early decision");
+      const dim3 grd((nx + 255) / 256, (ny + corr_rows - 1) / corr_rows);  // k_corrector_div's grid
+      cfdk::k_mg_reduce<R><<<1, 1024, 0, stream>>>(mg_fine(dt_sub), mg_scalars, mg_partials, (int)(grd.x * grd.y), 0);
+      ++launches;
+    } else {
       // MGCG: a step's first solve also needs ||rhs||^2 over the unknowns (reference of the relative stopping rule and of
       // the reported ||r|| / ||rhs||): rr_mode 4, or 5 when that solve starts cold (then rho = rhs and the sum is rho.rho too)
       const int rr_mode = mgcg && first_solve ? (cold ? 5 : 4) : 0;
@@ -1354,8 +1368,10 @@ struct ModelImpl final : ModelBase {
       const size_t n_vec = gx * (size_t)((ny + 3) / 4 + 1);
       const size_t n_sweep = (size_t)((nx / 2 + cfdk::kSweepWarps * 32 - 1) / (cfdk::kSweepWarps * 32)) * (size_t)((ny - 2 + sweep_rows_per_block - 1) / sweep_rows_per_block);
       const size_t n_leg = (size_t)((nx - 2 + 55) / 56) * (size_t)((ny - 2 + 15) / 16 + 1);  // at least the leg kernels' grids
+      const size_t n_div = (size_t)((nx + 255) / 256) * (size_t)((ny + cfdk::kCorrRows - 1) / cfdk::kCorrRows + 1);  // k_divergence, k_corrector_div
       size_t n_max = n_vec > n_sweep ? n_vec : n_sweep;
       if (n_leg > n_max) n_max = n_leg;
+      if (n_div > n_max) n_max = n_div;
       if ((rc = dalloc(&mg_partials, n_max))) return rc;
     }
     // the bottom of the V-cycle (every level from the first that fits 64 x 64) runs in one single-block launch
@@ -1918,6 +1934,15 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
 
+  // the finish of a dot product whose kernel left one partial per block (mg_finish_launch): sum in index order, advance the
+  // CG scalars (strips: leave the rank's sum for the exchange) — one single-block launch instead of a ticket tail per block
+  unsigned* dot_ticket() const { return mg_finish_launch ? nullptr : mg_ticket; }
+  void dot_finish(const cfdk::MgFine<R>& c, const dim3& grid, int mode) {
+    if (!mg_finish_launch) return;
+    cfdk::k_mg_reduce<R><<<1, 1024, 0, stream>>>(c, mg_scalars, mg_partials, (int)(grid.x * grid.y), mode);
+    ++launches;
+  }
+
   int mgcg_solve(R dt_sub, int call_index, R* residual_out, bool decided_early, bool* elided, size_t ev) {
     int rc;
     const cfdk::MgFine<R> c = mg_fine(dt_sub);
@@ -1961,8 +1986,9 @@ struct ModelImpl final : ModelBase {
     // first solve of a step: start from the extrapolated history (mg_warm_start); the stencil of the start vector needs
     // the neighbours' edge rows, which every p' carries since the exchange at the end of its solve
     if (warm && mg_guess_explicit && (rc = exchange_halo(mg_guess, ja, jb, 1))) return rc;
-    cfdk::k_mg_init<R><<<g_all, blk, 0, stream>>>(c, mg_scalars, rhs.v, mg_start(warm), x, mg_rho.v, mg_partials, mg_ticket);
+    cfdk::k_mg_init<R><<<g_all, blk, 0, stream>>>(c, mg_scalars, rhs.v, mg_start(warm), x, mg_rho.v, mg_partials, dot_ticket());
     launches += 1;
+    dot_finish(c, g_all, 0);
     if (warm) mg_guess_explicit = false;
     {
       NcclGroupGuard nb;  // strips: rho.rho and (legs) the halo rows of rho the first descending leg reads
@@ -1986,7 +2012,8 @@ struct ModelImpl final : ModelBase {
         // rho.z (-> beta) came out of the V-cycle's last sweep; d_new goes to the smoothing buffer that is free now
         const int dn = 3 - mg_id - zi;
         cfdk::k_mg_dir_apply<R><<<g_dir, blk, 0, stream>>>(c, mg_scalars, mg_b[zi].v, mg_b[mg_id].v, mg_b[dn].v, w, mg_partials,
-                                                           mg_ticket);
+                                                           dot_ticket());
+        dot_finish(c, g_dir, 2);
         mg_id = dn;
         mg_last_z = zi;
         {
@@ -1997,8 +2024,9 @@ struct ModelImpl final : ModelBase {
           if ((rc = nccl_batch_end(&nb))) return rc;
         }
         if ((rc = mg_advance_strips(c, 2))) return rc;
-        cfdk::k_mg_update<R><<<g_upd, blk, 0, stream>>>(c, mg_scalars, mg_b[mg_id].v, w, x, mg_rho.v, mg_partials, mg_ticket);
+        cfdk::k_mg_update<R><<<g_upd, blk, 0, stream>>>(c, mg_scalars, mg_b[mg_id].v, w, x, mg_rho.v, mg_partials, dot_ticket());
         launches += 2;
+        dot_finish(c, g_upd, 3);
         {
           NcclGroupGuard nb;  // strips: rho.rho and (legs) the new rho's halo rows for the next descending leg
           if ((rc = nccl_batch(&nb))) return rc;
@@ -2027,8 +2055,24 @@ struct ModelImpl final : ModelBase {
     return CFD_OK;
   }
 
+  // with_div: single domain, MGCG — the divergence of the new u, v (the rhs of the re-correction round that follows) and
+  // the partials of its rhs^2 come out of the same pass (k_corrector_div); the next pressure_solve skips its divergence
   int corrector(R dt_sub, const Field<R>& us, const Field<R>& vs, const Field<R>& uk, const Field<R>& vk,
-                const Field<R>& uo, const Field<R>& vo) {
+                const Field<R>& uo, const Field<R>& vo, bool with_div = false) {
+    if (with_div) {
+      dim3 blk(256), grd((nx + 255) / 256, (ny + corr_rows - 1) / corr_rows);
+      if (corr_rows == 8)
+        cfdk::k_corrector_div<R, 8><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, uk.v, vk.v, pp[ipp].v, uo.v, vo.v, p.v,
+                                                             rhs.v, h_divs.dx, h_divs.dy, h_divs.dt, mg_partials);
+      else
+        cfdk::k_corrector_div<R, cfdk::kCorrRows><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, uk.v, vk.v, pp[ipp].v, uo.v,
+                                                                           vo.v, p.v, rhs.v, h_divs.dx, h_divs.dy, h_divs.dt,
+                                                                           mg_partials);
+      ++launches;
+      corr_div_ready = true;
+      CFD_CUDA(cudaGetLastError());
+      return CFD_OK;
+    }
     dim3 blk(256), grd((nx + 1 + 255) / 256, v_row_end() - ja);
     cfdk::k_corrector<R><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, uk.v, vk.v, pp[ipp].v, uo.v, vo.v, p.v,
                                                   ja, jb, v_row_end(), h_divs.dx, h_divs.dy);
@@ -2105,7 +2149,11 @@ struct ModelImpl final : ModelBase {
     R residual = 0;
     if ((rc = pressure_solve(dt_sub, ubuf[Y], vbuf[Y], 0, &residual))) return rc;
     last_pressure_residual = residual;
-    if ((rc = corrector(dt_sub, ubuf[Y], vbuf[Y], ubuf[X], vbuf[X], ubuf[Z], vbuf[Z]))) return rc;
+    // the re-correction round that follows starts with the divergence of the corrected fields: when that solve is expected
+    // to be over before its first iteration (mg_pred), the corrector computes it on the way
+    const bool with_div = fuse_corr_div && world == 1 && pressure_solver == CFD_SOLVER_MGCG && opt.consts.outer_rounds > 0 &&
+                          mg_pred[1] == 0;
+    if ((rc = corrector(dt_sub, ubuf[Y], vbuf[Y], ubuf[X], vbuf[X], ubuf[Z], vbuf[Z], with_div))) return rc;
     int cur = Z, star = Y;
     // ---- outer re-correction loop (:696-724): `star <- current` is a role swap
     bool alias = false;
