@@ -275,7 +275,9 @@ struct ModelImpl final : ModelBase {
   unsigned* mg_ticket = nullptr;          // last-block ticket of the fused dot-product reductions
   bool mg_finish_launch = true;           // dot products of k_mg_init / k_mg_dir_apply / k_mg_update: per-block partials + k_mg_reduce
   bool fuse_corr_div = true;              // k_corrector_div (CFD_FUSED_CORRECTOR=0: the separate kernels)
-  int corr_rows = cfdk::kCorrRows;        // its tile height (CFD_CORR_ROWS=8: the A/B form)
+  int corr_rows = cfdk::kCorrRows;        // its tile height and width (CFD_CORR_ROWS / CFD_CORR_THREADS: A/B forms)
+  int corr_threads = cfdk::kCorrThreads;
+  int div_rows = cfdk::kDivRows;          // tile height of k_divergence (CFD_DIV_ROWS=8: A/B form)
   bool corr_div_ready = false;            // rhs and the rhs^2 partials of the fields the last corrector wrote are in place
   // measurement hook: CUDA-event pairs around every k_jacobi_sweep5 launch of the MGCG smoother (bench.py roofline)
   bool prof_smoother = false;
@@ -833,7 +835,9 @@ struct ModelImpl final : ModelBase {
       rpb = (int)(((want - 2) / 4) * 4 + 2);  // rows + 2 halo rows = whole number of 4-row boxes
     }
     if (const char* e = getenv("CFD_FUSED_CORRECTOR")) fuse_corr_div = atoi(e) != 0;  // A/B hooks
-    if (const char* e = getenv("CFD_CORR_ROWS")) corr_rows = atoi(e) == 8 ? 8 : cfdk::kCorrRows;
+    if (const char* e = getenv("CFD_CORR_ROWS")) { const int v = atoi(e); corr_rows = (v == 8 || v == 2 || v == 1) ? v : cfdk::kCorrRows; }
+    if (const char* e = getenv("CFD_DIV_ROWS")) div_rows = atoi(e) == 8 ? 8 : cfdk::kDivRows;
+    if (const char* e = getenv("CFD_CORR_THREADS")) corr_threads = atoi(e) == 128 && (corr_rows == 2 || corr_rows == 4) ? 128 : 256;
     if (const char* e = getenv("CFD_MG_FINISH_LAUNCH")) mg_finish_launch = atoi(e) != 0;
     if (const char* e = getenv("CFD_SWEEP_ROWS")) {  // tuning hook (tools/tune_sweep.py)
       const int v = atoi(e);
@@ -957,16 +961,21 @@ struct ModelImpl final : ModelBase {
     corr_div_ready = false;
     if (have_rhs) {
       if (!decide_early) return fail(CFD_ERR_UNSUPPORTED, "fused corrector + divergence without an early decision");
-      const dim3 grd((nx + 255) / 256, (ny + corr_rows - 1) / corr_rows);  // k_corrector_div's grid
+      const dim3 grd((nx + corr_threads - 1) / corr_threads, (ny + corr_rows - 1) / corr_rows);  // k_corrector_div's grid
       cfdk::k_mg_reduce<R><<<1, 1024, 0, stream>>>(mg_fine(dt_sub), mg_scalars, mg_partials, (int)(grd.x * grd.y), 0);
       ++launches;
     } else {
       // MGCG: a step's first solve also needs ||rhs||^2 over the unknowns (reference of the relative stopping rule and of
       // the reported ||r|| / ||rhs||): rr_mode 4, or 5 when that solve starts cold (then rho = rhs and the sum is rho.rho too)
       const int rr_mode = mgcg && first_solve ? (cold ? 5 : 4) : 0;
-      dim3 blk(256), grd((nx + 255) / 256, (jb - ja + cfdk::kDivRows - 1) / cfdk::kDivRows);
+      dim3 blk(256), grd((nx + 255) / 256, (jb - ja + div_rows - 1) / div_rows);
       if (decide_early || rr_mode != 0) {
         const cfdk::MgFine<R> c = mg_fine(dt_sub);
+        if (div_rows == 8)
+          cfdk::k_divergence<R, true, 8><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, rhs.v, ja, jb, err_slots, iters, tickets,
+                                                                  h_divs.dx, h_divs.dy, h_divs.dt, c, mg_scalars, mg_partials,
+                                                                  mg_ticket, rr_mode);
+        else
         cfdk::k_divergence<R, true><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, rhs.v, ja, jb, err_slots, iters, tickets,
                                                              h_divs.dx, h_divs.dy, h_divs.dt, c, mg_scalars, mg_partials,
                                                              mg_ticket, rr_mode);
@@ -974,6 +983,11 @@ struct ModelImpl final : ModelBase {
         ++launches;
         if (rr_mode != 0 && (rc = mg_finish_strips(c, rr_mode))) return rc;  // strips: the ranks' sums -> bb
       } else {
+        if (div_rows == 8)
+          cfdk::k_divergence<R, false, 8><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, rhs.v, ja, jb, err_slots, iters, tickets,
+                                                                   h_divs.dx, h_divs.dy, h_divs.dt, cfdk::MgFine<R>{}, nullptr,
+                                                                   nullptr, nullptr, 0);
+        else
         cfdk::k_divergence<R, false><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, rhs.v, ja, jb, err_slots, iters, tickets,
                                                               h_divs.dx, h_divs.dy, h_divs.dt, cfdk::MgFine<R>{}, nullptr,
                                                               nullptr, nullptr, 0);
@@ -1368,7 +1382,7 @@ struct ModelImpl final : ModelBase {
       const size_t n_vec = gx * (size_t)((ny + 3) / 4 + 1);
       const size_t n_sweep = (size_t)((nx / 2 + cfdk::kSweepWarps * 32 - 1) / (cfdk::kSweepWarps * 32)) * (size_t)((ny - 2 + sweep_rows_per_block - 1) / sweep_rows_per_block);
       const size_t n_leg = (size_t)((nx - 2 + 55) / 56) * (size_t)((ny - 2 + 15) / 16 + 1);  // at least the leg kernels' grids
-      const size_t n_div = (size_t)((nx + 255) / 256) * (size_t)((ny + cfdk::kCorrRows - 1) / cfdk::kCorrRows + 1);  // k_divergence, k_corrector_div
+      const size_t n_div = (size_t)((nx + 127) / 128) * (size_t)(ny + 1);  // k_divergence, every form of k_corrector_div
       size_t n_max = n_vec > n_sweep ? n_vec : n_sweep;
       if (n_leg > n_max) n_max = n_leg;
       if (n_div > n_max) n_max = n_div;
@@ -2060,14 +2074,18 @@ struct ModelImpl final : ModelBase {
   int corrector(R dt_sub, const Field<R>& us, const Field<R>& vs, const Field<R>& uk, const Field<R>& vk,
                 const Field<R>& uo, const Field<R>& vo, bool with_div = false) {
     if (with_div) {
-      dim3 blk(256), grd((nx + 255) / 256, (ny + corr_rows - 1) / corr_rows);
-      if (corr_rows == 8)
-        cfdk::k_corrector_div<R, 8><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, uk.v, vk.v, pp[ipp].v, uo.v, vo.v, p.v,
-                                                             rhs.v, h_divs.dx, h_divs.dy, h_divs.dt, mg_partials);
-      else
-        cfdk::k_corrector_div<R, cfdk::kCorrRows><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, uk.v, vk.v, pp[ipp].v, uo.v,
-                                                                           vo.v, p.v, rhs.v, h_divs.dx, h_divs.dy, h_divs.dt,
-                                                                           mg_partials);
+      const int ct = corr_threads, cr = corr_rows;
+      dim3 blk(ct), grd((nx + ct - 1) / ct, (ny + cr - 1) / cr);
+#define CFD_CORR_DIV(ROWS, THREADS)                                                                                          \
+  cfdk::k_corrector_div<R, ROWS, THREADS><<<grd, blk, 0, stream>>>(scalars(dt_sub), us.v, vs.v, uk.v, vk.v, pp[ipp].v, uo.v, \
+                                                                   vo.v, p.v, rhs.v, h_divs.dx, h_divs.dy, h_divs.dt, mg_partials)
+      if (cr == 8) CFD_CORR_DIV(8, 256);
+      else if (cr == 1) CFD_CORR_DIV(1, 256);
+      else if (cr == 4 && ct == 256) CFD_CORR_DIV(4, 256);
+      else if (cr == 4) CFD_CORR_DIV(4, 128);
+      else if (ct == 256) CFD_CORR_DIV(2, 256);
+      else CFD_CORR_DIV(cfdk::kCorrRows, cfdk::kCorrThreads);
+#undef CFD_CORR_DIV
       ++launches;
       corr_div_ready = true;
       CFD_CUDA(cudaGetLastError());
