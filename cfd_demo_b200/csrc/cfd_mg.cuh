@@ -112,17 +112,18 @@ __device__ __forceinline__ typename Vec2<R>::type mg_start_pair(const MgStart<R>
 
 // x = start vector (or 0) on the whole grid, rho = rhs - L x on the unknowns (0 on the ring), rho.rho; the search
 // direction needs no initialisation (k_mg_dir_apply takes it as zero in a solve's first iteration).
-// grid = (ceil(nx / 512), ceil(ny / kMgRows)); a thread walks its column pair up the tile, the start vector's rows
+// grid = (ceil(nx / 512), ceil(ny / rows_per_block)); a thread walks its column pair up the tile, the start vector's rows
 // j-1, j, j+1 rotate through registers.
 template <class R>
 __global__ void __launch_bounds__(kMgThreads) k_mg_init(MgFine<R> c, MgScalars* __restrict__ sc,
                                                          const R* __restrict__ rhs, const MgStart<R> g,
                                                          R* __restrict__ x, R* __restrict__ rho,
-                                                         double* __restrict__ partials, unsigned* __restrict__ ticket) {
+                                                         double* __restrict__ partials, unsigned* __restrict__ ticket,
+                                                         int rows_per_block) {
   using V = typename Vec2<R>::type;
   const int nx = c.nx;
   const int c0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-  const int j0 = c.init_lo + blockIdx.y * kMgRows, j1 = min(j0 + kMgRows, c.init_hi);
+  const int j0 = c.init_lo + blockIdx.y * rows_per_block, j1 = min(j0 + rows_per_block, c.init_hi);
   double acc = 0.0;
   if (c0 < nx && j0 < j1) {
     V zero;
@@ -216,9 +217,9 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_dot(MgFine<R> c, MgScalars* _
 
 // d_new = z + beta d_old and w = L d_new in one pass (d_new goes to its own buffer: neighbours still read d_old),
 // d_new.w -> alpha.  Tiles of kMgDirRows rows; grid = (ceil(nx / 512), ceil((ny - 2) / kMgDirRows)).
-constexpr int kMgDirRows = 4;
-template <class R>
-__global__ void __launch_bounds__(kMgThreads) k_mg_dir_apply(MgFine<R> c, MgScalars* __restrict__ sc,
+constexpr int kMgDirRows = 2;  // r2af, 4096^2, whole step: 2 rows x 256 threads 2.595 ms, 2 x 128 2.609, 4 x 256 2.613 (58 against 90 registers)
+template <class R, int kRows = kMgDirRows, int kThreads = kMgThreads>
+__global__ void __launch_bounds__(kThreads) k_mg_dir_apply(MgFine<R> c, MgScalars* __restrict__ sc,
                                                               const R* __restrict__ z, const R* __restrict__ d_old,
                                                               R* __restrict__ d_new, R* __restrict__ w,
                                                               double* __restrict__ partials, unsigned* __restrict__ ticket) {
@@ -230,15 +231,15 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_dir_apply(MgFine<R> c, MgScal
   const bool first = sc->iterations == 0;
   const int nx = c.nx;
   const int c0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-  const int j0 = c.row_lo + blockIdx.y * kMgDirRows, j1 = min(j0 + kMgDirRows, c.row_hi);
+  const int j0 = c.row_lo + blockIdx.y * kRows, j1 = min(j0 + kRows, c.row_hi);
   const bool any = c0 < nx, v0 = any && c0 >= 1, v1 = any && c0 + 1 <= nx - 2;
   double acc = 0.0;
   if (any) {
-    V dn[kMgDirRows + 2];            // d_new of the own pair on rows j0-1 .. j0+kMgDirRows
-    R dl[kMgDirRows], dr[kMgDirRows];  // d_new left / right of the pair on the tile's rows
+    V dn[kRows + 2];            // d_new of the own pair on rows j0-1 .. j0+kRows
+    R dl[kRows], dr[kRows];  // d_new left / right of the pair on the tile's rows
     const int cl = max(c0 - 1, 0), cr = min(c0 + 2, nx - 1);
 #pragma unroll
-    for (int m = 0; m < kMgDirRows + 2; ++m) {
+    for (int m = 0; m < kRows + 2; ++m) {
       const int j = min(j0 - 1 + m, c.row_hi);  // row_hi is the ring / halo row above the owned unknowns
       const size_t idx = (size_t)c0 + (size_t)j * nx;
       const V zv = *reinterpret_cast<const V*>(z + idx);
@@ -249,17 +250,17 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_dir_apply(MgFine<R> c, MgScal
       dn[m].y = zv.y + beta * dv.y;
     }
 #pragma unroll
-    for (int r = 0; r < kMgDirRows; ++r) {
+    for (int r = 0; r < kRows; ++r) {
       const int j = min(j0 + r, c.row_hi - 1);
       const size_t row = (size_t)j * nx;
       dl[r] = z[row + cl] + beta * (first ? R(0) : d_old[row + cl]);
       dr[r] = z[row + cr] + beta * (first ? R(0) : d_old[row + cr]);
     }
 #pragma unroll
-    V wv[kMgDirRows];
+    V wv[kRows];
     auto apply_tile = [&](auto& dv) {
 #pragma unroll
-      for (int r = 0; r < kMgDirRows; ++r) {
+      for (int r = 0; r < kRows; ++r) {
         const int j = min(j0 + r, j1 - 1);
         const V cen = dn[r + 1], south = dn[r], north = dn[r + 2];
         const R xw0 = (c0 == 1) ? cen.x : dl[r];
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_dir_apply(MgFine<R> c, MgScal
       apply_tile(exact);
     }
 #pragma unroll
-    for (int r = 0; r < kMgDirRows; ++r) {
+    for (int r = 0; r < kRows; ++r) {
       const int j = j0 + r;
       if (j < j1) {
         const V cen = dn[r + 1];
@@ -294,13 +295,13 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_dir_apply(MgFine<R> c, MgScal
       }
     }
   }
-  mg_finish_dot<R, kMgThreads>(c, sc, partials, ticket, acc, 2);
+  mg_finish_dot<R, kThreads>(c, sc, partials, ticket, acc, 2);
 }
 
 // x += alpha d, rho -= alpha w, rho.rho -> iteration count, stopping rule.  Tiles of kMgUpdRows rows.
-constexpr int kMgUpdRows = 4;
-template <class R>
-__global__ void __launch_bounds__(kMgThreads) k_mg_update(MgFine<R> c, MgScalars* __restrict__ sc,
+constexpr int kMgUpdRows = 4;  // r2af: 2-row tiles change nothing here (2.616 against 2.613 ms/step)
+template <class R, int kRows = kMgUpdRows, int kThreads = kMgThreads>
+__global__ void __launch_bounds__(kThreads) k_mg_update(MgFine<R> c, MgScalars* __restrict__ sc,
                                                            const R* __restrict__ d, const R* __restrict__ w,
                                                            R* __restrict__ x, R* __restrict__ rho,
                                                            double* __restrict__ partials, unsigned* __restrict__ ticket) {
@@ -308,13 +309,13 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_update(MgFine<R> c, MgScalars
   if (sc->done) return;
   const R alpha = (R)sc->alpha;
   const int c0 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
-  const int j0 = c.row_lo + blockIdx.y * kMgUpdRows, j1 = min(j0 + kMgUpdRows, c.row_hi);
+  const int j0 = c.row_lo + blockIdx.y * kRows, j1 = min(j0 + kRows, c.row_hi);
   const bool any = c0 < c.nx, v0 = any && c0 >= 1, v1 = any && c0 + 1 <= c.nx - 2;
   double acc = 0.0;
   if (any) {
-    V dv[kMgUpdRows], wv[kMgUpdRows], xv[kMgUpdRows], rv[kMgUpdRows];
+    V dv[kRows], wv[kRows], xv[kRows], rv[kRows];
 #pragma unroll
-    for (int r = 0; r < kMgUpdRows; ++r) {
+    for (int r = 0; r < kRows; ++r) {
       const int j = min(j0 + r, c.row_hi - 1);
       const size_t idx = (size_t)c0 + (size_t)j * c.nx;
       dv[r] = *reinterpret_cast<const V*>(d + idx);
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_update(MgFine<R> c, MgScalars
       rv[r] = *reinterpret_cast<const V*>(rho + idx);
     }
 #pragma unroll
-    for (int r = 0; r < kMgUpdRows; ++r) {
+    for (int r = 0; r < kRows; ++r) {
       const int j = j0 + r;
       if (j < j1) {
         if (v0) {
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(kMgThreads) k_mg_update(MgFine<R> c, MgScalars
       }
     }
   }
-  mg_finish_dot<R, kMgThreads>(c, sc, partials, ticket, acc, 3);
+  mg_finish_dot<R, kThreads>(c, sc, partials, ticket, acc, 3);
 }
 
 // strips: advance the CG scalars from the sum-allreduced local_sum (the single-domain kernels do this themselves)

@@ -277,6 +277,10 @@ struct ModelImpl final : ModelBase {
   bool fuse_corr_div = true;              // k_corrector_div (CFD_FUSED_CORRECTOR=0: the separate kernels)
   int corr_rows = cfdk::kCorrRows;        // its tile height and width (CFD_CORR_ROWS / CFD_CORR_THREADS: A/B forms)
   int corr_threads = cfdk::kCorrThreads;
+  int dir_rows = cfdk::kMgDirRows, dir_threads = cfdk::kMgThreads;  // tiles of k_mg_dir_apply / k_mg_update (CFD_DIR_TILE /
+  int upd_rows = cfdk::kMgUpdRows, upd_threads = cfdk::kMgThreads;  // CFD_UPD_TILE = "<rows>x<threads>": A/B forms)
+  int pred_rows = cfdk::kPredRows;        // rows a block of k_predict_first walks (CFD_PRED_ROWS: A/B hook)
+  int init_rows = cfdk::kMgRows;          // rows a block of k_mg_init walks (CFD_INIT_ROWS: A/B hook)
   int div_rows = cfdk::kDivRows;          // tile height of k_divergence (CFD_DIV_ROWS=8: A/B form)
   bool corr_div_ready = false;            // rhs and the rhs^2 partials of the fields the last corrector wrote are in place
   // measurement hook: CUDA-event pairs around every k_jacobi_sweep5 launch of the MGCG smoother (bench.py roofline)
@@ -836,6 +840,15 @@ struct ModelImpl final : ModelBase {
     }
     if (const char* e = getenv("CFD_FUSED_CORRECTOR")) fuse_corr_div = atoi(e) != 0;  // A/B hooks
     if (const char* e = getenv("CFD_CORR_ROWS")) { const int v = atoi(e); corr_rows = (v == 8 || v == 2 || v == 1) ? v : cfdk::kCorrRows; }
+    auto tile_hook = [](const char* name, int* rows_out, int* threads_out) {
+      int r = 0, t = 0;
+      const char* e = getenv(name);
+      if (e && sscanf(e, "%dx%d", &r, &t) == 2 && (r == 2 || r == 4) && (t == 128 || t == 256)) { *rows_out = r; *threads_out = t; }
+    };
+    tile_hook("CFD_DIR_TILE", &dir_rows, &dir_threads);
+    tile_hook("CFD_UPD_TILE", &upd_rows, &upd_threads);
+    if (const char* e = getenv("CFD_PRED_ROWS")) { const int v = atoi(e); if (v >= 2 && v <= 1024) pred_rows = v; }
+    if (const char* e = getenv("CFD_INIT_ROWS")) { const int v = atoi(e); if (v >= 2 && v <= 1024) init_rows = v; }
     if (const char* e = getenv("CFD_DIV_ROWS")) div_rows = atoi(e) == 8 ? 8 : cfdk::kDivRows;
     if (const char* e = getenv("CFD_CORR_THREADS")) corr_threads = atoi(e) == 128 && (corr_rows == 2 || corr_rows == 4) ? 128 : 256;
     if (const char* e = getenv("CFD_MG_FINISH_LAUNCH")) mg_finish_launch = atoi(e) != 0;
@@ -1378,8 +1391,7 @@ struct ModelImpl final : ModelBase {
     if ((rc = dalloc(&mg_ticket, (size_t)4))) return rc;
     {
       // one partial per block of the largest grid that ends in a dot product: the 4-row vector tiles, or the sweep
-      const size_t gx = (size_t)((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads));
-      const size_t n_vec = gx * (size_t)((ny + 3) / 4 + 1);
+      const size_t n_vec = (size_t)((nx + 255) / 256) * (size_t)((ny + 1) / 2 + 1);  // down to 2-row x 128-thread tiles
       const size_t n_sweep = (size_t)((nx / 2 + cfdk::kSweepWarps * 32 - 1) / (cfdk::kSweepWarps * 32)) * (size_t)((ny - 2 + sweep_rows_per_block - 1) / sweep_rows_per_block);
       const size_t n_leg = (size_t)((nx - 2 + 55) / 56) * (size_t)((ny - 2 + 15) / 16 + 1);  // at least the leg kernels' grids
       const size_t n_div = (size_t)((nx + 127) / 128) * (size_t)(ny + 1);  // k_divergence, every form of k_corrector_div
@@ -1963,9 +1975,10 @@ struct ModelImpl final : ModelBase {
     const dim3 blk(cfdk::kMgThreads);
     const unsigned gx = (unsigned)((nx + 2 * cfdk::kMgThreads - 1) / (2 * cfdk::kMgThreads));
     const int rows = c.row_hi - c.row_lo;
-    const dim3 g_all(gx, (jb - ja + cfdk::kMgRows - 1) / cfdk::kMgRows);            // every owned row (init)
-    const dim3 g_dir(gx, (rows + cfdk::kMgDirRows - 1) / cfdk::kMgDirRows);         // owned rows of unknowns, 4-row tiles
-    const dim3 g_upd(gx, (rows + cfdk::kMgUpdRows - 1) / cfdk::kMgUpdRows);
+    const dim3 g_all(gx, (jb - ja + init_rows - 1) / init_rows);                    // every owned row (init)
+    // owned rows of unknowns in tiles of dir_rows / upd_rows rows x 2 * threads columns
+    const dim3 b_dir(dir_threads), g_dir((unsigned)((nx + 2 * dir_threads - 1) / (2 * dir_threads)), (rows + dir_rows - 1) / dir_rows);
+    const dim3 b_upd(upd_threads), g_upd((unsigned)((nx + 2 * upd_threads - 1) / (2 * upd_threads)), (rows + upd_rows - 1) / upd_rows);
     const bool first_solve = call_index == 0;
     const bool warm = first_solve && opt.consts.mg_warm_start != 0;
     int& pred = mg_pred[first_solve ? 0 : 1];
@@ -2000,7 +2013,8 @@ struct ModelImpl final : ModelBase {
     // first solve of a step: start from the extrapolated history (mg_warm_start); the stencil of the start vector needs
     // the neighbours' edge rows, which every p' carries since the exchange at the end of its solve
     if (warm && mg_guess_explicit && (rc = exchange_halo(mg_guess, ja, jb, 1))) return rc;
-    cfdk::k_mg_init<R><<<g_all, blk, 0, stream>>>(c, mg_scalars, rhs.v, mg_start(warm), x, mg_rho.v, mg_partials, dot_ticket());
+    cfdk::k_mg_init<R><<<g_all, blk, 0, stream>>>(c, mg_scalars, rhs.v, mg_start(warm), x, mg_rho.v, mg_partials, dot_ticket(),
+                                                  init_rows);
     launches += 1;
     dot_finish(c, g_all, 0);
     if (warm) mg_guess_explicit = false;
@@ -2025,8 +2039,14 @@ struct ModelImpl final : ModelBase {
         if ((rc = mg_precondition(c, &zi))) return rc;
         // rho.z (-> beta) came out of the V-cycle's last sweep; d_new goes to the smoothing buffer that is free now
         const int dn = 3 - mg_id - zi;
-        cfdk::k_mg_dir_apply<R><<<g_dir, blk, 0, stream>>>(c, mg_scalars, mg_b[zi].v, mg_b[mg_id].v, mg_b[dn].v, w, mg_partials,
-                                                           dot_ticket());
+#define CFD_DIR_APPLY(ROWS, THREADS)                                                                                        \
+  cfdk::k_mg_dir_apply<R, ROWS, THREADS><<<g_dir, b_dir, 0, stream>>>(c, mg_scalars, mg_b[zi].v, mg_b[mg_id].v, mg_b[dn].v, w, \
+                                                                      mg_partials, dot_ticket())
+        if (dir_rows == 2 && dir_threads == 128) CFD_DIR_APPLY(2, 128);
+        else if (dir_rows == 2) CFD_DIR_APPLY(2, 256);
+        else if (dir_threads == 128) CFD_DIR_APPLY(4, 128);
+        else CFD_DIR_APPLY(4, 256);
+#undef CFD_DIR_APPLY
         dot_finish(c, g_dir, 2);
         mg_id = dn;
         mg_last_z = zi;
@@ -2038,7 +2058,14 @@ struct ModelImpl final : ModelBase {
           if ((rc = nccl_batch_end(&nb))) return rc;
         }
         if ((rc = mg_advance_strips(c, 2))) return rc;
-        cfdk::k_mg_update<R><<<g_upd, blk, 0, stream>>>(c, mg_scalars, mg_b[mg_id].v, w, x, mg_rho.v, mg_partials, dot_ticket());
+#define CFD_UPDATE(ROWS, THREADS)                                                                                      \
+  cfdk::k_mg_update<R, ROWS, THREADS><<<g_upd, b_upd, 0, stream>>>(c, mg_scalars, mg_b[mg_id].v, w, x, mg_rho.v, mg_partials, \
+                                                                   dot_ticket())
+        if (upd_rows == 2 && upd_threads == 128) CFD_UPDATE(2, 128);
+        else if (upd_rows == 2) CFD_UPDATE(2, 256);
+        else if (upd_threads == 128) CFD_UPDATE(4, 128);
+        else CFD_UPDATE(4, 256);
+#undef CFD_UPDATE
         launches += 2;
         dot_finish(c, g_upd, 3);
         {
@@ -2155,9 +2182,9 @@ struct ModelImpl final : ModelBase {
       } else {
         // first order: both equations in one pass over u and v
         const int j_end = ju_hi > jv_hi ? ju_hi : jv_hi;
-        dim3 blk(128), grd((nx + 127) / 128, (j_end - ju_lo + cfdk::kPredRows - 1) / cfdk::kPredRows);
+        dim3 blk(128), grd((nx + 127) / 128, (j_end - ju_lo + pred_rows - 1) / pred_rows);
         cfdk::k_predict_first<R><<<grd, blk, 0, stream>>>(s, pd, ubuf[X].v, vbuf[X].v, mask_u.v, mask_v.v, ubuf[Y].v, vbuf[Y].v,
-                                                          ju_lo, ju_hi, jv_hi);
+                                                          ju_lo, ju_hi, jv_hi, pred_rows);
         launches += 1;
       }
       CFD_CUDA(cudaGetLastError());
