@@ -418,7 +418,7 @@ def build_model(w, rk, strips, flags=0):
     return model, grid, params, strong
 
 
-def step_bytes_mode_c(nx, ny, solves_full, solves_elided, iterations, nu=2, fused=False):
+def step_bytes_mode_c(nx, ny, solves_full, solves_elided, iterations, nu=2, fused=False, corrector_div=False):
     """Algorithmic bytes of one Mode C step (SURVEY 8d's rule: every stage reads each of its inputs
     and writes each of its outputs once, s = 8 bytes): predictor 4 sN + 2 N, residual / CFL maxima 4 sN; a solve that runs
     = divergence 3 + set-up 4 + corrector 7; a re-correction round that is converged before its first iteration =
@@ -427,13 +427,16 @@ def step_bytes_mode_c(nx, ny, solves_full, solves_elided, iterations, nu=2, fuse
     prolongation 2.25 + nu sweeps 3 + rho.z 2 + direction 3 + L d 2 + update 6 = 19.5 + 3 (2 nu - 1) sN (28.5 at nu = 2);
     a coarse level = 6.5 + 3 (2 nu - 1) s N_l (sum N_l = N / 3).  fused=True: the compulsory traffic of the kernels as they
     run (each leg of the cycle is one pass: level 0 descending 2.25 + ascending 3.25 + direction / L d 5 + update 6 = 16.5,
-    a coarse level 5.5) -- the conservative figure beside the stage-by-stage one."""
+    a coarse level 5.5) -- the conservative figure beside the stage-by-stage one; corrector_div (single domain): the
+    divergence of an elided re-correction round comes out of the corrector that precedes it (k_corrector_div), which
+    leaves 1 sN (the rhs it writes) of that stage's 3 sN as traffic."""
     n = nx * ny
     if fused:
         per_it = 16.5 + 5.5 / 3.0
     else:
         per_it = 19.5 + 3 * (2 * nu - 1) + (6.5 + 3 * (2 * nu - 1)) / 3.0
-    return 8 * n * (8 + 14 * solves_full + 3 * solves_elided + per_it * iterations) + 2 * n
+    elided_sn = 1 if (fused and corrector_div) else 3
+    return 8 * n * (8 + 14 * solves_full + elided_sn * solves_elided + per_it * iterations) + 2 * n
 
 
 def legs_active(consts, flags):
@@ -582,7 +585,7 @@ def run_extra(args, name, rk, steps=3):
         out["sweep_frac_of_peak"] = None
         out["ascending_leg_us"] = sweep_us
         out["ascending_leg_frac_of_peak_stage_bytes"] = (3 * nu + 4.25) * 8 * rank_cells / (sweep_us * 1e-6) / 1e9 / peak if sweep_us > 0 else None
-        out["step_frac_of_peak_fused_traffic"] = step_bytes_mode_c(nx, ny, full, k - full, s_, nu=nu, fused=True) / (dev_s / steps) / 1e9 / (peak * rk.world)
+        out["step_frac_of_peak_fused_traffic"] = step_bytes_mode_c(nx, ny, full, k - full, s_, nu=nu, fused=True, corrector_div=rk.world == 1) / (dev_s / steps) / 1e9 / (peak * rk.world)
     if mode_c:
         out["cg_iterations_list"] = acc["its"]
         out["ms_per_cg_iteration"] = dev_s * 1e3 / max(acc["sweeps"], 1)
@@ -759,7 +762,7 @@ def run_ours(args, w):
         elided = (solves - steps) / steps if acc["first_its"] == sweeps else 0.0
         step_bytes = step_bytes_mode_c(nx, ny, k_per_step - elided, elided, s_per_step, nu=nu) * replicas
         step_bytes_r1 = step_bytes_mode_c(nx, ny, k_per_step, 0.0, s_per_step, nu=nu) * replicas
-        step_bytes_fused = step_bytes_mode_c(nx, ny, k_per_step - elided, elided, s_per_step, nu=nu, fused=legs) * replicas
+        step_bytes_fused = step_bytes_mode_c(nx, ny, k_per_step - elided, elided, s_per_step, nu=nu, fused=legs, corrector_div=world == 1) * replicas
     else:
         step_bytes = 8 * cells * (8 + 10 * k_per_step + 3 * s_per_step) + 2 * cells  # whole job
         step_bytes_r1 = step_bytes

@@ -79,3 +79,6 @@ def test_mode_c_byte_accounting_matches_design():
     assert abs(per_it3 - 8 * n * (34.5 + 21.5 / 3)) < 1e-6
     assert abs(fused - 8 * n * (16.5 + 5.5 / 3)) < 1e-6
     assert fused < per_it2 < per_it3
+    # single domain: the elided round's divergence rides on the corrector before it (k_corrector_div): 1 sN instead of 3
+    assert base - bench.step_bytes_mode_c(64, 64, 1, 1, 0, nu=2, fused=True, corrector_div=True) == 8 * n * 2
+    assert bench.step_bytes_mode_c(64, 64, 1, 1, 0, nu=2, corrector_div=True) == base  # the stage-by-stage count is unchanged
