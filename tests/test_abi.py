@@ -144,3 +144,20 @@ def test_python_constants_match_the_header():
                 break
     assert checked >= 20, checked
     assert defines["CFD_FIELD_COUNT"] == max(v for k, v in vars(_abi).items() if k.startswith("FIELD_") and isinstance(v, int)) + 1
+
+
+def test_every_environment_hook_of_the_library_is_documented():
+    """INTEGRATION.md lists the library's tuning / A-B hooks: every getenv() in csrc/ must appear there (doc drift check)."""
+    csrc = os.path.join(ROOT, "cfd_demo_b200", "csrc")
+    src = ""
+    for name in sorted(os.listdir(csrc)):
+        if name.endswith((".cu", ".cuh")):
+            with open(os.path.join(csrc, name)) as f:
+                src += f.read()
+    hooks = set(re.findall(r'getenv\("([A-Z0-9_]+)"\)', src))
+    hooks |= set(re.findall(r'tile_hook\("([A-Z0-9_]+)"', src))
+    assert len(hooks) >= 15, hooks
+    with open(os.path.join(ROOT, "INTEGRATION.md")) as f:
+        doc = f.read()
+    missing = sorted(h for h in hooks if h not in doc)
+    assert not missing, missing
