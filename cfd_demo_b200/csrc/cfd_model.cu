@@ -2133,6 +2133,7 @@ struct ModelImpl final : ModelBase {
     const auto t0 = std::chrono::steady_clock::now();
     launches = 0;
     ev_prof_used = 0;
+    corr_div_ready = false;  // (an update() that failed half-way must not leave it set)
     CFD_CUDA(cudaEventRecord(ev_step0, stream));
     if (simulation_step < (uint64_t)opt.consts.ramp_up_steps) {  // :311-316
       current_inlet_velocity = (R(simulation_step) / R(opt.consts.ramp_up_steps)) * target_inlet_velocity;
