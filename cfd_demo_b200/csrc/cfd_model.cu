@@ -839,7 +839,7 @@ struct ModelImpl final : ModelBase {
       rpb = (int)(((want - 2) / 4) * 4 + 2);  // rows + 2 halo rows = whole number of 4-row boxes
     }
     if (const char* e = getenv("CFD_FUSED_CORRECTOR")) fuse_corr_div = atoi(e) != 0;  // A/B hooks
-    if (const char* e = getenv("CFD_CORR_ROWS")) { const int v = atoi(e); corr_rows = (v == 8 || v == 2 || v == 1) ? v : cfdk::kCorrRows; }
+    if (const char* e = getenv("CFD_CORR_ROWS")) { const int v = atoi(e); corr_rows = (v == 8 || v == 4 || v == 1) ? v : cfdk::kCorrRows; }
     auto tile_hook = [](const char* name, int* rows_out, int* threads_out) {
       int r = 0, t = 0;
       const char* e = getenv(name);
@@ -850,7 +850,8 @@ struct ModelImpl final : ModelBase {
     if (const char* e = getenv("CFD_PRED_ROWS")) { const int v = atoi(e); if (v >= 2 && v <= 1024) pred_rows = v; }
     if (const char* e = getenv("CFD_INIT_ROWS")) { const int v = atoi(e); if (v >= 2 && v <= 1024) init_rows = v; }
     if (const char* e = getenv("CFD_DIV_ROWS")) div_rows = atoi(e) == 8 ? 8 : cfdk::kDivRows;
-    if (const char* e = getenv("CFD_CORR_THREADS")) corr_threads = atoi(e) == 128 && (corr_rows == 2 || corr_rows == 4) ? 128 : 256;
+    if (const char* e = getenv("CFD_CORR_THREADS")) corr_threads = atoi(e) == 256 ? 256 : cfdk::kCorrThreads;
+    if (corr_rows == 8 || corr_rows == 1) corr_threads = 256;  // forms that exist at one width only
     if (const char* e = getenv("CFD_MG_FINISH_LAUNCH")) mg_finish_launch = atoi(e) != 0;
     if (const char* e = getenv("CFD_SWEEP_ROWS")) {  // tuning hook (tools/tune_sweep.py)
       const int v = atoi(e);
