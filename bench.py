@@ -690,6 +690,16 @@ def run_ours(args, w):
         snap = model.get_snapshot(out=pinned)
     torch.cuda.synchronize()
     wall_e2e_sync = (time.perf_counter() - t1b) / min(args.steps, 5)
+    # (c) between two frames of the reference's UI no snapshot is requested at all (src/model.rs:1296-1306: the solver thread
+    # steps continuously and copies fields only on Command::GetSnapshot): parameters in, residual scalars out, every step
+    torch.cuda.synchronize()
+    t1c = time.perf_counter()
+    for _ in range(args.steps):
+        model.set_parameters(params)
+        model.update()
+        res = model.get_residuals()
+    torch.cuda.synchronize()
+    wall_e2e_scalars = (time.perf_counter() - t1c) / args.steps
     # the same with freshly allocated pageable buffers (what a caller holding plain Vec<f32>s gets)
     t2 = time.perf_counter()
     for _ in range(min(args.steps, 3)):
@@ -838,6 +848,7 @@ def run_ours(args, w):
                                "sides, max over ranks); value = the fastest pass, all passes listed (the boxes are shared: PCIe / "
                                "host-memory interference comes in bursts and is not a property of the path)"),
                     "ms_per_step_blocking_get_snapshot": wall_e2e_sync * 1e3,
+                    "ms_per_step_residuals_only": wall_e2e_scalars * 1e3,
                     "ms_per_step_pageable_destination": wall_e2e_pageable * 1e3,
                     "ms_per_step_rgba_image_instead": None if wall_e2e_image is None else wall_e2e_image * 1e3,
                     "calls": "cfd_model_set_params + cfd_model_update + cfd_model_get_residuals + cfd_model_snapshot_begin / _end "
